@@ -572,6 +572,9 @@ class OffPolicyOracle:
                 out[net.prefix + 'encoder.observation_normalizer._std'] = self.norm.t_std
         out['observation_normalizer._mean'] = self.norm.t_mean
         out['observation_normalizer._std'] = self.norm.t_std
+        if self.kind == 'TD3':     # td3.py:36 registers critic_1 again as `critic`
+            for k in [k for k in out if k.startswith('critic_1.')]:
+                out['critic.' + k[len('critic_1.'):]] = out[k]
         return out
 
     # -- acting -------------------------------------------------------------
