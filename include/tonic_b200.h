@@ -1,0 +1,283 @@
+/*
+ * tonic_b200 -- C ABI of the B200-native (sm_100a) backend for the data-parallel
+ * hot path of fabiopardo/tonic: the synchronous vector-environment collector and
+ * the PPO / A2C / DDPG / TD3 / SAC update loops with their replays.
+ *
+ * The reference has no FFI of its own (the boundary is a
+ * duck-typed Python protocol).  This header is the drop-in boundary one level
+ * below that protocol: one entry point per reference operation on the path, each
+ * citing the reference code it replaces (paths relative to the reference's
+ * `tonic/` package).  The Python classes in `tonic_b200/` that mirror the
+ * reference's classes call these through ctypes.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer, h_* a HOST pointer;
+ *   - all floating-point data are float32, row-major; "rows" are transitions
+ *     (flat index t*N+n, replays/utils.py:22-25);
+ *   - no entry point allocates device memory or synchronises the device; work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*), so calls can be
+ *     captured in CUDA graphs;
+ *   - return value: 0 on success, a cudaError_t (>0) or a negative TB_E* code
+ *     otherwise; tb_last_error() gives a readable message.
+ */
+#ifndef TONIC_B200_H
+#define TONIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_VERSION 1
+
+#define TB_EINVAL (-1)       /* bad argument / unsupported shape            */
+#define TB_ENOTSUP (-2)      /* configuration outside the implemented subset */
+
+/* activation ids (models/utils.py:15-16 passes torch.nn.Tanh / ReLU)         */
+#define TB_ACT_TANH 0
+#define TB_ACT_RELU 1
+
+int tb_version(void);
+const char* tb_last_error(void);
+/* Number of kernels launched by this library since process start (bench.py's
+ * `gpu_launches`).                                                            */
+int64_t tb_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* Vector environment  -- replaces environments/distributed.py:8-58           */
+/* (Sequential.{initialize,start,step}) and the ActionRescaler clip           */
+/* (environments/wrappers.py:18-22) for the synthetic SynthControl(O,A) env.  */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n_envs;            /* N workers on this device                    */
+    int32_t obs_dim;           /* O                                           */
+    int32_t act_dim;           /* A                                           */
+    int32_t max_episode_steps; /* time-limit: reset, NOT a termination (:40)  */
+    int64_t seed;              /* env i uses seed + first_worker + i (:18-20) */
+    int64_t first_worker;      /* global index of this device's first worker  */
+    float* d_state;            /* [N,O] current state x                       */
+    int32_t* d_length;         /* [N]  steps in the running episode (:25,38)  */
+    uint32_t* d_episode;       /* [N]  episodes started so far                */
+    double* d_score;           /* [N]  running episode score (trainer.py:37)  */
+    /* finished-episode log (trainer.py:64-71): ring of capacity log_cap      */
+    double* d_ep_scores;       /* [log_cap]                                   */
+    int32_t* d_ep_lengths;     /* [log_cap]                                   */
+    unsigned long long* d_ep_count; /* [1] total finished episodes            */
+    int32_t log_cap;
+} TbEnv;
+
+/* Sequential.start (:22-26): reset every env, lengths=0, writes obs [N,O].   */
+int tb_env_start(const TbEnv* env, float* d_obs, void* stream);
+
+/* Sequential.step (:28-58).  d_actions [N,A].  Outputs: d_obs [N,O] = acting
+ * observations (post auto-reset), d_next_obs [N,O] = transition observations
+ * (pre-reset), d_rewards/d_resets/d_terminations [N] float32 (0/1 flags, the
+ * dtype the replays store: replays/segments.py:33).                          */
+int tb_env_step(const TbEnv* env, const float* d_actions, float* d_obs,
+                float* d_next_obs, float* d_rewards, float* d_resets,
+                float* d_terminations, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Observation normaliser -- replaces torch/normalizers/mean_stds.py:44-74    */
+/* ------------------------------------------------------------------------ */
+/* MeanStd.record (:44-48): d_sums[0:dim] += sum_n x, d_sums[dim:2dim] += sum_n
+ * x^2 (float64 accumulators), d_sums[2*dim] += n.                            */
+int tb_moments_record(const float* d_x, int64_t n_rows, int32_t dim,
+                      double* d_sums, void* stream);
+/* MeanStd.update (:50-74): merges the recorded sums into the running
+ * mean / mean_sq (float32, d_running = [mean(dim) | mean_sq(dim)]), total count
+ * in d_count[0], writes d_mean/d_std (the `_mean`/`_std` parameters), clears
+ * d_sums.  eps = 1e-2 (:15,65-70).  No-op when nothing was recorded.          */
+int tb_moments_update(double* d_sums, float* d_running, double* d_count,
+                      float* d_mean, float* d_std, int32_t dim, float eps,
+                      void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Segment replay helpers -- replays/utils.py:4-19, replays/segments.py:38-78 */
+/* ------------------------------------------------------------------------ */
+/* lambda_returns (utils.py:4-19): all arrays [T,N]; reverse scan over T.     */
+int tb_lambda_returns(const float* d_values, const float* d_next_values,
+                      const float* d_rewards, const float* d_resets,
+                      const float* d_terminations, float* d_returns,
+                      int32_t T, int32_t N, double discount_factor,
+                      double trace_decay, void* stream);
+/* Segment.get_full advantage normalisation (segments.py:41-46):
+ * adv = returns - values; if std(adv) != 0: adv = (adv - mean) / std
+ * (population std, two-pass).  d_workspace: >= 4 doubles.  When `world` > 1 the
+ * caller all-reduces d_workspace[0:2] between phase 1 and 2 and d_workspace[2]
+ * between phase 2 and 3; single-GPU callers use phase 0 (= all).  */
+int tb_advantages(const float* d_returns, const float* d_values,
+                  float* d_advantages, int64_t n, double* d_workspace,
+                  int64_t n_global, int32_t phase, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Two-hidden-layer MLP (torch/models/utils.py:4-23) with a linear head        */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t d_in;      /* input width (obs, or obs+act for Q critics)         */
+    int32_t hidden;    /* H: both hidden layers (64, 128 or 256)              */
+    int32_t n_out;     /* head rows (A, 2A for loc+scale heads, 1 for values) */
+    int32_t act;       /* TB_ACT_*                                            */
+    /* float offsets into the flat parameter buffer (each multiple of 4)      */
+    int32_t off_w1, off_b1, off_w2, off_b2, off_w3, off_b3;
+    int32_t n_params;  /* padded length of the flat buffer                    */
+    /* float offsets into the packed buffer (transposes for the forward pass) */
+    int32_t off_w1t, off_w2t;
+    int32_t n_packed;
+} TbMlpShape;
+
+typedef struct {
+    /* source 1: rows of width dim1, optionally gathered through d_idx and
+     * normalised as (x - mean) / std (torch/normalizers/mean_stds.py:34-39)  */
+    const float* d_x1;
+    int32_t dim1;
+    const float* d_mean;   /* NULL = no normalisation (actor quirk) */
+    const float* d_std;
+    /* source 2 (optional): rows of width dim2 concatenated after source 1
+     * (models/encoders.py:28-31), gathered through d_idx iff gather2 != 0     */
+    const float* d_x2;
+    int32_t dim2;
+    int32_t gather2;
+    const int64_t* d_idx;  /* NULL = rows are 0..n_rows-1                     */
+} TbMlpInput;
+
+/* Forward pass for n_rows rows.  d_out [n_rows, n_out] = head pre-activations.
+ * Optional saves for the backward pass (NULL to skip): d_xin [n_rows, ldx] the
+ * assembled input with a trailing 1 column (ldx = round_up(d_in + 1, 4)),
+ * d_h1 / d_h2 [n_rows, H].  d_skip (optional, device int32): when *d_skip != 0
+ * the kernel exits immediately (device-side early stop, ppo.py:45-46).        */
+int tb_mlp_forward(const TbMlpShape* shape, const float* d_params,
+                   const float* d_packed, const TbMlpInput* in, int64_t n_rows,
+                   float* d_out, float* d_xin, float* d_h1, float* d_h2,
+                   const int32_t* d_skip, void* stream);
+
+/* Backward pass: given d_dout [n_rows, ld_dout >= n_out] (gradient w.r.t. head
+ * pre-activations) and the saved h1/h2, writes d_dz2, d_dz1 [n_rows, H]
+ * (gradients w.r.t. hidden pre-activations) and, if d_dx != NULL, the gradient
+ * w.r.t. input columns [dx_col0, dx_col0 + dx_cols) into d_dx [n_rows, dx_cols]
+ * (used for dQ/da, updaters/actors.py:177-181,254-257).                       */
+int tb_mlp_backward(const TbMlpShape* shape, const float* d_params,
+                    const float* d_dout, int32_t ld_dout, const float* d_h1, const float* d_h2,
+                    int64_t n_rows, float* d_dz2, float* d_dz1, float* d_dx,
+                    int32_t dx_col0, int32_t dx_cols, const int32_t* d_skip,
+                    void* stream);
+
+/* Weight gradients: per-split partial sums over rows, written (not
+ * accumulated) to d_gpart [n_split, n_params] in the flat parameter layout.
+ * `d_dout` has ld_dout >= n_out columns; columns [n_out, n_out + n_extra) are
+ * summed over rows into the flat buffer at off_extra (e.g. the per-sample
+ * log_scale gradients of the detached-scale Gaussian head).                   */
+int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const float* d_h1,
+                 const float* d_h2, const float* d_dz1, const float* d_dz2,
+                 const float* d_dout, int32_t ld_dout, int32_t n_extra,
+                 int32_t off_extra, int64_t n_rows, float* d_gpart,
+                 int32_t n_split, const int32_t* d_skip, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Optimiser -- torch.optim.Adam as constructed at updaters/actors.py:11-12,   */
+/* 58-59,161-162,228-229 and updaters/critics.py:9-10,59-60,143-144,190-191    */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    double lr, beta1, beta2, eps;   /* python floats of the reference ctor */
+    int32_t n_params;
+    float* d_params;       /* flat parameters                                 */
+    float* d_m;            /* exp_avg                                         */
+    float* d_v;            /* exp_avg_sq                                      */
+    int32_t* d_step;       /* [2] steps taken (device resident), block counter */
+} TbAdam;
+
+/* grad[i] = grad_scale * sum_s d_gpart[s, i]; Adam step; then refreshes the
+ * packed transposes (W1^T, W2^T) of `shape` in d_packed.
+ * Device-side control (all optional):
+ *   d_skip      -- if *d_skip != 0 nothing happens;
+ *   d_stats     -- double[TB_STAT_COUNT] statistics of the current minibatch
+ *                  produced by the loss kernel; if stats[TB_STAT_NONZERO_ADV]
+ *                  == 0 the step is skipped (updaters/actors.py:22,71);
+ *   kl_threshold-- if >= 0 and stats kl mean > kl_threshold, *d_stop is set to
+ *                  1 AFTER the step (updaters/actors.py:103,112; ppo.py:45-46).*/
+int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
+                 const float* d_gpart, int32_t n_split, float grad_scale,
+                 const int32_t* d_skip, const double* d_stats,
+                 float kl_threshold, int32_t* d_stop, void* stream);
+
+/* (Re)builds the packed transposes from the flat parameters.                 */
+int tb_mlp_pack(const TbMlpShape* shape, const float* d_params, float* d_packed,
+                void* stream);
+
+/* Target networks (models/actor_critics.py:68-72,126-130):
+ * target = (1 - tau) * target + tau * online, elementwise over n floats.      */
+int tb_soft_update(float* d_target, const float* d_online, int64_t n, double tau,
+                   void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Policy / value heads and losses                                            */
+/* ------------------------------------------------------------------------ */
+/* layout of the per-minibatch statistics block (doubles, sums over rows)     */
+enum {
+    TB_STAT_ROWS = 0,        /* rows in the minibatch                          */
+    TB_STAT_LOSS = 1,        /* sum of per-row loss terms                      */
+    TB_STAT_KL = 2,          /* sum(log_prob_old - log_prob_new)               */
+    TB_STAT_ENTROPY = 3,     /* sum over rows and action dims of the entropy   */
+    TB_STAT_CLIPPED = 4,     /* number of clipped ratios                       */
+    TB_STAT_NONZERO_ADV = 5, /* number of rows with advantage != 0             */
+    TB_STAT_STD = 6,         /* sum over rows and dims of the policy std       */
+    TB_STAT_VALUE = 7,       /* sum of predicted values (v / q / q1)           */
+    TB_STAT_VALUE2 = 8,      /* sum of q2 (twin critics)                       */
+    TB_STAT_COUNT = 12
+};
+
+/* DetachedScaleGaussianPolicyHead (models/actors.py:37-66) + Normal.sample +
+ * log_prob.sum(-1) (agents/a2c.py:75-85).  d_loc_pre [n, A] head
+ * pre-activations; loc = tanh(pre); scale = clamp(softplus(log_scale) + 1e-8,
+ * 1e-4, 1).  Noise: d_eps [n, A] host-generated standard normals (parity mode:
+ * action = loc + eps * scale, separately rounded like torch) or NULL to draw
+ * Philox normals from (seed, counter).                                        */
+int tb_gauss_sample(const float* d_loc_pre, const float* d_log_scale,
+                    const float* d_eps, uint64_t seed, uint64_t counter,
+                    int64_t n_rows, int32_t act_dim, float* d_actions,
+                    float* d_log_probs, void* stream);
+
+/* ClippedRatio (updaters/actors.py:70-112) when ratio_clip > 0, else
+ * StochasticPolicyGradient (updaters/actors.py:21-50).  Inputs are gathered
+ * through d_idx (NULL = identity).  Writes d_dout [n, 2A]: columns [0, A)
+ * gradient w.r.t. the loc pre-activation, [A, 2A) per-row gradient w.r.t.
+ * log_scale; gradients are for the SUM loss (the 1/rows factor is applied by
+ * tb_adam_step's grad_scale).  Accumulates d_stats (must be zeroed).          */
+int tb_gauss_policy_loss(const float* d_loc_pre, const float* d_log_scale,
+                         const float* d_actions, const float* d_advantages,
+                         const float* d_old_log_probs, const int64_t* d_idx,
+                         int64_t n_rows, int32_t act_dim, float ratio_clip,
+                         float entropy_coeff, float* d_dout, double* d_stats,
+                         const int32_t* d_skip, void* stream);
+
+/* MSE value regression (updaters/critics.py:18-28, and the Q losses at
+ * :77-86,169-182,222-235): d_dout[i * ld_dout] = 2 (v - target) for the SUM
+ * loss; targets gathered through d_idx when given.  Accumulates the squared
+ * error into TB_STAT_LOSS, the values into stat_slot (TB_STAT_VALUE/VALUE2) and,
+ * if count_rows != 0, the row count into TB_STAT_ROWS.                        */
+int tb_mse_loss(const float* d_values, const float* d_targets,
+                const int64_t* d_idx, int64_t n_rows, float* d_dout,
+                int32_t ld_dout, double* d_stats, int32_t stat_slot,
+                int32_t count_rows, const int32_t* d_skip, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Host-side numpy-compatible MT19937 streams (legacy numpy.random.RandomState)*/
+/* used for bit-exact minibatch / replay indices and exploration noise:        */
+/* replays/segments.py:20,62  replays/buffers.py:22,86  explorations/noisy.py  */
+/* ------------------------------------------------------------------------ */
+typedef struct TbRandomState TbRandomState;
+TbRandomState* tb_rs_create(uint32_t seed);            /* RandomState(seed)    */
+void tb_rs_destroy(TbRandomState* rs);
+/* RandomState.shuffle(x) for a 1-D int64 array                                */
+void tb_rs_shuffle_i64(TbRandomState* rs, int64_t* h_x, int64_t n);
+/* RandomState.randint(high, size=n) (dtype int64)                             */
+void tb_rs_randint(TbRandomState* rs, int64_t high, int64_t* h_out, int64_t n);
+/* RandomState.uniform(low, high, n) / RandomState.normal(size=n) (float64)    */
+void tb_rs_uniform(TbRandomState* rs, double low, double high, double* h_out, int64_t n);
+void tb_rs_normal(TbRandomState* rs, double* h_out, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TONIC_B200_H */

@@ -1,0 +1,178 @@
+// K1: device-resident synthetic vector environment.
+// Replaces the per-env Python loop of Sequential.step
+// (reference tonic/environments/distributed.py:28-58) and the ActionRescaler
+// clip (tonic/environments/wrappers.py:18-22) for SynthControl(O, A); the
+// dynamics are the ones defined in oracle/synth_env.py and are bit-identical
+// (separately rounded float32 ops, integer-quantised reward).
+//
+// Layout: state / observations are [N, O] row-major (the reference's layout);
+// a CTA stages a contiguous tile of `tile_envs` rows through shared memory with
+// coalesced loads/stores; inside the tile one warp owns one env at a time
+// (lanes over observation coordinates, warp-shuffle reduction for the cost).
+#include "common.cuh"
+
+namespace tb {
+
+__device__ __forceinline__ float reset_coordinate(uint32_t key, int j) {
+    const uint32_t h = fmix32(key ^ (0x85EBCA6Bu * (uint32_t)(j + 1)));
+    return __fsub_rn(__fmul_rn((float)(h >> 8), 1.1920928955078125e-07f), 1.0f);
+}
+__device__ __forceinline__ uint32_t reset_key(uint32_t seed, uint32_t episode) {
+    return fmix32(seed + 0x9E3779B9u * (episode + 1u));
+}
+
+constexpr float kDecay = 0.9f;
+constexpr float kGain = 0.1f;
+constexpr float kTermLimit = 1.0f;
+constexpr float kCostScale = (float)(0.01 * 9.5367431640625e-07);   // 0.01 * 2^-20
+
+__global__ void __launch_bounds__(256)
+env_start_kernel(TbEnv env, float* __restrict__ obs) {
+    const int64_t total = (int64_t)env.n_envs * env.obs_dim;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / env.obs_dim), j = (int)(i % env.obs_dim);
+        const uint32_t seed = (uint32_t)(env.seed + env.first_worker + n);
+        const float v = reset_coordinate(reset_key(seed, 0u), j);
+        env.d_state[i] = v;
+        obs[i] = v;
+        if (j == 0) {
+            env.d_length[n] = 0;
+            env.d_episode[n] = 1u;
+            env.d_score[n] = 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+env_step_kernel(TbEnv env, const float* __restrict__ actions, float* __restrict__ obs,
+                float* __restrict__ next_obs, float* __restrict__ rewards,
+                float* __restrict__ resets, float* __restrict__ terminations,
+                int tile_envs) {
+    extern __shared__ float smem[];
+    const int O = env.obs_dim, A = env.act_dim;
+    float* sx = smem;                          // [tile, O] state -> transition obs
+    float* so = sx + (size_t)tile_envs * O;    // [tile, O] acting obs (post reset)
+    float* sa = so + (size_t)tile_envs * O;    // [tile, A] clipped actions
+
+    const int e0 = blockIdx.x * tile_envs;
+    const int count = min(tile_envs, env.n_envs - e0);
+    const int tid = threadIdx.x;
+
+    const float* gx = env.d_state + (size_t)e0 * O;
+    for (int i = tid; i < count * O; i += blockDim.x) sx[i] = gx[i];
+    const float* ga = actions + (size_t)e0 * A;
+    for (int i = tid; i < count * A; i += blockDim.x)
+        sa[i] = fminf(fmaxf(ga[i], -1.0f), 1.0f);      // wrappers.py:22 np.clip
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int e = warp; e < count; e += nwarps) {
+        const int n = e0 + e;
+        float* x = sx + (size_t)e * O;
+        const float* a = sa + (size_t)e * A;
+        long long xcost = 0, acost = 0;
+        for (int j = lane; j < O; j += 32) {
+            const float drive = __fmul_rn(kGain, a[j % A]);
+            const float keep = (j == 0) ? x[0] : __fmul_rn(kDecay, x[j]);
+            const float nx = __fadd_rn(keep, drive);
+            x[j] = nx;
+            const long long q = __float2ll_rn(__fmul_rn(nx, 256.0f));
+            xcost += q * q;
+        }
+        for (int k = lane; k < A; k += 32) {
+            const long long q = __float2ll_rn(__fmul_rn(a[k], 1024.0f));
+            acost += q * q;
+        }
+        xcost = warp_sum(xcost);
+        acost = warp_sum(acost);
+        __syncwarp();
+        int reset = 0;
+        uint32_t episode = 0;
+        if (lane == 0) {
+            const long long cost = 100ll * acost + 16ll * xcost;
+            const float reward = __fsub_rn(1.0f, __fmul_rn(__ll2float_rn(cost), kCostScale));
+            const int term = fabsf(x[0]) > kTermLimit;
+            int length = env.d_length[n] + 1;
+            // distributed.py:40 -- a time-out resets without terminating
+            reset = term || (length == env.max_episode_steps);
+            double score = env.d_score[n] + (double)reward;    // trainer.py:52
+            episode = env.d_episode[n];
+            if (reset) {                                        // trainer.py:64-71
+                const unsigned long long slot = atomicAdd(env.d_ep_count, 1ull);
+                if (env.log_cap > 0) {
+                    env.d_ep_scores[slot % env.log_cap] = score;
+                    env.d_ep_lengths[slot % env.log_cap] = length;
+                }
+                env.d_episode[n] = episode + 1u;
+                length = 0;
+                score = 0.0;
+            }
+            env.d_length[n] = length;
+            env.d_score[n] = score;
+            rewards[n] = reward;
+            resets[n] = reset ? 1.0f : 0.0f;
+            terminations[n] = term ? 1.0f : 0.0f;
+        }
+        reset = __shfl_sync(0xffffffffu, reset, 0);
+        episode = __shfl_sync(0xffffffffu, episode, 0);
+        float* o = so + (size_t)e * O;
+        if (reset) {                                             // distributed.py:46-48
+            const uint32_t key = reset_key((uint32_t)(env.seed + env.first_worker + n), episode);
+            for (int j = lane; j < O; j += 32) o[j] = reset_coordinate(key, j);
+        } else {
+            for (int j = lane; j < O; j += 32) o[j] = x[j];
+        }
+    }
+    __syncthreads();
+
+    float* gs = env.d_state + (size_t)e0 * O;
+    float* go = obs + (size_t)e0 * O;
+    float* gn = next_obs + (size_t)e0 * O;
+    for (int i = tid; i < count * O; i += blockDim.x) {
+        const float v = so[i];
+        gs[i] = v;
+        go[i] = v;
+        gn[i] = sx[i];
+    }
+}
+
+static int pick_tile(const TbEnv* env, size_t* smem_bytes) {
+    const size_t per_env = (size_t)(2 * env->obs_dim + env->act_dim) * sizeof(float);
+    int tile = 256;
+    while (tile > 8 && ((size_t)tile * per_env > 96 * 1024 ||
+                        (int64_t)tile * kNumSMs > (int64_t)env->n_envs))
+        tile >>= 1;
+    *smem_bytes = (size_t)tile * per_env;
+    return tile;
+}
+
+}  // namespace tb
+
+extern "C" int tb_env_start(const TbEnv* env, float* d_obs, void* stream) {
+    TB_REQUIRE(env && d_obs && env->n_envs > 0 && env->obs_dim > 0 && env->act_dim > 0,
+               TB_EINVAL, "tb_env_start: bad arguments");
+    const int64_t total = (int64_t)env->n_envs * env->obs_dim;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    cudaMemsetAsync(env->d_ep_count, 0, sizeof(unsigned long long), tb::as_stream(stream));
+    tb::env_start_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(*env, d_obs);
+    return tb::check_launch("tb_env_start");
+}
+
+extern "C" int tb_env_step(const TbEnv* env, const float* d_actions, float* d_obs,
+                           float* d_next_obs, float* d_rewards, float* d_resets,
+                           float* d_terminations, void* stream) {
+    TB_REQUIRE(env && d_actions && d_obs && d_next_obs && d_rewards && d_resets && d_terminations,
+               TB_EINVAL, "tb_env_step: null pointer");
+    size_t smem = 0;
+    const int tile = tb::pick_tile(env, &smem);
+    TB_REQUIRE(smem <= 200 * 1024, TB_ENOTSUP, "tb_env_step: obs_dim %d too large", env->obs_dim);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(tb::env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+    }
+    const int blocks = (env->n_envs + tile - 1) / tile;
+    tb::env_step_kernel<<<blocks, 256, smem, tb::as_stream(stream)>>>(
+        *env, d_actions, d_obs, d_next_obs, d_rewards, d_resets, d_terminations, tile);
+    return tb::check_launch("tb_env_step");
+}

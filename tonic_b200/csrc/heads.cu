@@ -1,0 +1,210 @@
+// Policy / value heads and losses (small elementwise kernels on [rows, n_out]).
+//
+// Reference:
+//  * DetachedScaleGaussianPolicyHead  tonic/torch/models/actors.py:37-66
+//  * sampling + log-prob              tonic/torch/agents/a2c.py:75-85
+//    (torch.distributions.Normal: sample = eps * scale + loc, separately rounded;
+//     log_prob = -((a - loc)^2) / (2 scale^2) - log(scale) - log(sqrt(2 pi)))
+//  * ClippedRatio                     tonic/torch/updaters/actors.py:70-112
+//  * StochasticPolicyGradient         tonic/torch/updaters/actors.py:21-50
+//  * VRegression / Q losses (MSE)     tonic/torch/updaters/critics.py:18-28,77-86
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kMaxAct = 64;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;     // log(sqrt(2*pi))
+constexpr float kEntropyConst = 1.41893853320467274178f;   // 0.5 + 0.5*log(2*pi)
+
+__device__ __forceinline__ float softplus_f(float x) {     // torch softplus, beta=1, threshold=20
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+// scale = clamp(softplus(log_scale) + 1e-8, 1e-4, 1)   (actors.py:63-64)
+__device__ __forceinline__ float detached_scale(float log_scale, float* dscale_dls) {
+    const float sp = softplus_f(log_scale) + 1e-8f;
+    const float sc = fminf(fmaxf(sp, 1e-4f), 1.0f);
+    if (dscale_dls) {
+        const float sig = 1.0f / (1.0f + expf(-log_scale));
+        *dscale_dls = (sp >= 1e-4f && sp <= 1.0f) ? sig : 0.0f;    // clamp passes grad inside
+    }
+    return sc;
+}
+
+__global__ void __launch_bounds__(256)
+gauss_sample_kernel(const float* __restrict__ loc_pre, const float* __restrict__ log_scale,
+                    const float* __restrict__ eps, uint64_t seed, uint64_t counter,
+                    int64_t n_rows, int A, float* __restrict__ actions,
+                    float* __restrict__ log_probs) {
+    __shared__ float s_scale[kMaxAct];
+    if ((int)threadIdx.x < A) s_scale[threadIdx.x] = detached_scale(log_scale[threadIdx.x], nullptr);
+    __syncthreads();
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= n_rows) return;
+    Philox rng(seed);
+    float lp = 0.0f;
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < A; ++a) {
+        float e;
+        if (eps) {
+            e = eps[n * A + a];
+        } else {
+            if ((a & 3) == 0) {
+                const uint4 r = rng(counter + (uint64_t)n, (uint64_t)(a >> 2));
+                const float2 p = box_muller(r.x, r.y), q = box_muller(r.z, r.w);
+                z = make_float4(p.x, p.y, q.x, q.y);
+            }
+            e = (a & 3) == 0 ? z.x : (a & 3) == 1 ? z.y : (a & 3) == 2 ? z.z : z.w;
+        }
+        const float loc = tanhf(loc_pre[n * A + a]);
+        const float sc = s_scale[a];
+        const float act = __fadd_rn(__fmul_rn(e, sc), loc);       // Normal.sample
+        actions[n * A + a] = act;
+        const float d = act - loc;
+        lp += -(d * d) / (2.0f * (sc * sc)) - logf(sc) - kLogSqrt2Pi;
+    }
+    log_probs[n] = lp;
+}
+
+__global__ void __launch_bounds__(256)
+gauss_policy_loss_kernel(const float* __restrict__ loc_pre, const float* __restrict__ log_scale,
+                         const float* __restrict__ actions, const float* __restrict__ advantages,
+                         const float* __restrict__ old_log_probs, const int64_t* __restrict__ idx,
+                         int64_t n_rows, int A, float ratio_clip, float entropy_coeff,
+                         float* __restrict__ dout, double* stats, const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    __shared__ float s_scale[kMaxAct], s_dsc[kMaxAct];
+    __shared__ double scratch[32];
+    if ((int)threadIdx.x < A)
+        s_scale[threadIdx.x] = detached_scale(log_scale[threadIdx.x], &s_dsc[threadIdx.x]);
+    __syncthreads();
+    float ent_row = 0.0f, std_row = 0.0f;
+    for (int a = 0; a < A; ++a) {
+        ent_row += kEntropyConst + logf(s_scale[a]);
+        std_row += s_scale[a];
+    }
+    double st_loss = 0, st_kl = 0, st_clip = 0, st_nz = 0, st_rows = 0;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_rows) {
+        const int64_t r = idx ? idx[i] : i;
+        const float adv = advantages[r], old_lp = old_log_probs[r];
+        float lp = 0.0f;
+        for (int a = 0; a < A; ++a) {
+            const float loc = tanhf(loc_pre[i * A + a]);
+            const float sc = s_scale[a];
+            const float d = actions[r * A + a] - loc;
+            lp += -(d * d) / (2.0f * (sc * sc)) - logf(sc) - kLogSqrt2Pi;
+        }
+        float g_lp, loss;
+        if (ratio_clip > 0.0f) {                               // actors.py:84-90
+            const float ratio = expf(lp - old_lp);
+            const float lo = 1.0f - ratio_clip, hi = 1.0f + ratio_clip;
+            const float clipped = fminf(fmaxf(ratio, lo), hi);
+            const float s1 = adv * ratio, s2 = adv * clipped;
+            loss = -fminf(s1, s2);
+            // torch.min backward: grad to the smaller, split evenly on ties;
+            // clamp passes the gradient inside [lo, hi]
+            const float w1 = s1 < s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);
+            const float w2 = (1.0f - w1) * ((ratio >= lo && ratio <= hi) ? 1.0f : 0.0f);
+            g_lp = -adv * ratio * (w1 + w2);
+            st_clip = (ratio > hi || ratio < lo) ? 1.0 : 0.0;  // actors.py:105
+        } else {                                               // actors.py:34
+            loss = -adv * lp;
+            g_lp = -adv;
+        }
+        for (int a = 0; a < A; ++a) {
+            const float loc = tanhf(loc_pre[i * A + a]);
+            const float sc = s_scale[a];
+            const float d = actions[r * A + a] - loc;
+            const float inv_var = 1.0f / (sc * sc);
+            dout[i * 2 * A + a] = g_lp * d * inv_var * (1.0f - loc * loc);
+            const float dlp_dsc = d * d * inv_var / sc - 1.0f / sc;
+            const float dent_dsc = 1.0f / sc;                  // entropy = const + log(scale)
+            dout[i * 2 * A + A + a] =
+                (g_lp * dlp_dsc - (entropy_coeff / (float)A) * dent_dsc) * s_dsc[a];
+        }
+        st_loss = loss;
+        st_kl = old_lp - lp;                                    // actors.py:103
+        st_nz = adv != 0.0f ? 1.0 : 0.0;
+        st_rows = 1.0;
+    }
+    double v;
+    v = block_sum(st_loss, scratch); if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_LOSS], v);
+    v = block_sum(st_kl, scratch);   if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_KL], v);
+    v = block_sum(st_clip, scratch); if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_CLIPPED], v);
+    v = block_sum(st_nz, scratch);   if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_NONZERO_ADV], v);
+    v = block_sum(st_rows, scratch);
+    if (threadIdx.x == 0) {
+        atomicAdd(&stats[TB_STAT_ROWS], v);
+        atomicAdd(&stats[TB_STAT_ENTROPY], v * (double)ent_row);
+        atomicAdd(&stats[TB_STAT_STD], v * (double)std_row);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mse_loss_kernel(const float* __restrict__ values, const float* __restrict__ targets,
+                const int64_t* __restrict__ idx, int64_t n_rows, float* __restrict__ dout,
+                int ld_dout, double* stats, int stat_slot, int count_rows,
+                const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    __shared__ double scratch[32];
+    double st_loss = 0, st_val = 0, st_rows = 0;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_rows) {
+        const float v = values[i];
+        const float t = targets[idx ? idx[i] : i];
+        const float d = v - t;
+        dout[i * ld_dout] = 2.0f * d;                           // d/dv of (v - t)^2
+        st_loss = (double)d * (double)d;
+        st_val = v;
+        st_rows = 1.0;
+    }
+    double r;
+    r = block_sum(st_loss, scratch); if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_LOSS], r);
+    r = block_sum(st_val, scratch);  if (threadIdx.x == 0) atomicAdd(&stats[stat_slot], r);
+    if (count_rows) {
+        r = block_sum(st_rows, scratch);
+        if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_ROWS], r);
+    }
+}
+
+}  // namespace tb
+
+extern "C" int tb_gauss_sample(const float* d_loc_pre, const float* d_log_scale,
+                               const float* d_eps, uint64_t seed, uint64_t counter,
+                               int64_t n_rows, int32_t act_dim, float* d_actions,
+                               float* d_log_probs, void* stream) {
+    TB_REQUIRE(d_loc_pre && d_log_scale && d_actions && d_log_probs && n_rows > 0 &&
+               act_dim >= 1 && act_dim <= tb::kMaxAct, TB_EINVAL, "tb_gauss_sample: bad arguments");
+    const int blocks = (int)((n_rows + 255) / 256);
+    tb::gauss_sample_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
+        d_loc_pre, d_log_scale, d_eps, seed, counter, n_rows, act_dim, d_actions, d_log_probs);
+    return tb::check_launch("tb_gauss_sample");
+}
+
+extern "C" int tb_gauss_policy_loss(const float* d_loc_pre, const float* d_log_scale,
+                                    const float* d_actions, const float* d_advantages,
+                                    const float* d_old_log_probs, const int64_t* d_idx,
+                                    int64_t n_rows, int32_t act_dim, float ratio_clip,
+                                    float entropy_coeff, float* d_dout, double* d_stats,
+                                    const int32_t* d_skip, void* stream) {
+    TB_REQUIRE(d_loc_pre && d_log_scale && d_actions && d_advantages && d_old_log_probs &&
+               d_dout && d_stats && n_rows > 0 && act_dim >= 1 && act_dim <= tb::kMaxAct,
+               TB_EINVAL, "tb_gauss_policy_loss: bad arguments");
+    const int blocks = (int)((n_rows + 255) / 256);
+    tb::gauss_policy_loss_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
+        d_loc_pre, d_log_scale, d_actions, d_advantages, d_old_log_probs, d_idx, n_rows, act_dim,
+        ratio_clip, entropy_coeff, d_dout, d_stats, d_skip);
+    return tb::check_launch("tb_gauss_policy_loss");
+}
+
+extern "C" int tb_mse_loss(const float* d_values, const float* d_targets, const int64_t* d_idx,
+                           int64_t n_rows, float* d_dout, int32_t ld_dout, double* d_stats,
+                           int32_t stat_slot, int32_t count_rows, const int32_t* d_skip,
+                           void* stream) {
+    TB_REQUIRE(d_values && d_targets && d_dout && d_stats && n_rows > 0 && ld_dout >= 1 &&
+               stat_slot >= 0 && stat_slot < TB_STAT_COUNT, TB_EINVAL, "tb_mse_loss: bad arguments");
+    const int blocks = (int)((n_rows + 255) / 256);
+    tb::mse_loss_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
+        d_values, d_targets, d_idx, n_rows, d_dout, ld_dout, d_stats, stat_slot, count_rows, d_skip);
+    return tb::check_launch("tb_mse_loss");
+}

@@ -1,0 +1,687 @@
+// K2/K3/K6-K8/K13/K14 building blocks: two-hidden-layer MLP forward, backward
+// and weight-gradient kernels (float32, FFMA "parity" path).
+//
+// Reference: tonic/torch/models/utils.py:4-23 (MLP = Linear+activation x2),
+// tonic/torch/models/encoders.py:4-31 (input = [normalise(obs) | actions]),
+// tonic/torch/normalizers/mean_stds.py:34-39, and torch autograd for the
+// backward pass.  One CTA owns a tile of 64 rows (transitions); the hidden
+// activations of the tile live in shared memory; the weight matrices are
+// streamed from L2 through a double-buffered cp.async stage (they are shared by
+// all CTAs and stay L2 resident: <= 256 KB per matrix in a 126 MB L2).
+//
+//   forward : xin -> h1 = act(xin W1^T + b1) -> h2 = act(h1 W2^T + b2) -> out = h2 W3^T + b3
+//   backward: dout -> dz2 = (dout W3) * act'(h2) -> dz1 = (dz2 W2) * act'(h1) [-> dx = dz1 W1[:, cols]]
+//   wgrad   : dW = dz^T [inputs | 1]   (split over rows, partial sums per split)
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int TM = 64;          // rows per CTA tile
+constexpr int KC = 16;          // K rows of the streamed operand per stage
+constexpr int NTHREADS = 256;
+
+template <int H>
+struct Cfg {
+    static constexpr int NC = H / 32;                 // output columns per thread
+    static constexpr int VEC = NC >= 4 ? 4 : NC;      // vector width of column groups
+    static constexpr int LDH = H + 4;                 // smem row stride of activation tiles
+    __device__ static __forceinline__ int col(int tx, int i) {
+        return (i / VEC) * (32 * VEC) + tx * VEC + (i % VEC);
+    }
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+template <int ACT>
+__device__ __forceinline__ float activate(float x) {
+    if (ACT == TB_ACT_TANH) return tanhf(x);
+    return fmaxf(x, 0.0f);
+}
+// derivative of the activation expressed through its OUTPUT h
+template <int ACT>
+__device__ __forceinline__ float activate_grad(float h) {
+    if (ACT == TB_ACT_TANH) return 1.0f - h * h;
+    return h > 0.0f ? 1.0f : 0.0f;
+}
+
+// Stage rows [k0, k0+KC) of B (row-major [K, ldb], `bcols` valid columns) into
+// Bs [KC][H]; rows >= K and columns >= bcols are zero-filled.
+template <int H>
+__device__ __forceinline__ void stage_b(float* Bs, const float* __restrict__ B, int ldb, int K,
+                                        int bcols, int k0, bool aligned) {
+    if (aligned) {                                    // bcols == H, 16-byte aligned rows
+        constexpr int V4 = KC * H / 4;                // float4 slots
+        for (int v = threadIdx.x; v < V4; v += NTHREADS) {
+            const int r = v / (H / 4), c4 = v % (H / 4);
+            float* dst = Bs + r * H + c4 * 4;
+            if (k0 + r < K) {
+                cp_async16(dst, B + (size_t)(k0 + r) * ldb + c4 * 4);
+            } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    } else {
+        for (int v = threadIdx.x; v < KC * H; v += NTHREADS) {
+            const int r = v / H, c = v % H;
+            Bs[v] = (k0 + r < K && c < bcols) ? __ldg(B + (size_t)(k0 + r) * ldb + c) : 0.0f;
+        }
+    }
+}
+
+// acc[8][NC] += As[rows ty*8.., 0:K] * B[0:K, cols]   (As row-major smem, zero padded
+// to a multiple of 4 columns; Bs2 = staging area of 2*KC*H floats).
+// Ends with a __syncthreads(): As / Bs2 may be overwritten right after.
+template <int H>
+__device__ __forceinline__ void gemm_acc(float (&acc)[8][Cfg<H>::NC], const float* As, int lda,
+                                         int K, const float* __restrict__ B, int ldb, int bcols,
+                                         bool aligned, float* Bs2) {
+    using C = Cfg<H>;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int nchunks = (K + KC - 1) / KC;
+    stage_b<H>(Bs2, B, ldb, K, bcols, 0, aligned);
+    cp_async_commit();
+    for (int c = 0; c < nchunks; ++c) {
+        float* cur = Bs2 + (c & 1) * (KC * H);
+        if (c + 1 < nchunks) {
+            stage_b<H>(Bs2 + ((c + 1) & 1) * (KC * H), B, ldb, K, bcols, (c + 1) * KC, aligned);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int k0 = c * KC;
+        const int klen = min(KC, K - k0);
+        const float* arow = As + (size_t)(ty * 8) * lda + k0;
+        for (int kk = 0; kk < klen; kk += 4) {
+            float4 a[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                a[r] = *reinterpret_cast<const float4*>(arow + (size_t)r * lda + kk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float b[C::NC];
+                const float* brow = cur + (kk + q) * H;
+#pragma unroll
+                for (int g = 0; g < C::NC / C::VEC; ++g) {
+                    if constexpr (C::VEC == 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(brow + g * 128 + tx * 4);
+                        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+                    } else {
+                        const float2 v = *reinterpret_cast<const float2*>(brow + tx * 2);
+                        b[0] = v.x; b[1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float av = q == 0 ? a[r].x : q == 1 ? a[r].y : q == 2 ? a[r].z : a[r].w;
+#pragma unroll
+                    for (int j = 0; j < C::NC; ++j) acc[r][j] = fmaf(av, b[j], acc[r][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int H>
+__device__ __forceinline__ void zero_acc(float (&acc)[8][Cfg<H>::NC]) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < Cfg<H>::NC; ++j) acc[r][j] = 0.0f;
+}
+
+// Store a thread's 8 x NC micro-tile (after `f`) to a row-major destination.
+template <int H, typename F>
+__device__ __forceinline__ void store_tile(const float (&acc)[8][Cfg<H>::NC], float* dst, int ld,
+                                           int rows_valid, F f) {
+    using C = Cfg<H>;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = ty * 8 + r;
+        if (row >= rows_valid) continue;
+#pragma unroll
+        for (int g = 0; g < C::NC / C::VEC; ++g) {
+            const int c0 = C::col(tx, g * C::VEC);
+            if constexpr (C::VEC == 4) {
+                float4 v;
+                v.x = f(acc[r][g * 4 + 0], row, c0 + 0);
+                v.y = f(acc[r][g * 4 + 1], row, c0 + 1);
+                v.z = f(acc[r][g * 4 + 2], row, c0 + 2);
+                v.w = f(acc[r][g * 4 + 3], row, c0 + 3);
+                *reinterpret_cast<float4*>(dst + (size_t)row * ld + c0) = v;
+            } else {
+                float2 v;
+                v.x = f(acc[r][0], row, c0 + 0);
+                v.y = f(acc[r][1], row, c0 + 1);
+                *reinterpret_cast<float2*>(dst + (size_t)row * ld + c0) = v;
+            }
+        }
+    }
+}
+
+
+// acc = act(acc + bias[col]) in place
+template <int H, int ACT>
+__device__ __forceinline__ void bias_activate(float (&acc)[8][Cfg<H>::NC],
+                                              const float* __restrict__ bias) {
+    using C = Cfg<H>;
+    const int tx = threadIdx.x & 31;
+    float b[C::NC];
+#pragma unroll
+    for (int j = 0; j < C::NC; ++j) b[j] = __ldg(bias + C::col(tx, j));
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int j = 0; j < C::NC; ++j) acc[r][j] = activate<ACT>(acc[r][j] + b[j]);
+}
+
+// acc *= act'(h) with h read from the saved activations (global, row-major [*, H]);
+// rows >= valid are zeroed.
+template <int H, int ACT>
+__device__ __forceinline__ void mul_activation_grad(float (&acc)[8][Cfg<H>::NC],
+                                                    const float* __restrict__ h, int valid) {
+    using C = Cfg<H>;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = ty * 8 + r;
+#pragma unroll
+        for (int g = 0; g < C::NC / C::VEC; ++g) {
+            const int c0 = C::col(tx, g * C::VEC);
+            float hv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (row < valid) {
+                if constexpr (C::VEC == 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(h + (size_t)row * H + c0));
+                    hv[0] = v.x; hv[1] = v.y; hv[2] = v.z; hv[3] = v.w;
+                } else {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(h + (size_t)row * H + c0));
+                    hv[0] = v.x; hv[1] = v.y;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < C::VEC; ++e)
+                acc[r][g * C::VEC + e] =
+                    row < valid ? acc[r][g * C::VEC + e] * activate_grad<ACT>(hv[e]) : 0.0f;
+        }
+    }
+}
+
+template <int H>
+constexpr size_t mlp_smem_bytes() {
+    return (size_t)(2 * TM * Cfg<H>::LDH + 2 * KC * H) * sizeof(float) + TM * sizeof(int64_t) +
+           TM * 72 * sizeof(float);
+}
+
+// --------------------------------------------------------------------------------
+// Forward
+// --------------------------------------------------------------------------------
+template <int H, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_forward_kernel(TbMlpShape sh, const float* __restrict__ params,
+                   const float* __restrict__ packed, TbMlpInput in, int64_t n_rows,
+                   float* __restrict__ out, float* __restrict__ xin_save,
+                   float* __restrict__ h1_save, float* __restrict__ h2_save,
+                   const int32_t* d_skip) {
+    using C = Cfg<H>;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufA = reinterpret_cast<float*>(smem_raw);          // [TM][LDH]
+    float* bufB = bufA + TM * C::LDH;                          // [TM][LDH]
+    float* Bs2 = bufB + TM * C::LDH;                           // [2][KC][H]
+    int64_t* srow = reinterpret_cast<int64_t*>(Bs2 + 2 * KC * H);   // [TM] source rows
+
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const int64_t m0 = (int64_t)blockIdx.x * TM;
+    const int valid = (int)min((int64_t)TM, n_rows - m0);
+
+    if (tid < TM) srow[tid] = tid < valid ? (in.d_idx ? in.d_idx[m0 + tid] : m0 + tid) : -1;
+    __syncthreads();
+
+    const int d_in = sh.d_in;
+    const int ldx = (d_in + 1 + 3) & ~3;                       // saved-input row stride
+    float acc[8][C::NC];
+    zero_acc<H>(acc);
+
+    // ---- layer 1: input assembled in pieces of <= H columns into bufB ------------
+    for (int k0 = 0; k0 < d_in; k0 += H) {
+        const int klen = min(H, d_in - k0);
+        const int kpad = (klen + 3) & ~3;
+        for (int v = tid; v < TM * kpad; v += NTHREADS) {
+            const int m = v / kpad, cc = v % kpad;
+            const int c = k0 + cc;
+            float val = 0.0f;
+            const int64_t r = srow[m];
+            if (r >= 0 && cc < klen) {
+                if (c < in.dim1) {
+                    val = in.d_x1[r * in.dim1 + c];
+                    if (in.d_mean)      // mean_stds.py:36  (val - mean) / std
+                        val = __fdiv_rn(__fsub_rn(val, in.d_mean[c]), in.d_std[c]);
+                } else {
+                    const int64_t r2 = in.gather2 ? r : (m0 + m);
+                    val = in.d_x2[r2 * in.dim2 + (c - in.dim1)];
+                }
+                if (xin_save) xin_save[(m0 + m) * ldx + c] = val;
+            }
+            bufB[m * C::LDH + cc] = val;
+        }
+        __syncthreads();
+        gemm_acc<H>(acc, bufB, C::LDH, klen, packed + sh.off_w1t + (size_t)k0 * H, H, H, true, Bs2);
+    }
+    if (xin_save) {     // trailing 1 column (bias gradients) and zero padding
+        for (int v = tid; v < valid * (ldx - d_in); v += NTHREADS) {
+            const int m = v / (ldx - d_in), c = d_in + v % (ldx - d_in);
+            xin_save[(m0 + m) * ldx + c] = (c == d_in) ? 1.0f : 0.0f;
+        }
+    }
+    auto ident = [](float a, int, int) { return a; };
+    bias_activate<H, ACT>(acc, params + sh.off_b1);
+    store_tile<H>(acc, bufA, C::LDH, TM, ident);
+    if (h1_save) store_tile<H>(acc, h1_save + m0 * H, H, valid, ident);
+    __syncthreads();
+
+    // ---- layer 2 ----------------------------------------------------------------
+    zero_acc<H>(acc);
+    gemm_acc<H>(acc, bufA, C::LDH, H, packed + sh.off_w2t, H, H, true, Bs2);
+    bias_activate<H, ACT>(acc, params + sh.off_b2);
+    store_tile<H>(acc, bufB, C::LDH, TM, ident);
+    if (h2_save) store_tile<H>(acc, h2_save + m0 * H, H, valid, ident);
+    __syncthreads();
+
+    // ---- head: out[m][o] = b3[o] + h2[m,:] . W3[o,:]  (4 lanes per dot product) --
+    const int n_out = sh.n_out;
+    const float* W3 = params + sh.off_w3;
+    const float* b3 = params + sh.off_b3;
+    const int quad = tid >> 2, ql = tid & 3;
+    for (int p = quad; p < TM * n_out; p += NTHREADS / 4) {
+        const int m = p % TM, o = p / TM;
+        const float* hrow = bufB + m * C::LDH;
+        const float* wrow = W3 + (size_t)o * H;
+        float s = 0.0f;
+#pragma unroll 4
+        for (int i = ql; i < H / 4; i += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hrow + i * 4);
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + i * 4));
+            s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s);
+            s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (ql == 0 && m < valid) out[(m0 + m) * n_out + o] = s + b3[o];
+    }
+    (void)tx; (void)ty;
+}
+
+// --------------------------------------------------------------------------------
+// Backward (activation gradients)
+// --------------------------------------------------------------------------------
+template <int H, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_backward_kernel(TbMlpShape sh, const float* __restrict__ params,
+                    const float* __restrict__ dout, int ld_dout,
+                    const float* __restrict__ h1, const float* __restrict__ h2, int64_t n_rows,
+                    float* __restrict__ dz2, float* __restrict__ dz1, float* __restrict__ dx,
+                    int dx_col0, int dx_cols, const int32_t* d_skip) {
+    using C = Cfg<H>;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufA = reinterpret_cast<float*>(smem_raw);
+    float* bufB = bufA + TM * C::LDH;
+    float* Bs2 = bufB + TM * C::LDH;
+    float* sD = Bs2 + 2 * KC * H + TM * 2;                     // [TM][72] (after the srow area)
+
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * TM;
+    const int valid = (int)min((int64_t)TM, n_rows - m0);
+    const int n_out = sh.n_out;
+    const int ldo = (n_out + 3) & ~3;                          // <= 72
+
+    for (int v = tid; v < TM * ldo; v += NTHREADS) {
+        const int m = v / ldo, o = v % ldo;
+        sD[m * 72 + o] = (m < valid && o < n_out) ? dout[(m0 + m) * ld_dout + o] : 0.0f;
+    }
+    __syncthreads();
+
+    float acc[8][C::NC];
+    zero_acc<H>(acc);
+    gemm_acc<H>(acc, sD, 72, n_out, params + sh.off_w3, H, H, true, Bs2);     // dh2 = dout W3
+    auto ident = [](float a, int, int) { return a; };
+    mul_activation_grad<H, ACT>(acc, h2 + m0 * H, valid);
+    store_tile<H>(acc, bufB, C::LDH, TM, ident);
+    store_tile<H>(acc, dz2 + m0 * H, H, valid, ident);
+    __syncthreads();
+
+    zero_acc<H>(acc);
+    gemm_acc<H>(acc, bufB, C::LDH, H, params + sh.off_w2, H, H, true, Bs2);   // dh1 = dz2 W2
+    mul_activation_grad<H, ACT>(acc, h1 + m0 * H, valid);
+    if (dx) store_tile<H>(acc, bufA, C::LDH, TM, ident);
+    store_tile<H>(acc, dz1 + m0 * H, H, valid, ident);
+    if (!dx) return;
+    __syncthreads();
+
+    // dx[:, j] = sum_n dz1[:, n] W1[n, dx_col0 + j]   (W1 is [H, d_in] row-major)
+    zero_acc<H>(acc);
+    gemm_acc<H>(acc, bufA, C::LDH, H, params + sh.off_w1 + dx_col0, sh.d_in, dx_cols, false, Bs2);
+    {
+        const int tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = ty * 8 + r;
+            if (row >= valid) continue;
+#pragma unroll
+            for (int j = 0; j < C::NC; ++j) {
+                const int c = C::col(tx, j);
+                if (c < dx_cols) dx[(m0 + row) * dx_cols + c] = acc[r][j];
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------
+// Weight gradients:  out[n][k] = sum_m A[m][a_col0+n] * B[m][b_col0+k]
+// --------------------------------------------------------------------------------
+struct WJob {
+    const float* A; const float* B;
+    int lda, a_col0, a_cols;
+    int ldb, b_col0, b_cols;
+    int out_off, out_ld;        // gpart offset of out[0][0] and its row stride
+    int bias_col, bias_off;     // column k == bias_col goes to bias_off + n (or -1)
+    int variant;                // 0: 128x128, 1: 128x32, 2: 16x128
+};
+constexpr int kMaxJobs = 24;
+struct WJobTable { WJob jobs[kMaxJobs]; int n_jobs; };
+constexpr int WMC = 16;        // rows of m per smem chunk
+
+template <int TN, int TK>
+__device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t r1,
+                                           float* __restrict__ gout, float* smem) {
+    constexpr int MN = TN / 16, MK = TK / 16;
+    float* As = smem;                  // [2][WMC][TN]
+    float* Bsm = smem + 2 * WMC * TN;  // [2][WMC][TK]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[MN][MK];
+#pragma unroll
+    for (int i = 0; i < MN; ++i)
+#pragma unroll
+        for (int j = 0; j < MK; ++j) acc[i][j] = 0.0f;
+
+    const bool a_fast = TN == 128 && job.a_cols == 128 && (job.lda & 3) == 0 && (job.a_col0 & 3) == 0;
+    const bool b_fast = TK == 128 && job.b_cols == 128 && (job.ldb & 3) == 0 && (job.b_col0 & 3) == 0;
+
+    auto stage = [&](int buf, int64_t mbase) {
+        float* as = As + buf * WMC * TN;
+        float* bs = Bsm + buf * WMC * TK;
+        if (a_fast) {
+            for (int v = tid; v < WMC * TN / 4; v += NTHREADS) {
+                const int r = v / (TN / 4), c4 = v % (TN / 4);
+                float* dst = as + r * TN + c4 * 4;
+                if (mbase + r < r1) cp_async16(dst, job.A + (mbase + r) * job.lda + job.a_col0 + c4 * 4);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int v = tid; v < WMC * TN; v += NTHREADS) {
+                const int r = v / TN, c = v % TN;
+                as[v] = (mbase + r < r1 && c < job.a_cols)
+                            ? __ldg(job.A + (mbase + r) * job.lda + job.a_col0 + c) : 0.0f;
+            }
+        }
+        if (b_fast) {
+            for (int v = tid; v < WMC * TK / 4; v += NTHREADS) {
+                const int r = v / (TK / 4), c4 = v % (TK / 4);
+                float* dst = bs + r * TK + c4 * 4;
+                if (mbase + r < r1) cp_async16(dst, job.B + (mbase + r) * job.ldb + job.b_col0 + c4 * 4);
+                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int v = tid; v < WMC * TK; v += NTHREADS) {
+                const int r = v / TK, c = v % TK;
+                bs[v] = (mbase + r < r1 && c < job.b_cols)
+                            ? __ldg(job.B + (mbase + r) * job.ldb + job.b_col0 + c) : 0.0f;
+            }
+        }
+    };
+
+    const int nchunks = (int)((r1 - r0 + WMC - 1) / WMC);
+    if (nchunks > 0) {
+        stage(0, r0);
+        cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            stage((c + 1) & 1, r0 + (int64_t)(c + 1) * WMC);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* as = As + (c & 1) * WMC * TN;
+        const float* bs = Bsm + (c & 1) * WMC * TK;
+#pragma unroll 4
+        for (int r = 0; r < WMC; ++r) {
+            float a[MN], b[MK];
+            if constexpr (MN == 8) {
+                const float4 v0 = *reinterpret_cast<const float4*>(as + r * TN + ty * 4);
+                const float4 v1 = *reinterpret_cast<const float4*>(as + r * TN + 64 + ty * 4);
+                a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w;
+                a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
+            } else {
+                a[0] = as[r * TN + ty];
+            }
+            if constexpr (MK == 8) {
+                const float4 v0 = *reinterpret_cast<const float4*>(bs + r * TK + tx * 4);
+                const float4 v1 = *reinterpret_cast<const float4*>(bs + r * TK + 64 + tx * 4);
+                b[0] = v0.x; b[1] = v0.y; b[2] = v0.z; b[3] = v0.w;
+                b[4] = v1.x; b[5] = v1.y; b[6] = v1.z; b[7] = v1.w;
+            } else {
+                const float2 v = *reinterpret_cast<const float2*>(bs + r * TK + tx * 2);
+                b[0] = v.x; b[1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < MN; ++i)
+#pragma unroll
+                for (int j = 0; j < MK; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < MN; ++i) {
+        const int n = MN == 8 ? (i / 4) * 64 + ty * 4 + (i % 4) : ty;
+        if (n >= job.a_cols) continue;
+#pragma unroll
+        for (int j = 0; j < MK; ++j) {
+            const int k = MK == 8 ? (j / 4) * 64 + tx * 4 + (j % 4) : tx * 2 + j;
+            if (k >= job.b_cols) continue;
+            if (job.b_col0 + k == job.bias_col) gout[job.bias_off + n] = acc[i][j];
+            else gout[job.out_off + (size_t)n * job.out_ld + k] = acc[i][j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS)
+mlp_wgrad_kernel(WJobTable table, int64_t n_rows, int64_t rows_per_split,
+                 float* __restrict__ gpart, int n_params, const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* smem = reinterpret_cast<float*>(smem_raw);
+    const WJob& job = table.jobs[blockIdx.x];
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r1 = min(n_rows, r0 + rows_per_split);
+    float* gout = gpart + (size_t)blockIdx.y * n_params;
+    if (job.variant == 0) wgrad_tile<128, 128>(job, r0, max(r0, r1), gout, smem);
+    else if (job.variant == 1) wgrad_tile<128, 32>(job, r0, max(r0, r1), gout, smem);
+    else wgrad_tile<16, 128>(job, r0, max(r0, r1), gout, smem);
+}
+
+// --------------------------------------------------------------------------------
+// host dispatch
+// --------------------------------------------------------------------------------
+static int check_shape(const TbMlpShape* sh, const char* who) {
+    TB_REQUIRE(sh, TB_EINVAL, "%s: null shape", who);
+    TB_REQUIRE(sh->hidden == 64 || sh->hidden == 128 || sh->hidden == 256, TB_ENOTSUP,
+               "%s: hidden width %d not supported (64, 128, 256)", who, sh->hidden);
+    TB_REQUIRE(sh->act == TB_ACT_TANH || sh->act == TB_ACT_RELU, TB_ENOTSUP,
+               "%s: activation %d not supported", who, sh->act);
+    TB_REQUIRE(sh->n_out >= 1 && sh->n_out <= 64, TB_ENOTSUP, "%s: n_out %d not in [1,64]", who,
+               sh->n_out);
+    TB_REQUIRE(sh->d_in >= 1 && sh->d_in <= 4096, TB_ENOTSUP, "%s: d_in %d", who, sh->d_in);
+    TB_REQUIRE((sh->off_w1 | sh->off_w2 | sh->off_w3 | sh->off_w1t | sh->off_w2t) % 4 == 0,
+               TB_EINVAL, "%s: weight offsets must be multiples of 4 floats", who);
+    return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+#define TB_DISPATCH_H_ACT(H_, ACT_, CALL)                                   \
+    do {                                                                    \
+        if (H_ == 64 && ACT_ == TB_ACT_TANH) { CALL(64, TB_ACT_TANH); }     \
+        else if (H_ == 64) { CALL(64, TB_ACT_RELU); }                       \
+        else if (H_ == 128 && ACT_ == TB_ACT_TANH) { CALL(128, TB_ACT_TANH); } \
+        else if (H_ == 128) { CALL(128, TB_ACT_RELU); }                     \
+        else if (ACT_ == TB_ACT_TANH) { CALL(256, TB_ACT_TANH); }           \
+        else { CALL(256, TB_ACT_RELU); }                                    \
+    } while (0)
+
+}  // namespace tb
+
+extern "C" int tb_mlp_forward(const TbMlpShape* shape, const float* d_params,
+                              const float* d_packed, const TbMlpInput* in, int64_t n_rows,
+                              float* d_out, float* d_xin, float* d_h1, float* d_h2,
+                              const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    int rc = check_shape(shape, "tb_mlp_forward");
+    if (rc) return rc;
+    TB_REQUIRE(d_params && d_packed && in && in->d_x1 && d_out && n_rows > 0, TB_EINVAL,
+               "tb_mlp_forward: null pointer");
+    TB_REQUIRE(in->dim1 + (in->d_x2 ? in->dim2 : 0) == shape->d_in, TB_EINVAL,
+               "tb_mlp_forward: input widths %d+%d != d_in %d", in->dim1,
+               in->d_x2 ? in->dim2 : 0, shape->d_in);
+    TB_REQUIRE((in->d_mean == nullptr) == (in->d_std == nullptr), TB_EINVAL,
+               "tb_mlp_forward: mean/std must be given together");
+    const int blocks = (int)((n_rows + TM - 1) / TM);
+    cudaStream_t s = as_stream(stream);
+#define CALL(H_, A_)                                                                        \
+    {                                                                                       \
+        const size_t smem = mlp_smem_bytes<H_>();                                           \
+        set_smem(mlp_forward_kernel<H_, A_>, smem);                                         \
+        mlp_forward_kernel<H_, A_><<<blocks, NTHREADS, smem, s>>>(                          \
+            *shape, d_params, d_packed, *in, n_rows, d_out, d_xin, d_h1, d_h2, d_skip);     \
+    }
+    TB_DISPATCH_H_ACT(shape->hidden, shape->act, CALL);
+#undef CALL
+    return check_launch("tb_mlp_forward");
+}
+
+extern "C" int tb_mlp_backward(const TbMlpShape* shape, const float* d_params,
+                               const float* d_dout, int32_t ld_dout, const float* d_h1,
+                               const float* d_h2, int64_t n_rows, float* d_dz2, float* d_dz1,
+                               float* d_dx, int32_t dx_col0, int32_t dx_cols,
+                               const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    int rc = check_shape(shape, "tb_mlp_backward");
+    if (rc) return rc;
+    TB_REQUIRE(d_params && d_dout && d_h1 && d_h2 && d_dz2 && d_dz1 && n_rows > 0 &&
+               ld_dout >= shape->n_out, TB_EINVAL, "tb_mlp_backward: bad arguments");
+    TB_REQUIRE(!d_dx || (dx_cols >= 1 && dx_cols <= shape->hidden && dx_col0 >= 0 &&
+                         dx_col0 + dx_cols <= shape->d_in), TB_EINVAL,
+               "tb_mlp_backward: dx column range [%d,+%d) invalid", dx_col0, dx_cols);
+    const int blocks = (int)((n_rows + TM - 1) / TM);
+    cudaStream_t s = as_stream(stream);
+#define CALL(H_, A_)                                                                        \
+    {                                                                                       \
+        const size_t smem = mlp_smem_bytes<H_>();                                           \
+        set_smem(mlp_backward_kernel<H_, A_>, smem);                                        \
+        mlp_backward_kernel<H_, A_><<<blocks, NTHREADS, smem, s>>>(                         \
+            *shape, d_params, d_dout, ld_dout, d_h1, d_h2, n_rows, d_dz2, d_dz1, d_dx,      \
+            dx_col0, dx_cols, d_skip);                                                      \
+    }
+    TB_DISPATCH_H_ACT(shape->hidden, shape->act, CALL);
+#undef CALL
+    return check_launch("tb_mlp_backward");
+}
+
+extern "C" int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const float* d_h1,
+                            const float* d_h2, const float* d_dz1, const float* d_dz2,
+                            const float* d_dout, int32_t ld_dout, int32_t n_extra,
+                            int32_t off_extra, int64_t n_rows, float* d_gpart,
+                            int32_t n_split, const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    int rc = check_shape(shape, "tb_mlp_wgrad");
+    if (rc) return rc;
+    TB_REQUIRE(d_xin && d_h1 && d_h2 && d_dz1 && d_dz2 && d_dout && d_gpart && n_rows > 0 &&
+               n_split >= 1 && ld_dout >= shape->n_out + n_extra, TB_EINVAL,
+               "tb_mlp_wgrad: bad arguments");
+    const int H = shape->hidden, d_in = shape->d_in, n_out = shape->n_out;
+    const int ldx = (d_in + 1 + 3) & ~3;
+    WJobTable t;
+    t.n_jobs = 0;
+    auto add = [&](const float* A, int lda, int a0, int an, const float* B, int ldb, int b0, int bn,
+                   int out_off, int out_ld, int bias_col, int bias_off, int variant) {
+        if (t.n_jobs >= kMaxJobs) return false;
+        WJob& j = t.jobs[t.n_jobs++];
+        j.A = A; j.lda = lda; j.a_col0 = a0; j.a_cols = an;
+        j.B = B; j.ldb = ldb; j.b_col0 = b0; j.b_cols = bn;
+        j.out_off = out_off; j.out_ld = out_ld; j.bias_col = bias_col; j.bias_off = bias_off;
+        j.variant = variant;
+        return true;
+    };
+    bool ok = true;
+    const int ntile = (H + 127) / 128;
+    // dW2[n][k] = sum_m dz2[m][n] h1[m][k]
+    for (int tn = 0; tn < ntile; ++tn)
+        for (int tk = 0; tk < ntile; ++tk) {
+            const int an = std::min(128, H - tn * 128), bn = std::min(128, H - tk * 128);
+            ok &= add(d_dz2, H, tn * 128, an, d_h1, H, tk * 128, bn,
+                      shape->off_w2 + tn * 128 * H + tk * 128, H, -1, 0, 0);
+        }
+    // dW1[n][k] (+ db1 through the trailing ones column of xin)
+    for (int tn = 0; tn < ntile; ++tn) {
+        const int an = std::min(128, H - tn * 128);
+        for (int k0 = 0; k0 < d_in + 1; k0 += (d_in + 1 <= 32 ? 32 : 128)) {
+            const int tkw = d_in + 1 <= 32 ? 32 : 128;
+            const int bn = std::min(tkw, d_in + 1 - k0);
+            ok &= add(d_dz1, H, tn * 128, an, d_xin, ldx, k0, bn,
+                      shape->off_w1 + tn * 128 * d_in + k0, d_in, d_in,
+                      shape->off_b1 + tn * 128, tkw == 32 ? 1 : 0);
+        }
+        // db2[n] = sum_m dz2[m][n]  (ones column of xin)
+        ok &= add(d_dz2, H, tn * 128, an, d_xin, ldx, d_in, 1, 0, 1, d_in,
+                  shape->off_b2 + tn * 128, 1);
+    }
+    // dW3[o][k] = sum_m dout[m][o] h2[m][k]
+    for (int o0 = 0; o0 < n_out; o0 += 16)
+        for (int tk = 0; tk < ntile; ++tk) {
+            const int bn = std::min(128, H - tk * 128);
+            ok &= add(d_dout, ld_dout, o0, std::min(16, n_out - o0), d_h2, H, tk * 128, bn,
+                      shape->off_w3 + o0 * H + tk * 128, H, -1, 0, 2);
+        }
+    // db3 and the extra per-row columns (e.g. log_scale gradients)
+    ok &= add(d_dout, ld_dout, 0, n_out, d_xin, ldx, d_in, 1, 0, 1, d_in, shape->off_b3, 1);
+    if (n_extra > 0)
+        ok &= add(d_dout, ld_dout, n_out, n_extra, d_xin, ldx, d_in, 1, 0, 1, d_in, off_extra, 1);
+    TB_REQUIRE(ok, TB_ENOTSUP, "tb_mlp_wgrad: too many tiles (d_in=%d)", d_in);
+
+    int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
+    rows_per_split = (rows_per_split + WMC - 1) / WMC * WMC;
+    const size_t smem = (size_t)2 * WMC * (128 + 128) * sizeof(float);
+    dim3 grid(t.n_jobs, n_split);
+    mlp_wgrad_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(
+        t, n_rows, rows_per_split, d_gpart, shape->n_params, d_skip);
+    return check_launch("tb_mlp_wgrad");
+}
