@@ -1,0 +1,142 @@
+"""Device-resident vector environment.
+
+Replaces the reference's worker grid -- `Sequential` (a Python loop over M
+environments, tonic/environments/distributed.py:8-66) and `Parallel` (P forked
+processes exchanging pickled arrays, :69-155) -- by one fused sm_100a kernel
+that steps all N = P*M environments resident in HBM (csrc/env_step.cu).  The
+object keeps the reference's protocol: `initialize(seed)`, `start()`,
+`step(actions) -> (observations, infos)`, attributes `observation_space`,
+`action_space`, `name`, `max_episode_steps`.
+
+Worker i is seeded `seed + i` exactly like distributed.py:18-20,109; with several
+ranks (one process per GPU) rank r owns workers [r*N/W, (r+1)*N/W), the same
+contiguous split as `np.split` at distributed.py:137.
+
+Arrays handed back are views of device buffers that stay valid until the next
+`step` (the reference returns fresh host arrays).  If `step` is given a numpy
+array the results are copied to the host and returned as numpy arrays with the
+reference's dtypes (float32 / bool), which is the drop-in path for host code.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib, kernels
+from .._lib import ptr
+
+
+class DeviceVectorEnvironment:
+    def __init__(self, spec, workers, first_worker=0, episode_log_capacity=1 << 20):
+        self.spec = spec
+        self.workers = int(workers)
+        self.first_worker = int(first_worker)
+        self.observation_space = spec.observation_space
+        self.action_space = spec.action_space
+        self.name = spec.name
+        self.max_episode_steps = spec.max_episode_steps
+        self.episode_log_capacity = int(episode_log_capacity)
+        self.started = False
+
+    def __len__(self):
+        return self.workers
+
+    def initialize(self, seed):
+        dev = kernels.device()
+        N, O = self.workers, self.spec.observation_size
+        cap = self.episode_log_capacity
+        self.seed = int(seed)
+        self.state = torch.zeros(N, O, dtype=torch.float32, device=dev)
+        self.lengths = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.episodes = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.scores = torch.zeros(N, dtype=torch.float64, device=dev)
+        self.episode_scores = torch.zeros(cap, dtype=torch.float64, device=dev)
+        self.episode_lengths = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.episode_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._episodes_read = 0
+        # output buffers (views handed to the caller)
+        self.observations = torch.zeros(N, O, dtype=torch.float32, device=dev)
+        self.next_observations = torch.zeros(N, O, dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.resets = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.terminations = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.struct = _lib.TbEnv(
+            n_envs=N, obs_dim=O, act_dim=self.spec.action_size,
+            max_episode_steps=self.max_episode_steps, seed=self.seed,
+            first_worker=self.first_worker, d_state=ptr(self.state),
+            d_length=ptr(self.lengths), d_episode=ptr(self.episodes), d_score=ptr(self.scores),
+            d_ep_scores=ptr(self.episode_scores), d_ep_lengths=ptr(self.episode_lengths),
+            d_ep_count=ptr(self.episode_count), log_cap=cap)
+
+    def start(self, host=False):
+        """Resets every environment; returns the first observations [N, O]."""
+        assert not self.started or True
+        self.started = True
+        _lib.call('tb_env_start', ctypes.byref(self.struct), ptr(self.observations),
+                  kernels.stream())
+        if host:
+            return self.observations.cpu().numpy()
+        return self.observations
+
+    def step_into(self, actions, observations, next_observations, rewards, resets, terminations):
+        """Device-only step writing into caller-provided buffers (segment rows)."""
+        _lib.call('tb_env_step', ctypes.byref(self.struct), ptr(actions), ptr(observations),
+                  ptr(next_observations), ptr(rewards), ptr(resets), ptr(terminations),
+                  kernels.stream())
+
+    def step(self, actions):
+        host = not isinstance(actions, torch.Tensor) or not actions.is_cuda
+        actions = kernels.to_device(actions)
+        assert actions.shape == (self.workers, self.spec.action_size), actions.shape
+        self.step_into(actions, self.observations, self.next_observations, self.rewards,
+                       self.resets, self.terminations)
+        if host:
+            infos = dict(
+                observations=self.next_observations.cpu().numpy(),
+                rewards=self.rewards.cpu().numpy(),
+                resets=self.resets.cpu().numpy().astype(np.bool_),
+                terminations=self.terminations.cpu().numpy().astype(np.bool_))
+            return self.observations.cpu().numpy(), infos
+        infos = dict(observations=self.next_observations, rewards=self.rewards,
+                     resets=self.resets, terminations=self.terminations)
+        return self.observations, infos
+
+    def finished_episodes(self):
+        """(scores, lengths) of the episodes finished since the last call
+        (what trainer.py:64-71 collects with a per-worker Python loop)."""
+        total = int(self.episode_count.item())
+        new = total - self._episodes_read
+        cap = self.episode_log_capacity
+        if new <= 0:
+            return np.zeros(0), np.zeros(0, int)
+        new = min(new, cap)
+        idx = (torch.arange(total - new, total, device=self.state.device) % cap)
+        scores = self.episode_scores[idx].cpu().numpy()
+        lengths = self.episode_lengths[idx].cpu().numpy().astype(int)
+        self._episodes_read = total
+        return scores, lengths
+
+    def render(self, *args, **kwargs):
+        raise NotImplementedError('synthetic device environments have no renderer')
+
+
+def distribute(environment_builder, worker_groups=1, workers_per_group=1):
+    """Same signature as the reference's `distribute`
+    (tonic/environments/distributed.py:158-172).  `worker_groups *
+    workers_per_group` environments are created in total; under torchrun they are
+    sharded contiguously over the ranks (one GPU each)."""
+    spec = environment_builder()
+    if not hasattr(spec, 'observation_size'):
+        raise NotImplementedError(
+            'tonic_b200 steps device-resident synthetic environments only '
+            '(tonic_b200.environments.SynthControl); host Gym/dm_control '
+            'environments are outside the hot path (SURVEY.md section 2, row 14)')
+    total = int(worker_groups) * int(workers_per_group)
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    if total % world:
+        raise ValueError(f'{total} workers do not split over {world} ranks')
+    local = total // world
+    return DeviceVectorEnvironment(spec, local, first_worker=rank * local)

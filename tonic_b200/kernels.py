@@ -1,0 +1,227 @@
+"""Thin Python layer over the C ABI: owns device buffers (torch CUDA tensors are
+used only as memory + stream plumbing) and enqueues the sm_100a kernels.
+
+Nothing here computes with torch ops on the hot path, and nothing falls back to
+the CPU: every function ends in a `_lib.call(...)` into libtonic_b200.so.
+"""
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr
+
+F32 = torch.float32
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise _lib.TonicB200Error('tonic_b200 needs a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_device(x, dtype=F32):
+    """numpy / torch (host or device) -> contiguous device tensor of `dtype`."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device(), dtype=dtype).contiguous()
+    arr = np.asarray(x)
+    if arr.dtype == np.bool_:
+        arr = arr.astype(np.float32)
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    return t.to(device=device(), dtype=dtype, non_blocking=False)
+
+
+def round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------
+# MLP
+# ---------------------------------------------------------------------------
+
+class MlpLayout:
+    """Flat float32 parameter layout of a 2-hidden-layer MLP with a linear head.
+
+    Order: W1 [H, d_in] | b1 [H] | W2 [H, H] | b2 [H] | W3 [n_out, H] | b3 [n_out]
+    | extras (e.g. log_scale [A]); every tensor starts at a multiple of 4 floats.
+    """
+
+    def __init__(self, d_in, hidden, n_out, activation, extras=()):
+        self.d_in, self.hidden, self.n_out = int(d_in), int(hidden), int(n_out)
+        self.act = {'tanh': _lib.ACT_TANH, 'relu': _lib.ACT_RELU}[activation]
+        H = self.hidden
+        off = 0
+        self.offsets = {}
+        for name, size in [('w1', H * d_in), ('b1', H), ('w2', H * H), ('b2', H),
+                           ('w3', n_out * H), ('b3', n_out)] + \
+                          [(n, s) for n, s in extras]:
+            self.offsets[name] = (off, size)
+            off = round_up(off + size, 4)
+        self.n_params = off
+        self.off_w1t = 0
+        self.off_w2t = round_up(d_in * H, 4)
+        self.n_packed = self.off_w2t + H * H
+        self.ldx = round_up(d_in + 1, 4)
+        o = self.offsets
+        self.shape = _lib.TbMlpShape(
+            d_in=d_in, hidden=H, n_out=n_out, act=self.act,
+            off_w1=o['w1'][0], off_b1=o['b1'][0], off_w2=o['w2'][0], off_b2=o['b2'][0],
+            off_w3=o['w3'][0], off_b3=o['b3'][0], n_params=self.n_params,
+            off_w1t=self.off_w1t, off_w2t=self.off_w2t, n_packed=self.n_packed)
+
+
+class MlpInput:
+    """Describes how the network input is assembled (see TbMlpInput)."""
+
+    def __init__(self, x1, mean=None, std=None, x2=None, gather2=False, idx=None):
+        self.tensors = (x1, mean, std, x2, idx)   # keep alive
+        self.struct = _lib.TbMlpInput(
+            d_x1=ptr(x1), dim1=x1.shape[-1], d_mean=ptr(mean), d_std=ptr(std),
+            d_x2=ptr(x2), dim2=0 if x2 is None else x2.shape[-1], gather2=int(gather2),
+            d_idx=ptr(idx))
+
+
+class DeviceMlp:
+    """Device-resident parameters (+ packed transposes) and activation workspaces."""
+
+    def __init__(self, layout):
+        self.layout = layout
+        dev = device()
+        self.params = torch.zeros(layout.n_params, dtype=F32, device=dev)
+        self.packed = torch.zeros(layout.n_packed, dtype=F32, device=dev)
+        self._ws_rows = 0
+        self._gpart = None
+
+    # -- parameter views --------------------------------------------------
+    def view(self, name, shape):
+        off, size = self.layout.offsets[name]
+        assert int(np.prod(shape)) == size, (name, shape, size)
+        return self.params[off:off + size].view(*shape)
+
+    def pack(self):
+        _lib.call('tb_mlp_pack', ctypes.byref(self.layout.shape), ptr(self.params),
+                  ptr(self.packed), stream())
+
+    # -- workspaces ---------------------------------------------------------
+    def workspace(self, rows):
+        if rows > self._ws_rows:
+            L, dev = self.layout, device()
+            self.xin = torch.empty(rows, L.ldx, dtype=F32, device=dev)
+            self.h1 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
+            self.h2 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
+            self.dz1 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
+            self.dz2 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
+            self._ws_rows = rows
+
+    def gpart(self, n_split):
+        if self._gpart is None or self._gpart.shape[0] < n_split:
+            self._gpart = torch.zeros(n_split, self.layout.n_params, dtype=F32, device=device())
+        return self._gpart
+
+    # -- kernels ------------------------------------------------------------
+    def forward(self, inp, rows, out, save=False, skip=None, params=None, packed=None):
+        """out[rows, n_out] = head pre-activations. `params`/`packed` override the
+        parameter set (target networks share the layout)."""
+        if save:
+            self.workspace(rows)
+        _lib.call('tb_mlp_forward', ctypes.byref(self.layout.shape),
+                  ptr(self.params if params is None else params),
+                  ptr(self.packed if packed is None else packed),
+                  ctypes.byref(inp.struct), rows, ptr(out),
+                  ptr(self.xin) if save else None, ptr(self.h1) if save else None,
+                  ptr(self.h2) if save else None, ptr(skip), stream())
+        return out
+
+    def backward(self, dout, rows, dx=None, dx_col0=0, skip=None, params=None):
+        _lib.call('tb_mlp_backward', ctypes.byref(self.layout.shape),
+                  ptr(self.params if params is None else params), ptr(dout), dout.shape[-1],
+                  ptr(self.h1), ptr(self.h2), rows, ptr(self.dz2), ptr(self.dz1), ptr(dx),
+                  dx_col0, 0 if dx is None else dx.shape[-1], ptr(skip), stream())
+
+    def wgrad(self, dout, rows, n_split, n_extra=0, off_extra=0, skip=None):
+        gpart = self.gpart(n_split)
+        _lib.call('tb_mlp_wgrad', ctypes.byref(self.layout.shape), ptr(self.xin), ptr(self.h1),
+                  ptr(self.h2), ptr(self.dz1), ptr(self.dz2), ptr(dout), dout.shape[-1],
+                  n_extra, off_extra, rows, ptr(gpart), n_split, ptr(skip), stream())
+        return gpart
+
+
+class Adam:
+    """torch.optim.Adam state for one flat parameter buffer (device resident)."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8):
+        dev = device()
+        self.params = params
+        self.m = torch.zeros_like(params)
+        self.v = torch.zeros_like(params)
+        self.step_count = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.struct = _lib.TbAdam(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps,
+                                  n_params=params.numel(), d_params=ptr(params),
+                                  d_m=ptr(self.m), d_v=ptr(self.v), d_step=ptr(self.step_count))
+
+    def step(self, mlp, gpart, n_split, grad_scale, skip=None, stats=None,
+             kl_threshold=-1.0, stop=None):
+        _lib.call('tb_adam_step', ctypes.byref(self.struct), ctypes.byref(mlp.layout.shape),
+                  ptr(mlp.packed), ptr(gpart), n_split, grad_scale, ptr(skip), ptr(stats),
+                  kl_threshold, ptr(stop), stream())
+
+
+def soft_update(target, online, tau):
+    _lib.call('tb_soft_update', ptr(target), ptr(online), target.numel(), tau, stream())
+
+
+# ---------------------------------------------------------------------------
+# heads / losses
+# ---------------------------------------------------------------------------
+
+def gauss_sample(loc_pre, log_scale, actions, log_probs, eps=None, seed=0, counter=0):
+    rows, act = loc_pre.shape
+    _lib.call('tb_gauss_sample', ptr(loc_pre), ptr(log_scale), ptr(eps), seed, counter, rows,
+              act, ptr(actions), ptr(log_probs), stream())
+
+
+def gauss_policy_loss(loc_pre, log_scale, actions, advantages, old_log_probs, idx, rows, dout,
+                      stats, ratio_clip, entropy_coeff, skip=None):
+    _lib.call('tb_gauss_policy_loss', ptr(loc_pre), ptr(log_scale), ptr(actions),
+              ptr(advantages), ptr(old_log_probs), ptr(idx), rows, actions.shape[-1],
+              ratio_clip, entropy_coeff, ptr(dout), ptr(stats), ptr(skip), stream())
+
+
+def mse_loss(values, targets, idx, rows, dout, stats, stat_slot=_lib.STAT_VALUE,
+             count_rows=True, skip=None):
+    _lib.call('tb_mse_loss', ptr(values), ptr(targets), ptr(idx), rows, ptr(dout),
+              dout.shape[-1] if dout.dim() > 1 else 1, ptr(stats), stat_slot, int(count_rows),
+              ptr(skip), stream())
+
+
+# ---------------------------------------------------------------------------
+# replay helpers / normaliser
+# ---------------------------------------------------------------------------
+
+def lambda_returns(values, next_values, rewards, resets, terminations, returns,
+                   discount_factor, trace_decay):
+    T, N = rewards.shape
+    _lib.call('tb_lambda_returns', ptr(values), ptr(next_values), ptr(rewards), ptr(resets),
+              ptr(terminations), ptr(returns), T, N, discount_factor, trace_decay, stream())
+
+
+def advantages(returns, values, out, workspace, n_global=None, phase=0):
+    n = returns.numel()
+    _lib.call('tb_advantages', ptr(returns), ptr(values), ptr(out), n, ptr(workspace),
+              n if n_global is None else n_global, phase, stream())
+
+
+def moments_record(x, sums):
+    rows, dim = x.shape
+    _lib.call('tb_moments_record', ptr(x), rows, dim, ptr(sums), stream())
+
+
+def moments_update(sums, running, count, mean, std, eps=1e-2):
+    _lib.call('tb_moments_update', ptr(sums), ptr(running), ptr(count), ptr(mean), ptr(std),
+              mean.numel(), eps, stream())
