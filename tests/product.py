@@ -1,0 +1,78 @@
+"""Scenario config (oracle/scenarios.py) -> product objects (tonic_b200), the
+third adapter next to the reference one (oracle/make_golden.py) and the oracle
+port (oracle/port.py::build)."""
+
+import numpy as np
+import torch
+
+
+def build(cfg, log=None):
+    import tonic_b200
+    import tonic_b200.torch
+    from tonic_b200.utils import logger
+    m, n = tonic_b200.torch.models, tonic_b200.torch.normalizers
+    if log is not None:
+        logger.store = log
+    spec = tonic_b200.environments.SynthControl(
+        'synth', cfg['obs'], cfg['act'], cfg['max_episode_steps'])
+    env = tonic_b200.environments.distribute(lambda: spec, 1, cfg['workers'])
+    env.initialize(seed=cfg['seed'])
+    hidden = tuple(cfg['hidden'])
+    kind = cfg['agent']
+    if kind in ('PPO', 'A2C'):
+        model = m.ActorCritic(
+            actor=m.Actor(encoder=m.ObservationEncoder(), torso=m.MLP(hidden, torch.nn.Tanh),
+                          head=m.DetachedScaleGaussianPolicyHead()),
+            critic=m.Critic(encoder=m.ObservationEncoder(), torso=m.MLP(hidden, torch.nn.Tanh),
+                            head=m.ValueHead()),
+            observation_normalizer=n.MeanStd())
+        replay = tonic_b200.replays.Segment(**cfg['segment'])
+        agent = getattr(tonic_b200.torch.agents, kind)(model=model, replay=replay)
+    else:
+        critic = m.Critic(encoder=m.ObservationActionEncoder(),
+                          torso=m.MLP(hidden, torch.nn.ReLU), head=m.ValueHead())
+        if kind == 'SAC':
+            head = m.GaussianPolicyHead(loc_activation=torch.nn.Identity,
+                                        distribution=m.SquashedMultivariateNormalDiag)
+        else:
+            head = m.DeterministicPolicyHead()
+        actor = m.Actor(encoder=m.ObservationEncoder(), torso=m.MLP(hidden, torch.nn.ReLU),
+                        head=head)
+        wrapper = m.ActorCriticWithTargets if kind == 'DDPG' else m.ActorTwinCriticWithTargets
+        model = wrapper(actor=actor, critic=critic, observation_normalizer=n.MeanStd())
+        replay = tonic_b200.replays.Buffer(**cfg['buffer'])
+        if kind == 'SAC':
+            exploration = tonic_b200.explorations.NoActionNoise(cfg['start_steps'])
+        else:
+            exploration = tonic_b200.explorations.NormalActionNoise(
+                start_steps=cfg['start_steps'])
+        agent = getattr(tonic_b200.torch.agents, kind)(
+            model=model, replay=replay, exploration=exploration)
+    agent.initialize(env.observation_space, env.action_space, seed=cfg['seed'])
+    return agent, env
+
+
+def teacher_forced(agent, env, golden, vector_steps):
+    """Drives agent + device env with the golden trajectory's inputs: the env
+    receives the reference's actions (so its outputs must be bit-identical), the
+    agent sees the reference's observations (its actions must agree to float32
+    round-off)."""
+    obs = env.start(host=True)
+    np.testing.assert_array_equal(obs, golden['start_observations'])
+    workers = len(obs)
+    steps = 0
+    actions = []
+    for t in range(vector_steps):
+        a = agent.step(obs, steps)
+        actions.append(np.asarray(a, np.float64))
+        ref_a = golden['actions'][t]
+        ref_a = ref_a.astype(np.float32) if np.asarray(a).dtype == np.float32 else ref_a
+        obs, infos = env.step(ref_a)
+        np.testing.assert_array_equal(obs, golden['observations'][t])
+        np.testing.assert_array_equal(infos['observations'], golden['next_observations'][t])
+        np.testing.assert_array_equal(infos['rewards'], golden['rewards'][t])
+        np.testing.assert_array_equal(infos['resets'], golden['resets'][t])
+        np.testing.assert_array_equal(infos['terminations'], golden['terminations'][t])
+        agent.update(**infos, steps=steps)
+        steps += workers
+    return np.array(actions)

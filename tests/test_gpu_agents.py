@@ -1,0 +1,70 @@
+"""Agent-level parity on the GPU: the tonic_b200 agents, driven through the
+reference's protocol, against the golden trajectories / logged losses / final
+weights recorded from the unmodified reference (tests/golden/*.npz).
+
+Tolerances: action indices / minibatch indices / env transitions bit-exact;
+float32 losses and statistics within 1e-4 relative (BASELINE.json north_star);
+weights after the scenario within 2e-4 absolute (they accumulate ~50 Adam steps
+of float32 round-off differences)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import scenarios  # noqa: E402  (checker only)
+from tests import product  # noqa: E402
+
+ON_POLICY = ['ppo_small', 'ppo_wide', 'ppo_ragged', 'ppo_fullbatch', 'a2c_small']
+
+
+def by_key(keys, values):
+    out = {}
+    for k, v in zip(keys, values):
+        out.setdefault(str(k), []).append(float(v))
+    return out
+
+
+def check_infos(rec, g, skip=()):
+    got = by_key(rec.keys, rec.means)
+    ref = by_key(g['info_keys'], g['info_mean'])
+    assert set(got) == set(ref), (sorted(got), sorted(ref))
+    for k in ref:
+        if k in skip:
+            continue
+        assert len(got[k]) == len(ref[k]), k
+        # losses / statistics: 1e-4 relative (+1e-6 absolute for values near zero)
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-4, atol=2e-6, err_msg=k)
+
+
+def check_weights(agent, g, atol=2e-4):
+    w = scenarios.state_arrays(agent.model.state_dict(), 'w/')
+    ref_keys = {k.replace('digest_', '') for k in g if k.startswith(('w/', 'digest_w/'))}
+    assert ref_keys == set(w)
+    for k, v in w.items():
+        if k in g:
+            np.testing.assert_allclose(v, g[k], rtol=1e-3, atol=atol, err_msg=k)
+        else:
+            f = v.astype(np.float64).ravel()
+            d = g['digest_' + k]
+            np.testing.assert_allclose(f[:8], d[2:2 + min(8, f.size)], rtol=1e-3, atol=atol,
+                                       err_msg=k)
+            np.testing.assert_allclose(np.abs(f).sum(), d[1], rtol=1e-3, err_msg=k)
+
+
+@pytest.mark.parametrize('name', ON_POLICY)
+def test_on_policy_scenario_matches_reference(golden, name):
+    g = golden(name)
+    cfg = scenarios.SCENARIOS[name]
+    rec = scenarios.InfoRecorder()
+    agent, env = product.build(cfg, log=rec)
+    # initial weights: same torch.nn.Linear init stream as the reference
+    w0 = scenarios.state_arrays(agent.model.state_dict(), 'w0/')
+    for k, v in w0.items():
+        if k in g:
+            np.testing.assert_array_equal(v, g[k], err_msg=k)
+    actions = product.teacher_forced(agent, env, g, cfg['vector_steps'])
+    # sampled actions: same noise stream, float32 MLP round-off only
+    np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=2e-5)
+    check_infos(rec, g)
+    check_weights(agent, g)

@@ -1,0 +1,135 @@
+"""On-policy segment replay resident in HBM (reference:
+tonic/replays/segments.py:6-78).
+
+Storage is the reference's layout -- one float32 array [T, N, ...] per key, flat
+transition index t*N+n -- so minibatch indices drawn from the same
+`RandomState(seed)` stream address the same transitions.  lambda-returns and the
+advantage normalisation run as kernels (csrc/returns.cu); minibatches are never
+materialised: the update kernels gather rows through the index vector.
+"""
+
+import numpy as np
+import torch
+
+from .. import kernels
+from ..utils.random_state import RandomState
+from . import utils
+
+
+class Segment:
+    def __init__(self, size=4096, batch_iterations=80, batch_size=None, discount_factor=0.99,
+                 trace_decay=0.97):
+        self.max_size = size
+        self.batch_iterations = batch_iterations
+        self.batch_size = batch_size
+        self.discount_factor = discount_factor
+        self.trace_decay = trace_decay
+
+    def initialize(self, seed=None):
+        self.np_random = RandomState(seed)      # segments.py:20
+        self.buffers = None
+        self.index = 0
+        self._pinned = None
+
+    def ready(self):
+        return self.index == self.max_size
+
+    # -- storage ------------------------------------------------------------------
+    def allocate(self, **shapes):
+        """shapes: key -> per-step shape, e.g. observations=(N, O)."""
+        dev = kernels.device()
+        self.num_workers = next(iter(shapes.values()))[0]
+        self.buffers = {k: torch.zeros((self.max_size,) + tuple(s), dtype=torch.float32,
+                                       device=dev) for k, s in shapes.items()}
+        self._workspace = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def store(self, **kwargs):
+        if self.buffers is None:
+            self.allocate(**{k: tuple(np.shape(v)) if not isinstance(v, torch.Tensor)
+                             else tuple(v.shape) for k, v in kwargs.items()})
+        for key, val in kwargs.items():
+            self.buffers[key][self.index].copy_(kernels.to_device(val))
+        self.index += 1
+
+    def advance(self):
+        """For producers that wrote row `index` of the buffers in place."""
+        self.index += 1
+
+    # -- returns / advantages -----------------------------------------------------------
+    def compute_returns(self, values, next_values):
+        shape = self.buffers['rewards'].shape
+        self.buffers['values'] = kernels.to_device(values).view(shape)
+        self.buffers['next_values'] = kernels.to_device(next_values).view(shape)
+        if 'returns' not in self.buffers:
+            self.buffers['returns'] = torch.empty(shape, dtype=torch.float32,
+                                                  device=self.buffers['rewards'].device)
+        b = self.buffers
+        kernels.lambda_returns(b['values'], b['next_values'], b['rewards'], b['resets'],
+                               b['terminations'], b['returns'], self.discount_factor,
+                               self.trace_decay)
+
+    def compute_advantages(self, all_reduce=None):
+        """returns - values, normalised over the WHOLE segment (segments.py:41-46).
+        `all_reduce(tensor)` (sum over ranks) makes the statistics global when the
+        workers are sharded over several GPUs."""
+        b = self.buffers
+        if 'advantages' not in b:
+            b['advantages'] = torch.empty_like(b['returns'])
+        if all_reduce is None:
+            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace)
+        else:
+            n = torch.tensor([b['returns'].numel()], dtype=torch.float64,
+                             device=b['returns'].device)
+            all_reduce(n)
+            n_global = int(n.item())
+            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
+                               n_global, 1)
+            all_reduce(self._workspace)
+            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
+                               n_global, 2)
+            all_reduce(self._workspace[2:3])
+            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
+                               n_global, 3)
+
+    def get_full(self, *keys):
+        self.index = 0
+        if 'advantages' in keys:
+            self.compute_advantages()
+        return {k: utils.flatten_batch(self.buffers[k]) for k in keys}
+
+    # -- minibatches ------------------------------------------------------------------
+    def index_batches(self):
+        """Yields (idx, rows): idx is a device int64 vector of flat transition
+        indices (None = the whole segment in order), following segments.py:50-65:
+        per iteration one `RandomState.shuffle` of the running permutation, cut in
+        contiguous slices of `batch_size` (the last one may be short)."""
+        total = self.max_size * self.num_workers
+        if self.batch_size is None:
+            for _ in range(self.batch_iterations):
+                yield None, total
+            return
+        E = self.batch_iterations
+        if self._pinned is None or self._pinned.shape != (E, total):
+            self._pinned = torch.empty(E, total, dtype=torch.int64).pin_memory()
+            self._device_order = torch.empty(E, total, dtype=torch.int64,
+                                             device=kernels.device())
+        order = np.arange(total)
+        host = self._pinned.numpy()
+        for e in range(E):
+            self.np_random.shuffle(order)
+            host[e] = order
+        self._device_order.copy_(self._pinned, non_blocking=True)
+        for e in range(E):
+            for lo in range(0, total, self.batch_size):
+                rows = min(self.batch_size, total - lo)
+                yield self._device_order[e, lo:lo + rows], rows
+
+    def get(self, *keys):
+        """Reference-style generator of gathered minibatches (convenience; the
+        agents use `index_batches` and gather inside the kernels)."""
+        batch = self.get_full(*keys)
+        for idx, rows in self.index_batches():
+            if idx is None:
+                yield batch
+            else:
+                yield {k: v[idx] for k, v in batch.items()}

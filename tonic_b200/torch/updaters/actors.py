@@ -1,0 +1,108 @@
+"""Policy updaters (reference: tonic/torch/updaters/actors.py).
+
+Each updater enqueues, without any host synchronisation, the kernel sequence
+  forward (save activations) -> loss / head gradient -> backward -> weight
+  gradients (split partial sums) -> Adam (+ partial reduction, transposes, flags)
+for one minibatch addressed through an index vector.  Statistics are
+accumulated in a float64 device block (layout: TB_STAT_* in the C header) and
+read by the agent once per update.  `__call__` keeps the reference's
+batch-tensor signature for direct use.
+"""
+
+import torch
+
+from ... import _lib, config, kernels
+from . import optimizers
+
+FLOAT_EPSILON = 1e-8
+
+
+def splits_for(rows):
+    return max(1, min(config.wgrad_splits, rows // 128))
+
+
+class _GaussianPolicyUpdater:
+    ratio_clip = 0.0
+    kl_threshold = -1.0
+
+    def initialize(self, model):
+        self.model = model
+        actor = model.actor
+        if actor.head.kind != 'detached_gaussian':
+            raise NotImplementedError('policy-gradient kernels need the detached-scale '
+                                      'Gaussian head (the reference default)')
+        self.actor = actor
+        self.variables = [p for p in actor.parameters() if p.requires_grad]
+        self.adam = kernels.Adam(actor.network.params,
+                                 **optimizers.adam_hyperparameters(self.optimizer, 3e-4))
+        self._rows = 0
+
+    def _scratch(self, rows):
+        if rows > self._rows:
+            dev, A = kernels.device(), self.actor.action_size
+            self._pre = torch.empty(rows, A, dtype=torch.float32, device=dev)
+            self._dout = torch.empty(rows, 2 * A, dtype=torch.float32, device=dev)
+            self._rows = rows
+        return self._pre, self._dout
+
+    def launch(self, observations, actions, advantages, log_probs, idx, rows, stats, stop=None):
+        actor, net = self.actor, self.actor.network
+        A = actor.action_size
+        pre, dout = self._scratch(rows)
+        n_split = splits_for(rows)
+        actor.pre_activations(observations, out=pre, idx=idx, rows=rows, save=True, skip=stop)
+        kernels.gauss_policy_loss(pre, net.extra('log_scale'), actions, advantages, log_probs,
+                                  idx, rows, dout, stats, self.ratio_clip, self.entropy_coeff,
+                                  skip=stop)
+        net.mlp.backward(dout, rows, skip=stop)
+        gpart = net.mlp.wgrad(dout, rows, n_split, n_extra=A,
+                              off_extra=net.extra_offset('log_scale'), skip=stop)
+        self.adam.step(net.mlp, gpart, n_split, 1.0 / rows, skip=stop, stats=stats,
+                       kl_threshold=self.kl_threshold, stop=stop)
+
+    def infos(self, s):
+        """Statistics block (host copy) -> the reference's info dict (python floats)."""
+        rows = s[_lib.STAT_ROWS]
+        A = self.actor.action_size
+        trained = s[_lib.STAT_NONZERO_ADV] > 0
+        out = dict(
+            loss=(s[_lib.STAT_LOSS] / rows
+                  - self.entropy_coeff * s[_lib.STAT_ENTROPY] / (rows * A)) if trained else 0.0,
+            kl=s[_lib.STAT_KL] / rows if trained else 0.0,
+            entropy=s[_lib.STAT_ENTROPY] / (rows * A))
+        if self.ratio_clip > 0:
+            out['clip_fraction'] = s[_lib.STAT_CLIPPED] / rows if trained else 0.0
+        out['std'] = s[_lib.STAT_STD] / (rows * A)
+        if self.ratio_clip > 0:
+            out['stop'] = bool(out['kl'] > self.kl_threshold)
+        return out
+
+    def __call__(self, observations, actions, advantages, log_probs):
+        args = [kernels.to_device(a) for a in (observations, actions, advantages, log_probs)]
+        stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.float64, device=kernels.device())
+        self.launch(*args, None, args[0].shape[0], stats)
+        return {k: torch.as_tensor(v) for k, v in self.infos(stats.cpu().numpy()).items()}
+
+
+class StochasticPolicyGradient(_GaussianPolicyUpdater):
+    """A2C policy gradient, loss = -mean(advantages * log_prob)
+    (reference: updaters/actors.py:9-50)."""
+
+    def __init__(self, optimizer=None, entropy_coeff=0, gradient_clip=0):
+        if gradient_clip:
+            raise NotImplementedError('gradient clipping is not implemented')
+        self.optimizer, self.entropy_coeff = optimizer, entropy_coeff
+
+
+class ClippedRatio(_GaussianPolicyUpdater):
+    """PPO clipped surrogate with KL early stopping (reference:
+    updaters/actors.py:53-112; the stop decision is taken on the device by the
+    Adam kernel so the update loop never waits for the host)."""
+
+    def __init__(self, optimizer=None, ratio_clip=0.2, kl_threshold=0.015, entropy_coeff=0,
+                 gradient_clip=0):
+        if gradient_clip:
+            raise NotImplementedError('gradient clipping is not implemented')
+        self.optimizer = optimizer
+        self.ratio_clip, self.kl_threshold = ratio_clip, kl_threshold
+        self.entropy_coeff = entropy_coeff
