@@ -44,6 +44,12 @@ const char* tb_last_error(void);
  * `gpu_launches`).                                                            */
 int64_t tb_launch_count(void);
 
+/* Per-entry-point device timing with CUDA events recorded on the launching
+ * stream (bench.py's live roofline).  tb_profile_end synchronises the device and
+ * writes "name launches total_ms" lines into h_buf.                           */
+int tb_profile_begin(void);
+int tb_profile_end(char* h_buf, int32_t size);
+
 /* ------------------------------------------------------------------------ */
 /* Vector environment  -- replaces environments/distributed.py:8-58           */
 /* (Sequential.{initialize,start,step}) and the ActionRescaler clip           */
@@ -260,6 +266,12 @@ int tb_mse_loss(const float* d_values, const float* d_targets,
                 const int64_t* d_idx, int64_t n_rows, float* d_dout,
                 int32_t ld_dout, double* d_stats, int32_t stat_slot,
                 int32_t count_rows, const int32_t* d_skip, void* stream);
+
+/* Running statistics of a float32 array (trainer.py:46 logs the actions with
+ * stats=True): d_acc[0] += n, [1] += sum, [2] += sum of squares, [3] / [4] =
+ * min / max encoded as order-preserving int64 (initialise with
+ * tb_array_stats_init values: +inf / -inf encodings).                         */
+int tb_array_stats(const float* d_x, int64_t n, double* d_acc, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Host-side numpy-compatible MT19937 streams (legacy numpy.random.RandomState)*/

@@ -2,3 +2,4 @@
 
 from . import agents, config, environments, replays  # noqa: E402,F401
 from .utils import logger  # noqa: E402,F401
+from .utils.trainer import Trainer  # noqa: E402,F401

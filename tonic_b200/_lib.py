@@ -73,6 +73,9 @@ _PROTOTYPES = {
     'tb_gauss_policy_loss': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f, c_f,
                                      c_vp, c_vp, c_vp, c_vp]),
     'tb_mse_loss': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'tb_profile_begin': (c_int, []),
+    'tb_profile_end': (c_int, [ctypes.c_char_p, c_i32]),
     'tb_rs_create': (c_vp, [c_u32]),
     'tb_rs_destroy': (None, [c_vp]),
     'tb_rs_shuffle_i64': (None, [c_vp, c_vp, c_i64]),
@@ -83,7 +86,7 @@ _PROTOTYPES = {
 
 # entry points whose int return value is a status code
 _CHECKED = {name for name, (res, _) in _PROTOTYPES.items()
-            if res is c_int and name != 'tb_version'}
+            if res is c_int and name not in ('tb_version', 'tb_profile_end')}
 
 _lib = None
 

@@ -13,6 +13,24 @@ namespace tb {
 void set_error(const char* fmt, ...);
 void count_launch();
 
+// Optional per-kernel timing with CUDA events recorded on the launching stream
+// (tb_profile_begin / tb_profile_end): used by bench.py for the live roofline.
+bool profiling_enabled();
+void profile_mark(const char* name, cudaStream_t stream, bool begin);
+
+struct ProfScope {
+    const char* name;
+    cudaStream_t stream;
+    bool on;
+    ProfScope(const char* n, void* s) : name(n), stream(reinterpret_cast<cudaStream_t>(s)),
+                                        on(profiling_enabled()) {
+        if (on) profile_mark(name, stream, true);
+    }
+    ~ProfScope() {
+        if (on) profile_mark(name, stream, false);
+    }
+};
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

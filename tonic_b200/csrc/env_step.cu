@@ -150,6 +150,7 @@ static int pick_tile(const TbEnv* env, size_t* smem_bytes) {
 }  // namespace tb
 
 extern "C" int tb_env_start(const TbEnv* env, float* d_obs, void* stream) {
+    tb::ProfScope prof_scope("tb_env_start", stream);
     TB_REQUIRE(env && d_obs && env->n_envs > 0 && env->obs_dim > 0 && env->act_dim > 0,
                TB_EINVAL, "tb_env_start: bad arguments");
     const int64_t total = (int64_t)env->n_envs * env->obs_dim;
@@ -162,6 +163,7 @@ extern "C" int tb_env_start(const TbEnv* env, float* d_obs, void* stream) {
 extern "C" int tb_env_step(const TbEnv* env, const float* d_actions, float* d_obs,
                            float* d_next_obs, float* d_rewards, float* d_resets,
                            float* d_terminations, void* stream) {
+    tb::ProfScope prof_scope("tb_env_step", stream);
     TB_REQUIRE(env && d_actions && d_obs && d_next_obs && d_rewards && d_resets && d_terminations,
                TB_EINVAL, "tb_env_step: null pointer");
     size_t smem = 0;

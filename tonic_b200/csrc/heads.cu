@@ -173,6 +173,7 @@ extern "C" int tb_gauss_sample(const float* d_loc_pre, const float* d_log_scale,
                                const float* d_eps, uint64_t seed, uint64_t counter,
                                int64_t n_rows, int32_t act_dim, float* d_actions,
                                float* d_log_probs, void* stream) {
+    tb::ProfScope prof_scope("tb_gauss_sample", stream);
     TB_REQUIRE(d_loc_pre && d_log_scale && d_actions && d_log_probs && n_rows > 0 &&
                act_dim >= 1 && act_dim <= tb::kMaxAct, TB_EINVAL, "tb_gauss_sample: bad arguments");
     const int blocks = (int)((n_rows + 255) / 256);
@@ -187,6 +188,7 @@ extern "C" int tb_gauss_policy_loss(const float* d_loc_pre, const float* d_log_s
                                     int64_t n_rows, int32_t act_dim, float ratio_clip,
                                     float entropy_coeff, float* d_dout, double* d_stats,
                                     const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_gauss_policy_loss", stream);
     TB_REQUIRE(d_loc_pre && d_log_scale && d_actions && d_advantages && d_old_log_probs &&
                d_dout && d_stats && n_rows > 0 && act_dim >= 1 && act_dim <= tb::kMaxAct,
                TB_EINVAL, "tb_gauss_policy_loss: bad arguments");
@@ -201,10 +203,54 @@ extern "C" int tb_mse_loss(const float* d_values, const float* d_targets, const 
                            int64_t n_rows, float* d_dout, int32_t ld_dout, double* d_stats,
                            int32_t stat_slot, int32_t count_rows, const int32_t* d_skip,
                            void* stream) {
+    tb::ProfScope prof_scope("tb_mse_loss", stream);
     TB_REQUIRE(d_values && d_targets && d_dout && d_stats && n_rows > 0 && ld_dout >= 1 &&
                stat_slot >= 0 && stat_slot < TB_STAT_COUNT, TB_EINVAL, "tb_mse_loss: bad arguments");
     const int blocks = (int)((n_rows + 255) / 256);
     tb::mse_loss_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
         d_values, d_targets, d_idx, n_rows, d_dout, ld_dout, d_stats, stat_slot, count_rows, d_skip);
     return tb::check_launch("tb_mse_loss");
+}
+
+// ---- running statistics of an array (trainer.py:46 `logger.store('train/action',
+// actions, stats=True)` without shipping the array to the host) -------------------
+namespace tb {
+__global__ void __launch_bounds__(256)
+array_stats_kernel(const float* __restrict__ x, int64_t n, double* acc) {
+    __shared__ double scratch[32];
+    double s = 0, q = 0, lo = 1e300, hi = -1e300;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        s += v; q += v * v;
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    double r;
+    r = block_sum(s, scratch); if (threadIdx.x == 0) atomicAdd(&acc[1], r);
+    r = block_sum(q, scratch); if (threadIdx.x == 0) atomicAdd(&acc[2], r);
+    if ((threadIdx.x & 31) == 0) {
+        // atomic min / max on doubles through the ordered-integer trick
+        auto enc = [](double d) {
+            long long b = __double_as_longlong(d);
+            return b >= 0 ? b : b ^ 0x7fffffffffffffffll;
+        };
+        atomicMin(reinterpret_cast<long long*>(&acc[3]), enc(lo));
+        atomicMax(reinterpret_cast<long long*>(&acc[4]), enc(hi));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&acc[0], (double)n);
+}
+}  // namespace tb
+
+extern "C" int tb_array_stats(const float* d_x, int64_t n, double* d_acc, void* stream) {
+    tb::ProfScope prof_scope("tb_array_stats", stream);
+    TB_REQUIRE(d_x && d_acc && n > 0, TB_EINVAL, "tb_array_stats: bad arguments");
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 4 * tb::kNumSMs) blocks = 4 * tb::kNumSMs;
+    tb::array_stats_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(d_x, n, d_acc);
+    return tb::check_launch("tb_array_stats");
 }

@@ -564,6 +564,7 @@ extern "C" int tb_mlp_forward(const TbMlpShape* shape, const float* d_params,
                               const float* d_packed, const TbMlpInput* in, int64_t n_rows,
                               float* d_out, float* d_xin, float* d_h1, float* d_h2,
                               const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_mlp_forward", stream);
     using namespace tb;
     int rc = check_shape(shape, "tb_mlp_forward");
     if (rc) return rc;
@@ -593,6 +594,7 @@ extern "C" int tb_mlp_backward(const TbMlpShape* shape, const float* d_params,
                                const float* d_h2, int64_t n_rows, float* d_dz2, float* d_dz1,
                                float* d_dx, int32_t dx_col0, int32_t dx_cols,
                                const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_mlp_backward", stream);
     using namespace tb;
     int rc = check_shape(shape, "tb_mlp_backward");
     if (rc) return rc;
@@ -621,6 +623,7 @@ extern "C" int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const f
                             const float* d_dout, int32_t ld_dout, int32_t n_extra,
                             int32_t off_extra, int64_t n_rows, float* d_gpart,
                             int32_t n_split, const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_mlp_wgrad", stream);
     using namespace tb;
     int rc = check_shape(shape, "tb_mlp_wgrad");
     if (rc) return rc;

@@ -96,6 +96,7 @@ __global__ void moments_update_kernel(double* sums, float* running, double* coun
 
 extern "C" int tb_moments_record(const float* d_x, int64_t n_rows, int32_t dim,
                                  double* d_sums, void* stream) {
+    tb::ProfScope prof_scope("tb_moments_record", stream);
     TB_REQUIRE(d_x && d_sums && n_rows > 0 && dim > 0 && dim <= 256 * tb::kMomCols, TB_EINVAL,
                "tb_moments_record: bad arguments (dim=%d)", dim);
     int64_t rows_per_block = 512;
@@ -109,6 +110,7 @@ extern "C" int tb_moments_record(const float* d_x, int64_t n_rows, int32_t dim,
 extern "C" int tb_moments_update(double* d_sums, float* d_running, double* d_count,
                                  float* d_mean, float* d_std, int32_t dim, float eps,
                                  void* stream) {
+    tb::ProfScope prof_scope("tb_moments_update", stream);
     TB_REQUIRE(d_sums && d_running && d_count && d_mean && d_std && dim > 0, TB_EINVAL,
                "tb_moments_update: bad arguments");
     tb::moments_update_kernel<<<1, 256, 0, tb::as_stream(stream)>>>(

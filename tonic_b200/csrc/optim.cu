@@ -89,6 +89,7 @@ extern "C" int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d
                             const float* d_gpart, int32_t n_split, float grad_scale,
                             const int32_t* d_skip, const double* d_stats, float kl_threshold,
                             int32_t* d_stop, void* stream) {
+    tb::ProfScope prof_scope("tb_adam_step", stream);
     TB_REQUIRE(opt && opt->d_params && opt->d_m && opt->d_v && opt->d_step && d_gpart &&
                n_split >= 1 && opt->n_params > 0, TB_EINVAL, "tb_adam_step: bad arguments");
     TB_REQUIRE(!d_packed || (shape && shape->n_params == opt->n_params), TB_EINVAL,
@@ -103,6 +104,7 @@ extern "C" int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d
 
 extern "C" int tb_mlp_pack(const TbMlpShape* shape, const float* d_params, float* d_packed,
                            void* stream) {
+    tb::ProfScope prof_scope("tb_mlp_pack", stream);
     TB_REQUIRE(shape && d_params && d_packed, TB_EINVAL, "tb_mlp_pack: null pointer");
     const int blocks = (shape->n_params + 255) / 256;
     tb::pack_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(*shape, d_params, d_packed);
@@ -111,6 +113,7 @@ extern "C" int tb_mlp_pack(const TbMlpShape* shape, const float* d_params, float
 
 extern "C" int tb_soft_update(float* d_target, const float* d_online, int64_t n, double tau,
                               void* stream) {
+    tb::ProfScope prof_scope("tb_soft_update", stream);
     TB_REQUIRE(d_target && d_online && n > 0, TB_EINVAL, "tb_soft_update: bad arguments");
     int blocks = (int)((n + 255) / 256);
     if (blocks > 8 * tb::kNumSMs) blocks = 8 * tb::kNumSMs;

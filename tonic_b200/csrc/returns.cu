@@ -86,6 +86,7 @@ extern "C" int tb_lambda_returns(const float* d_values, const float* d_next_valu
                                  const float* d_terminations, float* d_returns,
                                  int32_t T, int32_t N, double discount_factor,
                                  double trace_decay, void* stream) {
+    tb::ProfScope prof_scope("tb_lambda_returns", stream);
     TB_REQUIRE(T > 0 && N > 0 && d_next_values && d_rewards && d_resets && d_terminations &&
                d_returns, TB_EINVAL, "tb_lambda_returns: bad arguments");
     const int blocks = (N + 127) / 128;
@@ -98,6 +99,7 @@ extern "C" int tb_lambda_returns(const float* d_values, const float* d_next_valu
 extern "C" int tb_advantages(const float* d_returns, const float* d_values,
                              float* d_advantages, int64_t n, double* d_workspace,
                              int64_t n_global, int32_t phase, void* stream) {
+    tb::ProfScope prof_scope("tb_advantages", stream);
     TB_REQUIRE(n > 0 && n_global >= n && d_advantages && d_workspace, TB_EINVAL,
                "tb_advantages: bad arguments");
     cudaStream_t s = tb::as_stream(stream);

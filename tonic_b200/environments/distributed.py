@@ -76,7 +76,7 @@ class DeviceVectorEnvironment:
         _lib.call('tb_env_start', ctypes.byref(self.struct), ptr(self.observations),
                   kernels.stream())
         if host:
-            return self.observations.cpu().numpy()
+            return kernels.to_host(self.observations)
         return self.observations
 
     def step_into(self, actions, observations, next_observations, rewards, resets, terminations):
@@ -93,11 +93,11 @@ class DeviceVectorEnvironment:
                        self.resets, self.terminations)
         if host:
             infos = dict(
-                observations=self.next_observations.cpu().numpy(),
-                rewards=self.rewards.cpu().numpy(),
-                resets=self.resets.cpu().numpy().astype(np.bool_),
-                terminations=self.terminations.cpu().numpy().astype(np.bool_))
-            return self.observations.cpu().numpy(), infos
+                observations=kernels.to_host(self.next_observations),
+                rewards=kernels.to_host(self.rewards),
+                resets=kernels.to_host(self.resets).astype(np.bool_),
+                terminations=kernels.to_host(self.terminations).astype(np.bool_))
+            return kernels.to_host(self.observations), infos
         infos = dict(observations=self.next_observations, rewards=self.rewards,
                      resets=self.resets, terminations=self.terminations)
         return self.observations, infos
@@ -112,8 +112,8 @@ class DeviceVectorEnvironment:
             return np.zeros(0), np.zeros(0, int)
         new = min(new, cap)
         idx = (torch.arange(total - new, total, device=self.state.device) % cap)
-        scores = self.episode_scores[idx].cpu().numpy()
-        lengths = self.episode_lengths[idx].cpu().numpy().astype(int)
+        scores = kernels.to_host(self.episode_scores[idx])
+        lengths = kernels.to_host(self.episode_lengths[idx]).astype(int)
         self._episodes_read = total
         return scores, lengths
 

@@ -26,15 +26,43 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# bytes moved across PCIe by the product's own API calls (bench.py's e2e accounting)
+transfers = {'h2d': 0, 'd2h': 0}
+# algorithmic FLOPs enqueued per entry point (bench.py's roofline accounting)
+flops = {}
+_pinned = {}
+
+
 def to_device(x, dtype=F32):
-    """numpy / torch (host or device) -> contiguous device tensor of `dtype`."""
-    if isinstance(x, torch.Tensor):
-        return x.to(device=device(), dtype=dtype).contiguous()
-    arr = np.asarray(x)
-    if arr.dtype == np.bool_:
-        arr = arr.astype(np.float32)
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    return t.to(device=device(), dtype=dtype, non_blocking=False)
+    """numpy / torch (host or device) -> contiguous device tensor of `dtype`.
+    Host arrays are staged through a cached pinned buffer."""
+    if isinstance(x, torch.Tensor) and x.is_cuda:
+        return x.to(dtype=dtype).contiguous()
+    arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    target = {torch.float32: np.float32, torch.float64: np.float64,
+              torch.int64: np.int64, torch.int32: np.int32}[dtype]
+    arr = np.ascontiguousarray(arr, dtype=target)
+    key = (arr.shape, arr.dtype.str)
+    stage = _pinned.get(key)
+    if stage is None:
+        stage = _pinned[key] = torch.empty(arr.shape, dtype=dtype).pin_memory()
+    out = torch.empty(arr.shape, dtype=dtype, device=device())
+    # the staging buffer is reused: wait for the previous copy out of it
+    torch.cuda.current_stream().synchronize()
+    stage.numpy()[...] = arr
+    out.copy_(stage, non_blocking=True)
+    transfers['h2d'] += arr.nbytes
+    return out
+
+
+def to_host(t):
+    """Device tensor -> numpy (synchronises)."""
+    transfers['d2h'] += t.numel() * t.element_size()
+    return t.detach().cpu().numpy()
+
+
+def _count_flops(name, value):
+    flops[name] = flops.get(name, 0.0) + value
 
 
 def round_up(x, m):
@@ -130,6 +158,9 @@ class DeviceMlp:
         parameter set (target networks share the layout)."""
         if save:
             self.workspace(rows)
+        L = self.layout
+        _count_flops('tb_mlp_forward',
+                     2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out))
         _lib.call('tb_mlp_forward', ctypes.byref(self.layout.shape),
                   ptr(self.params if params is None else params),
                   ptr(self.packed if packed is None else packed),
@@ -139,6 +170,9 @@ class DeviceMlp:
         return out
 
     def backward(self, dout, rows, dx=None, dx_col0=0, skip=None, params=None):
+        L = self.layout
+        _count_flops('tb_mlp_backward', 2.0 * rows * L.hidden * (
+            L.n_out + L.hidden + (0 if dx is None else dx.shape[-1])))
         _lib.call('tb_mlp_backward', ctypes.byref(self.layout.shape),
                   ptr(self.params if params is None else params), ptr(dout), dout.shape[-1],
                   ptr(self.h1), ptr(self.h2), rows, ptr(self.dz2), ptr(self.dz1), ptr(dx),
@@ -146,6 +180,9 @@ class DeviceMlp:
 
     def wgrad(self, dout, rows, n_split, n_extra=0, off_extra=0, skip=None):
         gpart = self.gpart(n_split)
+        L = self.layout
+        _count_flops('tb_mlp_wgrad', 2.0 * rows * (
+            L.hidden * L.hidden + L.hidden * (L.d_in + 2) + (L.n_out + n_extra) * (L.hidden + 1)))
         _lib.call('tb_mlp_wgrad', ctypes.byref(self.layout.shape), ptr(self.xin), ptr(self.h1),
                   ptr(self.h2), ptr(self.dz1), ptr(self.dz2), ptr(dout), dout.shape[-1],
                   n_extra, off_extra, rows, ptr(gpart), n_split, ptr(skip), stream())
@@ -225,3 +262,50 @@ def moments_record(x, sums):
 def moments_update(sums, running, count, mean, std, eps=1e-2):
     _lib.call('tb_moments_update', ptr(sums), ptr(running), ptr(count), ptr(mean), ptr(std),
               mean.numel(), eps, stream())
+
+
+class ArrayStats:
+    """Device accumulator of (count, sum, sum of squares, min, max) of float32
+    arrays (csrc/heads.cu::array_stats_kernel)."""
+
+    _NEG_INF_ENC = np.array([-np.inf]).view(np.int64)[0] ^ np.int64(0x7fffffffffffffff)
+
+    def __init__(self):
+        self.acc = torch.zeros(5, dtype=torch.float64, device=device())
+        self.reset()
+
+    def reset(self):
+        init = np.zeros(5)
+        init[3] = np.inf
+        init.view(np.int64)[4] = self._NEG_INF_ENC
+        self.acc.copy_(torch.from_numpy(init))
+        self.items = 0
+
+    def add(self, x, items=1):
+        _lib.call('tb_array_stats', ptr(x), x.numel(), ptr(self.acc), stream())
+        self.items += items
+
+    def read(self):
+        """-> (count, sum, sum_sq, min, max) as python floats (synchronises)."""
+        host = self.acc.cpu().numpy()
+        bits = host.view(np.int64)
+        ext = []
+        for b in (bits[3], bits[4]):
+            b = b if b >= 0 else b ^ np.int64(0x7fffffffffffffff)
+            ext.append(float(np.array([b], np.int64).view(np.float64)[0]))
+        return float(host[0]), float(host[1]), float(host[2]), ext[0], ext[1]
+
+
+def profile_begin():
+    _lib.call('tb_profile_begin')
+
+
+def profile_end():
+    """-> {entry point: (launches, total_ms)} since profile_begin()."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _lib.call('tb_profile_end', buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, count, ms = line.split()
+        out[name] = (int(count), float(ms))
+    return out

@@ -77,7 +77,7 @@ class A2C(agent.Agent):
         self.last_observations = observations.clone() if not host else observations
         self.last_actions = self._actions
         self.last_log_probs = self._log_probs
-        return self._actions.cpu().numpy() if host else self._actions
+        return kernels.to_host(self._actions) if host else self._actions
 
     def test_step(self, observations, steps):
         host = not (isinstance(observations, torch.Tensor) and observations.is_cuda)
@@ -87,7 +87,45 @@ class A2C(agent.Agent):
         log_probs = torch.empty(observations.shape[0], device=dev)
         self._buffers(max(self._workers, observations.shape[0]))
         self._sample(observations, actions, log_probs)      # a2c.py:87-90: stochastic
-        return actions.cpu().numpy() if host else actions
+        return kernels.to_host(actions) if host else actions
+
+    # -- fused collection (device environments) ------------------------------------
+    def rollout(self, environment, vector_steps, steps=0, action_stats=None):
+        """Runs up to `vector_steps` steps of agent.step -> environment.step ->
+        agent.update (trainer.py:44-50) without leaving the device: the acting
+        observations of step t live in row t of the segment, the environment
+        kernel writes next_observations / rewards / resets / terminations of step t
+        and the acting observations of step t+1 straight into the segment rows.
+        Stops when the segment is full (and then runs the update).  Returns the
+        number of vector steps done."""
+        seg, env = self.replay, environment
+        N, A = env.workers, self.action_size
+        O = env.observation_space.shape[0]
+        if seg.buffers is None:
+            seg.allocate(observations=(N, O), actions=(N, A), next_observations=(N, O),
+                         rewards=(N,), resets=(N,), terminations=(N,), log_probs=(N,))
+        self._buffers(N)
+        b, T = seg.buffers, seg.max_size
+        normalizer = self.model.observation_normalizer
+        done = 0
+        while done < vector_steps and seg.index < T:
+            t = seg.index
+            if t == 0:       # first acting observations come from the environment
+                b['observations'][0].copy_(env.observations)
+            obs = b['observations'][t]
+            self._sample(obs, b['actions'][t], b['log_probs'][t])
+            if normalizer:
+                normalizer.record(obs)
+            target = b['observations'][t + 1] if t + 1 < T else env.observations
+            env.step_into(b['actions'][t], target, b['next_observations'][t], b['rewards'][t],
+                          b['resets'][t], b['terminations'][t])
+            seg.advance()
+            done += 1
+        if action_stats is not None and done:
+            action_stats.add(b['actions'][seg.index - done:seg.index], items=done)
+        if seg.ready():
+            self._update()
+        return done
 
     # -- learning ---------------------------------------------------------------
     def update(self, observations, rewards, resets, terminations, steps):
@@ -129,7 +167,7 @@ class A2C(agent.Agent):
         for j, (idx, rows) in enumerate(batches):
             self.critic_updater.launch(flat['observations'], flat['returns'], idx, rows,
                                        stats[j + 1, 1])
-        host = stats.cpu().numpy()
+        host = kernels.to_host(stats)
         for k, v in self.actor_updater.infos(host[0, 0]).items():
             logger.store('actor/' + k, v)
         for j in range(len(batches)):

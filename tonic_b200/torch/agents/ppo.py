@@ -35,7 +35,7 @@ class PPO(a2c.A2C):
                                       stats[j, 0], stop=stop)
             self.critic_updater.launch(flat['observations'], flat['returns'], idx, rows,
                                        stats[j, 1])
-        host = stats.cpu().numpy()
+        host = kernels.to_host(stats)
         actor_iterations = 0
         for j in range(len(batches)):
             if host[j, 0, _lib.STAT_ROWS] > 0:      # the actor was still training

@@ -30,13 +30,13 @@ class _Aggregate:
         self.stats = stats
         self.items = 0          # number of store() calls (reference '/size')
 
-    def add(self, count, total, total_sq, low, high):
+    def add(self, count, total, total_sq, low, high, items=1):
         self.count += count
         self.total += total
         self.total_sq += total_sq
         self.low = min(self.low, low)
         self.high = max(self.high, high)
-        self.items += 1
+        self.items += items
 
     def mean(self):
         return self.total / max(self.count, 1)
@@ -81,11 +81,11 @@ class Logger:
         self.store_aggregate(key, v.size, v.sum(), np.square(v).sum(), v.min(), v.max(),
                              stats=stats)
 
-    def store_aggregate(self, key, count, total, total_sq, low, high, stats=False):
+    def store_aggregate(self, key, count, total, total_sq, low, high, stats=False, items=1):
         agg = self.epoch.get(key)
         if agg is None:
             agg = self.epoch[key] = _Aggregate(stats)
-        agg.add(count, float(total), float(total_sq), float(low), float(high))
+        agg.add(count, float(total), float(total_sq), float(low), float(high), items)
 
     # -- reporting --------------------------------------------------------------
     def _row(self):
