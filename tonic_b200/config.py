@@ -10,4 +10,4 @@ wgrad_splits     : number of row splits of the weight-gradient kernel.
 """
 
 noise = 'host'
-wgrad_splits = 32
+wgrad_splits = 37      # 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM

@@ -517,10 +517,12 @@ mlp_wgrad_kernel(WJobTable table, int64_t n_rows, int64_t rows_per_split,
     if (skip_requested(d_skip)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* smem = reinterpret_cast<float*>(smem_raw);
-    const WJob& job = table.jobs[blockIdx.x];
-    const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+    // grid = (splits, jobs): blocks are dispatched job-major, so the heavy 128x128
+    // tiles (jobs 0..3) go out first, one per SM when 4 * splits == #SMs
+    const WJob& job = table.jobs[blockIdx.y];
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_split;
     const int64_t r1 = min(n_rows, r0 + rows_per_split);
-    float* gout = gpart + (size_t)blockIdx.y * n_params;
+    float* gout = gpart + (size_t)blockIdx.x * n_params;
     if (job.variant == 0) wgrad_tile<128, 128>(job, r0, max(r0, r1), gout, smem);
     else if (job.variant == 1) wgrad_tile<128, 32>(job, r0, max(r0, r1), gout, smem);
     else wgrad_tile<16, 128>(job, r0, max(r0, r1), gout, smem);
@@ -683,7 +685,7 @@ extern "C" int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const f
     int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
     rows_per_split = (rows_per_split + WMC - 1) / WMC * WMC;
     const size_t smem = (size_t)2 * WMC * (128 + 128) * sizeof(float);
-    dim3 grid(t.n_jobs, n_split);
+    dim3 grid(n_split, t.n_jobs);
     mlp_wgrad_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(
         t, n_rows, rows_per_split, d_gpart, shape->n_params, d_skip);
     return check_launch("tb_mlp_wgrad");
