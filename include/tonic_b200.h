@@ -267,6 +267,56 @@ int tb_mse_loss(const float* d_values, const float* d_targets,
                 int32_t ld_dout, double* d_stats, int32_t stat_slot,
                 int32_t count_rows, const int32_t* d_skip, void* stream);
 
+/* ------------------------------------------------------------------------ */
+/* Off-policy heads, targets and actor losses (DDPG / TD3 / SAC)              */
+/* ------------------------------------------------------------------------ */
+/* DeterministicPolicyHead (models/actors.py:101-115) with optional noise.
+ * mode 0: out = tanh(pre)                                   (greedy, ddpg.py:78-81)
+ * mode 1: out = clip(tanh(pre) + clip(noise_scale * eps, +-noise_clip), -1, 1)
+ *         eps = d_noise64 (host numpy stream, explorations/noisy.py:38-47: float64
+ *         noise added to float32 actions then cast), else d_noise32 (host torch
+ *         stream, TargetActionNoise updaters/critics.py:125-134), else Philox;
+ * mode 2: out = uniform(-1, 1) from Philox (device warm-up actions, noisy.py:44-46) */
+int tb_tanh_action(const float* d_pre, int64_t n_rows, int32_t act_dim, int32_t mode,
+                   const float* d_noise32, const double* d_noise64, uint64_t seed,
+                   uint64_t counter, float noise_scale, float noise_clip, float* d_out,
+                   void* stream);
+
+/* GaussianPolicyHead in the SAC configuration + SquashedMultivariateNormalDiag
+ * (models/actors.py:7-34,69-98).  d_pre [n, 2A] = [loc | scale pre-activation];
+ * raw = loc + eps * clamp(softplus(.), 1e-4, 1); action = tanh(raw);
+ * log_prob = sum_j N(raw) - log(1 - action^2 + 1e-6).  greedy != 0: action =
+ * tanh(loc) (sac.py:48-51).  d_eps NULL = Philox; d_eps_out receives the noise
+ * used (needed by tb_sac_head_grad).                                          */
+int tb_squashed_sample(const float* d_pre, const float* d_eps, uint64_t seed,
+                       uint64_t counter, int64_t n_rows, int32_t act_dim, int32_t greedy,
+                       float* d_actions, float* d_log_probs, float* d_eps_out, void* stream);
+
+/* targets = r + (1 - termination) * gamma * (min(q1, q2) - alpha * log_prob);
+ * r / termination gathered through d_idx; d_q2 / d_log_probs may be NULL.
+ * DDPG critics.py:71-75, TD3 :159-167, SAC :205-220; discounts buffers.py:34-36. */
+int tb_q_target(const float* d_rewards, const float* d_terminations, const int64_t* d_idx,
+                double discount_factor, const float* d_q1, const float* d_q2,
+                const float* d_log_probs, double entropy_coeff, int64_t n_rows,
+                float* d_targets, void* stream);
+
+/* Actor losses through the critics: loss_i = alpha * log_prob_i - min(q1_i, q2_i)
+ * (DPG actors.py:177-179 with q2 = log_prob = NULL; soft DPG :254-257).  Writes
+ * d loss_i / d q_k into d_dout1 / d_dout2 and accumulates TB_STAT_LOSS / ROWS.  */
+int tb_q_actor_loss(const float* d_q1, const float* d_q2, const float* d_log_probs,
+                    double entropy_coeff, int64_t n_rows, float* d_dout1, float* d_dout2,
+                    double* d_stats, void* stream);
+
+/* Chain rule through the deterministic head: dout = dq/da * (1 - a^2).        */
+int tb_dpg_head_grad(const float* d_dqda, const float* d_actions, int64_t n_rows,
+                     int32_t act_dim, float* d_dout, void* stream);
+
+/* Chain rule through the squashed Gaussian head for the SAC actor loss; d_dqda2
+ * may be NULL.  Writes d_dout [n, 2A] (loc | scale pre-activation gradients).   */
+int tb_sac_head_grad(const float* d_pre, const float* d_eps, const float* d_actions,
+                     const float* d_dqda1, const float* d_dqda2, double entropy_coeff,
+                     int64_t n_rows, int32_t act_dim, float* d_dout, void* stream);
+
 /* Running statistics of a float32 array (trainer.py:46 logs the actions with
  * stats=True): d_acc[0] += n, [1] += sum, [2] += sum of squares, [3] / [4] =
  * min / max encoded as order-preserving int64 (initialise with

@@ -68,3 +68,24 @@ def test_on_policy_scenario_matches_reference(golden, name):
     np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=2e-5)
     check_infos(rec, g)
     check_weights(agent, g)
+
+
+OFF_POLICY = ['ddpg_small', 'td3_small', 'sac_small', 'sac_wrap']
+
+
+@pytest.mark.parametrize('name', OFF_POLICY)
+def test_off_policy_scenario_matches_reference(golden, name):
+    g = golden(name)
+    cfg = scenarios.SCENARIOS[name]
+    rec = scenarios.InfoRecorder()
+    agent, env = product.build(cfg, log=rec)
+    w0 = scenarios.state_arrays(agent.model.state_dict(), 'w0/')
+    for k, v in w0.items():
+        if k in g:
+            np.testing.assert_array_equal(v, g[k], err_msg=k)
+    actions = product.teacher_forced(agent, env, g, cfg['vector_steps'])
+    # warm-up actions: the numpy uniform stream (exact up to the float32 cast);
+    # afterwards policy actions + numpy / torch noise streams
+    np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=2e-5)
+    check_infos(rec, g)
+    check_weights(agent, g)

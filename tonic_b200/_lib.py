@@ -73,6 +73,12 @@ _PROTOTYPES = {
     'tb_gauss_policy_loss': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f, c_f,
                                      c_vp, c_vp, c_vp, c_vp]),
     'tb_mse_loss': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'tb_tanh_action': (c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_u64, c_u64, c_f, c_f, c_vp, c_vp]),
+    'tb_squashed_sample': (c_int, [c_vp, c_vp, c_u64, c_u64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    'tb_q_target': (c_int, [c_vp, c_vp, c_vp, c_d, c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp]),
+    'tb_q_actor_loss': (c_int, [c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'tb_dpg_head_grad': (c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'tb_sac_head_grad': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_i64, c_i32, c_vp, c_vp]),
     'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'tb_profile_begin': (c_int, []),
     'tb_profile_end': (c_int, [ctypes.c_char_p, c_i32]),

@@ -1,0 +1,244 @@
+// Off-policy heads, targets and actor losses (DDPG / TD3 / SAC).
+//
+// Reference:
+//  * DeterministicPolicyHead            tonic/torch/models/actors.py:101-115
+//  * NormalActionNoise / NoActionNoise  tonic/explorations/noisy.py:6-50
+//  * TargetActionNoise                  tonic/torch/updaters/critics.py:125-134
+//  * GaussianPolicyHead (SAC config) + SquashedMultivariateNormalDiag
+//                                       tonic/torch/models/actors.py:7-34,69-98
+//  * Q targets  DDPG critics.py:71-75, TD3 :159-167, SAC :205-220
+//  * actor losses  DPG actors.py:170-189, soft DPG :238-267
+#include "common.cuh"
+
+namespace tb {
+
+constexpr float kLogSqrt2PiO = 0.91893853320467274178f;
+
+__device__ __forceinline__ float softplus_o(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+// SAC scale = clamp(softplus(pre), 1e-4, 1) and its derivative w.r.t. pre
+__device__ __forceinline__ float sac_scale(float pre, float* dscale) {
+    const float sp = softplus_o(pre);
+    const float sc = fminf(fmaxf(sp, 1e-4f), 1.0f);
+    if (dscale) *dscale = (sp >= 1e-4f && sp <= 1.0f) ? 1.0f / (1.0f + expf(-pre)) : 0.0f;
+    return sc;
+}
+
+__device__ __forceinline__ float philox_normal(const Philox& rng, uint64_t row, int a, uint64_t counter) {
+    const uint4 r = rng(counter + row, (uint64_t)(a >> 2));
+    const float2 p = (a & 2) ? box_muller(r.z, r.w) : box_muller(r.x, r.y);
+    return (a & 1) ? p.y : p.x;
+}
+
+// mode 0: tanh(pre); mode 1: clip(tanh(pre) + clip(scale * eps, +-noise_clip), -1, 1);
+// mode 2: uniform(-1, 1) (device warm-up actions)
+__global__ void __launch_bounds__(256)
+tanh_action_kernel(const float* __restrict__ pre, int64_t total, int A, int mode,
+                   const float* __restrict__ noise32, const double* __restrict__ noise64,
+                   uint64_t seed, uint64_t counter, float noise_scale, float noise_clip,
+                   float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t row = i / A;
+    const int a = (int)(i % A);
+    Philox rng(seed);
+    if (mode == 2) {
+        const uint4 r = rng(counter + (uint64_t)row, (uint64_t)(a >> 2) + (1ull << 32));
+        const uint32_t u = (a & 3) == 0 ? r.x : (a & 3) == 1 ? r.y : (a & 3) == 2 ? r.z : r.w;
+        out[i] = __fsub_rn(__fmul_rn((float)(u >> 8), 1.1920928955078125e-07f), 1.0f);
+        return;
+    }
+    const float act = tanhf(pre[i]);
+    if (mode == 0) { out[i] = act; return; }
+    float noisy;
+    if (noise64) {        // noisy.py:41-42: float32 actions + float64 noise, cast to float32
+        noisy = (float)((double)act + (double)noise_scale * noise64[i]);
+    } else {
+        const float eps = noise32 ? noise32[i] : philox_normal(rng, row, a, counter);
+        float nz = __fmul_rn(noise_scale, eps);                  // critics.py:131
+        nz = fminf(fmaxf(nz, -noise_clip), noise_clip);          // critics.py:132
+        noisy = __fadd_rn(act, nz);
+    }
+    out[i] = fminf(fmaxf(noisy, -1.0f), 1.0f);
+}
+
+// pre [n, 2A] = [loc | scale pre-activation].  raw = loc + eps * scale, action = tanh(raw),
+// log_prob = sum_j Normal(loc, scale).log_prob(raw) - log(1 - action^2 + 1e-6)
+__global__ void __launch_bounds__(256)
+squashed_sample_kernel(const float* __restrict__ pre, const float* __restrict__ eps_in,
+                       uint64_t seed, uint64_t counter, int64_t n, int A, int greedy,
+                       float* __restrict__ actions, float* __restrict__ log_probs,
+                       float* __restrict__ eps_out) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    Philox rng(seed);
+    float lp = 0.0f;
+    for (int a = 0; a < A; ++a) {
+        const float loc = pre[row * 2 * A + a];
+        if (greedy) {                       // sac.py:48-51: tanh(mean)
+            actions[row * A + a] = tanhf(loc);
+            continue;
+        }
+        const float sc = sac_scale(pre[row * 2 * A + A + a], nullptr);
+        const float eps = eps_in ? eps_in[row * A + a] : philox_normal(rng, row, a, counter);
+        const float raw = __fadd_rn(loc, __fmul_rn(eps, sc));    // Normal.rsample / sample
+        const float act = tanhf(raw);
+        actions[row * A + a] = act;
+        if (eps_out) eps_out[row * A + a] = eps;
+        const float d = raw - loc;
+        lp += -(d * d) / (2.0f * (sc * sc)) - logf(sc) - kLogSqrt2PiO;
+        lp -= logf(1.0f - act * act + 1e-6f);                    // actors.py:16
+    }
+    if (log_probs && !greedy) log_probs[row] = lp;
+}
+
+// targets = r + (1 - term) * gamma * (min(q1, q2) - alpha * logp)   (buffers.py:34-36 discounts)
+__global__ void __launch_bounds__(256)
+q_target_kernel(const float* __restrict__ rewards, const float* __restrict__ terminations,
+                const int64_t* __restrict__ idx, float gamma, const float* __restrict__ q1,
+                const float* __restrict__ q2, const float* __restrict__ logp, float alpha,
+                int64_t n, float* __restrict__ targets) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t r = idx ? idx[i] : i;
+    const float disc = __fmul_rn(__fsub_rn(1.0f, terminations[r]), gamma);
+    float v = q1[i];
+    if (q2) v = fminf(v, q2[i]);
+    if (logp) v = __fsub_rn(v, __fmul_rn(alpha, logp[i]));
+    targets[i] = __fadd_rn(rewards[r], __fmul_rn(disc, v));
+}
+
+// loss_i = alpha * logp_i - min(q1_i, q2_i);  dout_k = d loss_i / d q_k (torch.min tie -> 1/2 each)
+__global__ void __launch_bounds__(256)
+q_actor_loss_kernel(const float* __restrict__ q1, const float* __restrict__ q2,
+                    const float* __restrict__ logp, float alpha, int64_t n,
+                    float* __restrict__ dout1, float* __restrict__ dout2, double* stats) {
+    __shared__ double scratch[32];
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double loss = 0.0, rows = 0.0;
+    if (i < n) {
+        float v = q1[i], w1 = 1.0f, w2 = 0.0f;
+        if (q2) {
+            const float b = q2[i];
+            if (b < v) { v = b; w1 = 0.0f; w2 = 1.0f; }
+            else if (b == v) { w1 = w2 = 0.5f; }
+            dout2[i] = -w2;
+        }
+        dout1[i] = -w1;
+        loss = (logp ? (double)(alpha * logp[i]) : 0.0) - (double)v;
+        rows = 1.0;
+    }
+    double r;
+    r = block_sum(loss, scratch); if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_LOSS], r);
+    r = block_sum(rows, scratch); if (threadIdx.x == 0) atomicAdd(&stats[TB_STAT_ROWS], r);
+}
+
+// deterministic head: dout = dq/da * (1 - a^2)
+__global__ void __launch_bounds__(256)
+dpg_head_grad_kernel(const float* __restrict__ dqda, const float* __restrict__ actions,
+                     int64_t total, float* __restrict__ dout) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float a = actions[i];
+    dout[i] = dqda[i] * (1.0f - a * a);
+}
+
+// squashed Gaussian head (SAC actor): gradient of  alpha * logp - min(q1, q2)  w.r.t. the
+// head pre-activations [loc | scale_pre]; dqda = dqda1 (+ dqda2) already carry the -w_k factors.
+__global__ void __launch_bounds__(256)
+sac_head_grad_kernel(const float* __restrict__ pre, const float* __restrict__ eps,
+                     const float* __restrict__ actions, const float* __restrict__ dqda1,
+                     const float* __restrict__ dqda2, float alpha, int64_t total, int A,
+                     float* __restrict__ dout) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t row = i / A;
+    const int a = (int)(i % A);
+    float dsc;
+    const float sc = sac_scale(pre[row * 2 * A + A + a], &dsc);
+    const float act = actions[i];
+    const float one_m = 1.0f - act * act;
+    float dq = dqda1[i];
+    if (dqda2) dq += dqda2[i];
+    // d/draw [ -alpha * log(1 - a^2 + 1e-6) ] = alpha * 2 a (1 - a^2) / (1 - a^2 + 1e-6)
+    const float draw = alpha * (2.0f * act * one_m / (one_m + 1e-6f)) + dq * one_m;
+    dout[row * 2 * A + a] = draw;                                   // d/dloc
+    dout[row * 2 * A + A + a] = (draw * eps[i] - alpha / sc) * dsc; // d/dscale * dscale/dpre
+}
+
+inline int blocks_for(int64_t n) { return (int)((n + 255) / 256); }
+
+}  // namespace tb
+
+extern "C" int tb_tanh_action(const float* d_pre, int64_t n_rows, int32_t act_dim, int32_t mode,
+                              const float* d_noise32, const double* d_noise64, uint64_t seed,
+                              uint64_t counter, float noise_scale, float noise_clip,
+                              float* d_out, void* stream) {
+    tb::ProfScope prof_scope("tb_tanh_action", stream);
+    TB_REQUIRE((d_pre || mode == 2) && d_out && n_rows > 0 && act_dim > 0 && mode >= 0 && mode <= 2,
+               TB_EINVAL, "tb_tanh_action: bad arguments");
+    const int64_t total = n_rows * act_dim;
+    tb::tanh_action_kernel<<<tb::blocks_for(total), 256, 0, tb::as_stream(stream)>>>(
+        d_pre, total, act_dim, mode, d_noise32, d_noise64, seed, counter, noise_scale, noise_clip,
+        d_out);
+    return tb::check_launch("tb_tanh_action");
+}
+
+extern "C" int tb_squashed_sample(const float* d_pre, const float* d_eps, uint64_t seed,
+                                  uint64_t counter, int64_t n_rows, int32_t act_dim,
+                                  int32_t greedy, float* d_actions, float* d_log_probs,
+                                  float* d_eps_out, void* stream) {
+    tb::ProfScope prof_scope("tb_squashed_sample", stream);
+    TB_REQUIRE(d_pre && d_actions && n_rows > 0 && act_dim > 0, TB_EINVAL,
+               "tb_squashed_sample: bad arguments");
+    tb::squashed_sample_kernel<<<tb::blocks_for(n_rows), 256, 0, tb::as_stream(stream)>>>(
+        d_pre, d_eps, seed, counter, n_rows, act_dim, greedy, d_actions, d_log_probs, d_eps_out);
+    return tb::check_launch("tb_squashed_sample");
+}
+
+extern "C" int tb_q_target(const float* d_rewards, const float* d_terminations,
+                           const int64_t* d_idx, double discount_factor, const float* d_q1,
+                           const float* d_q2, const float* d_log_probs, double entropy_coeff,
+                           int64_t n_rows, float* d_targets, void* stream) {
+    tb::ProfScope prof_scope("tb_q_target", stream);
+    TB_REQUIRE(d_rewards && d_terminations && d_q1 && d_targets && n_rows > 0, TB_EINVAL,
+               "tb_q_target: bad arguments");
+    tb::q_target_kernel<<<tb::blocks_for(n_rows), 256, 0, tb::as_stream(stream)>>>(
+        d_rewards, d_terminations, d_idx, (float)discount_factor, d_q1, d_q2, d_log_probs,
+        (float)entropy_coeff, n_rows, d_targets);
+    return tb::check_launch("tb_q_target");
+}
+
+extern "C" int tb_q_actor_loss(const float* d_q1, const float* d_q2, const float* d_log_probs,
+                               double entropy_coeff, int64_t n_rows, float* d_dout1,
+                               float* d_dout2, double* d_stats, void* stream) {
+    tb::ProfScope prof_scope("tb_q_actor_loss", stream);
+    TB_REQUIRE(d_q1 && d_dout1 && d_stats && n_rows > 0 && (!d_q2 || d_dout2), TB_EINVAL,
+               "tb_q_actor_loss: bad arguments");
+    tb::q_actor_loss_kernel<<<tb::blocks_for(n_rows), 256, 0, tb::as_stream(stream)>>>(
+        d_q1, d_q2, d_log_probs, (float)entropy_coeff, n_rows, d_dout1, d_dout2, d_stats);
+    return tb::check_launch("tb_q_actor_loss");
+}
+
+extern "C" int tb_dpg_head_grad(const float* d_dqda, const float* d_actions, int64_t n_rows,
+                                int32_t act_dim, float* d_dout, void* stream) {
+    tb::ProfScope prof_scope("tb_dpg_head_grad", stream);
+    TB_REQUIRE(d_dqda && d_actions && d_dout && n_rows > 0 && act_dim > 0, TB_EINVAL,
+               "tb_dpg_head_grad: bad arguments");
+    const int64_t total = n_rows * act_dim;
+    tb::dpg_head_grad_kernel<<<tb::blocks_for(total), 256, 0, tb::as_stream(stream)>>>(
+        d_dqda, d_actions, total, d_dout);
+    return tb::check_launch("tb_dpg_head_grad");
+}
+
+extern "C" int tb_sac_head_grad(const float* d_pre, const float* d_eps, const float* d_actions,
+                                const float* d_dqda1, const float* d_dqda2, double entropy_coeff,
+                                int64_t n_rows, int32_t act_dim, float* d_dout, void* stream) {
+    tb::ProfScope prof_scope("tb_sac_head_grad", stream);
+    TB_REQUIRE(d_pre && d_eps && d_actions && d_dqda1 && d_dout && n_rows > 0 && act_dim > 0,
+               TB_EINVAL, "tb_sac_head_grad: bad arguments");
+    const int64_t total = n_rows * act_dim;
+    tb::sac_head_grad_kernel<<<tb::blocks_for(total), 256, 0, tb::as_stream(stream)>>>(
+        d_pre, d_eps, d_actions, d_dqda1, d_dqda2, (float)entropy_coeff, total, act_dim, d_dout);
+    return tb::check_launch("tb_sac_head_grad");
+}

@@ -309,3 +309,43 @@ def profile_end():
         name, count, ms = line.split()
         out[name] = (int(count), float(ms))
     return out
+
+
+# ---------------------------------------------------------------------------
+# off-policy heads / targets / actor losses
+# ---------------------------------------------------------------------------
+
+def tanh_action(pre, out, mode=0, noise32=None, noise64=None, seed=0, counter=0,
+                noise_scale=0.0, noise_clip=float('inf')):
+    rows, act = out.shape
+    _lib.call('tb_tanh_action', ptr(pre), rows, act, mode, ptr(noise32), ptr(noise64), seed,
+              counter, noise_scale, noise_clip, ptr(out), stream())
+
+
+def squashed_sample(pre, actions, log_probs=None, eps=None, eps_out=None, seed=0, counter=0,
+                    greedy=False):
+    rows, act = actions.shape
+    _lib.call('tb_squashed_sample', ptr(pre), ptr(eps), seed, counter, rows, act, int(greedy),
+              ptr(actions), ptr(log_probs), ptr(eps_out), stream())
+
+
+def q_target(rewards, terminations, idx, discount_factor, q1, q2, log_probs, entropy_coeff,
+             rows, targets):
+    _lib.call('tb_q_target', ptr(rewards), ptr(terminations), ptr(idx), discount_factor, ptr(q1),
+              ptr(q2), ptr(log_probs), entropy_coeff, rows, ptr(targets), stream())
+
+
+def q_actor_loss(q1, q2, log_probs, entropy_coeff, rows, dout1, dout2, stats):
+    _lib.call('tb_q_actor_loss', ptr(q1), ptr(q2), ptr(log_probs), entropy_coeff, rows,
+              ptr(dout1), ptr(dout2), ptr(stats), stream())
+
+
+def dpg_head_grad(dqda, actions, dout):
+    rows, act = actions.shape
+    _lib.call('tb_dpg_head_grad', ptr(dqda), ptr(actions), rows, act, ptr(dout), stream())
+
+
+def sac_head_grad(pre, eps, actions, dqda1, dqda2, entropy_coeff, dout):
+    rows, act = actions.shape
+    _lib.call('tb_sac_head_grad', ptr(pre), ptr(eps), ptr(actions), ptr(dqda1), ptr(dqda2),
+              entropy_coeff, rows, act, ptr(dout), stream())

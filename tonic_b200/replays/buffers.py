@@ -1,7 +1,99 @@
 """Off-policy ring replay resident in HBM (reference: tonic/replays/buffers.py).
-Filled in with the off-policy agents."""
+
+Storage is the reference's layout -- per key a float32 array [max_size, N, ...]
+with max_size = size // N (buffers.py:40-45), written at row `index`, flat sample
+index = row * N + worker -- so `RandomState(seed).randint(size * N)` addresses
+the same transitions (buffers.py:84-89).  Batches are not materialised: the update
+kernels gather rows through the index vector.  `discounts = (1 - terminations) *
+discount_factor` (buffers.py:34-36) is recomputed inside the target kernel from
+the stored terminations (bit-identical float32 arithmetic).
+n-step returns (`return_steps > 1`, buffers.py:58-79) are a "next" row
+ and raise.
+"""
+
+import numpy as np
+import torch
+
+from .. import kernels
+from ..utils.random_state import RandomState
 
 
 class Buffer:
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError('device ring replay: see round notes')
+    def __init__(self, size=int(1e6), return_steps=1, batch_iterations=50, batch_size=100,
+                 discount_factor=0.99, steps_before_batches=int(1e4), steps_between_batches=50):
+        if return_steps != 1:
+            raise NotImplementedError('n-step returns are not implemented on the device')
+        self.full_max_size = size
+        self.return_steps = return_steps
+        self.batch_iterations = batch_iterations
+        self.batch_size = batch_size
+        self.discount_factor = discount_factor
+        self.steps_before_batches = steps_before_batches
+        self.steps_between_batches = steps_between_batches
+
+    def initialize(self, seed=None):
+        self.np_random = RandomState(seed)       # buffers.py:22
+        self.buffers = None
+        self.index = 0
+        self.size = 0
+        self.last_steps = 0
+
+    def ready(self, steps):                      # buffers.py:28-31
+        if steps < self.steps_before_batches:
+            return False
+        return (steps - self.last_steps) >= self.steps_between_batches
+
+    def allocate(self, **shapes):
+        dev = kernels.device()
+        self.num_workers = next(iter(shapes.values()))[0]
+        self.max_size = self.full_max_size // self.num_workers
+        self.buffers = {k: torch.full((self.max_size,) + tuple(s), float('nan'),
+                                      dtype=torch.float32, device=dev)
+                        for k, s in shapes.items()}
+        E, B = self.batch_iterations, self.batch_size
+        self._host_idx = torch.empty(E, B, dtype=torch.int64).pin_memory()
+        self._dev_idx = torch.empty(E, B, dtype=torch.int64, device=dev)
+
+    def store(self, **kwargs):
+        if self.buffers is None:
+            self.allocate(**{k: tuple(v.shape) if isinstance(v, torch.Tensor) else np.shape(v)
+                             for k, v in kwargs.items()})
+        for key, val in kwargs.items():
+            self.buffers[key][self.index].copy_(kernels.to_device(val))
+        self.advance()
+
+    def row(self, key):
+        """Row `index` of a buffer, for producers that write it in place."""
+        return self.buffers[key][self.index]
+
+    def advance(self):
+        self.index = (self.index + 1) % self.max_size
+        self.size = min(self.size + 1, self.max_size)
+
+    def flat(self, key):
+        b = self.buffers[key]
+        return b.view((b.shape[0] * b.shape[1],) + tuple(b.shape[2:]))
+
+    def index_batches(self, steps):
+        """Yields `batch_iterations` device int64 index vectors of length
+        `batch_size`, drawn like buffers.py:84-88; sets `last_steps` afterwards."""
+        total = self.size * self.num_workers
+        host = self._host_idx.numpy()
+        for e in range(self.batch_iterations):
+            self.np_random.randint(total, self.batch_size, out=host[e])
+        torch.cuda.current_stream().synchronize()      # previous use of the pinned block
+        self._dev_idx.copy_(self._host_idx, non_blocking=True)
+        for e in range(self.batch_iterations):
+            yield self._dev_idx[e]
+        self.last_steps = steps
+
+    def get(self, *keys, steps):
+        """Reference-style generator of gathered batches (convenience)."""
+        for idx in self.index_batches(steps):
+            out = {}
+            for k in keys:
+                if k == 'discounts':
+                    out[k] = (1 - self.flat('terminations')[idx]) * np.float32(self.discount_factor)
+                else:
+                    out[k] = self.flat(k)[idx]
+            yield out

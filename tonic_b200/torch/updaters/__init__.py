@@ -1,4 +1,9 @@
-from .actors import ClippedRatio, StochasticPolicyGradient
-from .critics import VRegression
+from .actors import (ClippedRatio, DeterministicPolicyGradient, StochasticPolicyGradient,
+                     TwinCriticSoftDeterministicPolicyGradient)
+from .critics import (DeterministicQLearning, TargetActionNoise, TwinCriticDeterministicQLearning,
+                      TwinCriticSoftQLearning, VRegression)
 
-__all__ = [ClippedRatio, StochasticPolicyGradient, VRegression]
+__all__ = [
+    ClippedRatio, DeterministicPolicyGradient, StochasticPolicyGradient,
+    TwinCriticSoftDeterministicPolicyGradient, DeterministicQLearning, TargetActionNoise,
+    TwinCriticDeterministicQLearning, TwinCriticSoftQLearning, VRegression]

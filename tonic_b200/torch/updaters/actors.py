@@ -106,3 +106,108 @@ class ClippedRatio(_GaussianPolicyUpdater):
         self.optimizer = optimizer
         self.ratio_clip, self.kl_threshold = ratio_clip, kl_threshold
         self.entropy_coeff = entropy_coeff
+
+
+class _CriticGradientUpdater:
+    """Actor updates that differentiate through frozen critics (the reference sets
+    `requires_grad = False` on the critic variables, actors.py:171-174,239-244;
+    here the critics' weight-gradient and Adam kernels are simply not launched)."""
+
+    default_lr = 1e-3
+
+    def initialize(self, model):
+        self.model = model
+        self.actor = model.actor
+        self.variables = [p for p in self.actor.parameters() if p.requires_grad]
+        self.adam = kernels.Adam(self.actor.network.params,
+                                 **optimizers.adam_hyperparameters(self.optimizer, self.default_lr))
+        self.obs_size = self.actor.network.layout.d_in
+        self.seed, self._counter, self._rows = 0, 0, 0
+
+    def _scratch(self, rows):
+        if rows > self._rows:
+            dev, A = kernels.device(), self.actor.action_size
+            new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)   # noqa: E731
+            self._pre = new(rows, self.actor.network.layout.n_out)
+            self._actions, self._eps, self._logp = new(rows, A), new(rows, A), new(rows)
+            self._q = [new(rows, 1), new(rows, 1)]
+            self._dq = [new(rows, 1), new(rows, 1)]
+            self._dqda = [new(rows, A), new(rows, A)]
+            self._dout = new(rows, self.actor.network.layout.n_out)
+            self._rows = rows
+
+    def _finish(self, rows, stats):
+        net = self.actor.network
+        n_split = splits_for(rows)
+        net.mlp.backward(self._dout, rows)
+        gpart = net.mlp.wgrad(self._dout, rows, n_split)
+        self.adam.step(net.mlp, gpart, n_split, 1.0 / rows)
+
+    @staticmethod
+    def infos(s):
+        return dict(loss=s[_lib.STAT_LOSS] / s[_lib.STAT_ROWS])
+
+
+class DeterministicPolicyGradient(_CriticGradientUpdater):
+    """loss = -mean Q(s, mu(s)) (reference: updaters/actors.py:159-189)."""
+
+    def __init__(self, optimizer=None, gradient_clip=0):
+        if gradient_clip:
+            raise NotImplementedError('gradient clipping is not implemented')
+        self.optimizer = optimizer
+
+    def launch(self, observations, idx, rows, stats):
+        self._scratch(rows)
+        actor, critic = self.actor, self.model.critic
+        A = actor.action_size
+        actor.pre_activations(observations, out=self._pre[:rows], idx=idx, rows=rows, save=True)
+        kernels.tanh_action(self._pre[:rows], self._actions[:rows], mode=0)
+        critic.values(observations, self._actions[:rows], out=self._q[0][:rows], idx=idx,
+                      rows=rows, gather_actions=False, save=True)
+        kernels.q_actor_loss(self._q[0], None, None, 0.0, rows, self._dq[0], None, stats)
+        critic.network.mlp.backward(self._dq[0], rows, dx=self._dqda[0][:rows],
+                                    dx_col0=self.obs_size)
+        kernels.dpg_head_grad(self._dqda[0][:rows], self._actions[:rows], self._dout[:rows])
+        self._finish(rows, stats)
+
+    def __call__(self, observations):
+        observations = kernels.to_device(observations)
+        stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.float64, device=kernels.device())
+        self.launch(observations, None, observations.shape[0], stats)
+        return {k: torch.as_tensor(v) for k, v in self.infos(kernels.to_host(stats)).items()}
+
+
+class TwinCriticSoftDeterministicPolicyGradient(_CriticGradientUpdater):
+    """SAC actor, loss = mean(alpha * log pi(a|s) - min(Q1, Q2)(s, a)), a ~ pi
+    reparameterised (reference: updaters/actors.py:226-267)."""
+
+    default_lr = 3e-4
+
+    def __init__(self, optimizer=None, entropy_coeff=0.2, gradient_clip=0):
+        if gradient_clip:
+            raise NotImplementedError('gradient clipping is not implemented')
+        self.optimizer, self.entropy_coeff = optimizer, entropy_coeff
+
+    def launch(self, observations, idx, rows, stats):
+        self._scratch(rows)
+        actor = self.actor
+        critics = [self.model.critic_1, self.model.critic_2]
+        A = actor.action_size
+        actor.pre_activations(observations, out=self._pre[:rows], idx=idx, rows=rows, save=True)
+        eps = torch.randn(rows, A).to(self._pre.device) if config.noise == 'host' else None
+        kernels.squashed_sample(self._pre[:rows], self._actions[:rows], self._logp[:rows],
+                                eps=eps, eps_out=self._eps[:rows], seed=self.seed ^ 0xac7,
+                                counter=self._counter)
+        self._counter += rows
+        for k, critic in enumerate(critics):
+            critic.values(observations, self._actions[:rows], out=self._q[k][:rows], idx=idx,
+                          rows=rows, gather_actions=False, save=True)
+        kernels.q_actor_loss(self._q[0], self._q[1], self._logp, self.entropy_coeff, rows,
+                             self._dq[0], self._dq[1], stats)
+        for k, critic in enumerate(critics):
+            critic.network.mlp.backward(self._dq[k], rows, dx=self._dqda[k][:rows],
+                                        dx_col0=self.obs_size)
+        kernels.sac_head_grad(self._pre[:rows], self._eps[:rows], self._actions[:rows],
+                              self._dqda[0][:rows], self._dqda[1][:rows], self.entropy_coeff,
+                              self._dout[:rows])
+        self._finish(rows, stats)

@@ -57,3 +57,154 @@ class VRegression:
         s = stats.cpu().numpy()
         return dict(loss=torch.as_tensor(s[_lib.STAT_LOSS] / rows),
                     v=self._values[:rows, 0].clone())
+
+
+class _QLearning:
+    """Shared launch sequence of the Q-learning updaters: target computation with
+    the target networks, then one MSE step per critic on the same targets."""
+
+    default_lr = 1e-3
+
+    def __init__(self, loss=None, optimizer=None, gradient_clip=0):
+        if loss is not None and not isinstance(loss, torch.nn.MSELoss):
+            raise NotImplementedError('only the MSE loss has a kernel')
+        if gradient_clip:
+            raise NotImplementedError('gradient clipping is not implemented')
+        self.optimizer = optimizer
+
+    def _critics(self, model):
+        raise NotImplementedError
+
+    def initialize(self, model):
+        self.model = model
+        self.critics, self.target_critics = self._critics(model)
+        self.variables = [p for c in self.critics for p in c.parameters() if p.requires_grad]
+        hyper = optimizers.adam_hyperparameters(self.optimizer, self.default_lr)
+        # one torch Adam over both critics == one Adam per critic with equal step counts
+        self.adams = [kernels.Adam(c.network.params, **hyper) for c in self.critics]
+        self.action_size = model.actor.action_size
+        self.seed, self._counter, self._rows = 0, 0, 0
+
+    def _scratch(self, rows):
+        if rows > self._rows:
+            dev, A = kernels.device(), self.action_size
+            new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)   # noqa: E731
+            self._next_pre = new(rows, self.model.actor.network.layout.n_out)
+            self._next_actions = new(rows, A)
+            self._next_logp = new(rows)
+            self._next_q = [new(rows, 1), new(rows, 1)]
+            self._targets = new(rows)
+            self._values = [new(rows, 1), new(rows, 1)]
+            self._dout = new(rows, 1)
+            self._rows = rows
+
+    def next_actions(self, next_observations, idx, rows):
+        """Fills self._next_actions; returns the log-probs to subtract or None."""
+        raise NotImplementedError
+
+    entropy_coeff = 0.0
+
+    def launch(self, replay, idx, rows, stats):
+        self._scratch(rows)
+        obs, acts = replay.flat('observations'), replay.flat('actions')
+        nobs = replay.flat('next_observations')
+        next_logp = self.next_actions(nobs, idx, rows)
+        for k, target in enumerate(self.target_critics):        # critics.py:73-74,162-166,214-218
+            target.values(nobs, self._next_actions[:rows], out=self._next_q[k][:rows], idx=idx,
+                          rows=rows, gather_actions=False)
+        q2 = self._next_q[1] if len(self.target_critics) > 1 else None
+        kernels.q_target(replay.flat('rewards'), replay.flat('terminations'), idx,
+                         replay.discount_factor, self._next_q[0], q2, next_logp,
+                         self.entropy_coeff, rows, self._targets)
+        for k, critic in enumerate(self.critics):               # critics.py:77-84,169-179
+            net = critic.network
+            n_split = splits_for(rows)
+            critic.values(obs, acts, out=self._values[k][:rows], idx=idx, rows=rows, save=True)
+            kernels.mse_loss(self._values[k], self._targets, None, rows, self._dout, stats,
+                             stat_slot=_lib.STAT_VALUE if k == 0 else _lib.STAT_VALUE2,
+                             count_rows=(k == 0))
+            net.mlp.backward(self._dout, rows)
+            gpart = net.mlp.wgrad(self._dout, rows, n_split)
+            self.adams[k].step(net.mlp, gpart, n_split, 1.0 / rows)
+
+    def infos(self, s):
+        rows = s[_lib.STAT_ROWS]
+        out = dict(loss=s[_lib.STAT_LOSS] / rows)
+        if len(self.critics) == 1:
+            out['q'] = s[_lib.STAT_VALUE] / rows
+        else:
+            out['q1'] = s[_lib.STAT_VALUE] / rows
+            out['q2'] = s[_lib.STAT_VALUE2] / rows
+        return out
+
+
+class DeterministicQLearning(_QLearning):
+    """DDPG critic (reference: updaters/critics.py:56-86)."""
+
+    def _critics(self, model):
+        return [model.critic], [model.target_critic]
+
+    def next_actions(self, next_observations, idx, rows):
+        pre = self._next_pre[:rows]
+        self.model.target_actor.pre_activations(next_observations, out=pre, idx=idx, rows=rows)
+        kernels.tanh_action(pre, self._next_actions[:rows], mode=0)
+        return None
+
+
+class TargetActionNoise:
+    """Clipped Gaussian noise on the target actions (reference:
+    updaters/critics.py:125-134); applied inside csrc/offpolicy.cu::tanh_action_kernel."""
+
+    def __init__(self, scale=0.2, clip=0.5):
+        self.scale, self.clip = scale, clip
+
+
+class TwinCriticDeterministicQLearning(_QLearning):
+    """TD3 critics (reference: updaters/critics.py:137-182)."""
+
+    def __init__(self, loss=None, optimizer=None, target_action_noise=None, gradient_clip=0):
+        super().__init__(loss, optimizer, gradient_clip)
+        self.target_action_noise = target_action_noise or TargetActionNoise(scale=0.2, clip=0.5)
+
+    def _critics(self, model):
+        return [model.critic_1, model.critic_2], [model.target_critic_1, model.target_critic_2]
+
+    def next_actions(self, next_observations, idx, rows):
+        from ... import config
+        A = self.action_size
+        pre = self._next_pre[:rows]
+        self.model.target_actor.pre_activations(next_observations, out=pre, idx=idx, rows=rows)
+        noise = None
+        if config.noise == 'host':      # torch.randn_like(next_actions), critics.py:131
+            noise = torch.randn(rows, A).to(pre.device)
+        kernels.tanh_action(pre, self._next_actions[:rows], mode=1, noise32=noise,
+                            seed=self.seed ^ 0x7d3, counter=self._counter,
+                            noise_scale=self.target_action_noise.scale,
+                            noise_clip=self.target_action_noise.clip)
+        self._counter += rows
+        return None
+
+
+class TwinCriticSoftQLearning(_QLearning):
+    """SAC critics (reference: updaters/critics.py:185-235): next actions from the
+    ONLINE actor, soft target min(Q1', Q2') - alpha * log pi."""
+
+    default_lr = 3e-4
+
+    def __init__(self, loss=None, optimizer=None, entropy_coeff=0.2, gradient_clip=0):
+        super().__init__(loss, optimizer, gradient_clip)
+        self.entropy_coeff = entropy_coeff
+
+    def _critics(self, model):
+        return [model.critic_1, model.critic_2], [model.target_critic_1, model.target_critic_2]
+
+    def next_actions(self, next_observations, idx, rows):
+        from ... import config
+        A = self.action_size
+        pre = self._next_pre[:rows]
+        self.model.actor.pre_activations(next_observations, out=pre, idx=idx, rows=rows)
+        eps = torch.randn(rows, A).to(pre.device) if config.noise == 'host' else None
+        kernels.squashed_sample(pre, self._next_actions[:rows], self._next_logp[:rows], eps=eps,
+                                seed=self.seed ^ 0x5ac, counter=self._counter)
+        self._counter += rows
+        return self._next_logp
