@@ -207,6 +207,11 @@ int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
                  const int32_t* d_skip, const double* d_stats,
                  float kl_threshold, int32_t* d_stop, void* stream);
 
+/* d_out[i] = sum_s d_gpart[s, i]: the flat gradient that is all-reduced over
+ * ranks before tb_adam_step(n_split = 1) in multi-GPU runs.      */
+int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_params,
+                       float* d_out, const int32_t* d_skip, void* stream);
+
 /* (Re)builds the packed transposes from the flat parameters.                 */
 int tb_mlp_pack(const TbMlpShape* shape, const float* d_params, float* d_packed,
                 void* stream);

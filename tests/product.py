@@ -52,27 +52,27 @@ def build(cfg, log=None):
     return agent, env
 
 
-def teacher_forced(agent, env, golden, vector_steps):
+def teacher_forced(agent, env, golden, vector_steps, rows=slice(None)):
     """Drives agent + device env with the golden trajectory's inputs: the env
     receives the reference's actions (so its outputs must be bit-identical), the
     agent sees the reference's observations (its actions must agree to float32
     round-off)."""
     obs = env.start(host=True)
-    np.testing.assert_array_equal(obs, golden['start_observations'])
-    workers = len(obs)
+    np.testing.assert_array_equal(obs, golden['start_observations'][rows])
+    workers = golden['start_observations'].shape[0]     # GLOBAL workers (trainer.py:54)
     steps = 0
     actions = []
     for t in range(vector_steps):
         a = agent.step(obs, steps)
         actions.append(np.asarray(a, np.float64))
-        ref_a = golden['actions'][t]
+        ref_a = golden['actions'][t][rows]
         ref_a = ref_a.astype(np.float32) if np.asarray(a).dtype == np.float32 else ref_a
         obs, infos = env.step(ref_a)
-        np.testing.assert_array_equal(obs, golden['observations'][t])
-        np.testing.assert_array_equal(infos['observations'], golden['next_observations'][t])
-        np.testing.assert_array_equal(infos['rewards'], golden['rewards'][t])
-        np.testing.assert_array_equal(infos['resets'], golden['resets'][t])
-        np.testing.assert_array_equal(infos['terminations'], golden['terminations'][t])
+        np.testing.assert_array_equal(obs, golden['observations'][t][rows])
+        np.testing.assert_array_equal(infos['observations'], golden['next_observations'][t][rows])
+        np.testing.assert_array_equal(infos['rewards'], golden['rewards'][t][rows])
+        np.testing.assert_array_equal(infos['resets'], golden['resets'][t][rows])
+        np.testing.assert_array_equal(infos['terminations'], golden['terminations'][t][rows])
         agent.update(**infos, steps=steps)
         steps += workers
     return np.array(actions)

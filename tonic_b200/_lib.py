@@ -67,6 +67,7 @@ _PROTOTYPES = {
                              c_i32, c_i64, c_vp, c_i32, c_vp, c_vp]),
     'tb_adam_step': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, c_vp, c_i32, c_f, c_vp, c_vp, c_f,
                              c_vp, c_vp]),
+    'tb_reduce_partials': (c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'tb_mlp_pack': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp]),
     'tb_soft_update': (c_int, [c_vp, c_vp, c_i64, c_d, c_vp]),
     'tb_gauss_sample': (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_i64, c_i32, c_vp, c_vp, c_vp]),

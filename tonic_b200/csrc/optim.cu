@@ -122,3 +122,27 @@ extern "C" int tb_soft_update(float* d_target, const float* d_online, int64_t n,
         d_target, d_online, n, (float)(1.0 - tau), (float)tau);
     return tb::check_launch("tb_soft_update");
 }
+
+// Sum of the split partial gradients into one flat buffer (the send buffer of the
+// multi-GPU gradient all-reduce).
+namespace tb {
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ gpart, int n_split, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g = 0.0f;
+    for (int s = 0; s < n_split; ++s) g += gpart[(size_t)s * n + i];
+    out[i] = g;
+}
+}  // namespace tb
+
+extern "C" int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_params,
+                                  float* d_out, const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_reduce_partials", stream);
+    TB_REQUIRE(d_gpart && d_out && n_split >= 1 && n_params > 0, TB_EINVAL,
+               "tb_reduce_partials: bad arguments");
+    (void)d_skip;
+    tb::reduce_partials_kernel<<<(n_params + 255) / 256, 256, 0, tb::as_stream(stream)>>>(
+        d_gpart, n_split, n_params, d_out);
+    return tb::check_launch("tb_reduce_partials");
+}

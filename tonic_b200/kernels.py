@@ -147,6 +147,11 @@ class DeviceMlp:
             self.dz2 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
             self._ws_rows = rows
 
+    def flat_grad(self):
+        if getattr(self, '_flat_grad', None) is None:
+            self._flat_grad = torch.zeros(self.layout.n_params, dtype=F32, device=device())
+        return self._flat_grad
+
     def gpart(self, n_split):
         if self._gpart is None or self._gpart.shape[0] < n_split:
             self._gpart = torch.zeros(n_split, self.layout.n_params, dtype=F32, device=device())
@@ -207,6 +212,34 @@ class Adam:
         _lib.call('tb_adam_step', ctypes.byref(self.struct), ctypes.byref(mlp.layout.shape),
                   ptr(mlp.packed), ptr(gpart), n_split, grad_scale, ptr(skip), ptr(stats),
                   kl_threshold, ptr(stop), stream())
+
+
+def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=None, stats=None,
+                    kl_threshold=-1.0, stop=None, reduce_stats=None):
+    """Adam step from the split weight gradients of this rank.  Single process:
+    the partial sums are reduced inside the Adam kernel.  Several ranks: partial
+    sums -> flat gradient -> all-reduce (and the statistics block) -> Adam with
+    1 / (global rows), which equals the single-process mean.
+    `stats` steers the Adam kernel (policy updaters: skip when every advantage is
+    zero, KL early stop); `reduce_stats` is a statistics block that only needs the
+    sum over ranks (defaults to `stats`)."""
+    from . import distributed
+    if distributed.world() == 1:
+        adam.step(mlp, gpart, n_split, 1.0 / rows_global, skip=skip, stats=stats,
+                  kl_threshold=kl_threshold, stop=stop)
+        return
+    flat = mlp.flat_grad()
+    if rows_local > 0:
+        _lib.call('tb_reduce_partials', ptr(gpart), n_split, mlp.layout.n_params, ptr(flat),
+                  None, stream())
+    else:
+        flat.zero_()
+    distributed.all_reduce(flat)
+    reduce_stats = stats if reduce_stats is None else reduce_stats
+    if reduce_stats is not None:
+        distributed.all_reduce(reduce_stats)
+    adam.step(mlp, flat, 1, 1.0 / rows_global, skip=skip, stats=stats,
+              kl_threshold=kl_threshold, stop=stop)
 
 
 def soft_update(target, online, tau):

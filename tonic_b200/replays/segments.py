@@ -11,7 +11,7 @@ materialised: the update kernels gather rows through the index vector.
 import numpy as np
 import torch
 
-from .. import kernels
+from .. import distributed, kernels
 from ..utils.random_state import RandomState
 from . import utils
 
@@ -99,36 +99,55 @@ class Segment:
 
     # -- minibatches ------------------------------------------------------------------
     def index_batches(self):
-        """Yields (idx, rows): idx is a device int64 vector of flat transition
-        indices (None = the whole segment in order), following segments.py:50-65:
-        per iteration one `RandomState.shuffle` of the running permutation, cut in
-        contiguous slices of `batch_size` (the last one may be short)."""
-        total = self.max_size * self.num_workers
+        """Yields (idx, rows, rows_global) per minibatch, following
+        segments.py:50-65: per iteration one `RandomState.shuffle` of the running
+        permutation of all T*N transitions, cut in contiguous slices of
+        `batch_size` (the last may be short).  `idx` is a device int64 vector of
+        flat LOCAL transition indices (None = the whole local segment in order);
+        with several ranks the permutation is over the GLOBAL segment (same seed on
+        every rank) and each rank keeps the entries it owns, so `rows` <=
+        `rows_global`."""
+        world, rank = distributed.world(), distributed.rank()
+        local_total = self.max_size * self.num_workers
+        total = local_total * world
         if self.batch_size is None:
             for _ in range(self.batch_iterations):
-                yield None, total
+                yield None, local_total, total
             return
         E = self.batch_iterations
-        if self._pinned is None or self._pinned.shape != (E, total):
-            self._pinned = torch.empty(E, total, dtype=torch.int64).pin_memory()
-            self._device_order = torch.empty(E, total, dtype=torch.int64,
+        cuts = list(range(0, total, self.batch_size))
+        if self._pinned is None or self._pinned.shape != (E, local_total):
+            self._pinned = torch.empty(E, local_total, dtype=torch.int64).pin_memory()
+            self._device_order = torch.empty(E, local_total, dtype=torch.int64,
                                              device=kernels.device())
         order = np.arange(total)
         host = self._pinned.numpy()
+        counts = np.zeros((E, len(cuts)), np.int64)
+        torch.cuda.current_stream().synchronize()      # previous use of the pinned block
         for e in range(E):
             self.np_random.shuffle(order)
-            host[e] = order
+            if world == 1:
+                host[e] = order
+                counts[e] = [min(self.batch_size, total - lo) for lo in cuts]
+            else:
+                local, mine = distributed.local_rows(
+                    order, self.num_workers * world, self.num_workers, rank)
+                host[e] = local
+                counts[e] = np.add.reduceat(mine.astype(np.int64), cuts)
         self._device_order.copy_(self._pinned, non_blocking=True)
         for e in range(E):
-            for lo in range(0, total, self.batch_size):
-                rows = min(self.batch_size, total - lo)
-                yield self._device_order[e, lo:lo + rows], rows
+            offset = 0
+            for j, lo in enumerate(cuts):
+                rows = int(counts[e, j])
+                yield (self._device_order[e, offset:offset + rows], rows,
+                       min(self.batch_size, total - lo))
+                offset += rows
 
     def get(self, *keys):
         """Reference-style generator of gathered minibatches (convenience; the
         agents use `index_batches` and gather inside the kernels)."""
         batch = self.get_full(*keys)
-        for idx, rows in self.index_batches():
+        for idx, rows, _ in self.index_batches():
             if idx is None:
                 yield batch
             else:

@@ -9,7 +9,7 @@ the statistics at the end.
 import numpy as np
 import torch
 
-from ... import _lib, config, kernels, replays
+from ... import _lib, config, distributed, kernels, replays
 from ...utils import logger
 from .. import models, normalizers, updaters
 from . import agent
@@ -59,12 +59,16 @@ class A2C(agent.Agent):
         """Normal(loc, scale).sample() and its summed log-prob (a2c.py:75-85)."""
         workers = observations.shape[0]
         self.model.actor.pre_activations(observations, out=self._pre[:workers])
-        eps, counter = None, self._noise_counter
+        world, rank = distributed.world(), distributed.rank()
+        eps, counter = None, self._noise_counter + rank * workers
         if config.noise == 'host':
-            # same draw as torch.distributions.Normal.sample() from the global CPU generator
-            eps = torch.randn(workers, self.action_size).to(observations.device)
+            # same draw as torch.distributions.Normal.sample() from the global CPU
+            # generator; with several ranks every rank draws the global block and
+            # keeps its workers' rows (identical to the single-process stream)
+            eps = torch.randn(workers * world, self.action_size)
+            eps = eps[rank * workers:(rank + 1) * workers].to(observations.device)
         else:
-            self._noise_counter += workers
+            self._noise_counter += workers * world
         kernels.gauss_sample(self._pre[:workers], self.model.actor.network.extra('log_scale'),
                              actions, log_probs, eps=eps, seed=self.seed or 0, counter=counter)
 
@@ -148,7 +152,8 @@ class A2C(agent.Agent):
         self.model.critic.values(flat['observations'], out=values)
         self.model.critic.values(flat['next_observations'], out=next_values)
         self.replay.compute_returns(values, next_values)
-        self.replay.compute_advantages()
+        self.replay.compute_advantages(
+            all_reduce=distributed.all_reduce if distributed.world() > 1 else None)
 
     def _stats(self, n):
         return torch.zeros(n, 2, _lib.STAT_COUNT, dtype=torch.float64, device=kernels.device())
@@ -162,11 +167,12 @@ class A2C(agent.Agent):
         stats = self._stats(len(batches) + 1)
         # one policy-gradient step on the full batch (a2c.py:107-114)
         self.actor_updater.launch(flat['observations'], flat['actions'], flat['advantages'],
-                                  flat['log_probs'], None, total, stats[0, 0])
+                                  flat['log_probs'], None, total, stats[0, 0],
+                                  rows_global=total * distributed.world())
         # several value-regression steps (a2c.py:116-121)
-        for j, (idx, rows) in enumerate(batches):
+        for j, (idx, rows, rows_global) in enumerate(batches):
             self.critic_updater.launch(flat['observations'], flat['returns'], idx, rows,
-                                       stats[j + 1, 1])
+                                       stats[j + 1, 1], rows_global=rows_global)
         host = kernels.to_host(stats)
         for k, v in self.actor_updater.infos(host[0, 0]).items():
             logger.store('actor/' + k, v)

@@ -29,12 +29,12 @@ class PPO(a2c.A2C):
         batches = list(self.replay.index_batches())
         stats = self._stats(len(batches))
         stop = torch.zeros(1, dtype=torch.int32, device=kernels.device())
-        for j, (idx, rows) in enumerate(batches):
+        for j, (idx, rows, rows_global) in enumerate(batches):
             self.actor_updater.launch(flat['observations'], flat['actions'],
                                       flat['advantages'], flat['log_probs'], idx, rows,
-                                      stats[j, 0], stop=stop)
+                                      stats[j, 0], stop=stop, rows_global=rows_global)
             self.critic_updater.launch(flat['observations'], flat['returns'], idx, rows,
-                                       stats[j, 1])
+                                       stats[j, 1], rows_global=rows_global)
         host = kernels.to_host(stats)
         actor_iterations = 0
         for j in range(len(batches)):

@@ -11,7 +11,7 @@ kernels of csrc/moments.cu; `forward` is fused into the first MLP layer
 import numpy as np
 import torch
 
-from ... import kernels
+from ... import distributed, kernels
 
 
 class MeanStd(torch.nn.Module):
@@ -63,5 +63,6 @@ class MeanStd(torch.nn.Module):
         kernels.moments_record(values.view(-1, self.size), self.sums)
 
     def update(self):
+        distributed.all_reduce(self.sums)       # global statistics when workers are sharded
         kernels.moments_update(self.sums, self.running, self.count_buffer, self._mean.data,
                                self._std.data, self.eps)

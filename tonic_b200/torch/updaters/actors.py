@@ -45,20 +45,25 @@ class _GaussianPolicyUpdater:
             self._rows = rows
         return self._pre, self._dout
 
-    def launch(self, observations, actions, advantages, log_probs, idx, rows, stats, stop=None):
+    def launch(self, observations, actions, advantages, log_probs, idx, rows, stats, stop=None,
+               rows_global=None):
+        """`rows` = transitions of this minibatch owned by this rank, `rows_global` =
+        size of the whole minibatch (the mean's denominator)."""
         actor, net = self.actor, self.actor.network
         A = actor.action_size
-        pre, dout = self._scratch(rows)
         n_split = splits_for(rows)
-        actor.pre_activations(observations, out=pre, idx=idx, rows=rows, save=True, skip=stop)
-        kernels.gauss_policy_loss(pre, net.extra('log_scale'), actions, advantages, log_probs,
-                                  idx, rows, dout, stats, self.ratio_clip, self.entropy_coeff,
-                                  skip=stop)
-        net.mlp.backward(dout, rows, skip=stop)
-        gpart = net.mlp.wgrad(dout, rows, n_split, n_extra=A,
-                              off_extra=net.extra_offset('log_scale'), skip=stop)
-        self.adam.step(net.mlp, gpart, n_split, 1.0 / rows, skip=stop, stats=stats,
-                       kl_threshold=self.kl_threshold, stop=stop)
+        gpart = None
+        if rows > 0:
+            pre, dout = self._scratch(rows)
+            actor.pre_activations(observations, out=pre, idx=idx, rows=rows, save=True, skip=stop)
+            kernels.gauss_policy_loss(pre, net.extra('log_scale'), actions, advantages,
+                                      log_probs, idx, rows, dout, stats, self.ratio_clip,
+                                      self.entropy_coeff, skip=stop)
+            net.mlp.backward(dout, rows, skip=stop)
+            gpart = net.mlp.wgrad(dout, rows, n_split, n_extra=A,
+                                  off_extra=net.extra_offset('log_scale'), skip=stop)
+        kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
+                                skip=stop, stats=stats, kl_threshold=self.kl_threshold, stop=stop)
 
     def infos(self, s):
         """Statistics block (host copy) -> the reference's info dict (python floats)."""
@@ -136,12 +141,15 @@ class _CriticGradientUpdater:
             self._dout = new(rows, self.actor.network.layout.n_out)
             self._rows = rows
 
-    def _finish(self, rows, stats):
+    def _finish(self, rows, stats, rows_global=None):
         net = self.actor.network
         n_split = splits_for(rows)
-        net.mlp.backward(self._dout, rows)
-        gpart = net.mlp.wgrad(self._dout, rows, n_split)
-        self.adam.step(net.mlp, gpart, n_split, 1.0 / rows)
+        gpart = None
+        if rows > 0:
+            net.mlp.backward(self._dout, rows)
+            gpart = net.mlp.wgrad(self._dout, rows, n_split)
+        kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
+                                reduce_stats=stats)
 
     @staticmethod
     def infos(s):
@@ -156,7 +164,9 @@ class DeterministicPolicyGradient(_CriticGradientUpdater):
             raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer = optimizer
 
-    def launch(self, observations, idx, rows, stats):
+    def launch(self, observations, idx, rows, stats, rows_global=None):
+        if rows == 0:
+            return self._finish(0, stats, rows_global)
         self._scratch(rows)
         actor, critic = self.actor, self.model.critic
         A = actor.action_size
@@ -168,7 +178,7 @@ class DeterministicPolicyGradient(_CriticGradientUpdater):
         critic.network.mlp.backward(self._dq[0], rows, dx=self._dqda[0][:rows],
                                     dx_col0=self.obs_size)
         kernels.dpg_head_grad(self._dqda[0][:rows], self._actions[:rows], self._dout[:rows])
-        self._finish(rows, stats)
+        self._finish(rows, stats, rows_global)
 
     def __call__(self, observations):
         observations = kernels.to_device(observations)
@@ -188,7 +198,9 @@ class TwinCriticSoftDeterministicPolicyGradient(_CriticGradientUpdater):
             raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer, self.entropy_coeff = optimizer, entropy_coeff
 
-    def launch(self, observations, idx, rows, stats):
+    def launch(self, observations, idx, rows, stats, rows_global=None):
+        if rows == 0:
+            return self._finish(0, stats, rows_global)
         self._scratch(rows)
         actor = self.actor
         critics = [self.model.critic_1, self.model.critic_2]
@@ -210,4 +222,4 @@ class TwinCriticSoftDeterministicPolicyGradient(_CriticGradientUpdater):
         kernels.sac_head_grad(self._pre[:rows], self._eps[:rows], self._actions[:rows],
                               self._dqda[0][:rows], self._dqda[1][:rows], self.entropy_coeff,
                               self._dout[:rows])
-        self._finish(rows, stats)
+        self._finish(rows, stats, rows_global)

@@ -34,15 +34,18 @@ class VRegression:
             self._rows = rows
         return self._values, self._dout
 
-    def launch(self, observations, returns, idx, rows, stats):
+    def launch(self, observations, returns, idx, rows, stats, rows_global=None):
         critic, net = self.critic, self.critic.network
-        values, dout = self._scratch(rows)
         n_split = splits_for(rows)
-        critic.values(observations, out=values, idx=idx, rows=rows, save=True)
-        kernels.mse_loss(values, returns, idx, rows, dout, stats)
-        net.mlp.backward(dout, rows)
-        gpart = net.mlp.wgrad(dout, rows, n_split)
-        self.adam.step(net.mlp, gpart, n_split, 1.0 / rows)
+        gpart = None
+        if rows > 0:
+            values, dout = self._scratch(rows)
+            critic.values(observations, out=values, idx=idx, rows=rows, save=True)
+            kernels.mse_loss(values, returns, idx, rows, dout, stats)
+            net.mlp.backward(dout, rows)
+            gpart = net.mlp.wgrad(dout, rows, n_split)
+        kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
+                                reduce_stats=stats)
 
     @staticmethod
     def infos(s):
@@ -104,7 +107,13 @@ class _QLearning:
 
     entropy_coeff = 0.0
 
-    def launch(self, replay, idx, rows, stats):
+    def launch(self, replay, idx, rows, stats, rows_global=None):
+        if rows == 0:
+            for k, critic in enumerate(self.critics):
+                kernels.apply_gradients(self.adams[k], critic.network.mlp, None, 1, 0,
+                                        rows_global,
+                                        reduce_stats=stats if k == len(self.critics) - 1 else None)
+            return
         self._scratch(rows)
         obs, acts = replay.flat('observations'), replay.flat('actions')
         nobs = replay.flat('next_observations')
@@ -125,7 +134,10 @@ class _QLearning:
                              count_rows=(k == 0))
             net.mlp.backward(self._dout, rows)
             gpart = net.mlp.wgrad(self._dout, rows, n_split)
-            self.adams[k].step(net.mlp, gpart, n_split, 1.0 / rows)
+            # the statistics block is all-reduced once (with the last critic)
+            kernels.apply_gradients(self.adams[k], net.mlp, gpart, n_split, rows,
+                                    rows_global or rows,
+                                    reduce_stats=stats if k == len(self.critics) - 1 else None)
 
     def infos(self, s):
         rows = s[_lib.STAT_ROWS]
