@@ -94,7 +94,7 @@ def build_ours(envs_local, total_envs, seed=0):
         critic=m.Critic(encoder=m.ObservationEncoder(), torso=m.MLP((HIDDEN, HIDDEN), torch.nn.Tanh),
                         head=m.ValueHead()),
         observation_normalizer=n.MeanStd())
-    batch = envs_local * SEGMENT // MINIBATCHES
+    batch = total_envs * SEGMENT // MINIBATCHES     # GLOBAL minibatch (weak scaling)
     replay = tonic_b200.replays.Segment(size=SEGMENT, batch_iterations=EPOCHS, batch_size=batch)
     agent = tonic_b200.torch.agents.PPO(model=model, replay=replay)
     agent.initialize(env.observation_space, env.action_space, seed=seed)
@@ -124,6 +124,7 @@ def run_ours(args):
 
     total_envs = ENVS_PER_GPU * world
     config.noise = 'device'      # Philox action noise inside the kernels (no host traffic)
+    config.indices = args.indices
     agent, env, batch = build_ours(ENVS_PER_GPU, total_envs)
     env.start()
 
@@ -194,6 +195,7 @@ def run_ours(args):
     e2e = None
     if world == 1:
         config.noise = 'host'     # noise drawn from torch's CPU generator like the reference
+        config.indices = 'host'   # numpy-compatible permutations generated on the host
         kernels.transfers['h2d'] = kernels.transfers['d2h'] = 0
         agent.replay.index = 0
         observations = env.start(host=True)
@@ -237,7 +239,8 @@ def run_ours(args):
                     hidden=HIDDEN, parallelism=f'dp{world} (envs sharded, grad all-reduce)',
                     l2='working set per iteration (segment 92 MB + activations 69 MB/minibatch) '
                        'exceeds the 126 MB L2; no explicit flush',
-                    noise='device Philox', indices='host MT19937 (numpy-compatible)'),
+                    noise='device Philox', indices=('device Feistel permutation' if args.indices == 'device'
+                                                          else 'host MT19937 (numpy-compatible)')),
         clocks=sampler.summary(), gpu_launches=launches, e2e=e2e, roofline=roofline,
         cpu_baseline=cpu,
         profiled_pass=dict(kernel_ms_per_step=round(total_kernel_ms / args.steps, 3),
@@ -318,6 +321,9 @@ def main():
     parser.add_argument('--steps', type=int, default=5)
     parser.add_argument('--warmup', type=int, default=3)
     parser.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    parser.add_argument('--indices', default='device', choices=['host', 'device'],
+                        help="minibatch permutations: 'device' (Feistel, on the GPU) or 'host' "
+                             "(numpy-compatible MT19937 stream, bit-identical to the reference)")
     parser.add_argument('--quick', action='store_true',
                         help='timed region only (for runs under ncu): no e2e / cpu_baseline / profile pass')
     args = parser.parse_args()

@@ -328,6 +328,11 @@ int tb_sac_head_grad(const float* d_pre, const float* d_eps, const float* d_acti
  * tb_array_stats_init values: +inf / -inf encodings).                         */
 int tb_array_stats(const float* d_x, int64_t n, double* d_acc, void* stream);
 
+/* Device-side pseudo-random permutation of [0, n) (Feistel bijection with cycle
+ * walking), the fast-mode replacement of the host `RandomState.shuffle` of
+ * replays/segments.py:62 (not numpy's stream; uniform minibatch coverage).     */
+int tb_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* d_out, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Host-side numpy-compatible MT19937 streams (legacy numpy.random.RandomState)*/
 /* used for bit-exact minibatch / replay indices and exploration noise:        */

@@ -35,8 +35,13 @@ def main(names):
         assert env.workers == n_local and env.first_worker == rank * n_local
         rows = slice(rank * n_local, (rank + 1) * n_local)
         actions = product.teacher_forced(agent, env, g, cfg['vector_steps'], rows=rows)
-        np.testing.assert_allclose(actions, g['actions'][:, rows], rtol=1e-5, atol=2e-5)
+        if rank == 0 and os.environ.get('TB_DEBUG'):
+            got = test_gpu_agents.by_key(rec.keys, rec.means)
+            ref = test_gpu_agents.by_key(g['info_keys'], g['info_mean'])
+            for k in sorted(ref):
+                print(k, 'ours', np.array(got.get(k, []))[:6], 'ref', np.array(ref[k])[:6], flush=True)
         test_gpu_agents.check_infos(rec, g)
+        np.testing.assert_allclose(actions, g['actions'][:, rows], rtol=1e-5, atol=2e-5)
         test_gpu_agents.check_weights(agent, g)
         # replicas stay in lock-step
         flat = torch.cat([n.params for n in agent.model.networks()])

@@ -389,3 +389,20 @@ def test_mse_loss(K):
     np.testing.assert_allclose(s[_lib.STAT_LOSS], ((v - t[idx]) ** 2).sum().item(), rtol=1e-5)
     np.testing.assert_allclose(s[_lib.STAT_VALUE], v.sum().item(), rtol=1e-5, atol=1e-5)
     assert s[_lib.STAT_ROWS] == rows
+
+
+def test_device_permutation_is_a_bijection(K):
+    for n in (1, 2, 7, 1000, 524288, 100003):
+        out = torch.empty(n, dtype=torch.int64, device='cuda')
+        K.permutation(12345, 0, out)
+        host = out.cpu().numpy()
+        np.testing.assert_array_equal(np.sort(host), np.arange(n))
+        if n >= 1000:
+            other = torch.empty_like(out)
+            K.permutation(12345, 1, other)
+            assert (other.cpu().numpy() != host).mean() > 0.99
+            # no structure left: position and value are uncorrelated
+            assert abs(np.corrcoef(np.arange(n), host)[0, 1]) < 0.05
+            # minibatch slices cover the index range evenly
+            chunk = host[:n // 8]
+            assert abs(chunk.mean() / n - 0.5) < 0.05

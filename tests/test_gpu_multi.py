@@ -18,4 +18,7 @@ def test_two_ranks_reproduce_single_process_reference():
            os.path.join(ROOT, 'tests', 'multi_rank_scenario.py'),
            'ppo_small', 'ppo_ragged', 'a2c_small', 'td3_small']
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'multi_rank_output.log'), 'w') as f:
+        f.write(res.stdout + '\n----\n' + res.stderr)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]

@@ -254,3 +254,48 @@ extern "C" int tb_array_stats(const float* d_x, int64_t n, double* d_acc, void* 
     tb::array_stats_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(d_x, n, d_acc);
     return tb::check_launch("tb_array_stats");
 }
+
+// ---- device-side minibatch permutation (fast mode) --------------------------------
+// A pseudo-random bijection of [0, n): 4-round Feistel network on the smallest
+// even-width power-of-two domain >= n with cycle walking.  Replaces the host
+// `RandomState.shuffle` of tonic/replays/segments.py:62 when bit-compatibility with
+// numpy's stream is not required (config.indices = 'device'): no host work and no
+// host->device copy, O(1) state.
+namespace tb {
+__global__ void __launch_bounds__(256)
+permutation_kernel(uint64_t seed, uint64_t stream_id, int64_t n, int half_bits,
+                   int64_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mask = (1u << half_bits) - 1u;
+    uint32_t keys[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        keys[r] = fmix32((uint32_t)seed ^ fmix32((uint32_t)(seed >> 32) + 0x9E3779B9u * (uint32_t)(r + 1)) ^
+                         fmix32((uint32_t)stream_id * 0x85EBCA6Bu + (uint32_t)(stream_id >> 32) + r));
+    uint64_t x = (uint64_t)i;
+    do {
+        uint32_t L = (uint32_t)(x >> half_bits) & mask, R = (uint32_t)x & mask;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t t = L ^ (fmix32(R ^ keys[r]) & mask);
+            L = R;
+            R = t;
+        }
+        x = ((uint64_t)L << half_bits) | R;
+    } while (x >= (uint64_t)n);
+    out[i] = (int64_t)x;
+}
+}  // namespace tb
+
+extern "C" int tb_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* d_out,
+                              void* stream) {
+    tb::ProfScope prof_scope("tb_permutation", stream);
+    TB_REQUIRE(d_out && n > 0 && n < (1ll << 40), TB_EINVAL, "tb_permutation: bad arguments");
+    int bits = 1;
+    while ((1ll << bits) < n) ++bits;
+    const int half = (bits + 1) / 2;
+    tb::permutation_kernel<<<(int)((n + 255) / 256), 256, 0, tb::as_stream(stream)>>>(
+        seed, stream_id, n, half < 1 ? 1 : half, d_out);
+    return tb::check_launch("tb_permutation");
+}

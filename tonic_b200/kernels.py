@@ -382,3 +382,8 @@ def sac_head_grad(pre, eps, actions, dqda1, dqda2, entropy_coeff, dout):
     rows, act = actions.shape
     _lib.call('tb_sac_head_grad', ptr(pre), ptr(eps), ptr(actions), ptr(dqda1), ptr(dqda2),
               entropy_coeff, rows, act, ptr(dout), stream())
+
+
+def permutation(seed, stream_id, out):
+    """out[i] = pseudo-random bijection of [0, len(out)) (device fast-mode indices)."""
+    _lib.call('tb_permutation', seed, stream_id, out.numel(), ptr(out), stream())

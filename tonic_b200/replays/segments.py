@@ -11,7 +11,7 @@ materialised: the update kernels gather rows through the index vector.
 import numpy as np
 import torch
 
-from .. import distributed, kernels
+from .. import config, distributed, kernels
 from ..utils.random_state import RandomState
 from . import utils
 
@@ -27,6 +27,7 @@ class Segment:
 
     def initialize(self, seed=None):
         self.np_random = RandomState(seed)      # segments.py:20
+        self.seed = seed
         self.buffers = None
         self.index = 0
         self._pinned = None
@@ -68,28 +69,26 @@ class Segment:
                                b['terminations'], b['returns'], self.discount_factor,
                                self.trace_decay)
 
-    def compute_advantages(self, all_reduce=None):
+    def compute_advantages(self):
         """returns - values, normalised over the WHOLE segment (segments.py:41-46).
-        `all_reduce(tensor)` (sum over ranks) makes the statistics global when the
-        workers are sharded over several GPUs."""
+        When the workers are sharded over several GPUs the mean / variance are
+        all-reduced (two passes, like numpy's std) so every rank normalises with the
+        statistics of the global segment."""
         b = self.buffers
         if 'advantages' not in b:
             b['advantages'] = torch.empty_like(b['returns'])
-        if all_reduce is None:
+        if distributed.world() == 1:
             kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace)
-        else:
-            n = torch.tensor([b['returns'].numel()], dtype=torch.float64,
-                             device=b['returns'].device)
-            all_reduce(n)
-            n_global = int(n.item())
-            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
-                               n_global, 1)
-            all_reduce(self._workspace)
-            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
-                               n_global, 2)
-            all_reduce(self._workspace[2:3])
-            kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
-                               n_global, 3)
+            return
+        n_global = b['returns'].numel() * distributed.world()
+        kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
+                           n_global, 1)
+        distributed.all_reduce(self._workspace)
+        kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
+                           n_global, 2)
+        distributed.all_reduce(self._workspace[2:3])
+        kernels.advantages(b['returns'], b['values'], b['advantages'], self._workspace,
+                           n_global, 3)
 
     def get_full(self, *keys):
         self.index = 0
@@ -115,6 +114,9 @@ class Segment:
                 yield None, local_total, total
             return
         E = self.batch_iterations
+        if config.indices == 'device':
+            yield from self._device_index_batches(world, rank, local_total)
+            return
         cuts = list(range(0, total, self.batch_size))
         if self._pinned is None or self._pinned.shape != (E, local_total):
             self._pinned = torch.empty(E, local_total, dtype=torch.int64).pin_memory()
@@ -142,6 +144,25 @@ class Segment:
                 yield (self._device_order[e, offset:offset + rows], rows,
                        min(self.batch_size, total - lo))
                 offset += rows
+
+    def _device_index_batches(self, world, rank, local_total):
+        E = self.batch_iterations
+        if self.batch_size % world:
+            raise ValueError('batch_size must be divisible by the number of ranks')
+        local_batch = self.batch_size // world
+        if getattr(self, '_device_perm', None) is None or \
+                self._device_perm.shape != (E, local_total):
+            self._device_perm = torch.empty(E, local_total, dtype=torch.int64,
+                                            device=kernels.device())
+            self._perm_calls = 0
+        seed = ((self.seed or 0) << 8) ^ rank
+        for e in range(E):
+            kernels.permutation(seed, self._perm_calls, self._device_perm[e])
+            self._perm_calls += 1
+        for e in range(E):
+            for lo in range(0, local_total, local_batch):
+                rows = min(local_batch, local_total - lo)
+                yield self._device_perm[e, lo:lo + rows], rows, rows * world
 
     def get(self, *keys):
         """Reference-style generator of gathered minibatches (convenience; the

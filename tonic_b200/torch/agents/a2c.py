@@ -152,8 +152,6 @@ class A2C(agent.Agent):
         self.model.critic.values(flat['observations'], out=values)
         self.model.critic.values(flat['next_observations'], out=next_values)
         self.replay.compute_returns(values, next_values)
-        self.replay.compute_advantages(
-            all_reduce=distributed.all_reduce if distributed.world() > 1 else None)
 
     def _stats(self, n):
         return torch.zeros(n, 2, _lib.STAT_COUNT, dtype=torch.float64, device=kernels.device())
