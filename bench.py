@@ -119,7 +119,12 @@ def run_ours(args):
         dist.barrier()
     from tonic_b200 import _lib, config, kernels
     from tonic_b200.utils import logger
-    logger.store = lambda *a, **k: None          # statistics are still read back every update
+    iterations = dict(actor=0, critic=0)          # statistics are still read back every update
+
+    def capture(key, value, stats=False):
+        if key.endswith('/iterations'):
+            iterations[key.split('/')[0]] += int(value)
+    logger.store = capture
     logger.store_aggregate = lambda *a, **k: None
 
     total_envs = ENVS_PER_GPU * world
@@ -144,6 +149,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
+    iterations.update(actor=0, critic=0)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
@@ -157,6 +163,7 @@ def run_ours(args):
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
     launches = _lib.launch_count() - launches0
+    timed_iterations = dict(iterations)
     env_steps = args.steps * SEGMENT * total_envs
     value = env_steps / (elapsed_ms / 1e3)
 
@@ -241,7 +248,13 @@ def run_ours(args):
                        'exceeds the 126 MB L2; no explicit flush',
                     noise='device Philox', indices=('device Feistel permutation' if args.indices == 'device'
                                                           else 'host MT19937 (numpy-compatible)')),
-        clocks=sampler.summary(), gpu_launches=launches, e2e=e2e, roofline=roofline,
+        clocks=sampler.summary(), gpu_launches=launches,
+        minibatch_updates=dict(
+            critic=timed_iterations['critic'], actor=timed_iterations['actor'],
+            note='actor updates stop early inside an iteration when KL > 0.015 (reference '
+                 'default, ppo.py:45-46): a device flag turns the remaining actor kernels of '
+                 'that iteration into no-ops; critic updates always run'),
+        e2e=e2e, roofline=roofline,
         cpu_baseline=cpu,
         profiled_pass=dict(kernel_ms_per_step=round(total_kernel_ms / args.steps, 3),
                            wall_ms_per_step=round(prof_wall_ms / args.steps, 3)))

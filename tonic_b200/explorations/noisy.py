@@ -14,7 +14,7 @@ The OU process (noisy.py:53-88) is a "next" row.
 import numpy as np
 import torch
 
-from .. import config, kernels
+from .. import config, distributed, kernels
 from ..utils.random_state import RandomState
 
 
@@ -34,7 +34,9 @@ class NoActionNoise:
     def warmup_actions(self, workers):
         """Uniform(-1, 1) actions (noisy.py:20-21,44-46) as a device float32 tensor."""
         if config.noise == 'host':
-            return kernels.to_device(self.np_random.uniform(-1, 1, (workers, self.action_size)))
+            return kernels.to_device(self._own(
+                self.np_random.uniform(-1, 1, (workers * distributed.world(), self.action_size)),
+                workers))
         out = torch.empty(workers, self.action_size, dtype=torch.float32, device=kernels.device())
         kernels.tanh_action(None, out, mode=2, seed=self.seed ^ 0x5eed, counter=self._counter)
         self._counter += workers
@@ -42,6 +44,12 @@ class NoActionNoise:
 
     def noise(self, workers):
         return None
+
+    @staticmethod
+    def _own(block, workers):
+        """Rows of the global (single-process) draw that belong to this rank."""
+        rank = distributed.rank()
+        return block[rank * workers:(rank + 1) * workers]
 
     def __call__(self, observations, steps):
         if steps > self.start_steps:
@@ -61,6 +69,7 @@ class NormalActionNoise(NoActionNoise):
         """float64 standard normals from the numpy-compatible stream, or None to
         let the kernel draw Philox noise."""
         if config.noise == 'host':
-            return kernels.to_device(self.np_random.normal((workers, self.action_size)),
-                                     dtype=torch.float64)
+            return kernels.to_device(self._own(
+                self.np_random.normal((workers * distributed.world(), self.action_size)),
+                workers), dtype=torch.float64)
         return None

@@ -75,33 +75,37 @@ class Buffer:
         return b.view((b.shape[0] * b.shape[1],) + tuple(b.shape[2:]))
 
     def index_batches(self, steps):
-        """Yields `batch_iterations` tuples (idx, rows, rows_global): device int64
+        """Yields `batch_iterations` tuples (idx, rows, rows_global, mine): device int64
         flat LOCAL indices of one batch, drawn like buffers.py:84-88 from the GLOBAL
         ring (`size * N_global`, same seed on every rank); a rank keeps the samples
         whose worker column it owns.  Sets `last_steps` afterwards."""
         world, rank = distributed.world(), distributed.rank()
         total = self.size * self.num_workers * world
         host = self._host_idx.numpy()
-        counts = []
+        counts, masks = [], []
         torch.cuda.current_stream().synchronize()      # previous use of the pinned block
         for e in range(self.batch_iterations):
             if world == 1:
                 self.np_random.randint(total, self.batch_size, out=host[e])
                 counts.append(self.batch_size)
+                masks.append(None)
             else:
                 drawn = self.np_random.randint(total, self.batch_size)
-                local, _ = distributed.local_rows(drawn, self.num_workers * world,
-                                                  self.num_workers, rank)
+                local, mine = distributed.local_rows(drawn, self.num_workers * world,
+                                                     self.num_workers, rank)
                 host[e, :len(local)] = local
                 counts.append(len(local))
+                masks.append(torch.from_numpy(mine))
         self._dev_idx.copy_(self._host_idx, non_blocking=True)
         for e in range(self.batch_iterations):
-            yield self._dev_idx[e, :counts[e]], counts[e], self.batch_size
+            # masks[e]: which samples of the global batch this rank owns (used to take
+            # the matching rows of host-generated noise); None in a single process
+            yield self._dev_idx[e, :counts[e]], counts[e], self.batch_size, masks[e]
         self.last_steps = steps
 
     def get(self, *keys, steps):
         """Reference-style generator of gathered batches (convenience)."""
-        for idx, _, _ in self.index_batches(steps):
+        for idx, _, _, _ in self.index_batches(steps):
             out = {}
             for k in keys:
                 if k == 'discounts':

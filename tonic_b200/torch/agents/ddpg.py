@@ -101,11 +101,12 @@ class DDPG(agent.Agent):
         stats = torch.zeros(len(batches), 2, _lib.STAT_COUNT, dtype=torch.float64,
                             device=kernels.device())
         obs = self.replay.flat('observations')
-        for i, (idx, rows, rows_global) in enumerate(batches):  # ddpg.py:105-112, td3.py:41-46
+        for i, (idx, rows, rows_global, mine) in enumerate(batches):  # ddpg.py:105-112, td3.py:41-46
             self.critic_updater.launch(self.replay, idx, rows, stats[i, 0],
-                                       rows_global=rows_global)
+                                       rows_global=rows_global, mine=mine)
             if self._actor_turn(i):
-                self.actor_updater.launch(obs, idx, rows, stats[i, 1], rows_global=rows_global)
+                self.actor_updater.launch(obs, idx, rows, stats[i, 1], rows_global=rows_global,
+                                          mine=mine)
                 self.model.update_targets()
         host = kernels.to_host(stats)
         for i in range(len(batches)):

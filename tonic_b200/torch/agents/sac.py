@@ -2,7 +2,7 @@
 
 import torch
 
-from ... import config, explorations, kernels
+from ... import config, distributed, explorations, kernels
 from .. import models, normalizers, updaters
 from . import ddpg
 
@@ -37,7 +37,9 @@ class SAC(ddpg.DDPG):
         out = self._new_actions(observations)
         eps = None
         if config.noise == 'host':      # Normal.sample() from torch's global CPU generator
-            eps = torch.randn(observations.shape[0], self.action_size).to(pre.device)
+            workers, world, rank = observations.shape[0], distributed.world(), distributed.rank()
+            eps = torch.randn(workers * world, self.action_size)
+            eps = eps[rank * workers:(rank + 1) * workers].to(pre.device)
         kernels.squashed_sample(pre, out, eps=eps, seed=(self.seed or 0) ^ 0x5ac0,
                                 counter=self._noise_counter)
         self._noise_counter += observations.shape[0]

@@ -164,7 +164,7 @@ class DeterministicPolicyGradient(_CriticGradientUpdater):
             raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer = optimizer
 
-    def launch(self, observations, idx, rows, stats, rows_global=None):
+    def launch(self, observations, idx, rows, stats, rows_global=None, mine=None):
         if rows == 0:
             return self._finish(0, stats, rows_global)
         self._scratch(rows)
@@ -198,15 +198,18 @@ class TwinCriticSoftDeterministicPolicyGradient(_CriticGradientUpdater):
             raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer, self.entropy_coeff = optimizer, entropy_coeff
 
-    def launch(self, observations, idx, rows, stats, rows_global=None):
+    def launch(self, observations, idx, rows, stats, rows_global=None, mine=None):
+        A = self.actor.action_size
+        eps = None
+        if config.noise == 'host':      # rsample() of the whole batch, this rank's rows
+            eps = torch.randn(rows_global or rows, A)
+            eps = (eps if mine is None else eps[mine]).to(kernels.device())
         if rows == 0:
             return self._finish(0, stats, rows_global)
         self._scratch(rows)
         actor = self.actor
         critics = [self.model.critic_1, self.model.critic_2]
-        A = actor.action_size
         actor.pre_activations(observations, out=self._pre[:rows], idx=idx, rows=rows, save=True)
-        eps = torch.randn(rows, A).to(self._pre.device) if config.noise == 'host' else None
         kernels.squashed_sample(self._pre[:rows], self._actions[:rows], self._logp[:rows],
                                 eps=eps, eps_out=self._eps[:rows], seed=self.seed ^ 0xac7,
                                 counter=self._counter)

@@ -101,14 +101,27 @@ class _QLearning:
             self._dout = new(rows, 1)
             self._rows = rows
 
-    def next_actions(self, next_observations, idx, rows):
+    def next_actions(self, next_observations, idx, rows, rows_global, mine):
         """Fills self._next_actions; returns the log-probs to subtract or None."""
         raise NotImplementedError
 
+    def skip_noise(self, rows_global):
+        """Keeps the host noise stream aligned when this rank owns no sample."""
+
+    def host_noise(self, rows, rows_global, mine, device):
+        """[rows, A] standard normals from torch's global CPU generator: the block
+        the single-process reference would draw for the whole batch, restricted to
+        the samples this rank owns."""
+        noise = torch.randn(rows_global, self.action_size)
+        if mine is not None:
+            noise = noise[mine]
+        return noise.to(device)
+
     entropy_coeff = 0.0
 
-    def launch(self, replay, idx, rows, stats, rows_global=None):
+    def launch(self, replay, idx, rows, stats, rows_global=None, mine=None):
         if rows == 0:
+            self.skip_noise(rows_global)
             for k, critic in enumerate(self.critics):
                 kernels.apply_gradients(self.adams[k], critic.network.mlp, None, 1, 0,
                                         rows_global,
@@ -117,7 +130,7 @@ class _QLearning:
         self._scratch(rows)
         obs, acts = replay.flat('observations'), replay.flat('actions')
         nobs = replay.flat('next_observations')
-        next_logp = self.next_actions(nobs, idx, rows)
+        next_logp = self.next_actions(nobs, idx, rows, rows_global or rows, mine)
         for k, target in enumerate(self.target_critics):        # critics.py:73-74,162-166,214-218
             target.values(nobs, self._next_actions[:rows], out=self._next_q[k][:rows], idx=idx,
                           rows=rows, gather_actions=False)
@@ -156,7 +169,7 @@ class DeterministicQLearning(_QLearning):
     def _critics(self, model):
         return [model.critic], [model.target_critic]
 
-    def next_actions(self, next_observations, idx, rows):
+    def next_actions(self, next_observations, idx, rows, rows_global, mine):
         pre = self._next_pre[:rows]
         self.model.target_actor.pre_activations(next_observations, out=pre, idx=idx, rows=rows)
         kernels.tanh_action(pre, self._next_actions[:rows], mode=0)
@@ -181,14 +194,19 @@ class TwinCriticDeterministicQLearning(_QLearning):
     def _critics(self, model):
         return [model.critic_1, model.critic_2], [model.target_critic_1, model.target_critic_2]
 
-    def next_actions(self, next_observations, idx, rows):
+    def skip_noise(self, rows_global):
+        from ... import config
+        if config.noise == 'host':
+            torch.randn(rows_global, self.action_size)
+
+    def next_actions(self, next_observations, idx, rows, rows_global, mine):
         from ... import config
         A = self.action_size
         pre = self._next_pre[:rows]
         self.model.target_actor.pre_activations(next_observations, out=pre, idx=idx, rows=rows)
         noise = None
         if config.noise == 'host':      # torch.randn_like(next_actions), critics.py:131
-            noise = torch.randn(rows, A).to(pre.device)
+            noise = self.host_noise(rows, rows_global, mine, pre.device)
         kernels.tanh_action(pre, self._next_actions[:rows], mode=1, noise32=noise,
                             seed=self.seed ^ 0x7d3, counter=self._counter,
                             noise_scale=self.target_action_noise.scale,
@@ -210,12 +228,15 @@ class TwinCriticSoftQLearning(_QLearning):
     def _critics(self, model):
         return [model.critic_1, model.critic_2], [model.target_critic_1, model.target_critic_2]
 
-    def next_actions(self, next_observations, idx, rows):
+    skip_noise = TwinCriticDeterministicQLearning.skip_noise
+
+    def next_actions(self, next_observations, idx, rows, rows_global, mine):
         from ... import config
         A = self.action_size
         pre = self._next_pre[:rows]
         self.model.actor.pre_activations(next_observations, out=pre, idx=idx, rows=rows)
-        eps = torch.randn(rows, A).to(pre.device) if config.noise == 'host' else None
+        eps = self.host_noise(rows, rows_global, mine, pre.device) \
+            if config.noise == 'host' else None
         kernels.squashed_sample(pre, self._next_actions[:rows], self._next_logp[:rows], eps=eps,
                                 seed=self.seed ^ 0x5ac, counter=self._counter)
         self._counter += rows
