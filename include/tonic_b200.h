@@ -180,6 +180,22 @@ int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const float* d_h1,
                  int32_t off_extra, int64_t n_rows, float* d_gpart,
                  int32_t n_split, const int32_t* d_skip, void* stream);
 
+/* ---- tensor-core path (tcgen05.mma kind::tf32, TMA, TMEM) for the 256-wide ---- */
+/* hidden-layer GEMMs of the MLP above (models/utils.py:15-23 and its autograd)    */
+/* hi = x with the low 13 mantissa bits cleared (tf32-exact), lo = x - hi.        */
+int tb_split_tf32(const float* d_x, float* d_hi, float* d_lo, int64_t n, void* stream);
+
+/* out[n_rows, 256] = epilogue(A[n_rows, 256] . B[256, 256]^T), A and B given as
+ * tf32 splits (hi [+ lo]); passes = 3: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (fp32
+ * grade), passes = 1: plain TF32.  epilogue 0: act(. + bias) (forward layer 2,
+ * B = W2); 1: . * act'(aux_hi + aux_lo) (backward dz1, B = W2^T); 2: none.
+ * d_out_lo != NULL: the result is written as a tf32 split (d_out = hi).          */
+int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const float* d_b_hi,
+                  const float* d_b_lo, int64_t n_rows, int32_t passes, int32_t epilogue,
+                  int32_t act, const float* d_bias, const float* d_aux_hi,
+                  const float* d_aux_lo, float* d_out, float* d_out_lo,
+                  const int32_t* d_skip, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Optimiser -- torch.optim.Adam as constructed at updaters/actors.py:11-12,   */
 /* 58-59,161-162,228-229 and updaters/critics.py:9-10,59-60,143-144,190-191    */

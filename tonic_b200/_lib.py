@@ -80,6 +80,9 @@ _PROTOTYPES = {
     'tb_q_actor_loss': (c_int, [c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'tb_dpg_head_grad': (c_int, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     'tb_sac_head_grad': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_i64, c_i32, c_vp, c_vp]),
+    'tb_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    'tb_tc_gemm256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
+                              c_vp, c_vp, c_vp, c_vp]),
     'tb_permutation': (c_int, [c_u64, c_u64, c_i64, c_vp, c_vp]),
     'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'tb_profile_begin': (c_int, []),

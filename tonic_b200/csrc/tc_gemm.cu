@@ -1,0 +1,406 @@
+// Tensor-core path for the 256-wide hidden-layer GEMMs (sm_100a only):
+//
+//     out[M, 256] = epilogue( A[M, 256] . B[256, 256]^T )        (both operands K-major)
+//
+// used for the second hidden layer of the forward pass (A = h1, B = W2, epilogue =
+// bias + activation) and for the hidden-layer gradient of the backward pass
+// (A = dz2, B = W2^T, epilogue = * act'(h1)); reference arithmetic:
+// tonic/torch/models/utils.py:15-23 (Linear + activation) and its autograd.
+//
+// Design (one CTA per SM, persistent over 128-row tiles):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of the
+//            A row-block and the whole B matrix, K in chunks of 32 floats, into a
+//            multi-stage shared-memory ring guarded by full/empty mbarriers;
+//   warp 1   MMA issuer: one elected thread issues tcgen05.mma.kind::tf32
+//            (M=128, N=256, K=8) with the accumulator in TMEM; two accumulator
+//            stages (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
+//            tile i+1; tcgen05.commit releases smem stages / publishes accumulators;
+//   warp 2   TMEM allocation / deallocation;
+//   warps 4-7 epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers ->
+//            padded smem transpose -> bias/activation (or activation gradient) ->
+//            coalesced 128-byte global stores.
+//
+// Precision: float32 operands are pre-split into tf32-exact parts a = a_hi + a_lo
+// (a_hi = a with the low 13 mantissa bits cleared, a_lo = a - a_hi, exact).  With
+// PASSES = 3 the kernel accumulates a_hi.b_hi + a_lo.b_hi + a_hi.b_lo in the fp32
+// TMEM accumulator ("3xTF32"): the dropped terms are O(2^-22) relative, i.e. fp32
+// grade, which keeps the 1e-4 loss parity with the reference's fp32 CPU path.
+// PASSES = 1 is plain TF32 (fast mode).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int TC_BM = 128;      // rows per tile (UMMA M)
+constexpr int TC_BN = 256;      // output columns (UMMA N) = hidden width
+constexpr int TC_BK = 32;       // K chunk: 32 floats = 128 bytes = one swizzle row
+constexpr int TC_K = 256;       // reduction length = hidden width
+constexpr int TC_THREADS = 256;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 32 KB
+constexpr int TC_STAGE_ROWSTRIDE = 36;          // padded floats per staged row (bank-conflict free)
+
+template <int PASSES>
+struct TcCfg {
+    static constexpr int PARTS = PASSES == 3 ? 2 : 1;
+    static constexpr int STAGE_BYTES = PARTS * (TC_A_BYTES + TC_B_BYTES);
+    static constexpr int STAGES = PASSES == 3 ? 2 : 4;
+    static constexpr int EPI_BYTES = 4 * 32 * TC_STAGE_ROWSTRIDE * 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tcgen05_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, dense [rows x 128 B]
+// tile (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
+// layout SWIZZLE_128B (2) <<61); SBO = 1024 B between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, K-major both,
+// N = 256, M = 128.
+constexpr uint32_t kIdescTf32 =
+    (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+enum { TC_EPI_BIAS_ACT = 0, TC_EPI_ACT_GRAD = 1, TC_EPI_NONE = 2 };
+
+struct TcParams {
+    int64_t n_rows;
+    float* out;                 // [n_rows, 256]
+    const float* bias;          // [256]            (EPI_BIAS_ACT)
+    const float* aux_hi;        // [n_rows, 256]    (EPI_ACT_GRAD: saved activations, split)
+    const float* aux_lo;
+    float* out_lo;              // optional: also write the tf32 split of the result (out = hi)
+    int act;
+    const int32_t* skip;
+};
+
+template <int PASSES, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const TcParams p) {
+    using Cfg = TcCfg<PASSES>;
+    if (skip_requested(p.skip)) return;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* stage_base = smem;
+    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    uint64_t* full_bar = bars;                       // [STAGES]
+    uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // [2]
+    uint64_t* tmem_empty = tmem_full + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {        // TMEM: 512 columns = two 128 x 256 fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < TC_K / TC_BK; ++c) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* st = stage_base + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, &full_bar[stage], c * TC_BK, tile * TC_BM);
+                    tma_load_2d(st + Cfg::PARTS * TC_A_BYTES, &map_b_hi, &full_bar[stage], c * TC_BK, 0);
+                    if (PASSES == 3) {
+                        tma_load_2d(st + TC_A_BYTES, &map_a_lo, &full_bar[stage], c * TC_BK, tile * TC_BM);
+                        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &map_b_lo, &full_bar[stage],
+                                    c * TC_BK, 0);
+                    }
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+                for (int c = 0; c < TC_K / TC_BK; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    unsigned char* st = stage_base + stage * Cfg::STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc_kmajor_sw128(st);
+                    const uint64_t a_lo = umma_desc_kmajor_sw128(st + TC_A_BYTES);
+                    const uint64_t b_hi = umma_desc_kmajor_sw128(st + Cfg::PARTS * TC_A_BYTES);
+                    const uint64_t b_lo = umma_desc_kmajor_sw128(st + 2 * TC_A_BYTES + TC_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 32 >> 4);       // 8 tf32 = 32 bytes
+                        if (PASSES == 3) {
+                            // small cross terms first, the dominant term last
+                            tcgen05_mma_tf32(d_tmem, a_lo + koff, b_hi + koff, kIdescTf32, (c | k) != 0);
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_lo + koff, kIdescTf32, 1);
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, 1);
+                        } else {
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, (c | k) != 0);
+                        }
+                    }
+                    tcgen05_commit(&empty_bar[stage]);          // frees the smem stage
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tcgen05_commit(&tmem_full[acc]);                // accumulator ready
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int w = warp - 4;                                 // == warp % 4: TMEM lanes 32w..32w+31
+        float* stg = epi + w * 32 * TC_STAGE_ROWSTRIDE;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            tcgen05_fence_after();
+            const int64_t row0 = (int64_t)tile * TC_BM + w * 32;
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32);
+                tcgen05_ld_32x32(taddr, v);
+                float* mine = stg + lane * TC_STAGE_ROWSTRIDE;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(mine + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+                const int col = c * 32 + lane;
+                const float bias = EPI == TC_EPI_BIAS_ACT ? __ldg(p.bias + col) : 0.0f;
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int64_t row = row0 + r;
+                    if (row >= p.n_rows) break;
+                    float x = stg[r * TC_STAGE_ROWSTRIDE + lane];
+                    if (EPI == TC_EPI_BIAS_ACT) {
+                        x += bias;
+                        x = p.act == TB_ACT_TANH ? tanhf(x) : fmaxf(x, 0.0f);
+                    } else if (EPI == TC_EPI_ACT_GRAD) {
+                        const float h = __ldg(p.aux_hi + row * TC_BN + col) + __ldg(p.aux_lo + row * TC_BN + col);
+                        x *= p.act == TB_ACT_TANH ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f);
+                    }
+                    if (p.out_lo) {
+                        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                        p.out[row * TC_BN + col] = hi;
+                        p.out_lo[row * TC_BN + col] = x - hi;
+                    } else {
+                        p.out[row * TC_BN + col] = x;
+                    }
+                }
+                __syncwarp();
+            }
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
+                     : "memory");
+    }
+}
+
+// ---- split helper: hi = x with the low 13 mantissa bits cleared, lo = x - hi -------------
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[i] = h;
+        lo[i] = v - h;
+    }
+}
+
+// ---- host: tensor maps --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D row-major float matrix [rows, 256]; box = [box_rows, 32 floats]; 128-byte swizzle.
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    TB_REQUIRE(fn, TB_ENOTSUP, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TB_REQUIRE(r == CUDA_SUCCESS, TB_EINVAL, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return 0;
+}
+
+template <int PASSES, int EPI>
+static int launch_tc(const CUtensorMap* maps, const TcParams& p, cudaStream_t s) {
+    using Cfg = TcCfg<PASSES>;
+    auto kernel = tc_gemm_kernel<PASSES, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        configured = true;
+    }
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    kernel<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+    return 0;
+}
+
+}  // namespace tb
+
+extern "C" int tb_split_tf32(const float* d_x, float* d_hi, float* d_lo, int64_t n, void* stream) {
+    tb::ProfScope prof_scope("tb_split_tf32", stream);
+    TB_REQUIRE(d_x && d_hi && d_lo && n > 0, TB_EINVAL, "tb_split_tf32: bad arguments");
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 8 * tb::kNumSMs) blocks = 8 * tb::kNumSMs;
+    tb::split_tf32_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(d_x, d_hi, d_lo, n);
+    return tb::check_launch("tb_split_tf32");
+}
+
+extern "C" int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const float* d_b_hi,
+                             const float* d_b_lo, int64_t n_rows, int32_t passes, int32_t epilogue,
+                             int32_t act, const float* d_bias, const float* d_aux_hi,
+                             const float* d_aux_lo, float* d_out, float* d_out_lo,
+                             const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    ProfScope prof_scope("tb_tc_gemm256", stream);
+    TB_REQUIRE(d_a_hi && d_b_hi && d_out && n_rows > 0, TB_EINVAL, "tb_tc_gemm256: null pointer");
+    TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_gemm256: passes must be 1 or 3");
+    TB_REQUIRE(passes == 1 || (d_a_lo && d_b_lo), TB_EINVAL, "tb_tc_gemm256: 3 passes need the lo parts");
+    TB_REQUIRE(epilogue >= 0 && epilogue <= 2, TB_EINVAL, "tb_tc_gemm256: bad epilogue");
+    TB_REQUIRE(epilogue != TC_EPI_BIAS_ACT || d_bias, TB_EINVAL, "tb_tc_gemm256: bias missing");
+    TB_REQUIRE(epilogue != TC_EPI_ACT_GRAD || (d_aux_hi && d_aux_lo), TB_EINVAL, "tb_tc_gemm256: aux missing");
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = make_map(&maps[0], d_a_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[1], d_a_lo ? d_a_lo : d_a_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[2], d_b_hi, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[3], d_b_lo ? d_b_lo : d_b_hi, TC_BN, TC_BN))) return rc;
+    TcParams p;
+    p.n_rows = n_rows; p.out = d_out; p.bias = d_bias; p.aux_hi = d_aux_hi; p.aux_lo = d_aux_lo;
+    p.out_lo = d_out_lo; p.act = act; p.skip = d_skip;
+    cudaStream_t s = as_stream(stream);
+#define TB_TC(P_, E_) launch_tc<P_, E_>(maps, p, s)
+    if (passes == 3) {
+        if (epilogue == 0) TB_TC(3, 0); else if (epilogue == 1) TB_TC(3, 1); else TB_TC(3, 2);
+    } else {
+        if (epilogue == 0) TB_TC(1, 0); else if (epilogue == 1) TB_TC(1, 1); else TB_TC(1, 2);
+    }
+#undef TB_TC
+    return check_launch("tb_tc_gemm256");
+}

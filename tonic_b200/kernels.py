@@ -387,3 +387,19 @@ def sac_head_grad(pre, eps, actions, dqda1, dqda2, entropy_coeff, dout):
 def permutation(seed, stream_id, out):
     """out[i] = pseudo-random bijection of [0, len(out)) (device fast-mode indices)."""
     _lib.call('tb_permutation', seed, stream_id, out.numel(), ptr(out), stream())
+
+
+# ---------------------------------------------------------------------------
+# tensor-core GEMM (tcgen05 / TMA / TMEM)
+# ---------------------------------------------------------------------------
+
+def split_tf32(x, hi, lo):
+    _lib.call('tb_split_tf32', ptr(x), ptr(hi), ptr(lo), x.numel(), stream())
+
+
+def tc_gemm256(a_hi, a_lo, b_hi, b_lo, rows, out, passes=3, epilogue=2, act=0, bias=None,
+               aux_hi=None, aux_lo=None, out_lo=None, skip=None):
+    """out[rows, 256] = epilogue(A . B^T) on the tensor cores (see tb_tc_gemm256)."""
+    _count_flops('tb_tc_gemm256', 2.0 * rows * 256 * 256)
+    _lib.call('tb_tc_gemm256', ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), rows, passes, epilogue,
+              act, ptr(bias), ptr(aux_hi), ptr(aux_lo), ptr(out), ptr(out_lo), ptr(skip), stream())
