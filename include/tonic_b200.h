@@ -131,6 +131,9 @@ typedef struct {
     /* float offsets into the packed buffer (transposes for the forward pass) */
     int32_t off_w1t, off_w2t;
     int32_t n_packed;
+    /* tensor-core path (hidden == 256 only; 0 = absent): tf32 splits of W2 [H, H]
+     * (B operand of the forward GEMM) and of W2^T (B operand of the backward GEMM) */
+    int32_t off_w2_hi, off_w2_lo, off_w2t_hi, off_w2t_lo;
 } TbMlpShape;
 
 typedef struct {
@@ -195,6 +198,36 @@ int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const float* d_b_hi,
                   int32_t act, const float* d_bias, const float* d_aux_hi,
                   const float* d_aux_lo, float* d_out, float* d_out_lo,
                   const int32_t* d_skip, void* stream);
+
+/* The MLP entry points above with the two hidden-layer GEMMs (and the W2 weight
+ * gradient) on the tensor cores: layer 1, the head, the head gradient and the
+ * narrow weight gradients stay FFMA kernels; activations that feed a tensor-core
+ * GEMM are kept as tf32 splits (d_h1_hi/lo, d_dz2_hi/lo).  passes = 3 (fp32 grade)
+ * or 1 (TF32).  Same semantics as tb_mlp_forward / _backward / _wgrad.            */
+int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                      const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                      float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                      const int32_t* d_skip, void* stream);
+int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                       const float* d_dout, int32_t ld_dout, const float* d_h1_hi,
+                       const float* d_h1_lo, const float* d_h2, int64_t n_rows,
+                       float* d_dz2_hi, float* d_dz2_lo, float* d_dz1, float* d_dx,
+                       int32_t dx_col0, int32_t dx_cols, int32_t passes, const int32_t* d_skip,
+                       void* stream);
+int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, const float* d_h1_hi,
+                    const float* d_h1_lo, const float* d_h2, const float* d_dz1,
+                    const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
+                    int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
+                    float* d_gpart, int32_t n_split, int32_t passes, const int32_t* d_skip,
+                    void* stream);
+
+/* Hidden-layer weight gradient on the tensor cores (MN-major tf32 operands):
+ * gpart[s, off_w2 + n * 256 + k] = sum over the rows m of split s of
+ * dz2[m, n] * h1[m, k]; operands as tf32 splits like tb_tc_gemm256.             */
+int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const float* d_h_hi,
+                   const float* d_h_lo, int64_t n_rows, int32_t passes, float* d_gpart,
+                   int32_t n_split, int32_t n_params, int32_t off_w2, const int32_t* d_skip,
+                   void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Optimiser -- torch.optim.Adam as constructed at updaters/actors.py:11-12,   */

@@ -41,8 +41,8 @@ def test_tc_gemm_plain(K, rows, passes):
     torch.cuda.synchronize()
     err = (out.cpu().double() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    # 3xTF32: fp32-grade (<= 2e-6 of the output scale); plain TF32: ~1e-3
-    assert err <= (3e-6 if passes == 3 else 5e-3) * scale, (err, scale)
+    # 3xTF32: fp32-grade (lo operands are truncated to 11 bits: <= 1e-5 of the output scale, typically 3e-6); plain TF32: ~1e-3
+    assert err <= (1e-5 if passes == 3 else 5e-3) * scale, (err, scale)
     if passes == 1:
         assert err > 1e-6 * scale     # really ran on the tf32 path
 
@@ -63,7 +63,7 @@ def test_tc_gemm_epilogues(K, act):
     K.tc_gemm256(a_hi, a_lo, w_hi, w_lo, rows, out_hi, passes=3, epilogue=0, act=act_id,
                  bias=bias.cuda(), out_lo=out_lo)
     ref = f(a @ w.T + bias)
-    np.testing.assert_allclose((out_hi + out_lo).cpu(), ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose((out_hi + out_lo).cpu(), ref, rtol=2e-5, atol=2e-5)
     assert (out_hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0
     # backward: dz1 = (dz2 W) * act'(h1): B operand is W^T (rows = output index)
     h1 = f(torch.randn(rows, 256))
@@ -74,7 +74,27 @@ def test_tc_gemm_epilogues(K, act):
                  aux_hi=h_hi, aux_lo=h_lo)
     grad = (1 - h1 * h1) if act == 'tanh' else (h1 > 0).float()
     ref = (a @ w) * grad
-    np.testing.assert_allclose(out.cpu(), ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out.cpu(), ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('rows,n_split', [(64, 1), (1000, 3), (16384, 74), (100, 7)])
+@pytest.mark.parametrize('passes', [3, 1])
+def test_tc_wgrad(K, rows, n_split, passes):
+    g = torch.Generator().manual_seed(rows)
+    dz = torch.randn(rows, 256, generator=g) * 0.1
+    h = torch.randn(rows, 256, generator=g)
+    ref = dz.double().T @ h.double()
+    dz_hi, dz_lo = split(K, dz.cuda())
+    h_hi, h_lo = split(K, h.cuda())
+    n_params, off = 70000, 4352
+    gpart = torch.full((n_split, n_params), float('nan'), device='cuda')
+    K.tc_wgrad256(dz_hi, dz_lo, h_hi, h_lo, rows, gpart, n_split, n_params, off, passes=passes)
+    got = gpart[:, off:off + 65536].sum(0).view(256, 256).cpu().double()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= (1e-5 if passes == 3 else 5e-3) * scale, (err, scale)
+    # nothing outside the W2 block is touched
+    assert torch.isnan(gpart[:, :off]).all() and torch.isnan(gpart[:, off + 65536:]).all()
 
 
 def test_tc_gemm_throughput_smoke(K):
@@ -95,4 +115,15 @@ def test_tc_gemm_throughput_smoke(K):
         torch.cuda.synchronize()
         us = start.elapsed_time(end) / 20 * 1e3
         print(f'tc_gemm256 rows={rows} passes={passes}: {us:.1f} us, '
+              f'{2 * rows * 65536 / us / 1e6:.1f} TFLOP/s (fp32-equivalent)')
+        gpart = torch.empty(74, 70000, device='cuda')
+        for _ in range(3):
+            K.tc_wgrad256(a_hi, a_lo, a_hi, a_lo, rows, gpart, 74, 70000, 0, passes=passes)
+        start.record()
+        for _ in range(20):
+            K.tc_wgrad256(a_hi, a_lo, a_hi, a_lo, rows, gpart, 74, 70000, 0, passes=passes)
+        end.record()
+        torch.cuda.synchronize()
+        us = start.elapsed_time(end) / 20 * 1e3
+        print(f'tc_wgrad256 rows={rows} passes={passes}: {us:.1f} us, '
               f'{2 * rows * 65536 / us / 1e6:.1f} TFLOP/s (fp32-equivalent)')

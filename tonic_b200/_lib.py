@@ -33,7 +33,9 @@ class TbMlpShape(ctypes.Structure):
     _fields_ = [('d_in', c_i32), ('hidden', c_i32), ('n_out', c_i32), ('act', c_i32),
                 ('off_w1', c_i32), ('off_b1', c_i32), ('off_w2', c_i32), ('off_b2', c_i32),
                 ('off_w3', c_i32), ('off_b3', c_i32), ('n_params', c_i32),
-                ('off_w1t', c_i32), ('off_w2t', c_i32), ('n_packed', c_i32)]
+                ('off_w1t', c_i32), ('off_w2t', c_i32), ('n_packed', c_i32),
+                ('off_w2_hi', c_i32), ('off_w2_lo', c_i32), ('off_w2t_hi', c_i32),
+                ('off_w2t_lo', c_i32)]
 
 
 class TbMlpInput(ctypes.Structure):
@@ -83,6 +85,13 @@ _PROTOTYPES = {
     'tb_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'tb_tc_gemm256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp]),
+    'tb_mlp_forward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'tb_mlp_backward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64,
+                                   c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'tb_mlp_wgrad_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
+                                c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_permutation': (c_int, [c_u64, c_u64, c_i64, c_vp, c_vp]),
     'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'tb_profile_begin': (c_int, []),

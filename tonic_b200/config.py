@@ -13,9 +13,20 @@ indices 'host'   : minibatch permutations come from the native numpy-compatible
                    several ranks each rank permutes ITS OWN rows and contributes
                    batch_size / world rows to every minibatch (static shapes, no host
                    work that grows with the number of GPUs).
+gemm    'tf32x3' : the 256-wide hidden-layer GEMMs (forward layer 2, backward dz1, weight
+                   gradient dW2) run on the tensor cores (tcgen05.mma kind::tf32, TMA,
+                   TMEM) with the 3xTF32 operand split -> fp32-grade results (default
+                   for hidden width 256; other widths use the FFMA kernels).
+        'tf32'   : single-pass TF32 on the tensor cores (fast mode, ~1e-3 relative).
+        'ffma'   : everything on the FP32 FFMA kernels (csrc/mlp.cu).
+                   Environment override: TONIC_B200_GEMM.
 wgrad_splits     : number of row splits of the weight-gradient kernel.
 """
 
+import os
+
 noise = 'host'
+gemm = os.environ.get('TONIC_B200_GEMM', 'tf32x3')
 indices = 'host'
-wgrad_splits = 37      # 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
+wgrad_splits = 37      # FFMA: 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
+wgrad_splits_tc = 74   # tensor cores: 2 row tiles x 74 splits = 148 CTAs

@@ -394,6 +394,7 @@ mlp_backward_kernel(TbMlpShape sh, const float* __restrict__ params,
 // --------------------------------------------------------------------------------
 struct WJob {
     const float* A; const float* B;
+    const float* A_lo;          // optional second part added to A on load (tf32 splits)
     int lda, a_col0, a_cols;
     int ldb, b_col0, b_cols;
     int out_off, out_ld;        // gpart offset of out[0][0] and its row stride
@@ -417,7 +418,8 @@ __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t 
 #pragma unroll
         for (int j = 0; j < MK; ++j) acc[i][j] = 0.0f;
 
-    const bool a_fast = TN == 128 && job.a_cols == 128 && (job.lda & 3) == 0 && (job.a_col0 & 3) == 0;
+    const bool a_fast = TN == 128 && job.a_cols == 128 && (job.lda & 3) == 0 && (job.a_col0 & 3) == 0 &&
+                        job.A_lo == nullptr;
     const bool b_fast = TK == 128 && job.b_cols == 128 && (job.ldb & 3) == 0 && (job.b_col0 & 3) == 0;
 
     auto stage = [&](int buf, int64_t mbase) {
@@ -433,8 +435,12 @@ __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t 
         } else {
             for (int v = tid; v < WMC * TN; v += NTHREADS) {
                 const int r = v / TN, c = v % TN;
-                as[v] = (mbase + r < r1 && c < job.a_cols)
-                            ? __ldg(job.A + (mbase + r) * job.lda + job.a_col0 + c) : 0.0f;
+                float av = 0.0f;
+                if (mbase + r < r1 && c < job.a_cols) {
+                    av = __ldg(job.A + (mbase + r) * job.lda + job.a_col0 + c);
+                    if (job.A_lo) av += __ldg(job.A_lo + (mbase + r) * job.lda + job.a_col0 + c);
+                }
+                as[v] = av;
             }
         }
         if (b_fast) {
@@ -620,6 +626,72 @@ extern "C" int tb_mlp_backward(const TbMlpShape* shape, const float* d_params,
     return check_launch("tb_mlp_backward");
 }
 
+static int launch_wgrad_jobs(const TbMlpShape* shape, const float* d_xin, const float* d_h1,
+                             const float* d_h2, const float* d_dz1, const float* d_dz2,
+                             const float* d_dz2_lo, const float* d_dout, int32_t ld_dout,
+                             int32_t n_extra, int32_t off_extra, int64_t n_rows, float* d_gpart,
+                             int32_t n_split, bool include_w2, const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    const int H = shape->hidden, d_in = shape->d_in, n_out = shape->n_out;
+    const int ldx = (d_in + 1 + 3) & ~3;
+    WJobTable t;
+    t.n_jobs = 0;
+    auto add = [&](const float* A, const float* A_lo, int lda, int a0, int an, const float* B, int ldb,
+                   int b0, int bn, int out_off, int out_ld, int bias_col, int bias_off, int variant) {
+        if (t.n_jobs >= kMaxJobs) return false;
+        WJob& j = t.jobs[t.n_jobs++];
+        j.A = A; j.A_lo = A_lo; j.lda = lda; j.a_col0 = a0; j.a_cols = an;
+        j.B = B; j.ldb = ldb; j.b_col0 = b0; j.b_cols = bn;
+        j.out_off = out_off; j.out_ld = out_ld; j.bias_col = bias_col; j.bias_off = bias_off;
+        j.variant = variant;
+        return true;
+    };
+    bool ok = true;
+    const int ntile = (H + 127) / 128;
+    // dW2[n][k] = sum_m dz2[m][n] h1[m][k]  (heavy 128x128 tiles first)
+    if (include_w2)
+        for (int tn = 0; tn < ntile; ++tn)
+            for (int tk = 0; tk < ntile; ++tk) {
+                const int an = std::min(128, H - tn * 128), bn = std::min(128, H - tk * 128);
+                ok &= add(d_dz2, nullptr, H, tn * 128, an, d_h1, H, tk * 128, bn,
+                          shape->off_w2 + tn * 128 * H + tk * 128, H, -1, 0, 0);
+            }
+    // dW1[n][k] (+ db1 through the trailing ones column of xin)
+    for (int tn = 0; tn < ntile; ++tn) {
+        const int an = std::min(128, H - tn * 128);
+        const int tkw = d_in + 1 <= 32 ? 32 : 128;
+        for (int k0 = 0; k0 < d_in + 1; k0 += tkw) {
+            const int bn = std::min(tkw, d_in + 1 - k0);
+            ok &= add(d_dz1, nullptr, H, tn * 128, an, d_xin, ldx, k0, bn,
+                      shape->off_w1 + tn * 128 * d_in + k0, d_in, d_in,
+                      shape->off_b1 + tn * 128, tkw == 32 ? 1 : 0);
+        }
+        // db2[n] = sum_m dz2[m][n]  (ones column of xin)
+        ok &= add(d_dz2, d_dz2_lo, H, tn * 128, an, d_xin, ldx, d_in, 1, 0, 1, d_in,
+                  shape->off_b2 + tn * 128, 1);
+    }
+    // dW3[o][k] = sum_m dout[m][o] h2[m][k]
+    for (int o0 = 0; o0 < n_out; o0 += 16)
+        for (int tk = 0; tk < ntile; ++tk) {
+            const int bn = std::min(128, H - tk * 128);
+            ok &= add(d_dout, nullptr, ld_dout, o0, std::min(16, n_out - o0), d_h2, H, tk * 128, bn,
+                      shape->off_w3 + o0 * H + tk * 128, H, -1, 0, 2);
+        }
+    // db3 and the extra per-row columns (e.g. log_scale gradients)
+    ok &= add(d_dout, nullptr, ld_dout, 0, n_out, d_xin, ldx, d_in, 1, 0, 1, d_in, shape->off_b3, 1);
+    if (n_extra > 0)
+        ok &= add(d_dout, nullptr, ld_dout, n_out, n_extra, d_xin, ldx, d_in, 1, 0, 1, d_in, off_extra, 1);
+    TB_REQUIRE(ok, TB_ENOTSUP, "tb_mlp_wgrad: too many tiles (d_in=%d)", d_in);
+
+    int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
+    rows_per_split = (rows_per_split + WMC - 1) / WMC * WMC;
+    const size_t smem = (size_t)2 * WMC * (128 + 128) * sizeof(float);
+    dim3 grid(n_split, t.n_jobs);
+    mlp_wgrad_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(
+        t, n_rows, rows_per_split, d_gpart, shape->n_params, d_skip);
+    return check_launch("tb_mlp_wgrad");
+}
+
 extern "C" int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const float* d_h1,
                             const float* d_h2, const float* d_dz1, const float* d_dz2,
                             const float* d_dout, int32_t ld_dout, int32_t n_extra,
@@ -632,61 +704,293 @@ extern "C" int tb_mlp_wgrad(const TbMlpShape* shape, const float* d_xin, const f
     TB_REQUIRE(d_xin && d_h1 && d_h2 && d_dz1 && d_dz2 && d_dout && d_gpart && n_rows > 0 &&
                n_split >= 1 && ld_dout >= shape->n_out + n_extra, TB_EINVAL,
                "tb_mlp_wgrad: bad arguments");
-    const int H = shape->hidden, d_in = shape->d_in, n_out = shape->n_out;
-    const int ldx = (d_in + 1 + 3) & ~3;
-    WJobTable t;
-    t.n_jobs = 0;
-    auto add = [&](const float* A, int lda, int a0, int an, const float* B, int ldb, int b0, int bn,
-                   int out_off, int out_ld, int bias_col, int bias_off, int variant) {
-        if (t.n_jobs >= kMaxJobs) return false;
-        WJob& j = t.jobs[t.n_jobs++];
-        j.A = A; j.lda = lda; j.a_col0 = a0; j.a_cols = an;
-        j.B = B; j.ldb = ldb; j.b_col0 = b0; j.b_cols = bn;
-        j.out_off = out_off; j.out_ld = out_ld; j.bias_col = bias_col; j.bias_off = bias_off;
-        j.variant = variant;
-        return true;
-    };
-    bool ok = true;
-    const int ntile = (H + 127) / 128;
-    // dW2[n][k] = sum_m dz2[m][n] h1[m][k]
-    for (int tn = 0; tn < ntile; ++tn)
-        for (int tk = 0; tk < ntile; ++tk) {
-            const int an = std::min(128, H - tn * 128), bn = std::min(128, H - tk * 128);
-            ok &= add(d_dz2, H, tn * 128, an, d_h1, H, tk * 128, bn,
-                      shape->off_w2 + tn * 128 * H + tk * 128, H, -1, 0, 0);
-        }
-    // dW1[n][k] (+ db1 through the trailing ones column of xin)
-    for (int tn = 0; tn < ntile; ++tn) {
-        const int an = std::min(128, H - tn * 128);
-        for (int k0 = 0; k0 < d_in + 1; k0 += (d_in + 1 <= 32 ? 32 : 128)) {
-            const int tkw = d_in + 1 <= 32 ? 32 : 128;
-            const int bn = std::min(tkw, d_in + 1 - k0);
-            ok &= add(d_dz1, H, tn * 128, an, d_xin, ldx, k0, bn,
-                      shape->off_w1 + tn * 128 * d_in + k0, d_in, d_in,
-                      shape->off_b1 + tn * 128, tkw == 32 ? 1 : 0);
-        }
-        // db2[n] = sum_m dz2[m][n]  (ones column of xin)
-        ok &= add(d_dz2, H, tn * 128, an, d_xin, ldx, d_in, 1, 0, 1, d_in,
-                  shape->off_b2 + tn * 128, 1);
-    }
-    // dW3[o][k] = sum_m dout[m][o] h2[m][k]
-    for (int o0 = 0; o0 < n_out; o0 += 16)
-        for (int tk = 0; tk < ntile; ++tk) {
-            const int bn = std::min(128, H - tk * 128);
-            ok &= add(d_dout, ld_dout, o0, std::min(16, n_out - o0), d_h2, H, tk * 128, bn,
-                      shape->off_w3 + o0 * H + tk * 128, H, -1, 0, 2);
-        }
-    // db3 and the extra per-row columns (e.g. log_scale gradients)
-    ok &= add(d_dout, ld_dout, 0, n_out, d_xin, ldx, d_in, 1, 0, 1, d_in, shape->off_b3, 1);
-    if (n_extra > 0)
-        ok &= add(d_dout, ld_dout, n_out, n_extra, d_xin, ldx, d_in, 1, 0, 1, d_in, off_extra, 1);
-    TB_REQUIRE(ok, TB_ENOTSUP, "tb_mlp_wgrad: too many tiles (d_in=%d)", d_in);
+    return launch_wgrad_jobs(shape, d_xin, d_h1, d_h2, d_dz1, d_dz2, nullptr, d_dout, ld_dout, n_extra,
+                             off_extra, n_rows, d_gpart, n_split, true, d_skip, stream);
+}
 
-    int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
-    rows_per_split = (rows_per_split + WMC - 1) / WMC * WMC;
-    const size_t smem = (size_t)2 * WMC * (128 + 128) * sizeof(float);
-    dim3 grid(n_split, t.n_jobs);
-    mlp_wgrad_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(
-        t, n_rows, rows_per_split, d_gpart, shape->n_params, d_skip);
-    return check_launch("tb_mlp_wgrad");
+// =====================================================================================
+// Tensor-core variant: the FFMA pieces around csrc/tc_gemm.cu
+// =====================================================================================
+namespace tb {
+
+__device__ __forceinline__ float tf32_hi(float x) {
+    return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+// h1 = act(xin W1^T + b1), written as a tf32 split (A operand of the layer-2 GEMM)
+template <int H, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_layer1_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ packed,
+                  TbMlpInput in, int64_t n_rows, float* __restrict__ xin_save,
+                  float* __restrict__ h1_hi, float* __restrict__ h1_lo, const int32_t* d_skip) {
+    using C = Cfg<H>;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufB = reinterpret_cast<float*>(smem_raw);          // [TM][LDH] input staging
+    float* Bs2 = bufB + TM * C::LDH;                           // [2][KC][H]
+    int64_t* srow = reinterpret_cast<int64_t*>(Bs2 + 2 * KC * H);
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * TM;
+    const int valid = (int)min((int64_t)TM, n_rows - m0);
+    if (tid < TM) srow[tid] = tid < valid ? (in.d_idx ? in.d_idx[m0 + tid] : m0 + tid) : -1;
+    __syncthreads();
+    const int d_in = sh.d_in;
+    const int ldx = (d_in + 1 + 3) & ~3;
+    float acc[8][C::NC];
+    zero_acc<H>(acc);
+    for (int k0 = 0; k0 < d_in; k0 += H) {
+        const int klen = min(H, d_in - k0);
+        const int kpad = (klen + 3) & ~3;
+        for (int v = tid; v < TM * kpad; v += NTHREADS) {
+            const int m = v / kpad, cc = v % kpad;
+            const int c = k0 + cc;
+            float val = 0.0f;
+            const int64_t r = srow[m];
+            if (r >= 0 && cc < klen) {
+                if (c < in.dim1) {
+                    val = in.d_x1[r * in.dim1 + c];
+                    if (in.d_mean) val = __fdiv_rn(__fsub_rn(val, in.d_mean[c]), in.d_std[c]);
+                } else {
+                    const int64_t r2 = in.gather2 ? r : (m0 + m);
+                    val = in.d_x2[r2 * in.dim2 + (c - in.dim1)];
+                }
+                if (xin_save) xin_save[(m0 + m) * ldx + c] = val;
+            }
+            bufB[m * C::LDH + cc] = val;
+        }
+        __syncthreads();
+        gemm_acc<H>(acc, bufB, C::LDH, klen, packed + sh.off_w1t + (size_t)k0 * H, H, H, true, Bs2);
+    }
+    if (xin_save) {
+        for (int v = tid; v < valid * (ldx - d_in); v += NTHREADS) {
+            const int m = v / (ldx - d_in), c = d_in + v % (ldx - d_in);
+            xin_save[(m0 + m) * ldx + c] = (c == d_in) ? 1.0f : 0.0f;
+        }
+    }
+    bias_activate<H, ACT>(acc, params + sh.off_b1);
+    store_tile<H>(acc, h1_hi + m0 * H, H, valid, [](float a, int, int) { return tf32_hi(a); });
+    store_tile<H>(acc, h1_lo + m0 * H, H, valid, [](float a, int, int) { return a - tf32_hi(a); });
+}
+
+// out[m][o] = b3[o] + h2[m, :] . W3[o, :]
+template <int H>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_head_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ h2,
+                int64_t n_rows, float* __restrict__ out, const int32_t* d_skip) {
+    using C = Cfg<H>;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufB = reinterpret_cast<float*>(smem_raw);          // [TM][LDH]
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * TM;
+    const int valid = (int)min((int64_t)TM, n_rows - m0);
+    for (int v = tid; v < TM * (H / 4); v += NTHREADS) {
+        const int m = v / (H / 4), c4 = v % (H / 4);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < valid) x = __ldg(reinterpret_cast<const float4*>(h2 + (m0 + m) * H) + c4);
+        *reinterpret_cast<float4*>(bufB + m * C::LDH + c4 * 4) = x;
+    }
+    __syncthreads();
+    const int n_out = sh.n_out;
+    const float* W3 = params + sh.off_w3;
+    const float* b3 = params + sh.off_b3;
+    const int quad = tid >> 2, ql = tid & 3;
+    for (int p = quad; p < TM * n_out; p += NTHREADS / 4) {
+        const int m = p % TM, o = p / TM;
+        const float* hrow = bufB + m * C::LDH;
+        const float* wrow = W3 + (size_t)o * H;
+        float s = 0.0f;
+#pragma unroll 4
+        for (int i = ql; i < H / 4; i += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hrow + i * 4);
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + i * 4));
+            s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s);
+            s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (ql == 0 && m < valid) out[(m0 + m) * n_out + o] = s + b3[o];
+    }
+}
+
+// dz2 = (dout W3) * act'(h2), written as a tf32 split (A operand of the backward GEMM and
+// of the weight-gradient GEMM)
+template <int H, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_head_backward_kernel(TbMlpShape sh, const float* __restrict__ params,
+                         const float* __restrict__ dout, int ld_dout, const float* __restrict__ h2,
+                         int64_t n_rows, float* __restrict__ dz2_hi, float* __restrict__ dz2_lo,
+                         const int32_t* d_skip) {
+    using C = Cfg<H>;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Bs2 = reinterpret_cast<float*>(smem_raw);           // [2][KC][H]
+    float* sD = Bs2 + 2 * KC * H;                              // [TM][72]
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * TM;
+    const int valid = (int)min((int64_t)TM, n_rows - m0);
+    const int n_out = sh.n_out;
+    const int ldo = (n_out + 3) & ~3;
+    for (int v = tid; v < TM * ldo; v += NTHREADS) {
+        const int m = v / ldo, o = v % ldo;
+        sD[m * 72 + o] = (m < valid && o < n_out) ? dout[(m0 + m) * ld_dout + o] : 0.0f;
+    }
+    __syncthreads();
+    float acc[8][C::NC];
+    zero_acc<H>(acc);
+    gemm_acc<H>(acc, sD, 72, n_out, params + sh.off_w3, H, H, true, Bs2);
+    mul_activation_grad<H, ACT>(acc, h2 + m0 * H, valid);
+    store_tile<H>(acc, dz2_hi + m0 * H, H, valid, [](float a, int, int) { return tf32_hi(a); });
+    store_tile<H>(acc, dz2_lo + m0 * H, H, valid, [](float a, int, int) { return a - tf32_hi(a); });
+}
+
+// dx[:, j] = sum_n dz1[:, n] W1[n, col0 + j]
+template <int H>
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_dx_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ dz1,
+              int64_t n_rows, float* __restrict__ dx, int dx_col0, int dx_cols, const int32_t* d_skip) {
+    using C = Cfg<H>;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufA = reinterpret_cast<float*>(smem_raw);          // [TM][LDH]
+    float* Bs2 = bufA + TM * C::LDH;
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * TM;
+    const int valid = (int)min((int64_t)TM, n_rows - m0);
+    for (int v = tid; v < TM * (H / 4); v += NTHREADS) {
+        const int m = v / (H / 4), c4 = v % (H / 4);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < valid) x = __ldg(reinterpret_cast<const float4*>(dz1 + (m0 + m) * H) + c4);
+        *reinterpret_cast<float4*>(bufA + m * C::LDH + c4 * 4) = x;
+    }
+    __syncthreads();
+    float acc[8][C::NC];
+    zero_acc<H>(acc);
+    gemm_acc<H>(acc, bufA, C::LDH, H, params + sh.off_w1 + dx_col0, sh.d_in, dx_cols, false, Bs2);
+    const int tx = tid & 31, ty = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int row = ty * 8 + r;
+        if (row >= valid) continue;
+#pragma unroll
+        for (int j = 0; j < C::NC; ++j) {
+            const int c = C::col(tx, j);
+            if (c < dx_cols) dx[(m0 + row) * dx_cols + c] = acc[r][j];
+        }
+    }
+}
+
+static int check_tc_shape(const TbMlpShape* sh, const char* who) {
+    int rc = check_shape(sh, who);
+    if (rc) return rc;
+    TB_REQUIRE(sh->hidden == 256 && sh->off_w2_hi > 0, TB_ENOTSUP,
+               "%s: the tensor-core path needs hidden == 256 and the tf32 weight splits", who);
+    return 0;
+}
+
+}  // namespace tb
+
+extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
+                                 const float* d_packed, const TbMlpInput* in, int64_t n_rows,
+                                 float* d_out, float* d_xin, float* d_h1_hi, float* d_h1_lo,
+                                 float* d_h2, int32_t passes, const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    int rc = check_tc_shape(shape, "tb_mlp_forward_tc");
+    if (rc) return rc;
+    TB_REQUIRE(d_params && d_packed && in && in->d_x1 && d_out && d_h1_hi && d_h1_lo && d_h2 &&
+               n_rows > 0, TB_EINVAL, "tb_mlp_forward_tc: null pointer");
+    TB_REQUIRE(in->dim1 + (in->d_x2 ? in->dim2 : 0) == shape->d_in, TB_EINVAL,
+               "tb_mlp_forward_tc: input widths do not add up to d_in");
+    const int blocks = (int)((n_rows + TM - 1) / TM);
+    cudaStream_t s = as_stream(stream);
+    const size_t smem = mlp_smem_bytes<256>();
+    {
+        ProfScope prof_scope("tb_mlp_layer1", stream);
+        if (shape->act == TB_ACT_TANH) {
+            set_smem(mlp_layer1_kernel<256, TB_ACT_TANH>, smem);
+            mlp_layer1_kernel<256, TB_ACT_TANH><<<blocks, NTHREADS, smem, s>>>(
+                *shape, d_params, d_packed, *in, n_rows, d_xin, d_h1_hi, d_h1_lo, d_skip);
+        } else {
+            set_smem(mlp_layer1_kernel<256, TB_ACT_RELU>, smem);
+            mlp_layer1_kernel<256, TB_ACT_RELU><<<blocks, NTHREADS, smem, s>>>(
+                *shape, d_params, d_packed, *in, n_rows, d_xin, d_h1_hi, d_h1_lo, d_skip);
+        }
+        if ((rc = check_launch("tb_mlp_forward_tc/layer1"))) return rc;
+    }
+    rc = tb_tc_gemm256(d_h1_hi, d_h1_lo, d_packed + shape->off_w2_hi, d_packed + shape->off_w2_lo, n_rows,
+                       passes, 0, shape->act, d_params + shape->off_b2, nullptr, nullptr, d_h2, nullptr,
+                       d_skip, stream);
+    if (rc) return rc;
+    {
+        ProfScope prof_scope("tb_mlp_head", stream);
+        set_smem(mlp_head_kernel<256>, smem);
+        mlp_head_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_h2, n_rows, d_out, d_skip);
+        rc = check_launch("tb_mlp_forward_tc/head");
+    }
+    return rc;
+}
+
+extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params,
+                                  const float* d_packed, const float* d_dout, int32_t ld_dout,
+                                  const float* d_h1_hi, const float* d_h1_lo, const float* d_h2,
+                                  int64_t n_rows, float* d_dz2_hi, float* d_dz2_lo, float* d_dz1,
+                                  float* d_dx, int32_t dx_col0, int32_t dx_cols, int32_t passes,
+                                  const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    int rc = check_tc_shape(shape, "tb_mlp_backward_tc");
+    if (rc) return rc;
+    TB_REQUIRE(d_params && d_packed && d_dout && d_h1_hi && d_h1_lo && d_h2 && d_dz2_hi && d_dz2_lo &&
+               d_dz1 && n_rows > 0 && ld_dout >= shape->n_out, TB_EINVAL,
+               "tb_mlp_backward_tc: bad arguments");
+    TB_REQUIRE(!d_dx || (dx_cols >= 1 && dx_cols <= 256 && dx_col0 >= 0 &&
+                         dx_col0 + dx_cols <= shape->d_in), TB_EINVAL,
+               "tb_mlp_backward_tc: dx column range invalid");
+    const int blocks = (int)((n_rows + TM - 1) / TM);
+    cudaStream_t s = as_stream(stream);
+    const size_t smem = mlp_smem_bytes<256>();
+    {
+        ProfScope prof_scope("tb_mlp_head_backward", stream);
+        if (shape->act == TB_ACT_TANH) {
+            set_smem(mlp_head_backward_kernel<256, TB_ACT_TANH>, smem);
+            mlp_head_backward_kernel<256, TB_ACT_TANH><<<blocks, NTHREADS, smem, s>>>(
+                *shape, d_params, d_dout, ld_dout, d_h2, n_rows, d_dz2_hi, d_dz2_lo, d_skip);
+        } else {
+            set_smem(mlp_head_backward_kernel<256, TB_ACT_RELU>, smem);
+            mlp_head_backward_kernel<256, TB_ACT_RELU><<<blocks, NTHREADS, smem, s>>>(
+                *shape, d_params, d_dout, ld_dout, d_h2, n_rows, d_dz2_hi, d_dz2_lo, d_skip);
+        }
+        if ((rc = check_launch("tb_mlp_backward_tc/head"))) return rc;
+    }
+    rc = tb_tc_gemm256(d_dz2_hi, d_dz2_lo, d_packed + shape->off_w2t_hi, d_packed + shape->off_w2t_lo,
+                       n_rows, passes, 1, shape->act, nullptr, d_h1_hi, d_h1_lo, d_dz1, nullptr, d_skip,
+                       stream);
+    if (rc || !d_dx) return rc;
+    {
+        ProfScope prof_scope("tb_mlp_dx", stream);
+        set_smem(mlp_dx_kernel<256>, smem);
+        mlp_dx_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_dz1, n_rows, d_dx, dx_col0,
+                                                       dx_cols, d_skip);
+        rc = check_launch("tb_mlp_backward_tc/dx");
+    }
+    return rc;
+}
+
+extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, const float* d_h1_hi,
+                               const float* d_h1_lo, const float* d_h2, const float* d_dz1,
+                               const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
+                               int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
+                               float* d_gpart, int32_t n_split, int32_t passes,
+                               const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    int rc = check_tc_shape(shape, "tb_mlp_wgrad_tc");
+    if (rc) return rc;
+    TB_REQUIRE(d_xin && d_h1_hi && d_h1_lo && d_h2 && d_dz1 && d_dz2_hi && d_dz2_lo && d_dout &&
+               d_gpart && n_rows > 0 && n_split >= 1 && ld_dout >= shape->n_out + n_extra, TB_EINVAL,
+               "tb_mlp_wgrad_tc: bad arguments");
+    rc = tb_tc_wgrad256(d_dz2_hi, d_dz2_lo, d_h1_hi, d_h1_lo, n_rows, passes, d_gpart, n_split,
+                        shape->n_params, shape->off_w2, d_skip, stream);
+    if (rc) return rc;
+    ProfScope prof_scope("tb_mlp_wgrad_small", stream);
+    return launch_wgrad_jobs(shape, d_xin, d_h1_hi, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout,
+                             n_extra, off_extra, n_rows, d_gpart, n_split, false, d_skip, stream);
 }

@@ -19,6 +19,14 @@ __device__ __forceinline__ void pack_one(const TbMlpShape& sh, int i, float p, f
     } else if (i >= sh.off_w2 && i < sh.off_w2 + H * H) {          // W2 [H, H] -> W2T
         const int e = i - sh.off_w2, n = e / H, k = e % H;
         packed[sh.off_w2t + k * H + n] = p;
+        if (sh.off_w2_hi > 0) {      // tf32 splits for the tensor-core path (csrc/tc_gemm.cu)
+            const float hi = __uint_as_float(__float_as_uint(p) & 0xFFFFE000u);
+            const float lo = p - hi;
+            packed[sh.off_w2_hi + e] = hi;
+            packed[sh.off_w2_lo + e] = lo;
+            packed[sh.off_w2t_hi + k * H + n] = hi;
+            packed[sh.off_w2t_lo + k * H + n] = lo;
+        }
     }
 }
 

@@ -301,6 +301,172 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
 }
 
+
+// =====================================================================================
+// Weight gradient of the hidden layer on the tensor cores:
+//     dW2[n, k] = sum_m dz2[m, n] * h1[m, k]          (reduction over the rows m)
+// Both operands are "MN-major" for the MMA (the reduction index m is the slow axis of the
+// row-major activation arrays), which tcgen05 supports for tf32 through the a_major /
+// b_major bits of the instruction descriptor.  CTA (tile, split): output rows
+// n in [128 tile, 128 tile + 128), all 256 columns k, rows m of split `split`; the fp32
+// partial sum goes to gpart[split] (reduced by the Adam kernel in a fixed order).
+// Shared-memory operand layout = what TMA writes for a box of 32 floats x 32 rows with the
+// 128-byte swizzle: [32 m-rows][128 B]; one MMA (K = 8) consumes an 8-row group (1024 B);
+// 32-column groups along M / N are LBO = 4096 B apart.
+// =====================================================================================
+constexpr int TCW_ROWS = 32;                                   // m rows per pipeline chunk
+constexpr int TCW_A_BYTES = TC_BM * TCW_ROWS * 4;               // 16 KB (4 boxes of 4 KB)
+constexpr int TCW_B_BYTES = TC_BN * TCW_ROWS * 4;               // 32 KB (8 boxes of 4 KB)
+
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
+    d |= (uint64_t)(4096 >> 4) << 16;       // LBO: next 32-element group along M / N
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row group along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);   // A and B MN-major
+
+struct TcWgradParams {
+    int64_t n_rows;
+    int64_t rows_per_split;     // multiple of TCW_ROWS
+    float* gpart;               // [n_split, n_params]
+    int n_params;
+    int off_w2;                 // offset of W2 [256, 256] in the flat layout
+    const int32_t* skip;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
+                const __grid_constant__ CUtensorMap map_h_hi, const __grid_constant__ CUtensorMap map_h_lo,
+                const TcWgradParams p) {
+    using Cfg = TcCfg<PASSES>;
+    if (skip_requested(p.skip)) return;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::STAGES;
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;                                 // 0 / 1: output rows 128*tile..
+    const int split = blockIdx.y;
+    const int64_t m_begin = (int64_t)split * p.rows_per_split;
+    const int64_t m_end = min(p.n_rows, m_begin + p.rows_per_split);
+    const int n_chunks = m_end > m_begin ? (int)((m_end - m_begin + TCW_ROWS - 1) / TCW_ROWS) : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                const int m0 = (int)(m_begin + (int64_t)c * TCW_ROWS);
+                // rows >= n_rows are zero-filled by TMA; rows in [m_end, chunk end) belong to
+                // the next split, so the chunk grid must align with the split boundaries
+                for (int b = 0; b < TC_BM / 32; ++b)
+                    tma_load_2d(st + b * 4096, &map_dz_hi, &full_bar[stage], tile * TC_BM + b * 32, m0);
+                unsigned char* bh = st + Cfg::PARTS * TCW_A_BYTES;
+                for (int b = 0; b < TC_BN / 32; ++b)
+                    tma_load_2d(bh + b * 4096, &map_h_hi, &full_bar[stage], b * 32, m0);
+                if (PASSES == 3) {
+                    for (int b = 0; b < TC_BM / 32; ++b)
+                        tma_load_2d(st + TCW_A_BYTES + b * 4096, &map_dz_lo, &full_bar[stage],
+                                    tile * TC_BM + b * 32, m0);
+                    unsigned char* bl = st + 2 * TCW_A_BYTES + TCW_B_BYTES;
+                    for (int b = 0; b < TC_BN / 32; ++b)
+                        tma_load_2d(bl + b * 4096, &map_h_lo, &full_bar[stage], b * 32, m0);
+                }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_mnmajor_sw128(st);
+                const uint64_t a_lo = umma_desc_mnmajor_sw128(st + TCW_A_BYTES);
+                const uint64_t b_hi = umma_desc_mnmajor_sw128(st + Cfg::PARTS * TCW_A_BYTES);
+                const uint64_t b_lo = umma_desc_mnmajor_sw128(st + 2 * TCW_A_BYTES + TCW_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TCW_ROWS / 8; ++k) {
+                    const uint64_t koff = (uint64_t)(k * 1024 >> 4);      // next 8-row group
+                    if (PASSES == 3) {
+                        tcgen05_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
+                        tcgen05_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, kIdescTf32MN, 1);
+                        tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32MN, 1);
+                    } else {
+                        tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
+                    }
+                }
+                tcgen05_commit(&empty_bar[stage]);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            tcgen05_commit(tmem_full);
+        }
+    } else if (warp >= 4) {
+        const int w = warp - 4;
+        float* stg = epi + w * 32 * TC_STAGE_ROWSTRIDE;
+        float* out = p.gpart + (size_t)split * p.n_params + p.off_w2 + (size_t)(tile * TC_BM + w * 32) * TC_BN;
+        if (n_chunks > 0) {
+            mbar_wait(tmem_full, 0);
+            tcgen05_fence_after();
+        }
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; ++c) {
+            if (n_chunks > 0) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(c * 32), v);
+                float* mine = stg + lane * TC_STAGE_ROWSTRIDE;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(mine + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+            }
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r)
+                out[(size_t)r * TC_BN + c * 32 + lane] = n_chunks > 0 ? stg[r * TC_STAGE_ROWSTRIDE + lane] : 0.0f;
+            __syncwarp();
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256)
+                     : "memory");
+    }
+}
+
 // ---- split helper: hi = x with the low 13 mantissa bits cleared, lo = x - hi -------------
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
@@ -403,4 +569,46 @@ extern "C" int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const flo
     }
 #undef TB_TC
     return check_launch("tb_tc_gemm256");
+}
+
+extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const float* d_h_hi,
+                              const float* d_h_lo, int64_t n_rows, int32_t passes, float* d_gpart,
+                              int32_t n_split, int32_t n_params, int32_t off_w2,
+                              const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    ProfScope prof_scope("tb_tc_wgrad256", stream);
+    TB_REQUIRE(d_dz_hi && d_h_hi && d_gpart && n_rows > 0 && n_split >= 1, TB_EINVAL,
+               "tb_tc_wgrad256: bad arguments");
+    TB_REQUIRE(passes == 1 || (passes == 3 && d_dz_lo && d_h_lo), TB_EINVAL,
+               "tb_tc_wgrad256: passes must be 1, or 3 with the lo parts");
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = make_map(&maps[0], d_dz_hi, n_rows, TCW_ROWS))) return rc;
+    if ((rc = make_map(&maps[1], d_dz_lo ? d_dz_lo : d_dz_hi, n_rows, TCW_ROWS))) return rc;
+    if ((rc = make_map(&maps[2], d_h_hi, n_rows, TCW_ROWS))) return rc;
+    if ((rc = make_map(&maps[3], d_h_lo ? d_h_lo : d_h_hi, n_rows, TCW_ROWS))) return rc;
+    TcWgradParams p;
+    p.n_rows = n_rows;
+    p.rows_per_split = ((n_rows + n_split - 1) / n_split + TCW_ROWS - 1) / TCW_ROWS * TCW_ROWS;
+    p.gpart = d_gpart; p.n_params = n_params; p.off_w2 = off_w2; p.skip = d_skip;
+    dim3 grid(TC_BN / TC_BM, n_split);
+    cudaStream_t s = as_stream(stream);
+    if (passes == 3) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(tc_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcCfg<3>::SMEM_BYTES);
+            configured = true;
+        }
+        tc_wgrad_kernel<3><<<grid, TC_THREADS, TcCfg<3>::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 TcCfg<1>::SMEM_BYTES);
+            configured = true;
+        }
+        tc_wgrad_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], p);
+    }
+    return check_launch("tb_tc_wgrad256");
 }

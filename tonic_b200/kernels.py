@@ -95,13 +95,22 @@ class MlpLayout:
         self.off_w1t = 0
         self.off_w2t = round_up(d_in * H, 4)
         self.n_packed = self.off_w2t + H * H
+        # tf32 splits of W2 and W2^T for the tensor-core path (256-wide layers only);
+        # 256-float (1 KB) aligned so they can be TMA sources
+        self.tensor_core = H == 256
+        split = [0, 0, 0, 0]
+        if self.tensor_core:
+            base = round_up(self.n_packed, 256)
+            split = [base + i * H * H for i in range(4)]
+            self.n_packed = base + 4 * H * H
         self.ldx = round_up(d_in + 1, 4)
         o = self.offsets
         self.shape = _lib.TbMlpShape(
             d_in=d_in, hidden=H, n_out=n_out, act=self.act,
             off_w1=o['w1'][0], off_b1=o['b1'][0], off_w2=o['w2'][0], off_b2=o['b2'][0],
             off_w3=o['w3'][0], off_b3=o['b3'][0], n_params=self.n_params,
-            off_w1t=self.off_w1t, off_w2t=self.off_w2t, n_packed=self.n_packed)
+            off_w1t=self.off_w1t, off_w2t=self.off_w2t, n_packed=self.n_packed,
+            off_w2_hi=split[0], off_w2_lo=split[1], off_w2t_hi=split[2], off_w2t_lo=split[3])
 
 
 class MlpInput:
@@ -137,14 +146,23 @@ class DeviceMlp:
                   ptr(self.packed), stream())
 
     # -- workspaces ---------------------------------------------------------
+    def passes(self):
+        """0 = FFMA kernels; 3 / 1 = tensor-core path (3xTF32 / TF32)."""
+        from . import config
+        if not self.layout.tensor_core or config.gemm == 'ffma':
+            return 0
+        if config.gemm not in ('tf32x3', 'tf32'):
+            raise ValueError(f'unknown config.gemm {config.gemm!r}')
+        return 3 if config.gemm == 'tf32x3' else 1
+
     def workspace(self, rows):
         if rows > self._ws_rows:
             L, dev = self.layout, device()
-            self.xin = torch.empty(rows, L.ldx, dtype=F32, device=dev)
-            self.h1 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
-            self.h2 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
-            self.dz1 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
-            self.dz2 = torch.empty(rows, L.hidden, dtype=F32, device=dev)
+            new = lambda cols: torch.empty(rows, cols, dtype=F32, device=dev)   # noqa: E731
+            self.xin = new(L.ldx)
+            self.h1, self.h2, self.dz1, self.dz2 = (new(L.hidden) for _ in range(4))
+            if L.tensor_core:       # low parts of the tf32 splits (h1 / dz2 hold the high parts)
+                self.h1_lo, self.dz2_lo = new(L.hidden), new(L.hidden)
             self._ws_rows = rows
 
     def flat_grad(self):
@@ -157,38 +175,69 @@ class DeviceMlp:
             self._gpart = torch.zeros(n_split, self.layout.n_params, dtype=F32, device=device())
         return self._gpart
 
+    def splits_for(self, rows):
+        from . import config
+        if self.passes():
+            return max(1, min(config.wgrad_splits_tc, rows // 64))
+        return max(1, min(config.wgrad_splits, rows // 128))
+
     # -- kernels ------------------------------------------------------------
     def forward(self, inp, rows, out, save=False, skip=None, params=None, packed=None):
         """out[rows, n_out] = head pre-activations. `params`/`packed` override the
         parameter set (target networks share the layout)."""
-        if save:
+        passes = self.passes()
+        if save or passes:
             self.workspace(rows)
         L = self.layout
-        _count_flops('tb_mlp_forward',
-                     2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out))
-        _lib.call('tb_mlp_forward', ctypes.byref(self.layout.shape),
-                  ptr(self.params if params is None else params),
-                  ptr(self.packed if packed is None else packed),
+        params = self.params if params is None else params
+        packed = self.packed if packed is None else packed
+        flops = 2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out)
+        if passes:
+            _count_flops('tb_mlp_forward_tc', flops)
+            _lib.call('tb_mlp_forward_tc', ctypes.byref(L.shape), ptr(params), ptr(packed),
+                      ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
+                      ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), passes, ptr(skip), stream())
+            return out
+        _count_flops('tb_mlp_forward', flops)
+        _lib.call('tb_mlp_forward', ctypes.byref(L.shape), ptr(params), ptr(packed),
                   ctypes.byref(inp.struct), rows, ptr(out),
                   ptr(self.xin) if save else None, ptr(self.h1) if save else None,
                   ptr(self.h2) if save else None, ptr(skip), stream())
         return out
 
-    def backward(self, dout, rows, dx=None, dx_col0=0, skip=None, params=None):
+    def backward(self, dout, rows, dx=None, dx_col0=0, skip=None, params=None, packed=None):
         L = self.layout
-        _count_flops('tb_mlp_backward', 2.0 * rows * L.hidden * (
-            L.n_out + L.hidden + (0 if dx is None else dx.shape[-1])))
-        _lib.call('tb_mlp_backward', ctypes.byref(self.layout.shape),
-                  ptr(self.params if params is None else params), ptr(dout), dout.shape[-1],
+        params = self.params if params is None else params
+        flops = 2.0 * rows * L.hidden * (L.n_out + L.hidden + (0 if dx is None else dx.shape[-1]))
+        passes = self.passes()
+        if passes:
+            _count_flops('tb_mlp_backward_tc', flops)
+            _lib.call('tb_mlp_backward_tc', ctypes.byref(L.shape), ptr(params),
+                      ptr(self.packed if packed is None else packed), ptr(dout), dout.shape[-1],
+                      ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), rows, ptr(self.dz2),
+                      ptr(self.dz2_lo), ptr(self.dz1), ptr(dx), dx_col0,
+                      0 if dx is None else dx.shape[-1], passes, ptr(skip), stream())
+            return
+        _count_flops('tb_mlp_backward', flops)
+        _lib.call('tb_mlp_backward', ctypes.byref(L.shape), ptr(params), ptr(dout), dout.shape[-1],
                   ptr(self.h1), ptr(self.h2), rows, ptr(self.dz2), ptr(self.dz1), ptr(dx),
                   dx_col0, 0 if dx is None else dx.shape[-1], ptr(skip), stream())
 
     def wgrad(self, dout, rows, n_split, n_extra=0, off_extra=0, skip=None):
         gpart = self.gpart(n_split)
         L = self.layout
-        _count_flops('tb_mlp_wgrad', 2.0 * rows * (
-            L.hidden * L.hidden + L.hidden * (L.d_in + 2) + (L.n_out + n_extra) * (L.hidden + 1)))
-        _lib.call('tb_mlp_wgrad', ctypes.byref(self.layout.shape), ptr(self.xin), ptr(self.h1),
+        flops = 2.0 * rows * (L.hidden * L.hidden + L.hidden * (L.d_in + 2)
+                              + (L.n_out + n_extra) * (L.hidden + 1))
+        passes = self.passes()
+        if passes:
+            _count_flops('tb_mlp_wgrad_tc', flops)
+            _lib.call('tb_mlp_wgrad_tc', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
+                      ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
+                      ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
+                      ptr(gpart), n_split, passes, ptr(skip), stream())
+            return gpart
+        _count_flops('tb_mlp_wgrad', flops)
+        _lib.call('tb_mlp_wgrad', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
                   ptr(self.h2), ptr(self.dz1), ptr(self.dz2), ptr(dout), dout.shape[-1],
                   n_extra, off_extra, rows, ptr(gpart), n_split, ptr(skip), stream())
         return gpart
@@ -403,3 +452,11 @@ def tc_gemm256(a_hi, a_lo, b_hi, b_lo, rows, out, passes=3, epilogue=2, act=0, b
     _count_flops('tb_tc_gemm256', 2.0 * rows * 256 * 256)
     _lib.call('tb_tc_gemm256', ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), rows, passes, epilogue,
               act, ptr(bias), ptr(aux_hi), ptr(aux_lo), ptr(out), ptr(out_lo), ptr(skip), stream())
+
+
+def tc_wgrad256(dz_hi, dz_lo, h_hi, h_lo, rows, gpart, n_split, n_params, off_w2, passes=3,
+                skip=None):
+    """gpart[s, off_w2 + n*256 + k] = sum_m dz[m, n] h[m, k] over the rows of split s."""
+    _count_flops('tb_tc_wgrad256', 2.0 * rows * 256 * 256)
+    _lib.call('tb_tc_wgrad256', ptr(dz_hi), ptr(dz_lo), ptr(h_hi), ptr(h_lo), rows, passes,
+              ptr(gpart), n_split, n_params, off_w2, ptr(skip), stream())

@@ -66,9 +66,10 @@ class BoundNetwork:
         self.mlp.packed.copy_(other.mlp.packed)
 
     def soft_update_from(self, other, tau):
-        # packed = a permutation of params, so the elementwise update keeps them in sync
         kernels.soft_update(self.mlp.params, other.mlp.params, tau)
-        kernels.soft_update(self.mlp.packed, other.mlp.packed, tau)
+        # transposes / tf32 splits are rebuilt from the updated parameters (a blend of
+        # two tf32-exact numbers is not tf32-exact, so the splits cannot be blended)
+        self.mlp.pack()
 
 
 def scratch(rows, cols, like):

@@ -51,7 +51,7 @@ class _GaussianPolicyUpdater:
         size of the whole minibatch (the mean's denominator)."""
         actor, net = self.actor, self.actor.network
         A = actor.action_size
-        n_split = splits_for(rows)
+        n_split = net.mlp.splits_for(rows)
         gpart = None
         if rows > 0:
             pre, dout = self._scratch(rows)
@@ -143,7 +143,7 @@ class _CriticGradientUpdater:
 
     def _finish(self, rows, stats, rows_global=None):
         net = self.actor.network
-        n_split = splits_for(rows)
+        n_split = net.mlp.splits_for(rows)
         gpart = None
         if rows > 0:
             net.mlp.backward(self._dout, rows)

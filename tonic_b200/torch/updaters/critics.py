@@ -36,7 +36,7 @@ class VRegression:
 
     def launch(self, observations, returns, idx, rows, stats, rows_global=None):
         critic, net = self.critic, self.critic.network
-        n_split = splits_for(rows)
+        n_split = net.mlp.splits_for(rows)
         gpart = None
         if rows > 0:
             values, dout = self._scratch(rows)
@@ -140,7 +140,7 @@ class _QLearning:
                          self.entropy_coeff, rows, self._targets)
         for k, critic in enumerate(self.critics):               # critics.py:77-84,169-179
             net = critic.network
-            n_split = splits_for(rows)
+            n_split = net.mlp.splits_for(rows)
             critic.values(obs, acts, out=self._values[k][:rows], idx=idx, rows=rows, save=True)
             kernels.mse_loss(self._values[k], self._targets, None, rows, self._dout, stats,
                              stat_slot=_lib.STAT_VALUE if k == 0 else _lib.STAT_VALUE2,
