@@ -28,6 +28,8 @@
 // PASSES = 1 is plain TF32 (fast mode).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tb {
@@ -310,21 +312,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // b_major bits of the instruction descriptor.  CTA (tile, split): output rows
 // n in [128 tile, 128 tile + 128), all 256 columns k, rows m of split `split`; the fp32
 // partial sum goes to gpart[split] (reduced by the Adam kernel in a fixed order).
-// Shared-memory operand layout = what TMA writes for a box of 32 floats x 32 rows with the
-// 128-byte swizzle: [32 m-rows][128 B]; one MMA (K = 8) consumes an 8-row group (1024 B);
-// 32-column groups along M / N are LBO = 4096 B apart.
+// For MN-major tf32 operands the only shared-memory layout the tensor core accepts is the
+// 128-byte swizzle with a 32-byte atom (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B,
+// Swizzle<2,5,2>; bring-up on B200: with the plain 128B swizzle and a_major / b_major set the
+// MMA silently returns zeros).  TMA writes exactly that layout with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B for a box of 32 floats x 32 rows: [32 m-rows][128 B],
+// 32-byte chunks XOR-ed with (row % 4).  Swizzle atoms are 4 rows (512 B) apart along K (SBO),
+// one MMA (K = 8) consumes two of them (1024 B), 32-column groups along M / N are LBO = 4096 B
+// apart.
 // =====================================================================================
 constexpr int TCW_ROWS = 32;                                   // m rows per pipeline chunk
 constexpr int TCW_A_BYTES = TC_BM * TCW_ROWS * 4;               // 16 KB (4 boxes of 4 KB)
 constexpr int TCW_B_BYTES = TC_BN * TCW_ROWS * 4;               // 32 KB (8 boxes of 4 KB)
 
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(const void* smem) {
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(const void* smem, int lbo = 4096,
+                                                            int sbo = 512, int layout = 1) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF);
-    d |= (uint64_t)(4096 >> 4) << 16;       // LBO: next 32-element group along M / N
-    d |= (uint64_t)(1024 >> 4) << 32;       // SBO: next 8-row group along K
+    d |= (uint64_t)(lbo >> 4) << 16;        // LBO: next 32-element group along M / N
+    d |= (uint64_t)(sbo >> 4) << 32;        // SBO: next 4-row swizzle atom along K
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    d |= (uint64_t)layout << 61;            // 1 = SWIZZLE_128B_BASE32B
     return d;
 }
 constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);   // A and B MN-major
@@ -336,6 +344,7 @@ struct TcWgradParams {
     int n_params;
     int off_w2;                 // offset of W2 [256, 256] in the flat layout
     const int32_t* skip;
+    int dbg_lbo, dbg_sbo, dbg_kstep, dbg_idesc_xor;   // bring-up knobs (0 = defaults)
 };
 
 template <int PASSES>
@@ -412,13 +421,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
                 unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                const uint64_t a_hi = umma_desc_mnmajor_sw128(st);
-                const uint64_t a_lo = umma_desc_mnmajor_sw128(st + TCW_A_BYTES);
-                const uint64_t b_hi = umma_desc_mnmajor_sw128(st + Cfg::PARTS * TCW_A_BYTES);
-                const uint64_t b_lo = umma_desc_mnmajor_sw128(st + 2 * TCW_A_BYTES + TCW_B_BYTES);
+                const int lbo = p.dbg_lbo ? p.dbg_lbo : 4096, sbo = p.dbg_sbo ? p.dbg_sbo : 512;
+                const int kstep = p.dbg_kstep ? p.dbg_kstep : 1024;
+                const uint32_t kIdescTf32MN = tb::kIdescTf32MN ^ (uint32_t)p.dbg_idesc_xor;
+                const uint64_t a_hi = umma_desc_mnmajor_sw128(st, lbo, sbo);
+                const uint64_t a_lo = umma_desc_mnmajor_sw128(st + TCW_A_BYTES, lbo, sbo);
+                const uint64_t b_hi = umma_desc_mnmajor_sw128(st + Cfg::PARTS * TCW_A_BYTES, lbo, sbo);
+                const uint64_t b_lo = umma_desc_mnmajor_sw128(st + 2 * TCW_A_BYTES + TCW_B_BYTES, lbo, sbo);
 #pragma unroll
                 for (int k = 0; k < TCW_ROWS / 8; ++k) {
-                    const uint64_t koff = (uint64_t)(k * 1024 >> 4);      // next 8-row group
+                    const uint64_t koff = (uint64_t)(k * kstep >> 4);     // next 8-row group
                     if (PASSES == 3) {
                         tcgen05_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
                         tcgen05_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, kIdescTf32MN, 1);
@@ -498,7 +510,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D row-major float matrix [rows, 256]; box = [box_rows, 32 floats]; 128-byte swizzle.
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int box_rows,
+                    CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     TB_REQUIRE(fn, TB_ENOTSUP, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
@@ -506,7 +519,7 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int box_r
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     TB_REQUIRE(r == CUDA_SUCCESS, TB_EINVAL, "cuTensorMapEncodeTiled failed with %d", (int)r);
     return 0;
@@ -583,14 +596,17 @@ extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const 
                "tb_tc_wgrad256: passes must be 1, or 3 with the lo parts");
     CUtensorMap maps[4];
     int rc;
-    if ((rc = make_map(&maps[0], d_dz_hi, n_rows, TCW_ROWS))) return rc;
-    if ((rc = make_map(&maps[1], d_dz_lo ? d_dz_lo : d_dz_hi, n_rows, TCW_ROWS))) return rc;
-    if ((rc = make_map(&maps[2], d_h_hi, n_rows, TCW_ROWS))) return rc;
-    if ((rc = make_map(&maps[3], d_h_lo ? d_h_lo : d_h_hi, n_rows, TCW_ROWS))) return rc;
+    if ((rc = make_map(&maps[0], d_dz_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[1], d_dz_lo ? d_dz_lo : d_dz_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[2], d_h_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[3], d_h_lo ? d_h_lo : d_h_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     TcWgradParams p;
     p.n_rows = n_rows;
     p.rows_per_split = ((n_rows + n_split - 1) / n_split + TCW_ROWS - 1) / TCW_ROWS * TCW_ROWS;
     p.gpart = d_gpart; p.n_params = n_params; p.off_w2 = off_w2; p.skip = d_skip;
+    auto knob = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
+    p.dbg_lbo = knob("TB_TCW_LBO"); p.dbg_sbo = knob("TB_TCW_SBO"); p.dbg_kstep = knob("TB_TCW_KSTEP");
+    p.dbg_idesc_xor = knob("TB_TCW_IDESC_XOR");
     dim3 grid(TC_BN / TC_BM, n_split);
     cudaStream_t s = as_stream(stream);
     if (passes == 3) {
