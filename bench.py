@@ -173,12 +173,15 @@ def run_ours(args):
                                   gpu_launches=launches, quick=True)))
         return
     # ---- instrumented pass: CUDA events around every launch (same workload) ----------
+    # (graphs off: the per-launch events are recorded by the C entry points)
+    config.graphs = False
     kernels.flops.clear()
     kernels.profile_begin()
     t0 = time.time()
     for _ in range(args.steps):
         iteration()
     prof = kernels.profile_end()
+    config.graphs = True
     prof_wall_ms = (time.time() - t0) * 1e3
     total_kernel_ms = sum(ms for _, ms in prof.values())
     top = max(prof, key=lambda k: prof[k][1])
@@ -193,7 +196,7 @@ def run_ours(args):
         avg_launch_us=round(top_ms / top_count * 1e3, 2),
         share_of_kernel_time=round(top_ms / total_kernel_ms, 4),
         flops_per_launch=top_flops / max(top_count, 1),
-        note='fp32 FFMA path (parity mode); peak is the tensor-pipe figure',
+        note='hidden-layer GEMMs: ' + ('FP32 FFMA' if config.gemm == 'ffma' else 'tcgen05 kind::tf32, ' + ('3xTF32 split (fp32-grade), achieved counts fp32-equivalent FLOPs (1 of the 3 MMA passes)' if config.gemm == 'tf32x3' else 'single pass')) + '; peak is the measured bf16 tensor-pipe figure',
         kernels={k: dict(launches=c, ms=round(ms, 3),
                          tflops=round(kernels.flops.get(k, 0.0) / (ms / 1e3) / 1e12, 3) if ms else 0)
                  for k, (c, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])})
@@ -246,7 +249,7 @@ def run_ours(args):
                     hidden=HIDDEN, parallelism=f'dp{world} (envs sharded, grad all-reduce)',
                     l2='working set per iteration (segment 92 MB + activations 69 MB/minibatch) '
                        'exceeds the 126 MB L2; no explicit flush',
-                    noise='device Philox', indices=('device Feistel permutation' if args.indices == 'device'
+                    gemm=config.gemm, cuda_graphs=bool(config.graphs), noise='device Philox', indices=('device Feistel permutation' if args.indices == 'device'
                                                           else 'host MT19937 (numpy-compatible)')),
         clocks=sampler.summary(), gpu_launches=launches,
         minibatch_updates=dict(

@@ -192,12 +192,15 @@ int tb_split_tf32(const float* d_x, float* d_hi, float* d_lo, int64_t n, void* s
  * tf32 splits (hi [+ lo]); passes = 3: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (fp32
  * grade), passes = 1: plain TF32.  epilogue 0: act(. + bias) (forward layer 2,
  * B = W2); 1: . * act'(aux_hi + aux_lo) (backward dz1, B = W2^T); 2: none.
- * d_out_lo != NULL: the result is written as a tf32 split (d_out = hi).          */
+ * d_out_lo != NULL: the result is written as a tf32 split (d_out = hi).
+ * n_head in [1, 8] (epilogue 0 only): additionally d_head_out[row, o] = d_head_b[o] +
+ * out[row, :] . d_head_w[o, :], the linear head fused into the epilogue.          */
 int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const float* d_b_hi,
                   const float* d_b_lo, int64_t n_rows, int32_t passes, int32_t epilogue,
                   int32_t act, const float* d_bias, const float* d_aux_hi,
                   const float* d_aux_lo, float* d_out, float* d_out_lo,
-                  const int32_t* d_skip, void* stream);
+                  const float* d_head_w, const float* d_head_b, float* d_head_out,
+                  int32_t n_head, const int32_t* d_skip, void* stream);
 
 /* The MLP entry points above with the two hidden-layer GEMMs (and the W2 weight
  * gradient) on the tensor cores: layer 1, the head, the head gradient and the
@@ -292,11 +295,12 @@ enum {
  * pre-activations; loc = tanh(pre); scale = clamp(softplus(log_scale) + 1e-8,
  * 1e-4, 1).  Noise: d_eps [n, A] host-generated standard normals (parity mode:
  * action = loc + eps * scale, separately rounded like torch) or NULL to draw
- * Philox normals from (seed, counter).                                        */
+ * Philox normals from (seed, counter [+ *d_counter, a device-resident stream
+ * position advanced with tb_counter_add so the call can live in a CUDA graph]).  */
 int tb_gauss_sample(const float* d_loc_pre, const float* d_log_scale,
                     const float* d_eps, uint64_t seed, uint64_t counter,
-                    int64_t n_rows, int32_t act_dim, float* d_actions,
-                    float* d_log_probs, void* stream);
+                    const uint64_t* d_counter, int64_t n_rows, int32_t act_dim,
+                    float* d_actions, float* d_log_probs, void* stream);
 
 /* ClippedRatio (updaters/actors.py:70-112) when ratio_clip > 0, else
  * StochasticPolicyGradient (updaters/actors.py:21-50).  Inputs are gathered
@@ -380,7 +384,10 @@ int tb_array_stats(const float* d_x, int64_t n, double* d_acc, void* stream);
 /* Device-side pseudo-random permutation of [0, n) (Feistel bijection with cycle
  * walking), the fast-mode replacement of the host `RandomState.shuffle` of
  * replays/segments.py:62 (not numpy's stream; uniform minibatch coverage).     */
-int tb_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* d_out, void* stream);
+int tb_permutation(uint64_t seed, uint64_t stream_id, const uint64_t* d_counter, int64_t n,
+                   int64_t* d_out, void* stream);
+/* *d_counter += delta (device-resident RNG stream positions).                  */
+int tb_counter_add(uint64_t* d_counter, uint64_t delta, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Host-side numpy-compatible MT19937 streams (legacy numpy.random.RandomState)*/

@@ -89,3 +89,30 @@ def test_off_policy_scenario_matches_reference(golden, name):
     np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=2e-5)
     check_infos(rec, g)
     check_weights(agent, g)
+
+
+def test_cuda_graph_sections_match_eager():
+    """Fast mode (device noise + device permutations): replaying the captured rollout /
+    update graphs gives the same weights as issuing the kernels one by one."""
+    import torch
+    from tonic_b200 import config
+    cfg = dict(scenarios.SCENARIOS['ppo_wide'], workers=64,
+               segment=dict(size=8, batch_iterations=2, batch_size=128))
+    results = []
+    old = config.noise, config.indices, config.graphs
+    try:
+        for use_graphs in (False, True):
+            config.noise, config.indices, config.graphs = 'device', 'device', use_graphs
+            agent, env = product.build(cfg)
+            env.start()
+            for _ in range(5):          # 2 eager warm-ups, capture, 2 replays
+                assert agent.rollout(env, cfg['segment']['size']) == cfg['segment']['size']
+            torch.cuda.synchronize()
+            results.append(torch.cat([n.params for n in agent.model.networks()]).cpu())
+            if use_graphs:
+                assert agent._update_graph.graph is not None
+                assert agent._rollout_graph.graph is not None
+    finally:
+        config.noise, config.indices, config.graphs = old
+    # same kernels, same device-resident RNG streams -> bit-identical parameters
+    assert torch.equal(results[0], results[1])

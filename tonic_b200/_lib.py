@@ -72,7 +72,7 @@ _PROTOTYPES = {
     'tb_reduce_partials': (c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'tb_mlp_pack': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp]),
     'tb_soft_update': (c_int, [c_vp, c_vp, c_i64, c_d, c_vp]),
-    'tb_gauss_sample': (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    'tb_gauss_sample': (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     'tb_gauss_policy_loss': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f, c_f,
                                      c_vp, c_vp, c_vp, c_vp]),
     'tb_mse_loss': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp]),
@@ -84,7 +84,7 @@ _PROTOTYPES = {
     'tb_sac_head_grad': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_i64, c_i32, c_vp, c_vp]),
     'tb_split_tf32': (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'tb_tc_gemm256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
-                              c_vp, c_vp, c_vp, c_vp]),
+                              c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_mlp_forward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_mlp_backward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64,
@@ -92,7 +92,8 @@ _PROTOTYPES = {
     'tb_mlp_wgrad_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                 c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp]),
     'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    'tb_permutation': (c_int, [c_u64, c_u64, c_i64, c_vp, c_vp]),
+    'tb_permutation': (c_int, [c_u64, c_u64, c_vp, c_i64, c_vp, c_vp]),
+    'tb_counter_add': (c_int, [c_vp, c_u64, c_vp]),
     'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'tb_profile_begin': (c_int, []),
     'tb_profile_end': (c_int, [ctypes.c_char_p, c_i32]),

@@ -20,6 +20,9 @@ gemm    'tf32x3' : the 256-wide hidden-layer GEMMs (forward layer 2, backward dz
         'tf32'   : single-pass TF32 on the tensor cores (fast mode, ~1e-3 relative).
         'ffma'   : everything on the FP32 FFMA kernels (csrc/mlp.cu).
                    Environment override: TONIC_B200_GEMM.
+graphs  True     : sections with static shapes (PPO / A2C rollout of a whole segment and
+                   the update, when noise == indices == 'device' in a single process)
+                   are captured into CUDA graphs and replayed (tonic_b200/graphs.py).
 wgrad_splits     : number of row splits of the weight-gradient kernel.
 """
 
@@ -28,5 +31,6 @@ import os
 noise = 'host'
 gemm = os.environ.get('TONIC_B200_GEMM', 'tf32x3')
 indices = 'host'
+graphs = os.environ.get('TONIC_B200_GRAPHS', '1') != '0'
 wgrad_splits = 37      # FFMA: 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
 wgrad_splits_tc = 74   # tensor cores: 2 row tiles x 74 splits = 148 CTAs

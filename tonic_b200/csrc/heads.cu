@@ -33,8 +33,9 @@ __device__ __forceinline__ float detached_scale(float log_scale, float* dscale_d
 __global__ void __launch_bounds__(256)
 gauss_sample_kernel(const float* __restrict__ loc_pre, const float* __restrict__ log_scale,
                     const float* __restrict__ eps, uint64_t seed, uint64_t counter,
-                    int64_t n_rows, int A, float* __restrict__ actions,
-                    float* __restrict__ log_probs) {
+                    const uint64_t* __restrict__ d_counter, int64_t n_rows, int A,
+                    float* __restrict__ actions, float* __restrict__ log_probs) {
+    if (d_counter) counter += *d_counter;      // device-resident stream position (CUDA graphs)
     __shared__ float s_scale[kMaxAct];
     if ((int)threadIdx.x < A) s_scale[threadIdx.x] = detached_scale(log_scale[threadIdx.x], nullptr);
     __syncthreads();
@@ -171,14 +172,15 @@ mse_loss_kernel(const float* __restrict__ values, const float* __restrict__ targ
 
 extern "C" int tb_gauss_sample(const float* d_loc_pre, const float* d_log_scale,
                                const float* d_eps, uint64_t seed, uint64_t counter,
-                               int64_t n_rows, int32_t act_dim, float* d_actions,
-                               float* d_log_probs, void* stream) {
+                               const uint64_t* d_counter, int64_t n_rows, int32_t act_dim,
+                               float* d_actions, float* d_log_probs, void* stream) {
     tb::ProfScope prof_scope("tb_gauss_sample", stream);
     TB_REQUIRE(d_loc_pre && d_log_scale && d_actions && d_log_probs && n_rows > 0 &&
                act_dim >= 1 && act_dim <= tb::kMaxAct, TB_EINVAL, "tb_gauss_sample: bad arguments");
     const int blocks = (int)((n_rows + 255) / 256);
     tb::gauss_sample_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
-        d_loc_pre, d_log_scale, d_eps, seed, counter, n_rows, act_dim, d_actions, d_log_probs);
+        d_loc_pre, d_log_scale, d_eps, seed, counter, d_counter, n_rows, act_dim, d_actions,
+        d_log_probs);
     return tb::check_launch("tb_gauss_sample");
 }
 
@@ -263,10 +265,11 @@ extern "C" int tb_array_stats(const float* d_x, int64_t n, double* d_acc, void* 
 // host->device copy, O(1) state.
 namespace tb {
 __global__ void __launch_bounds__(256)
-permutation_kernel(uint64_t seed, uint64_t stream_id, int64_t n, int half_bits,
-                   int64_t* __restrict__ out) {
+permutation_kernel(uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ d_counter,
+                   int64_t n, int half_bits, int64_t* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (d_counter) stream_id += *d_counter;
     const uint32_t mask = (1u << half_bits) - 1u;
     uint32_t keys[4];
 #pragma unroll
@@ -288,14 +291,27 @@ permutation_kernel(uint64_t seed, uint64_t stream_id, int64_t n, int half_bits,
 }
 }  // namespace tb
 
-extern "C" int tb_permutation(uint64_t seed, uint64_t stream_id, int64_t n, int64_t* d_out,
-                              void* stream) {
+extern "C" int tb_permutation(uint64_t seed, uint64_t stream_id, const uint64_t* d_counter,
+                              int64_t n, int64_t* d_out, void* stream) {
     tb::ProfScope prof_scope("tb_permutation", stream);
     TB_REQUIRE(d_out && n > 0 && n < (1ll << 40), TB_EINVAL, "tb_permutation: bad arguments");
     int bits = 1;
     while ((1ll << bits) < n) ++bits;
     const int half = (bits + 1) / 2;
     tb::permutation_kernel<<<(int)((n + 255) / 256), 256, 0, tb::as_stream(stream)>>>(
-        seed, stream_id, n, half < 1 ? 1 : half, d_out);
+        seed, stream_id, d_counter, n, half < 1 ? 1 : half, d_out);
     return tb::check_launch("tb_permutation");
+}
+
+// Device-resident stream counters (Philox offsets, permutation ids): kernels captured in a
+// CUDA graph read their position from memory, this kernel advances it after they ran.
+namespace tb {
+__global__ void counter_add_kernel(uint64_t* counter, uint64_t delta) { *counter += delta; }
+}  // namespace tb
+
+extern "C" int tb_counter_add(uint64_t* d_counter, uint64_t delta, void* stream) {
+    tb::ProfScope prof_scope("tb_counter_add", stream);
+    TB_REQUIRE(d_counter, TB_EINVAL, "tb_counter_add: null pointer");
+    tb::counter_add_kernel<<<1, 1, 0, tb::as_stream(stream)>>>(d_counter, delta);
+    return tb::check_launch("tb_counter_add");
 }

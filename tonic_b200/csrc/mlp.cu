@@ -36,6 +36,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -409,8 +413,9 @@ template <int TN, int TK>
 __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t r1,
                                            float* __restrict__ gout, float* smem) {
     constexpr int MN = TN / 16, MK = TK / 16;
-    float* As = smem;                  // [2][WMC][TN]
-    float* Bsm = smem + 2 * WMC * TN;  // [2][WMC][TK]
+    float* As = smem;                        // [2][WMC][TN]
+    float* Bsm = As + 2 * WMC * TN;          // [2][WMC][TK]
+    float* Alo = Bsm + 2 * WMC * TK;         // [2][WMC][TN]  (only when job.A_lo)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     float acc[MN][MK];
 #pragma unroll
@@ -418,45 +423,35 @@ __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t 
 #pragma unroll
         for (int j = 0; j < MK; ++j) acc[i][j] = 0.0f;
 
-    const bool a_fast = TN == 128 && job.a_cols == 128 && (job.lda & 3) == 0 && (job.a_col0 & 3) == 0 &&
-                        job.A_lo == nullptr;
+    const bool has_lo = job.A_lo != nullptr;
+    const bool a_fast = TN == 128 && job.a_cols == 128 && (job.lda & 3) == 0 && (job.a_col0 & 3) == 0;
     const bool b_fast = TK == 128 && job.b_cols == 128 && (job.ldb & 3) == 0 && (job.b_col0 & 3) == 0;
 
+    // every element goes through cp.async (16-byte copies for aligned full-width operands,
+    // 4-byte copies for the narrow / unaligned ones), so the next chunk is always in flight
+    // while the current one is being multiplied
+    auto stage_operand = [&](float* dst, const float* __restrict__ src, int ld, int col0, int cols,
+                             bool fast, int64_t mbase, int width) {
+        if (fast) {
+            for (int v = tid; v < WMC * width / 4; v += NTHREADS) {
+                const int r = v / (width / 4), c4 = v % (width / 4);
+                float* d = dst + r * width + c4 * 4;
+                if (mbase + r < r1) cp_async16(d, src + (mbase + r) * ld + col0 + c4 * 4);
+                else *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int v = tid; v < WMC * width; v += NTHREADS) {
+                const int r = v / width, c = v % width;
+                if (mbase + r < r1 && c < cols) cp_async4(dst + v, src + (mbase + r) * ld + col0 + c);
+                else dst[v] = 0.0f;
+            }
+        }
+    };
     auto stage = [&](int buf, int64_t mbase) {
-        float* as = As + buf * WMC * TN;
-        float* bs = Bsm + buf * WMC * TK;
-        if (a_fast) {
-            for (int v = tid; v < WMC * TN / 4; v += NTHREADS) {
-                const int r = v / (TN / 4), c4 = v % (TN / 4);
-                float* dst = as + r * TN + c4 * 4;
-                if (mbase + r < r1) cp_async16(dst, job.A + (mbase + r) * job.lda + job.a_col0 + c4 * 4);
-                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else {
-            for (int v = tid; v < WMC * TN; v += NTHREADS) {
-                const int r = v / TN, c = v % TN;
-                float av = 0.0f;
-                if (mbase + r < r1 && c < job.a_cols) {
-                    av = __ldg(job.A + (mbase + r) * job.lda + job.a_col0 + c);
-                    if (job.A_lo) av += __ldg(job.A_lo + (mbase + r) * job.lda + job.a_col0 + c);
-                }
-                as[v] = av;
-            }
-        }
-        if (b_fast) {
-            for (int v = tid; v < WMC * TK / 4; v += NTHREADS) {
-                const int r = v / (TK / 4), c4 = v % (TK / 4);
-                float* dst = bs + r * TK + c4 * 4;
-                if (mbase + r < r1) cp_async16(dst, job.B + (mbase + r) * job.ldb + job.b_col0 + c4 * 4);
-                else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else {
-            for (int v = tid; v < WMC * TK; v += NTHREADS) {
-                const int r = v / TK, c = v % TK;
-                bs[v] = (mbase + r < r1 && c < job.b_cols)
-                            ? __ldg(job.B + (mbase + r) * job.ldb + job.b_col0 + c) : 0.0f;
-            }
-        }
+        stage_operand(As + buf * WMC * TN, job.A, job.lda, job.a_col0, job.a_cols, a_fast, mbase, TN);
+        if (has_lo)
+            stage_operand(Alo + buf * WMC * TN, job.A_lo, job.lda, job.a_col0, job.a_cols, a_fast, mbase, TN);
+        stage_operand(Bsm + buf * WMC * TK, job.B, job.ldb, job.b_col0, job.b_cols, b_fast, mbase, TK);
     };
 
     const int nchunks = (int)((r1 - r0 + WMC - 1) / WMC);
@@ -474,17 +469,24 @@ __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t 
         }
         __syncthreads();
         const float* as = As + (c & 1) * WMC * TN;
+        const float* al = Alo + (c & 1) * WMC * TN;
         const float* bs = Bsm + (c & 1) * WMC * TK;
 #pragma unroll 4
         for (int r = 0; r < WMC; ++r) {
             float a[MN], b[MK];
             if constexpr (MN == 8) {
-                const float4 v0 = *reinterpret_cast<const float4*>(as + r * TN + ty * 4);
-                const float4 v1 = *reinterpret_cast<const float4*>(as + r * TN + 64 + ty * 4);
+                float4 v0 = *reinterpret_cast<const float4*>(as + r * TN + ty * 4);
+                float4 v1 = *reinterpret_cast<const float4*>(as + r * TN + 64 + ty * 4);
+                if (has_lo) {
+                    const float4 l0 = *reinterpret_cast<const float4*>(al + r * TN + ty * 4);
+                    const float4 l1 = *reinterpret_cast<const float4*>(al + r * TN + 64 + ty * 4);
+                    v0.x += l0.x; v0.y += l0.y; v0.z += l0.z; v0.w += l0.w;
+                    v1.x += l1.x; v1.y += l1.y; v1.z += l1.z; v1.w += l1.w;
+                }
                 a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w;
                 a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
             } else {
-                a[0] = as[r * TN + ty];
+                a[0] = as[r * TN + ty] + (has_lo ? al[r * TN + ty] : 0.0f);
             }
             if constexpr (MK == 8) {
                 const float4 v0 = *reinterpret_cast<const float4*>(bs + r * TK + tx * 4);
@@ -685,7 +687,12 @@ static int launch_wgrad_jobs(const TbMlpShape* shape, const float* d_xin, const 
 
     int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
     rows_per_split = (rows_per_split + WMC - 1) / WMC * WMC;
-    const size_t smem = (size_t)2 * WMC * (128 + 128) * sizeof(float);
+    const size_t smem = (size_t)2 * WMC * (128 + 128 + 128) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
     dim3 grid(n_split, t.n_jobs);
     mlp_wgrad_kernel<<<grid, NTHREADS, smem, as_stream(stream)>>>(
         t, n_rows, rows_per_split, d_gpart, shape->n_params, d_skip);
@@ -917,10 +924,13 @@ extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
         }
         if ((rc = check_launch("tb_mlp_forward_tc/layer1"))) return rc;
     }
+    const bool fused_head = shape->n_out <= 8;
     rc = tb_tc_gemm256(d_h1_hi, d_h1_lo, d_packed + shape->off_w2_hi, d_packed + shape->off_w2_lo, n_rows,
                        passes, 0, shape->act, d_params + shape->off_b2, nullptr, nullptr, d_h2, nullptr,
-                       d_skip, stream);
-    if (rc) return rc;
+                       fused_head ? d_params + shape->off_w3 : nullptr,
+                       fused_head ? d_params + shape->off_b3 : nullptr, fused_head ? d_out : nullptr,
+                       fused_head ? shape->n_out : 0, d_skip, stream);
+    if (rc || fused_head) return rc;
     {
         ProfScope prof_scope("tb_mlp_head", stream);
         set_smem(mlp_head_kernel<256>, smem);
@@ -962,8 +972,8 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
         if ((rc = check_launch("tb_mlp_backward_tc/head"))) return rc;
     }
     rc = tb_tc_gemm256(d_dz2_hi, d_dz2_lo, d_packed + shape->off_w2t_hi, d_packed + shape->off_w2t_lo,
-                       n_rows, passes, 1, shape->act, nullptr, d_h1_hi, d_h1_lo, d_dz1, nullptr, d_skip,
-                       stream);
+                       n_rows, passes, 1, shape->act, nullptr, d_h1_hi, d_h1_lo, d_dz1, nullptr, nullptr,
+                       nullptr, nullptr, 0, d_skip, stream);
     if (rc || !d_dx) return rc;
     {
         ProfScope prof_scope("tb_mlp_dx", stream);

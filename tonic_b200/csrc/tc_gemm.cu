@@ -148,7 +148,13 @@ struct TcParams {
     float* out_lo;              // optional: also write the tf32 split of the result (out = hi)
     int act;
     const int32_t* skip;
+    // optional fused linear head (EPI_BIAS_ACT): head_out[row, o] = head_b[o] + out[row, :] . head_w[o, :]
+    const float* head_w;        // [n_head, 256]
+    const float* head_b;        // [n_head]
+    float* head_out;            // [n_rows, n_head]
+    int n_head;                 // 0 = no fused head, <= TC_MAX_HEAD
 };
+constexpr int TC_MAX_HEAD = 8;
 
 template <int PASSES, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -255,11 +261,48 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             tcgen05_fence_after();
             const int64_t row0 = (int64_t)tile * TC_BM + w * 32;
+            float hacc[TC_MAX_HEAD];
+#pragma unroll
+            for (int o = 0; o < TC_MAX_HEAD; ++o) hacc[o] = 0.0f;
 #pragma unroll 1
             for (int c = 0; c < TC_BN / 32; ++c) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(acc * TC_BN + c * 32);
                 tcgen05_ld_32x32(taddr, v);
+                if (EPI == TC_EPI_BIAS_ACT) {
+                    // this thread holds columns c*32 .. c*32+31 of ITS row: bias + activation
+                    // in registers, then the row's contribution to the fused linear head
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(b4 + j / 4);
+                        float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
+                        float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
+                        if (p.act == TB_ACT_TANH) {
+                            x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3);
+                        } else {
+                            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+                        }
+                        v[j] = __float_as_uint(x0); v[j + 1] = __float_as_uint(x1);
+                        v[j + 2] = __float_as_uint(x2); v[j + 3] = __float_as_uint(x3);
+                    }
+#pragma unroll
+                    for (int o = 0; o < TC_MAX_HEAD; ++o) {
+                        if (o < p.n_head) {
+                            const float4* w4 = reinterpret_cast<const float4*>(p.head_w + o * TC_BN + c * 32);
+                            float s = hacc[o];
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 wv = __ldg(w4 + j / 4);
+                                s = fmaf(__uint_as_float(v[j]), wv.x, s);
+                                s = fmaf(__uint_as_float(v[j + 1]), wv.y, s);
+                                s = fmaf(__uint_as_float(v[j + 2]), wv.z, s);
+                                s = fmaf(__uint_as_float(v[j + 3]), wv.w, s);
+                            }
+                            hacc[o] = s;
+                        }
+                    }
+                }
                 float* mine = stg + lane * TC_STAGE_ROWSTRIDE;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -268,16 +311,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 __syncwarp();
                 const int col = c * 32 + lane;
-                const float bias = EPI == TC_EPI_BIAS_ACT ? __ldg(p.bias + col) : 0.0f;
 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
                     const int64_t row = row0 + r;
                     if (row >= p.n_rows) break;
                     float x = stg[r * TC_STAGE_ROWSTRIDE + lane];
-                    if (EPI == TC_EPI_BIAS_ACT) {
-                        x += bias;
-                        x = p.act == TB_ACT_TANH ? tanhf(x) : fmaxf(x, 0.0f);
-                    } else if (EPI == TC_EPI_ACT_GRAD) {
+                    if (EPI == TC_EPI_ACT_GRAD) {
                         const float h = __ldg(p.aux_hi + row * TC_BN + col) + __ldg(p.aux_lo + row * TC_BN + col);
                         x *= p.act == TB_ACT_TANH ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f);
                     }
@@ -290,6 +329,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                 }
                 __syncwarp();
+            }
+            if (EPI == TC_EPI_BIAS_ACT && p.n_head > 0 && row0 + lane < p.n_rows) {
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o)
+                    if (o < p.n_head) p.head_out[(row0 + lane) * p.n_head + o] = hacc[o] + __ldg(p.head_b + o);
             }
             tcgen05_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -555,9 +599,12 @@ extern "C" int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const flo
                              const float* d_b_lo, int64_t n_rows, int32_t passes, int32_t epilogue,
                              int32_t act, const float* d_bias, const float* d_aux_hi,
                              const float* d_aux_lo, float* d_out, float* d_out_lo,
-                             const int32_t* d_skip, void* stream) {
+                             const float* d_head_w, const float* d_head_b, float* d_head_out,
+                             int32_t n_head, const int32_t* d_skip, void* stream) {
     using namespace tb;
-    ProfScope prof_scope("tb_tc_gemm256", stream);
+    TB_REQUIRE(n_head == 0 || (epilogue == TC_EPI_BIAS_ACT && n_head <= TC_MAX_HEAD && d_head_w &&
+                               d_head_b && d_head_out), TB_EINVAL,
+               "tb_tc_gemm256: the fused head needs epilogue 0, n_head <= 8 and its pointers");
     TB_REQUIRE(d_a_hi && d_b_hi && d_out && n_rows > 0, TB_EINVAL, "tb_tc_gemm256: null pointer");
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_gemm256: passes must be 1 or 3");
     TB_REQUIRE(passes == 1 || (d_a_lo && d_b_lo), TB_EINVAL, "tb_tc_gemm256: 3 passes need the lo parts");
@@ -573,7 +620,9 @@ extern "C" int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const flo
     TcParams p;
     p.n_rows = n_rows; p.out = d_out; p.bias = d_bias; p.aux_hi = d_aux_hi; p.aux_lo = d_aux_lo;
     p.out_lo = d_out_lo; p.act = act; p.skip = d_skip;
+    p.head_w = d_head_w; p.head_b = d_head_b; p.head_out = d_head_out; p.n_head = n_head;
     cudaStream_t s = as_stream(stream);
+    ProfScope prof_scope("tb_tc_gemm256", stream);      // after the host-side tensor-map encoding
 #define TB_TC(P_, E_) launch_tc<P_, E_>(maps, p, s)
     if (passes == 3) {
         if (epilogue == 0) TB_TC(3, 0); else if (epilogue == 1) TB_TC(3, 1); else TB_TC(3, 2);
@@ -589,7 +638,6 @@ extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const 
                               int32_t n_split, int32_t n_params, int32_t off_w2,
                               const int32_t* d_skip, void* stream) {
     using namespace tb;
-    ProfScope prof_scope("tb_tc_wgrad256", stream);
     TB_REQUIRE(d_dz_hi && d_h_hi && d_gpart && n_rows > 0 && n_split >= 1, TB_EINVAL,
                "tb_tc_wgrad256: bad arguments");
     TB_REQUIRE(passes == 1 || (passes == 3 && d_dz_lo && d_h_lo), TB_EINVAL,
@@ -609,6 +657,7 @@ extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const 
     p.dbg_idesc_xor = knob("TB_TCW_IDESC_XOR");
     dim3 grid(TC_BN / TC_BM, n_split);
     cudaStream_t s = as_stream(stream);
+    ProfScope prof_scope("tb_tc_wgrad256", stream);
     if (passes == 3) {
         static bool configured = false;
         if (!configured) {

@@ -299,10 +299,19 @@ def soft_update(target, online, tau):
 # heads / losses
 # ---------------------------------------------------------------------------
 
-def gauss_sample(loc_pre, log_scale, actions, log_probs, eps=None, seed=0, counter=0):
+def gauss_sample(loc_pre, log_scale, actions, log_probs, eps=None, seed=0, counter=0,
+                 device_counter=None):
     rows, act = loc_pre.shape
-    _lib.call('tb_gauss_sample', ptr(loc_pre), ptr(log_scale), ptr(eps), seed, counter, rows,
-              act, ptr(actions), ptr(log_probs), stream())
+    _lib.call('tb_gauss_sample', ptr(loc_pre), ptr(log_scale), ptr(eps), seed, counter,
+              ptr(device_counter), rows, act, ptr(actions), ptr(log_probs), stream())
+
+
+def counter_add(counter, delta):
+    _lib.call('tb_counter_add', ptr(counter), int(delta), stream())
+
+
+def new_counter():
+    return torch.zeros(1, dtype=torch.int64, device=device())
 
 
 def gauss_policy_loss(loc_pre, log_scale, actions, advantages, old_log_probs, idx, rows, dout,
@@ -433,9 +442,10 @@ def sac_head_grad(pre, eps, actions, dqda1, dqda2, entropy_coeff, dout):
               entropy_coeff, rows, act, ptr(dout), stream())
 
 
-def permutation(seed, stream_id, out):
+def permutation(seed, stream_id, out, device_counter=None):
     """out[i] = pseudo-random bijection of [0, len(out)) (device fast-mode indices)."""
-    _lib.call('tb_permutation', seed, stream_id, out.numel(), ptr(out), stream())
+    _lib.call('tb_permutation', seed, stream_id, ptr(device_counter), out.numel(), ptr(out),
+              stream())
 
 
 # ---------------------------------------------------------------------------
@@ -447,11 +457,14 @@ def split_tf32(x, hi, lo):
 
 
 def tc_gemm256(a_hi, a_lo, b_hi, b_lo, rows, out, passes=3, epilogue=2, act=0, bias=None,
-               aux_hi=None, aux_lo=None, out_lo=None, skip=None):
+               aux_hi=None, aux_lo=None, out_lo=None, head_w=None, head_b=None, head_out=None,
+               skip=None):
     """out[rows, 256] = epilogue(A . B^T) on the tensor cores (see tb_tc_gemm256)."""
     _count_flops('tb_tc_gemm256', 2.0 * rows * 256 * 256)
     _lib.call('tb_tc_gemm256', ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), rows, passes, epilogue,
-              act, ptr(bias), ptr(aux_hi), ptr(aux_lo), ptr(out), ptr(out_lo), ptr(skip), stream())
+              act, ptr(bias), ptr(aux_hi), ptr(aux_lo), ptr(out), ptr(out_lo), ptr(head_w),
+              ptr(head_b), ptr(head_out), 0 if head_w is None else head_w.shape[0], ptr(skip),
+              stream())
 
 
 def tc_wgrad256(dz_hi, dz_lo, h_hi, h_lo, rows, gpart, n_split, n_params, off_w2, passes=3,

@@ -154,11 +154,11 @@ class Segment:
                 self._device_perm.shape != (E, local_total):
             self._device_perm = torch.empty(E, local_total, dtype=torch.int64,
                                             device=kernels.device())
-            self._perm_calls = 0
+            self._perm_counter = kernels.new_counter()      # permutations drawn so far
         seed = ((self.seed or 0) << 8) ^ rank
         for e in range(E):
-            kernels.permutation(seed, self._perm_calls, self._device_perm[e])
-            self._perm_calls += 1
+            kernels.permutation(seed, e, self._device_perm[e], device_counter=self._perm_counter)
+        kernels.counter_add(self._perm_counter, E)
         for e in range(E):
             for lo in range(0, local_total, local_batch):
                 rows = min(local_batch, local_total - lo)

@@ -9,7 +9,7 @@ the statistics at the end.
 import numpy as np
 import torch
 
-from ... import _lib, config, distributed, kernels, replays
+from ... import _lib, config, distributed, graphs, kernels, replays
 from ...utils import logger
 from .. import models, normalizers, updaters
 from . import agent
@@ -42,8 +42,10 @@ class A2C(agent.Agent):
         self.actor_updater.initialize(self.model)
         self.critic_updater.initialize(self.model)
         self.action_size = action_space.shape[0]
-        self._noise_counter = 0
+        self._noise_counter = None      # device-resident Philox stream position
         self._workers = 0
+        self._rollout_graph = self._update_graph = None
+        self._update_buffers = None
 
     # -- acting -----------------------------------------------------------------
     def _buffers(self, workers):
@@ -60,17 +62,20 @@ class A2C(agent.Agent):
         workers = observations.shape[0]
         self.model.actor.pre_activations(observations, out=self._pre[:workers])
         world, rank = distributed.world(), distributed.rank()
-        eps, counter = None, self._noise_counter + rank * workers
+        eps = None
+        if self._noise_counter is None:
+            self._noise_counter = kernels.new_counter()
         if config.noise == 'host':
             # same draw as torch.distributions.Normal.sample() from the global CPU
             # generator; with several ranks every rank draws the global block and
             # keeps its workers' rows (identical to the single-process stream)
             eps = torch.randn(workers * world, self.action_size)
             eps = eps[rank * workers:(rank + 1) * workers].to(observations.device)
-        else:
-            self._noise_counter += workers * world
         kernels.gauss_sample(self._pre[:workers], self.model.actor.network.extra('log_scale'),
-                             actions, log_probs, eps=eps, seed=self.seed or 0, counter=counter)
+                             actions, log_probs, eps=eps, seed=self.seed or 0,
+                             counter=rank * workers, device_counter=self._noise_counter)
+        if eps is None:     # same streams whatever the number of ranks
+            kernels.counter_add(self._noise_counter, workers * world)
 
     def step(self, observations, steps):
         host = not (isinstance(observations, torch.Tensor) and observations.is_cuda)
@@ -111,9 +116,8 @@ class A2C(agent.Agent):
         self._buffers(N)
         b, T = seg.buffers, seg.max_size
         normalizer = self.model.observation_normalizer
-        done = 0
-        while done < vector_steps and seg.index < T:
-            t = seg.index
+
+        def one_step(t):
             if t == 0:       # first acting observations come from the environment
                 b['observations'][0].copy_(env.observations)
             obs = b['observations'][t]
@@ -123,6 +127,18 @@ class A2C(agent.Agent):
             target = b['observations'][t + 1] if t + 1 < T else env.observations
             env.step_into(b['actions'][t], target, b['next_observations'][t], b['rewards'][t],
                           b['resets'][t], b['terminations'][t])
+
+        done = 0
+        if self._graphable() and seg.index == 0 and vector_steps >= T:
+            # whole segment in one CUDA graph (tonic_b200/graphs.py)
+            if self._rollout_graph is None:
+                self._rollout_graph = graphs.CapturedSection(
+                    lambda: [one_step(t) for t in range(T)])
+            self._rollout_graph()
+            seg.index = T
+            done = T
+        while done < vector_steps and seg.index < T:
+            one_step(seg.index)
             seg.advance()
             done += 1
         if action_stats is not None and done:
@@ -130,6 +146,10 @@ class A2C(agent.Agent):
         if seg.ready():
             self._update()
         return done
+
+    def _graphable(self):
+        return (config.graphs and config.noise == 'device' and config.indices == 'device'
+                and distributed.world() == 1)
 
     # -- learning ---------------------------------------------------------------
     def update(self, observations, rewards, resets, terminations, steps):
@@ -147,35 +167,66 @@ class A2C(agent.Agent):
         flat = self.replay.get_full('observations', 'next_observations')
         total = flat['observations'].shape[0]
         dev = flat['observations'].device
-        values = torch.empty(total, 1, dtype=torch.float32, device=dev)
-        next_values = torch.empty(total, 1, dtype=torch.float32, device=dev)
+        if getattr(self, '_value_buffers', None) is None or self._value_buffers[0].shape[0] != total:
+            self._value_buffers = (torch.empty(total, 1, dtype=torch.float32, device=dev),
+                                   torch.empty(total, 1, dtype=torch.float32, device=dev))
+        values, next_values = self._value_buffers
         self.model.critic.values(flat['observations'], out=values)
         self.model.critic.values(flat['next_observations'], out=next_values)
         self.replay.compute_returns(values, next_values)
 
-    def _stats(self, n):
-        return torch.zeros(n, 2, _lib.STAT_COUNT, dtype=torch.float64, device=kernels.device())
+    def _buffers_for_update(self, n_batches):
+        """Persistent device blocks (graph-safe): statistics [n, 2, TB_STAT_COUNT] and
+        the KL early-stop flag."""
+        if self._update_buffers is None or self._update_buffers[0].shape[0] != n_batches:
+            dev = kernels.device()
+            self._update_buffers = (
+                torch.zeros(n_batches, 2, _lib.STAT_COUNT, dtype=torch.float64, device=dev),
+                torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._update_buffers
 
-    def _update(self):
+    def _batch_count(self):
+        seg = self.replay
+        if seg.batch_size is None:
+            return seg.batch_iterations
+        total = seg.max_size * seg.num_workers * distributed.world()
+        return seg.batch_iterations * -(-total // seg.batch_size)
+
+    def _enqueue_update(self, stats, stop):
+        """All kernels of one update, no host synchronisation (CUDA-graph capturable)."""
+        stats.zero_()
         self._evaluate()
         flat = self.replay.get_full('observations', 'actions', 'advantages', 'log_probs',
                                     'returns')
         total = flat['observations'].shape[0]
-        batches = list(self.replay.index_batches())
-        stats = self._stats(len(batches) + 1)
         # one policy-gradient step on the full batch (a2c.py:107-114)
         self.actor_updater.launch(flat['observations'], flat['actions'], flat['advantages'],
                                   flat['log_probs'], None, total, stats[0, 0],
                                   rows_global=total * distributed.world())
         # several value-regression steps (a2c.py:116-121)
-        for j, (idx, rows, rows_global) in enumerate(batches):
+        for j, (idx, rows, rows_global) in enumerate(self.replay.index_batches()):
             self.critic_updater.launch(flat['observations'], flat['returns'], idx, rows,
                                        stats[j + 1, 1], rows_global=rows_global)
-        host = kernels.to_host(stats)
-        for k, v in self.actor_updater.infos(host[0, 0]).items():
-            logger.store('actor/' + k, v)
-        for j in range(len(batches)):
-            for k, v in self.critic_updater.infos(host[j + 1, 1]).items():
-                logger.store('critic/' + k, v)
         if self.model.observation_normalizer:
             self.model.observation_normalizer.update()
+
+    def _report(self, host):
+        for k, v in self.actor_updater.infos(host[0, 0]).items():
+            logger.store('actor/' + k, v)
+        for j in range(1, host.shape[0]):
+            for k, v in self.critic_updater.infos(host[j, 1]).items():
+                logger.store('critic/' + k, v)
+
+    extra_stat_rows = 1      # A2C: row 0 holds the single policy-gradient step
+
+    def _update(self):
+        stats, stop = self._buffers_for_update(self._batch_count() + self.extra_stat_rows)
+        if self._graphable():
+            if self._update_graph is None:
+                self._update_graph = graphs.CapturedSection(
+                    lambda: self._enqueue_update(stats, stop))
+            self._update_graph()
+            self.replay.index = 0
+        else:
+            self._enqueue_update(stats, stop)
+        self._report(kernels.to_host(stats))

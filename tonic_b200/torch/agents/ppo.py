@@ -22,22 +22,28 @@ class PPO(a2c.A2C):
         super().__init__(model=model, replay=replay, actor_updater=actor_updater,
                          critic_updater=critic_updater)
 
-    def _update(self):
+    extra_stat_rows = 0
+
+    def _enqueue_update(self, stats, stop):
+        """All kernels of one update, no host synchronisation (CUDA-graph capturable):
+        the KL decision of ppo.py:45-46 is taken by the Adam kernel on the device."""
+        stats.zero_()
+        stop.zero_()
         self._evaluate()
         flat = self.replay.get_full('observations', 'actions', 'advantages', 'log_probs',
                                     'returns')
-        batches = list(self.replay.index_batches())
-        stats = self._stats(len(batches))
-        stop = torch.zeros(1, dtype=torch.int32, device=kernels.device())
-        for j, (idx, rows, rows_global) in enumerate(batches):
+        for j, (idx, rows, rows_global) in enumerate(self.replay.index_batches()):
             self.actor_updater.launch(flat['observations'], flat['actions'],
                                       flat['advantages'], flat['log_probs'], idx, rows,
                                       stats[j, 0], stop=stop, rows_global=rows_global)
             self.critic_updater.launch(flat['observations'], flat['returns'], idx, rows,
                                        stats[j, 1], rows_global=rows_global)
-        host = kernels.to_host(stats)
+        if self.model.observation_normalizer:
+            self.model.observation_normalizer.update()
+
+    def _report(self, host):
         actor_iterations = 0
-        for j in range(len(batches)):
+        for j in range(host.shape[0]):
             if host[j, 0, _lib.STAT_ROWS] > 0:      # the actor was still training
                 actor_iterations += 1
                 for k, v in self.actor_updater.infos(host[j, 0]).items():
@@ -45,6 +51,4 @@ class PPO(a2c.A2C):
             for k, v in self.critic_updater.infos(host[j, 1]).items():
                 logger.store('critic/' + k, v)
         logger.store('actor/iterations', actor_iterations)
-        logger.store('critic/iterations', len(batches))
-        if self.model.observation_normalizer:
-            self.model.observation_normalizer.update()
+        logger.store('critic/iterations', host.shape[0])
