@@ -177,8 +177,8 @@ __device__ __forceinline__ void store_tile(const float (&acc)[8][Cfg<H>::NC], fl
 }
 
 
-// acc = act(acc + bias[col]) in place
-template <int H, int ACT>
+// acc = act(acc + bias[col]) in place; FAST selects the MUFU-based tanh (tensor-core path)
+template <int H, int ACT, bool FAST = false>
 __device__ __forceinline__ void bias_activate(float (&acc)[8][Cfg<H>::NC],
                                               const float* __restrict__ bias) {
     using C = Cfg<H>;
@@ -189,7 +189,9 @@ __device__ __forceinline__ void bias_activate(float (&acc)[8][Cfg<H>::NC],
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int j = 0; j < C::NC; ++j) acc[r][j] = activate<ACT>(acc[r][j] + b[j]);
+        for (int j = 0; j < C::NC; ++j)
+            acc[r][j] = (FAST && ACT == TB_ACT_TANH) ? tanh_fast(acc[r][j] + b[j])
+                                                     : activate<ACT>(acc[r][j] + b[j]);
 }
 
 // acc *= act'(h) with h read from the saved activations (global, row-major [*, H]);
@@ -408,14 +410,15 @@ struct WJob {
 constexpr int kMaxJobs = 24;
 struct WJobTable { WJob jobs[kMaxJobs]; int n_jobs; };
 constexpr int WMC = 16;        // rows of m per smem chunk
+constexpr int WST = 4;         // cp.async pipeline depth of the weight-gradient kernel
 
 template <int TN, int TK>
 __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t r1,
                                            float* __restrict__ gout, float* smem) {
     constexpr int MN = TN / 16, MK = TK / 16;
-    float* As = smem;                        // [2][WMC][TN]
-    float* Bsm = As + 2 * WMC * TN;          // [2][WMC][TK]
-    float* Alo = Bsm + 2 * WMC * TK;         // [2][WMC][TN]  (only when job.A_lo)
+    float* As = smem;                        // [WST][WMC][TN]
+    float* Bsm = As + WST * WMC * TN;        // [WST][WMC][TK]
+    float* Alo = Bsm + WST * WMC * TK;       // [WST][WMC][TN]  (only when job.A_lo)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     float acc[MN][MK];
 #pragma unroll
@@ -455,22 +458,19 @@ __device__ __forceinline__ void wgrad_tile(const WJob& job, int64_t r0, int64_t 
     };
 
     const int nchunks = (int)((r1 - r0 + WMC - 1) / WMC);
-    if (nchunks > 0) {
-        stage(0, r0);
+    // WST-deep ring: chunks c+1 .. c+WST-1 are in flight while chunk c is multiplied
+    for (int c = 0; c < WST - 1; ++c) {
+        if (c < nchunks) stage(c, r0 + (int64_t)c * WMC);
         cp_async_commit();
     }
     for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) {
-            stage((c + 1) & 1, r0 + (int64_t)(c + 1) * WMC);
-            cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        const float* as = As + (c & 1) * WMC * TN;
-        const float* al = Alo + (c & 1) * WMC * TN;
-        const float* bs = Bsm + (c & 1) * WMC * TK;
+        cp_async_wait<WST - 2>();
+        __syncthreads();             // chunk c landed; everyone finished computing chunk c-1
+        if (c + WST - 1 < nchunks) stage((c + WST - 1) % WST, r0 + (int64_t)(c + WST - 1) * WMC);
+        cp_async_commit();
+        const float* as = As + (c % WST) * WMC * TN;
+        const float* al = Alo + (c % WST) * WMC * TN;
+        const float* bs = Bsm + (c % WST) * WMC * TK;
 #pragma unroll 4
         for (int r = 0; r < WMC; ++r) {
             float a[MN], b[MK];
@@ -687,7 +687,7 @@ static int launch_wgrad_jobs(const TbMlpShape* shape, const float* d_xin, const 
 
     int64_t rows_per_split = (n_rows + n_split - 1) / n_split;
     rows_per_split = (rows_per_split + WMC - 1) / WMC * WMC;
-    const size_t smem = (size_t)2 * WMC * (128 + 128 + 128) * sizeof(float);
+    const size_t smem = (size_t)WST * WMC * (128 + 128 + 128) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -774,7 +774,7 @@ mlp_layer1_kernel(TbMlpShape sh, const float* __restrict__ params, const float* 
             xin_save[(m0 + m) * ldx + c] = (c == d_in) ? 1.0f : 0.0f;
         }
     }
-    bias_activate<H, ACT>(acc, params + sh.off_b1);
+    bias_activate<H, ACT, true>(acc, params + sh.off_b1);
     store_tile<H>(acc, h1_hi + m0 * H, H, valid, [](float a, int, int) { return tf32_hi(a); });
     store_tile<H>(acc, h1_lo + m0 * H, H, valid, [](float a, int, int) { return a - tf32_hi(a); });
 }
@@ -884,6 +884,97 @@ mlp_dx_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __re
             const int c = C::col(tx, j);
             if (c < dx_cols) dx[(m0 + row) * dx_cols + c] = acc[r][j];
         }
+    }
+}
+
+
+// =====================================================================================
+// Narrow weight gradients in one streaming pass (tensor-core path companion):
+//   dW1[n][j] = sum_m dz1[m][n] xin[m][j]  (j <= d_in: the ones column gives db1)
+//   db2[n]    = sum_m (dz2_hi + dz2_lo)[m][n]
+//   dW3[o][n] = sum_m dout[m][o] h2[m][n],   db3[o] / extras = column sums of dout
+// One CTA per row split; thread (g, n): column n of the 256-wide activations, rows of
+// parity g.  Every activation element is read exactly once, coalesced; xin / dout rows are
+// staged in shared memory and broadcast.  Replaces the generic tile jobs when
+// d_in + 1 <= KIN and n_out + n_extra <= NO (they spent most of their time on padding).
+// =====================================================================================
+constexpr int NW_ROWS = 32;          // rows staged per block
+
+template <int KIN, int NO>
+__global__ void __launch_bounds__(512, 1)
+narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* __restrict__ h2,
+                    const float* __restrict__ dz1, const float* __restrict__ dz2_hi,
+                    const float* __restrict__ dz2_lo, const float* __restrict__ dout, int ld_dout,
+                    int n_extra, int off_extra, int64_t n_rows, int64_t rows_per_split,
+                    float* __restrict__ gpart, const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    constexpr int H = 256;
+    __shared__ float xs[NW_ROWS][KIN];
+    __shared__ float ds[NW_ROWS][NO];
+    extern __shared__ __align__(16) float comb[];         // [256][KIN + NO + 1] combine buffer
+    const int n = threadIdx.x & 255, g = threadIdx.x >> 8;
+    const int d_in = sh.d_in, n_out = sh.n_out, nd = n_out + n_extra;
+    const int ldx = (d_in + 1 + 3) & ~3;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_split;
+    const int64_t r1 = min(n_rows, r0 + rows_per_split);
+    float w1[KIN], w3[NO], b2 = 0.0f, dsum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < KIN; ++j) w1[j] = 0.0f;
+#pragma unroll
+    for (int o = 0; o < NO; ++o) w3[o] = 0.0f;
+
+    for (int64_t base = r0; base < r1; base += NW_ROWS) {
+        const int rows = (int)min((int64_t)NW_ROWS, r1 - base);
+        __syncthreads();
+        for (int v = threadIdx.x; v < NW_ROWS * KIN; v += 512) {
+            const int r = v / KIN, j = v % KIN;
+            xs[r][j] = (r < rows && j <= d_in) ? xin[(base + r) * ldx + j] : 0.0f;
+        }
+        for (int v = threadIdx.x; v < NW_ROWS * NO; v += 512) {
+            const int r = v / NO, o = v % NO;
+            ds[r][o] = (r < rows && o < nd) ? dout[(base + r) * ld_dout + o] : 0.0f;
+        }
+        __syncthreads();
+        if (g == 0 && n < nd)
+            for (int r = 0; r < rows; ++r) dsum += ds[r][n];
+#pragma unroll 4
+        for (int r = g; r < rows; r += 2) {
+            const int64_t e = (base + r) * H + n;
+            const float a1 = dz1[e], hv = h2[e], a2 = dz2_hi[e] + dz2_lo[e];
+            b2 += a2;
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) w1[j] = fmaf(a1, xs[r][j], w1[j]);
+#pragma unroll
+            for (int o = 0; o < NO; ++o) w3[o] = fmaf(ds[r][o], hv, w3[o]);
+        }
+    }
+    // combine the two row-parity groups, then write this split's partial sums
+    constexpr int LDC = KIN + NO + 1;
+    __syncthreads();
+    if (g == 1) {
+        float* c = comb + n * LDC;
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) c[j] = w1[j];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) c[KIN + o] = w3[o];
+        c[KIN + NO] = b2;
+    }
+    __syncthreads();
+    if (g == 0) {
+        const float* c = comb + n * LDC;
+        float* out = gpart + (size_t)blockIdx.x * sh.n_params;
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) {
+            const float v = w1[j] + c[j];
+            if (j < d_in) out[sh.off_w1 + n * d_in + j] = v;
+            else if (j == d_in) out[sh.off_b1 + n] = v;
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o)
+            if (o < n_out) out[sh.off_w3 + o * H + n] = w3[o] + c[KIN + o];
+        out[sh.off_b2 + n] = b2 + c[KIN + NO];
+        if (n < n_out) out[sh.off_b3 + n] = dsum;
+        else if (n < nd) out[off_extra + (n - n_out)] = dsum;
     }
 }
 
@@ -1000,6 +1091,26 @@ extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, cons
     rc = tb_tc_wgrad256(d_dz2_hi, d_dz2_lo, d_h1_hi, d_h1_lo, n_rows, passes, d_gpart, n_split,
                         shape->n_params, shape->off_w2, d_skip, stream);
     if (rc) return rc;
+    if (shape->d_in + 1 <= 32 && shape->n_out + n_extra <= 16) {
+        // streaming single-pass kernel for the narrow gradients
+        ProfScope prof_scope("tb_mlp_wgrad_narrow", stream);
+        int64_t rows_per_split = ((n_rows + n_split - 1) / n_split + NW_ROWS - 1) / NW_ROWS * NW_ROWS;
+        const bool small_in = shape->d_in + 1 <= 20, small_out = shape->n_out + n_extra <= 8;
+#define TB_NARROW(KIN_, NO_)                                                                       \
+    {                                                                                             \
+        const size_t smem = (size_t)256 * (KIN_ + NO_ + 1) * sizeof(float);                       \
+        set_smem(narrow_wgrad_kernel<KIN_, NO_>, smem);                                           \
+        narrow_wgrad_kernel<KIN_, NO_><<<n_split, 512, smem, as_stream(stream)>>>(                \
+            *shape, d_xin, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout, n_extra, off_extra,  \
+            n_rows, rows_per_split, d_gpart, d_skip);                                             \
+    }
+        if (small_in && small_out) TB_NARROW(20, 8)
+        else if (small_in) TB_NARROW(20, 16)
+        else if (small_out) TB_NARROW(32, 8)
+        else TB_NARROW(32, 16)
+#undef TB_NARROW
+        return check_launch("tb_mlp_wgrad_tc/narrow");
+    }
     ProfScope prof_scope("tb_mlp_wgrad_small", stream);
     return launch_wgrad_jobs(shape, d_xin, d_h1_hi, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout,
                              n_extra, off_extra, n_rows, d_gpart, n_split, false, d_skip, stream);

@@ -49,7 +49,8 @@ struct TcCfg {
     static constexpr int STAGE_BYTES = PARTS * (TC_A_BYTES + TC_B_BYTES);
     static constexpr int STAGES = PASSES == 3 ? 2 : 4;
     static constexpr int EPI_BYTES = 4 * 32 * TC_STAGE_ROWSTRIDE * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int HEAD_BYTES = (8 + 1) * TC_BN * 4;      // fused head weights [8, 256] + bias [256]
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + HEAD_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -119,6 +120,14 @@ __device__ __forceinline__ void tcgen05_ld_32x32(uint32_t taddr, uint32_t (&v)[3
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Read-only global load that the compiler may not reorder or sink (used to put a whole batch
+// of independent loads in flight before the first use).
+__device__ __forceinline__ float ldg_nc_volatile(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, dense [rows x 128 B]
 // tile (cute::UMMA::SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 |
 // layout SWIZZLE_128B (2) <<61); SBO = 1024 B between 8-row groups.
@@ -164,11 +173,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     using Cfg = TcCfg<PASSES>;
     if (skip_requested(p.skip)) return;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the shared symbol (an integer round trip
+    // would turn every staging access into a generic LD / ST)
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* stage_base = smem;
     float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    float* s_head_w = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    float* s_bias = s_head_w + 8 * TC_BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
+                                                 Cfg::HEAD_BYTES);
     uint64_t* full_bar = bars;                       // [STAGES]
     uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;    // [2]
@@ -187,6 +200,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (EPI == TC_EPI_BIAS_ACT) {       // epilogue constants -> shared memory (broadcast reads)
+        for (int i = threadIdx.x; i < TC_BN; i += TC_THREADS) s_bias[i] = p.bias[i];
+        for (int i = threadIdx.x; i < p.n_head * TC_BN; i += TC_THREADS) s_head_w[i] = p.head_w[i];
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -255,6 +272,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ===================== epilogue =====================
         const int w = warp - 4;                                 // == warp % 4: TMEM lanes 32w..32w+31
         float* stg = epi + w * 32 * TC_STAGE_ROWSTRIDE;
+        float* __restrict__ g_out = p.out;
+        float* __restrict__ g_out_lo = p.out_lo;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -272,14 +291,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (EPI == TC_EPI_BIAS_ACT) {
                     // this thread holds columns c*32 .. c*32+31 of ITS row: bias + activation
                     // in registers, then the row's contribution to the fused linear head
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + c * 32);
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 b = __ldg(b4 + j / 4);
+                        const float4 b = b4[j / 4];
                         float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
                         float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
                         if (p.act == TB_ACT_TANH) {
-                            x0 = tanhf(x0); x1 = tanhf(x1); x2 = tanhf(x2); x3 = tanhf(x3);
+                            x0 = tanh_fast(x0); x1 = tanh_fast(x1); x2 = tanh_fast(x2); x3 = tanh_fast(x3);
                         } else {
                             x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
                         }
@@ -289,17 +308,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                     for (int o = 0; o < TC_MAX_HEAD; ++o) {
                         if (o < p.n_head) {
-                            const float4* w4 = reinterpret_cast<const float4*>(p.head_w + o * TC_BN + c * 32);
-                            float s = hacc[o];
+                            const float4* w4 = reinterpret_cast<const float4*>(s_head_w + o * TC_BN + c * 32);
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // independent chains
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
-                                const float4 wv = __ldg(w4 + j / 4);
-                                s = fmaf(__uint_as_float(v[j]), wv.x, s);
-                                s = fmaf(__uint_as_float(v[j + 1]), wv.y, s);
-                                s = fmaf(__uint_as_float(v[j + 2]), wv.z, s);
-                                s = fmaf(__uint_as_float(v[j + 3]), wv.w, s);
+                                const float4 wv = w4[j / 4];
+                                s0 = fmaf(__uint_as_float(v[j]), wv.x, s0);
+                                s1 = fmaf(__uint_as_float(v[j + 1]), wv.y, s1);
+                                s2 = fmaf(__uint_as_float(v[j + 2]), wv.z, s2);
+                                s3 = fmaf(__uint_as_float(v[j + 3]), wv.w, s3);
                             }
-                            hacc[o] = s;
+                            hacc[o] += (s0 + s1) + (s2 + s3);
                         }
                     }
                 }
@@ -311,21 +330,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 __syncwarp();
                 const int col = c * 32 + lane;
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const int64_t row = row0 + r;
-                    if (row >= p.n_rows) break;
-                    float x = stg[r * TC_STAGE_ROWSTRIDE + lane];
-                    if (EPI == TC_EPI_ACT_GRAD) {
-                        const float h = __ldg(p.aux_hi + row * TC_BN + col) + __ldg(p.aux_lo + row * TC_BN + col);
-                        x *= p.act == TB_ACT_TANH ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f);
+                if (EPI == TC_EPI_ACT_GRAD) {
+                    // all 64 loads of the chunk are issued before the first use (the row-by-row
+                    // form left ~4 loads in flight per warp and was latency bound)
+                    float gh[32], gl[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {       // 64 independent loads, no use in between
+                        const int64_t row = min(row0 + r, p.n_rows - 1);
+                        gh[r] = ldg_nc_volatile(p.aux_hi + row * TC_BN + col);
+                        gl[r] = ldg_nc_volatile(p.aux_lo + row * TC_BN + col);
                     }
-                    if (p.out_lo) {
-                        const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-                        p.out[row * TC_BN + col] = hi;
-                        p.out_lo[row * TC_BN + col] = x - hi;
-                    } else {
-                        p.out[row * TC_BN + col] = x;
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) gh[r] += gl[r];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const int64_t row = row0 + r;
+                        if (row < p.n_rows) {
+                            const float h = gh[r];
+                            const float g = p.act == TB_ACT_TANH ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f);
+                            g_out[row * TC_BN + col] = stg[r * TC_STAGE_ROWSTRIDE + lane] * g;
+                        }
+                    }
+                } else {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r) {
+                        const int64_t row = row0 + r;
+                        if (row >= p.n_rows) break;
+                        const float x = stg[r * TC_STAGE_ROWSTRIDE + lane];
+                        if (g_out_lo) {
+                            const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+                            g_out[row * TC_BN + col] = hi;
+                            g_out_lo[row * TC_BN + col] = x - hi;
+                        } else {
+                            g_out[row * TC_BN + col] = x;
+                        }
                     }
                 }
                 __syncwarp();
@@ -399,8 +437,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
     using Cfg = TcCfg<PASSES>;
     if (skip_requested(p.skip)) return;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
     uint64_t* full_bar = bars;
@@ -622,7 +659,8 @@ extern "C" int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const flo
     p.out_lo = d_out_lo; p.act = act; p.skip = d_skip;
     p.head_w = d_head_w; p.head_b = d_head_b; p.head_out = d_head_out; p.n_head = n_head;
     cudaStream_t s = as_stream(stream);
-    ProfScope prof_scope("tb_tc_gemm256", stream);      // after the host-side tensor-map encoding
+    ProfScope prof_scope(epilogue == 0 ? "tb_tc_gemm256_fwd" : epilogue == 1 ? "tb_tc_gemm256_bwd"
+                                                            : "tb_tc_gemm256", stream);
 #define TB_TC(P_, E_) launch_tc<P_, E_>(maps, p, s)
     if (passes == 3) {
         if (epilogue == 0) TB_TC(3, 0); else if (epilogue == 1) TB_TC(3, 1); else TB_TC(3, 2);
