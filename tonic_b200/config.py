@@ -32,5 +32,6 @@ noise = 'host'
 gemm = os.environ.get('TONIC_B200_GEMM', 'tf32x3')
 indices = 'host'
 graphs = os.environ.get('TONIC_B200_GRAPHS', '1') != '0'
+graphs_multi_gpu = os.environ.get('TONIC_B200_GRAPHS_MULTI', '1') != '0'   # capture NCCL too
 wgrad_splits = 37      # FFMA: 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
 wgrad_splits_tc = 74   # tensor cores: 2 row tiles x 74 splits = 148 CTAs

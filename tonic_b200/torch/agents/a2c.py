@@ -148,8 +148,11 @@ class A2C(agent.Agent):
         return done
 
     def _graphable(self):
+        """Static shapes + device-resident RNG: the section can be replayed as a CUDA
+        graph.  With several ranks the NCCL all-reduces are captured too
+        (config.graphs_multi_gpu)."""
         return (config.graphs and config.noise == 'device' and config.indices == 'device'
-                and distributed.world() == 1)
+                and (distributed.world() == 1 or config.graphs_multi_gpu))
 
     # -- learning ---------------------------------------------------------------
     def update(self, observations, rewards, resets, terminations, steps):
