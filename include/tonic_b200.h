@@ -264,6 +264,31 @@ int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
 int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_params,
                        float* d_out, const int32_t* d_skip, void* stream);
 
+/* ---- fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU) ---- */
+/* base[r] = address, in THIS process, of rank r's symmetric region of
+ * tb_peer_region_bytes(n_params) bytes (zero-initialised; obtained from
+ * torch.distributed._symmetric_memory or cudaIpc / fabric handles).            */
+typedef struct {
+    int32_t world, rank;
+    void* base[8];
+} TbPeers;
+int64_t tb_peer_region_bytes(int32_t n_params);
+/* This rank's flat gradient (sum of the n_split partial sums; zeros when d_gpart is
+ * NULL) and statistics block -> its slot (epoch & 1) of the region, then a
+ * system-scope release flag into every peer's region.                          */
+int tb_peer_publish(const TbPeers* peers, const float* d_gpart, int32_t n_split,
+                    int32_t n_params, const double* d_stats, const uint64_t* d_epoch,
+                    int32_t* d_block_counter, const int32_t* d_skip, void* stream);
+/* Waits for every rank's flag, sums the slots of all ranks with peer loads in rank
+ * order (grad_scale * sum), applies tb_adam_step's update, writes the global
+ * statistics to d_stats, advances *d_epoch.  use_stats != 0: the PPO controls of
+ * tb_adam_step (skip when all advantages are zero, KL early stop) on the GLOBAL
+ * statistics.                                                                   */
+int tb_adam_step_peers(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
+                       const TbPeers* peers, float grad_scale, uint64_t* d_epoch,
+                       const int32_t* d_skip, double* d_stats, int32_t use_stats,
+                       float kl_threshold, int32_t* d_stop, void* stream);
+
 /* (Re)builds the packed transposes from the flat parameters.                 */
 int tb_mlp_pack(const TbMlpShape* shape, const float* d_params, float* d_packed,
                 void* stream);

@@ -43,6 +43,10 @@ class TbMlpInput(ctypes.Structure):
                 ('d_x2', c_vp), ('dim2', c_i32), ('gather2', c_i32), ('d_idx', c_vp)]
 
 
+class TbPeers(ctypes.Structure):
+    _fields_ = [('world', c_i32), ('rank', c_i32), ('base', c_vp * 8)]
+
+
 class TbAdam(ctypes.Structure):
     _fields_ = [('lr', c_d), ('beta1', c_d), ('beta2', c_d), ('eps', c_d),
                 ('n_params', c_i32), ('d_params', c_vp), ('d_m', c_vp), ('d_v', c_vp),
@@ -70,6 +74,10 @@ _PROTOTYPES = {
     'tb_adam_step': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, c_vp, c_i32, c_f, c_vp, c_vp, c_f,
                              c_vp, c_vp]),
     'tb_reduce_partials': (c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'tb_peer_region_bytes': (c_i64, [c_i32]),
+    'tb_peer_publish': (c_int, [_P(TbPeers), c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tb_adam_step_peers': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, _P(TbPeers), c_f, c_vp, c_vp, c_vp,
+                                   c_i32, c_f, c_vp, c_vp]),
     'tb_mlp_pack': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp]),
     'tb_soft_update': (c_int, [c_vp, c_vp, c_i64, c_d, c_vp]),
     'tb_gauss_sample': (c_int, [c_vp, c_vp, c_vp, c_u64, c_u64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
@@ -108,6 +116,7 @@ _PROTOTYPES = {
 # entry points whose int return value is a status code
 _CHECKED = {name for name, (res, _) in _PROTOTYPES.items()
             if res is c_int and name not in ('tb_version', 'tb_profile_end')}
+_PROTOTYPES_DONE = True
 
 _lib = None
 

@@ -23,6 +23,9 @@ gemm    'tf32x3' : the 256-wide hidden-layer GEMMs (forward layer 2, backward dz
 graphs  True     : sections with static shapes (PPO / A2C rollout of a whole segment and
                    the update, when noise == indices == 'device' in a single process)
                    are captured into CUDA graphs and replayed (tonic_b200/graphs.py).
+peer_reduce True : with several ranks the gradient all-reduce is fused into the Adam
+                   kernel over NVLink peer memory (symmetric memory); False = NCCL
+                   all-reduce of the flat gradient + statistics, then Adam.
 wgrad_splits     : number of row splits of the weight-gradient kernel.
 """
 
@@ -32,6 +35,7 @@ noise = 'host'
 gemm = os.environ.get('TONIC_B200_GEMM', 'tf32x3')
 indices = 'host'
 graphs = os.environ.get('TONIC_B200_GRAPHS', '1') != '0'
+peer_reduce = os.environ.get('TONIC_B200_PEER_REDUCE', '1') != '0'   # fused NVLink reduce + Adam
 graphs_multi_gpu = os.environ.get('TONIC_B200_GRAPHS_MULTI', '1') != '0'   # capture NCCL too
 wgrad_splits = 37      # FFMA: 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
 wgrad_splits_tc = 74   # tensor cores: 2 row tiles x 74 splits = 148 CTAs

@@ -154,3 +154,174 @@ extern "C" int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t
         d_gpart, n_split, n_params, d_out);
     return tb::check_launch("tb_reduce_partials");
 }
+
+// =====================================================================================
+// Fused gradient all-reduce + Adam over NVLink peer memory (SURVEY.md section 8e, K9+K10).
+//
+// Every rank owns a "symmetric" region (same layout on every GPU, mapped into every
+// process: torch.distributed._symmetric_memory):
+//     flags  uint64 [2 slots][8 ranks]            (256 B)
+//     slot s: float grad[n_params] | double stats[TB_STAT_COUNT]     (s = epoch & 1)
+// tb_peer_publish : flat gradient (sum of the split partials) and the statistics block of
+//                   this rank -> its own slot; then a release-store of epoch+1 into
+//                   flags[slot][rank] of EVERY peer (st.release.sys over NVLink).
+// tb_adam_step_peers: waits until all flags of the slot show epoch+1, sums the slot of
+//                   every rank with direct peer loads in RANK ORDER (identical result on all
+//                   ranks -> replicas stay bit-identical), runs the Adam update, writes the
+//                   global statistics back and advances the epoch.
+// A slot is rewritten two epochs later; the flag wait of the epoch in between orders that
+// write after every peer's reads.  Replaces 2 NCCL all-reduces (~30 us each at this
+// message size) + 1 reduction kernel per network and minibatch.
+// =====================================================================================
+namespace tb {
+
+constexpr int kMaxPeers = 8;
+constexpr int kPeerFlagBytes = 256;
+
+__host__ __device__ inline size_t peer_slot_bytes(int n_params) {
+    return ((size_t)n_params * 4 + TB_STAT_COUNT * 8 + 255) / 256 * 256;
+}
+__device__ __forceinline__ unsigned long long* peer_flags(void* base, int slot) {
+    return reinterpret_cast<unsigned long long*>(base) + slot * kMaxPeers;
+}
+__device__ __forceinline__ float* peer_grad(void* base, int slot, int n_params) {
+    return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + kPeerFlagBytes +
+                                    slot * peer_slot_bytes(n_params));
+}
+__device__ __forceinline__ double* peer_stats(void* base, int slot, int n_params) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(peer_grad(base, slot, n_params)) +
+                                     ((size_t)n_params * 4 + 15) / 16 * 16);
+}
+
+__global__ void __launch_bounds__(256)
+peer_publish_kernel(TbPeers peers, const float* __restrict__ gpart, int n_split, int n_params,
+                    const double* __restrict__ stats, const unsigned long long* d_epoch,
+                    int* block_counter, const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    const unsigned long long epoch = *d_epoch;
+    const int slot = (int)(epoch & 1);
+    void* mine = peers.base[peers.rank];
+    float* flat = peer_grad(mine, slot, n_params);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_params) {
+        float g = 0.0f;
+        if (gpart)
+            for (int s = 0; s < n_split; ++s) g += gpart[(size_t)s * n_params + i];
+        flat[i] = g;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < TB_STAT_COUNT)
+        peer_stats(mine, slot, n_params)[threadIdx.x] = stats ? stats[threadIdx.x] : 0.0;
+    // last block to finish: make this rank's slot visible system-wide, then raise its flag
+    // in every peer's region
+    __shared__ bool is_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(block_counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x == 0) *block_counter = 0;
+        __threadfence_system();
+        if ((int)threadIdx.x < peers.world) {
+            unsigned long long* flag = peer_flags(peers.base[threadIdx.x], slot) + peers.rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch + 1) : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+adam_peers_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed, TbPeers peers,
+                  float grad_scale, unsigned long long* d_epoch, const int32_t* d_skip,
+                  double* d_stats, int use_stats, float kl_threshold, int32_t* d_stop) {
+    if (skip_requested(d_skip)) return;
+    const unsigned long long epoch = *d_epoch;
+    const int slot = (int)(epoch & 1);
+    const int n_params = opt.n_params;
+    __shared__ double s_stats[TB_STAT_COUNT];
+    // wait for the flag of every rank (one lane per rank), then gather the global statistics
+    if ((int)threadIdx.x < peers.world) {
+        const unsigned long long* flag = peer_flags(peers.base[peers.rank], slot) + threadIdx.x;
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        } while (seen < epoch + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < TB_STAT_COUNT) {
+        double s = 0.0;
+        for (int r = 0; r < peers.world; ++r)
+            s += __ldcv(peer_stats(peers.base[r], slot, n_params) + threadIdx.x);
+        s_stats[threadIdx.x] = s;
+        if (blockIdx.x == 0 && d_stats) d_stats[threadIdx.x] = s;      // global statistics
+    }
+    __syncthreads();
+    const bool do_step = !(use_stats && s_stats[TB_STAT_NONZERO_ADV] == 0.0);   // actors.py:22,71
+    const int t = opt.d_step[0] + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (do_step && i < n_params) {
+        float g = 0.0f;
+        for (int r = 0; r < peers.world; ++r) g += __ldcv(peer_grad(peers.base[r], slot, n_params) + i);
+        g *= grad_scale;
+        const float w1 = (float)(1.0 - opt.beta1), w2 = (float)(1.0 - opt.beta2);
+        const float m = opt.d_m[i] + w1 * (g - opt.d_m[i]);
+        const float v = opt.d_v[i] * (float)opt.beta2 + w2 * g * g;
+        const double bc1 = 1.0 - pow(opt.beta1, (double)t);
+        const double bc2 = 1.0 - pow(opt.beta2, (double)t);
+        const float step_size = (float)(opt.lr / bc1);
+        const float bc2_sqrt = (float)sqrt(bc2);
+        const float denom = sqrtf(v) / bc2_sqrt + (float)opt.eps;
+        const float p = opt.d_params[i] - step_size * (m / denom);
+        opt.d_m[i] = m;
+        opt.d_v[i] = v;
+        opt.d_params[i] = p;
+        if (packed) pack_one(sh, i, p, packed);
+    }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(&opt.d_step[1], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        opt.d_step[1] = 0;
+        if (do_step) opt.d_step[0] = t;
+        *d_epoch = epoch + 1;
+        if (do_step && use_stats && d_stop && kl_threshold >= 0.0f) {
+            const float kl = (float)(s_stats[TB_STAT_KL] / s_stats[TB_STAT_ROWS]);
+            if (kl > kl_threshold) *d_stop = 1;
+        }
+    }
+}
+
+}  // namespace tb
+
+extern "C" int64_t tb_peer_region_bytes(int32_t n_params) {
+    return (int64_t)(tb::kPeerFlagBytes + 2 * tb::peer_slot_bytes(n_params));
+}
+
+extern "C" int tb_peer_publish(const TbPeers* peers, const float* d_gpart, int32_t n_split,
+                               int32_t n_params, const double* d_stats, const uint64_t* d_epoch,
+                               int32_t* d_block_counter, const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_peer_publish", stream);
+    TB_REQUIRE(peers && peers->world >= 1 && peers->world <= tb::kMaxPeers && d_epoch &&
+               d_block_counter && n_params > 0 && n_split >= 0, TB_EINVAL,
+               "tb_peer_publish: bad arguments");
+    tb::peer_publish_kernel<<<(n_params + 255) / 256, 256, 0, tb::as_stream(stream)>>>(
+        *peers, d_gpart, n_split, n_params, d_stats,
+        reinterpret_cast<const unsigned long long*>(d_epoch), d_block_counter, d_skip);
+    return tb::check_launch("tb_peer_publish");
+}
+
+extern "C" int tb_adam_step_peers(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
+                                  const TbPeers* peers, float grad_scale, uint64_t* d_epoch,
+                                  const int32_t* d_skip, double* d_stats, int32_t use_stats,
+                                  float kl_threshold, int32_t* d_stop, void* stream) {
+    tb::ProfScope prof_scope("tb_adam_step_peers", stream);
+    TB_REQUIRE(opt && opt->d_params && opt->d_m && opt->d_v && opt->d_step && peers && d_epoch &&
+               peers->world >= 1 && peers->world <= tb::kMaxPeers, TB_EINVAL,
+               "tb_adam_step_peers: bad arguments");
+    TbMlpShape sh;
+    if (shape) sh = *shape; else memset(&sh, 0, sizeof(sh));
+    tb::adam_peers_kernel<<<(opt->n_params + 255) / 256, 256, 0, tb::as_stream(stream)>>>(
+        *opt, sh, d_packed, *peers, grad_scale, reinterpret_cast<unsigned long long*>(d_epoch),
+        d_skip, d_stats, use_stats, kl_threshold, d_stop);
+    return tb::check_launch("tb_adam_step_peers");
+}

@@ -43,3 +43,33 @@ def local_rows(global_indices, workers_global, workers_local, rank_):
     row, worker = g // workers_global, g % workers_global
     mine = (worker // workers_local) == rank_
     return row[mine] * workers_local + (worker[mine] - rank_ * workers_local), mine
+
+
+class PeerRegion:
+    """Symmetric (NVLink peer-mapped) buffer of one network for the fused gradient
+    all-reduce + Adam kernels (csrc/optim.cu: tb_peer_publish / tb_adam_step_peers).
+    Creating it is a collective: every rank must construct its regions in the same
+    order (they are created on the first update of each network)."""
+
+    def __init__(self, n_params):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib, kernels
+        dev = kernels.device()
+        nbytes = int(_lib.load().tb_peer_region_bytes(n_params))
+        self.buffer = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        self.buffer.zero_()
+        if hasattr(symm_mem, 'enable_symm_mem_for_group'):
+            try:
+                symm_mem.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+            except Exception:
+                pass
+        self.handle = symm_mem.rendezvous(self.buffer, dist.group.WORLD)
+        pointers = list(self.handle.buffer_ptrs)
+        assert len(pointers) == world() <= 8, pointers
+        self.struct = _lib.TbPeers(world=world(), rank=rank(),
+                                   base=(ctypes.c_void_p * 8)(*pointers))
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.block_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()          # every region is zeroed before anybody raises a flag

@@ -165,6 +165,12 @@ class DeviceMlp:
                 self.h1_lo, self.dz2_lo = new(L.hidden), new(L.hidden)
             self._ws_rows = rows
 
+    def peer_region(self):
+        if getattr(self, '_peer_region', None) is None:
+            from . import distributed
+            self._peer_region = distributed.PeerRegion(self.layout.n_params)
+        return self._peer_region
+
     def flat_grad(self):
         if getattr(self, '_flat_grad', None) is None:
             self._flat_grad = torch.zeros(self.layout.n_params, dtype=F32, device=device())
@@ -277,6 +283,20 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
         adam.step(mlp, gpart, n_split, 1.0 / rows_global, skip=skip, stats=stats,
                   kl_threshold=kl_threshold, stop=stop)
         return
+    if config_peer_reduce():
+        # fused path: publish flat gradient + statistics to the NVLink-mapped region, then one
+        # kernel sums every rank's slot with peer loads and applies Adam
+        region = mlp.peer_region()
+        reduce_stats = stats if reduce_stats is None else reduce_stats
+        _lib.call('tb_peer_publish', ctypes.byref(region.struct),
+                  ptr(gpart) if rows_local > 0 else None, n_split, mlp.layout.n_params,
+                  ptr(reduce_stats), ptr(region.epoch), ptr(region.block_counter), ptr(skip),
+                  stream())
+        _lib.call('tb_adam_step_peers', ctypes.byref(adam.struct), ctypes.byref(mlp.layout.shape),
+                  ptr(mlp.packed), ctypes.byref(region.struct), 1.0 / rows_global,
+                  ptr(region.epoch), ptr(skip), ptr(reduce_stats), int(stats is not None),
+                  kl_threshold, ptr(stop), stream())
+        return
     flat = mlp.flat_grad()
     if rows_local > 0:
         _lib.call('tb_reduce_partials', ptr(gpart), n_split, mlp.layout.n_params, ptr(flat),
@@ -289,6 +309,11 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
         distributed.all_reduce(reduce_stats)
     adam.step(mlp, flat, 1, 1.0 / rows_global, skip=skip, stats=stats,
               kl_threshold=kl_threshold, stop=stop)
+
+
+def config_peer_reduce():
+    from . import config
+    return config.peer_reduce
 
 
 def soft_update(target, online, tau):
