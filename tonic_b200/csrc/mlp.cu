@@ -726,7 +726,7 @@ __device__ __forceinline__ float tf32_hi(float x) {
 
 // h1 = act(xin W1^T + b1), written as a tf32 split (A operand of the layer-2 GEMM)
 template <int H, int ACT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 mlp_layer1_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ packed,
                   TbMlpInput in, int64_t n_rows, float* __restrict__ xin_save,
                   float* __restrict__ h1_hi, float* __restrict__ h1_lo, const int32_t* d_skip) {
@@ -823,7 +823,7 @@ mlp_head_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __
 // dz2 = (dout W3) * act'(h2), written as a tf32 split (A operand of the backward GEMM and
 // of the weight-gradient GEMM)
 template <int H, int ACT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 mlp_head_backward_kernel(TbMlpShape sh, const float* __restrict__ params,
                          const float* __restrict__ dout, int ld_dout, const float* __restrict__ h2,
                          int64_t n_rows, float* __restrict__ dz2_hi, float* __restrict__ dz2_lo,
@@ -978,6 +978,18 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
     }
 }
 
+// shared memory actually used by the split kernels (2 or more CTAs per SM instead of 1)
+template <int H>
+constexpr size_t layer1_smem_bytes() {       // input staging + weight ring + source rows
+    return (size_t)(TM * Cfg<H>::LDH + 2 * KC * H) * sizeof(float) + TM * sizeof(int64_t);
+}
+template <int H>
+constexpr size_t head_smem_bytes() { return (size_t)TM * Cfg<H>::LDH * sizeof(float); }
+template <int H>
+constexpr size_t head_backward_smem_bytes() { return (size_t)(2 * KC * H + TM * 72) * sizeof(float); }
+template <int H>
+constexpr size_t dx_smem_bytes() { return (size_t)(TM * Cfg<H>::LDH + 2 * KC * H) * sizeof(float); }
+
 static int check_tc_shape(const TbMlpShape* sh, const char* who) {
     int rc = check_shape(sh, who);
     if (rc) return rc;
@@ -1001,8 +1013,8 @@ extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
                "tb_mlp_forward_tc: input widths do not add up to d_in");
     const int blocks = (int)((n_rows + TM - 1) / TM);
     cudaStream_t s = as_stream(stream);
-    const size_t smem = mlp_smem_bytes<256>();
     {
+        const size_t smem = layer1_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_layer1", stream);
         if (shape->act == TB_ACT_TANH) {
             set_smem(mlp_layer1_kernel<256, TB_ACT_TANH>, smem);
@@ -1023,6 +1035,7 @@ extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
                        fused_head ? shape->n_out : 0, d_skip, stream);
     if (rc || fused_head) return rc;
     {
+        const size_t smem = head_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_head", stream);
         set_smem(mlp_head_kernel<256>, smem);
         mlp_head_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_h2, n_rows, d_out, d_skip);
@@ -1048,8 +1061,8 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
                "tb_mlp_backward_tc: dx column range invalid");
     const int blocks = (int)((n_rows + TM - 1) / TM);
     cudaStream_t s = as_stream(stream);
-    const size_t smem = mlp_smem_bytes<256>();
     {
+        const size_t smem = head_backward_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_head_backward", stream);
         if (shape->act == TB_ACT_TANH) {
             set_smem(mlp_head_backward_kernel<256, TB_ACT_TANH>, smem);
@@ -1067,6 +1080,7 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
                        nullptr, nullptr, 0, d_skip, stream);
     if (rc || !d_dx) return rc;
     {
+        const size_t smem = dx_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_dx", stream);
         set_smem(mlp_dx_kernel<256>, smem);
         mlp_dx_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_dz1, n_rows, d_dx, dx_col0,

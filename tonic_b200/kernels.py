@@ -200,6 +200,7 @@ class DeviceMlp:
         flops = 2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out)
         if passes:
             _count_flops('tb_mlp_forward_tc', flops)
+            _count_flops('tb_tc_gemm256_fwd', 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_forward_tc', ctypes.byref(L.shape), ptr(params), ptr(packed),
                       ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
                       ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), passes, ptr(skip), stream())
@@ -218,6 +219,7 @@ class DeviceMlp:
         passes = self.passes()
         if passes:
             _count_flops('tb_mlp_backward_tc', flops)
+            _count_flops('tb_tc_gemm256_bwd', 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_backward_tc', ctypes.byref(L.shape), ptr(params),
                       ptr(self.packed if packed is None else packed), ptr(dout), dout.shape[-1],
                       ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), rows, ptr(self.dz2),
@@ -237,6 +239,7 @@ class DeviceMlp:
         passes = self.passes()
         if passes:
             _count_flops('tb_mlp_wgrad_tc', flops)
+            _count_flops('tb_tc_wgrad256', 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_wgrad_tc', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
                       ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
                       ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
