@@ -37,34 +37,34 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
     if (skip_requested(d_skip)) return;
     if (d_stats && d_stats[TB_STAT_NONZERO_ADV] == 0.0) return;    // actors.py:22,71: no step
     const int t = opt.d_step[0] + 1;                               // incremented by the last block
-    const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;   // 4 consecutive parameters
-    if (i0 < opt.n_params) {       // n_params is a multiple of 4 (layout padding)
-        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-        for (int s = 0; s < n_split; ++s) {
-            const float4 v = *reinterpret_cast<const float4*>(gpart + (size_t)s * opt.n_params + i0);
-            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < opt.n_params) {
+        // one parameter per thread keeps ~72k threads in flight; the n_split partial loads
+        // of a thread are independent (4-way unrolled sums)
+        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+        int s = 0;
+        for (; s + 4 <= n_split; s += 4) {
+            g0 += gpart[(size_t)(s + 0) * opt.n_params + i];
+            g1 += gpart[(size_t)(s + 1) * opt.n_params + i];
+            g2 += gpart[(size_t)(s + 2) * opt.n_params + i];
+            g3 += gpart[(size_t)(s + 3) * opt.n_params + i];
         }
-        const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+        for (; s < n_split; ++s) g0 += gpart[(size_t)s * opt.n_params + i];
+        const float g = ((g0 + g1) + (g2 + g3)) * grad_scale;
+        // torch/optim/adam.py::_single_tensor_adam
+        const float w1 = (float)(1.0 - opt.beta1), w2 = (float)(1.0 - opt.beta2);
+        const float m = opt.d_m[i] + w1 * (g - opt.d_m[i]);                          // lerp_
+        const float v = opt.d_v[i] * (float)opt.beta2 + w2 * g * g;                  // mul_.addcmul_
         const double bc1 = 1.0 - pow(opt.beta1, (double)t);
         const double bc2 = 1.0 - pow(opt.beta2, (double)t);
         const float step_size = (float)(opt.lr / bc1);
         const float bc2_sqrt = (float)sqrt(bc2);
-        const float w1 = (float)(1.0 - opt.beta1), w2 = (float)(1.0 - opt.beta2);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int i = i0 + e;
-            const float g = gs[e] * grad_scale;
-            // torch/optim/adam.py::_single_tensor_adam
-            const float m = opt.d_m[i] + w1 * (g - opt.d_m[i]);                          // lerp_
-            const float v = opt.d_v[i] * (float)opt.beta2 + w2 * g * g;                  // mul_.addcmul_
-            const float denom = sqrtf(v) / bc2_sqrt + (float)opt.eps;
-            const float p = opt.d_params[i] - step_size * (m / denom);                   // addcdiv_
-            opt.d_m[i] = m;
-            opt.d_v[i] = v;
-            opt.d_params[i] = p;
-            if (packed) pack_one(sh, i, p, packed);
-        }
+        const float denom = sqrtf(v) / bc2_sqrt + (float)opt.eps;
+        const float p = opt.d_params[i] - step_size * (m / denom);                   // addcdiv_
+        opt.d_m[i] = m;
+        opt.d_v[i] = v;
+        opt.d_params[i] = p;
+        if (packed) pack_one(sh, i, p, packed);
     }
     // last block to finish publishes the new step count and the KL early-stop flag
     __shared__ bool is_last;
@@ -113,8 +113,7 @@ extern "C" int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d
                "tb_adam_step: shape/optimizer size mismatch");
     TbMlpShape sh;
     if (shape) sh = *shape; else memset(&sh, 0, sizeof(sh));
-    TB_REQUIRE(opt->n_params % 4 == 0, TB_EINVAL, "tb_adam_step: n_params must be a multiple of 4");
-    const int blocks = (opt->n_params / 4 + 255) / 256;
+    const int blocks = (opt->n_params + 255) / 256;
     tb::adam_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
         *opt, sh, d_packed, d_gpart, n_split, grad_scale, d_skip, d_stats, kl_threshold, d_stop);
     return tb::check_launch("tb_adam_step");

@@ -1,8 +1,8 @@
 """Command line with the reference's flags (tonic/train.py:140-159):
 
-    python -m tonic_b200.train --header "import tonic_b200.torch" \\
-        --agent "tonic_b200.torch.agents.PPO()" \\
-        --environment "tonic_b200.environments.SynthControl('HalfCheetah')" \\
+    python -m tonic_b200.train --header "import tonic_b200.torch" \
+        --agent "tonic_b200.torch.agents.PPO()" \
+        --environment "tonic_b200.environments.SynthControl('HalfCheetah')" \
         --parallel 1 --sequential 4096 --seed 0
 
 `--parallel P --sequential S` create P*S environments in total (sharded over the
@@ -32,7 +32,7 @@ def train(header, agent, environment, test_environment, trainer, before_training
         tonic_b200.logger.log(f'Loading experiment from {path}')
         if not (checkpoint == 'none' or agent is not None):
             folder = os.path.join(path, 'checkpoints')
-            ids = [int(f.split('.')[0][5:]) for f in os.listdir(folder) if f.startswith('step_')] \\
+            ids = [int(f.split('.')[0][5:]) for f in os.listdir(folder) if f.startswith('step_')] \
                 if os.path.isdir(folder) else []
             if not ids:
                 tonic_b200.logger.error(f'No checkpoint found in {folder}')
