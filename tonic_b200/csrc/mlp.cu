@@ -899,9 +899,11 @@ mlp_dx_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __re
 // d_in + 1 <= KIN and n_out + n_extra <= NO (they spent most of their time on padding).
 // =====================================================================================
 constexpr int NW_ROWS = 32;          // rows staged per block
+constexpr int NW_COLS = 128;         // activation columns per CTA (2 CTAs per row split)
+constexpr int NW_GROUPS = 4;         // row-interleaved thread groups per CTA
 
 template <int KIN, int NO>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(NW_COLS * NW_GROUPS, 1)
 narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* __restrict__ h2,
                     const float* __restrict__ dz1, const float* __restrict__ dz2_hi,
                     const float* __restrict__ dz2_lo, const float* __restrict__ dout, int ld_dout,
@@ -909,10 +911,12 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
                     float* __restrict__ gpart, const int32_t* d_skip) {
     if (skip_requested(d_skip)) return;
     constexpr int H = 256;
+    constexpr int NT = NW_COLS * NW_GROUPS;
     __shared__ float xs[NW_ROWS][KIN];
     __shared__ float ds[NW_ROWS][NO];
-    extern __shared__ __align__(16) float comb[];         // [256][KIN + NO + 1] combine buffer
-    const int n = threadIdx.x & 255, g = threadIdx.x >> 8;
+    extern __shared__ __align__(16) float comb[];         // [groups-1][128][KIN + NO + 1]
+    const int half = blockIdx.y;                          // columns [128 half, 128 half + 128)
+    const int n = half * NW_COLS + (threadIdx.x & (NW_COLS - 1)), g = threadIdx.x / NW_COLS;
     const int d_in = sh.d_in, n_out = sh.n_out, nd = n_out + n_extra;
     const int ldx = (d_in + 1 + 3) & ~3;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_split;
@@ -926,55 +930,75 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
     for (int64_t base = r0; base < r1; base += NW_ROWS) {
         const int rows = (int)min((int64_t)NW_ROWS, r1 - base);
         __syncthreads();
-        for (int v = threadIdx.x; v < NW_ROWS * KIN; v += 512) {
+        for (int v = threadIdx.x; v < NW_ROWS * KIN; v += NT) {
             const int r = v / KIN, j = v % KIN;
             xs[r][j] = (r < rows && j <= d_in) ? xin[(base + r) * ldx + j] : 0.0f;
         }
-        for (int v = threadIdx.x; v < NW_ROWS * NO; v += 512) {
+        for (int v = threadIdx.x; v < NW_ROWS * NO; v += NT) {
             const int r = v / NO, o = v % NO;
             ds[r][o] = (r < rows && o < nd) ? dout[(base + r) * ld_dout + o] : 0.0f;
         }
         __syncthreads();
-        if (g == 0 && n < nd)
-            for (int r = 0; r < rows; ++r) dsum += ds[r][n];
-#pragma unroll 4
-        for (int r = g; r < rows; r += 2) {
-            const int64_t e = (base + r) * H + n;
-            const float a1 = dz1[e], hv = h2[e], a2 = dz2_hi[e] + dz2_lo[e];
-            b2 += a2;
+        if (half == 0 && threadIdx.x < nd)
+            for (int r = 0; r < rows; ++r) dsum += ds[r][threadIdx.x];
+        // 8 rows per group and block: all 32 loads are issued before the first use
+        float a1[NW_ROWS / NW_GROUPS], hv[NW_ROWS / NW_GROUPS], a2[NW_ROWS / NW_GROUPS];
 #pragma unroll
-            for (int j = 0; j < KIN; ++j) w1[j] = fmaf(a1, xs[r][j], w1[j]);
+        for (int q = 0; q < NW_ROWS / NW_GROUPS; ++q) {
+            const int r = g + q * NW_GROUPS;
+            const int64_t e = (base + min(r, rows - 1)) * H + n;
+            a1[q] = __ldg(dz1 + e);
+            hv[q] = __ldg(h2 + e);
+            a2[q] = __ldg(dz2_hi + e) + __ldg(dz2_lo + e);
+        }
 #pragma unroll
-            for (int o = 0; o < NO; ++o) w3[o] = fmaf(ds[r][o], hv, w3[o]);
+        for (int q = 0; q < NW_ROWS / NW_GROUPS; ++q) {
+            const int r = g + q * NW_GROUPS;
+            if (r < rows) {
+                b2 += a2[q];
+#pragma unroll
+                for (int j = 0; j < KIN; ++j) w1[j] = fmaf(a1[q], xs[r][j], w1[j]);
+#pragma unroll
+                for (int o = 0; o < NO; ++o) w3[o] = fmaf(ds[r][o], hv[q], w3[o]);
+            }
         }
     }
-    // combine the two row-parity groups, then write this split's partial sums
+    // combine the row groups (fixed order), then write this split's partial sums
     constexpr int LDC = KIN + NO + 1;
+    const int c = threadIdx.x & (NW_COLS - 1);
     __syncthreads();
-    if (g == 1) {
-        float* c = comb + n * LDC;
+    if (g > 0) {
+        float* dst = comb + ((size_t)(g - 1) * NW_COLS + c) * LDC;
 #pragma unroll
-        for (int j = 0; j < KIN; ++j) c[j] = w1[j];
+        for (int j = 0; j < KIN; ++j) dst[j] = w1[j];
 #pragma unroll
-        for (int o = 0; o < NO; ++o) c[KIN + o] = w3[o];
-        c[KIN + NO] = b2;
+        for (int o = 0; o < NO; ++o) dst[KIN + o] = w3[o];
+        dst[KIN + NO] = b2;
     }
     __syncthreads();
     if (g == 0) {
-        const float* c = comb + n * LDC;
+        for (int gg = 1; gg < NW_GROUPS; ++gg) {
+            const float* src = comb + ((size_t)(gg - 1) * NW_COLS + c) * LDC;
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) w1[j] += src[j];
+#pragma unroll
+            for (int o = 0; o < NO; ++o) w3[o] += src[KIN + o];
+            b2 += src[KIN + NO];
+        }
         float* out = gpart + (size_t)blockIdx.x * sh.n_params;
 #pragma unroll
         for (int j = 0; j < KIN; ++j) {
-            const float v = w1[j] + c[j];
-            if (j < d_in) out[sh.off_w1 + n * d_in + j] = v;
-            else if (j == d_in) out[sh.off_b1 + n] = v;
+            if (j < d_in) out[sh.off_w1 + n * d_in + j] = w1[j];
+            else if (j == d_in) out[sh.off_b1 + n] = w1[j];
         }
 #pragma unroll
         for (int o = 0; o < NO; ++o)
-            if (o < n_out) out[sh.off_w3 + o * H + n] = w3[o] + c[KIN + o];
-        out[sh.off_b2 + n] = b2 + c[KIN + NO];
-        if (n < n_out) out[sh.off_b3 + n] = dsum;
-        else if (n < nd) out[off_extra + (n - n_out)] = dsum;
+            if (o < n_out) out[sh.off_w3 + o * H + n] = w3[o];
+        out[sh.off_b2 + n] = b2;
+        if (half == 0) {
+            if ((int)threadIdx.x < n_out) out[sh.off_b3 + threadIdx.x] = dsum;
+            else if ((int)threadIdx.x < nd) out[off_extra + (threadIdx.x - n_out)] = dsum;
+        }
     }
 }
 
@@ -1112,9 +1136,10 @@ extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, cons
         const bool small_in = shape->d_in + 1 <= 20, small_out = shape->n_out + n_extra <= 8;
 #define TB_NARROW(KIN_, NO_)                                                                       \
     {                                                                                             \
-        const size_t smem = (size_t)256 * (KIN_ + NO_ + 1) * sizeof(float);                       \
+        const size_t smem = (size_t)(NW_GROUPS - 1) * NW_COLS * (KIN_ + NO_ + 1) * sizeof(float); \
         set_smem(narrow_wgrad_kernel<KIN_, NO_>, smem);                                           \
-        narrow_wgrad_kernel<KIN_, NO_><<<n_split, 512, smem, as_stream(stream)>>>(                \
+        narrow_wgrad_kernel<KIN_, NO_><<<dim3(n_split, 256 / NW_COLS), NW_COLS * NW_GROUPS, smem, \
+                                         as_stream(stream)>>>(                                    \
             *shape, d_xin, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout, n_extra, off_extra,  \
             n_rows, rows_per_split, d_gpart, d_skip);                                             \
     }
