@@ -221,8 +221,8 @@ int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, const float* d_
                     const float* d_h1_lo, const float* d_h2, const float* d_dz1,
                     const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
                     int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
-                    float* d_gpart, int32_t n_split, int32_t passes, const int32_t* d_skip,
-                    void* stream);
+                    float* d_gpart, int32_t n_split, int32_t n_split_w2, int32_t passes,
+                    const int32_t* d_skip, void* stream);
 
 /* Hidden-layer weight gradient on the tensor cores (MN-major tf32 operands):
  * gpart[s, off_w2 + n * 256 + k] = sum over the rows m of split s of
@@ -245,7 +245,9 @@ typedef struct {
     int32_t* d_step;       /* [2] steps taken (device resident), block counter */
 } TbAdam;
 
-/* grad[i] = grad_scale * sum_s d_gpart[s, i]; Adam step; then refreshes the
+/* grad[i] = grad_scale * sum_s d_gpart[s, i] (n_split_w2 > 0: the W2 block of `shape`
+ * only has n_split_w2 partial sums -- the tensor-core weight-gradient kernel uses fewer
+ * row splits than the narrow gradients); Adam step; then refreshes the
  * packed transposes (W1^T, W2^T) of `shape` in d_packed.
  * Device-side control (all optional):
  *   d_skip      -- if *d_skip != 0 nothing happens;
@@ -255,14 +257,15 @@ typedef struct {
  *   kl_threshold-- if >= 0 and stats kl mean > kl_threshold, *d_stop is set to
  *                  1 AFTER the step (updaters/actors.py:103,112; ppo.py:45-46).*/
 int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
-                 const float* d_gpart, int32_t n_split, float grad_scale,
+                 const float* d_gpart, int32_t n_split, int32_t n_split_w2, float grad_scale,
                  const int32_t* d_skip, const double* d_stats,
                  float kl_threshold, int32_t* d_stop, void* stream);
 
 /* d_out[i] = sum_s d_gpart[s, i]: the flat gradient that is all-reduced over
  * ranks before tb_adam_step(n_split = 1) in multi-GPU runs.      */
-int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_params,
-                       float* d_out, const int32_t* d_skip, void* stream);
+int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2,
+                       int32_t w2_begin, int32_t w2_end, int32_t n_params, float* d_out,
+                       const int32_t* d_skip, void* stream);
 
 /* ---- fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU) ---- */
 /* base[r] = address, in THIS process, of rank r's symmetric region of
@@ -277,6 +280,7 @@ int64_t tb_peer_region_bytes(int32_t n_params);
  * NULL) and statistics block -> its slot (epoch & 1) of the region, then a
  * system-scope release flag into every peer's region.                          */
 int tb_peer_publish(const TbPeers* peers, const float* d_gpart, int32_t n_split,
+                    int32_t n_split_w2, int32_t w2_begin, int32_t w2_end,
                     int32_t n_params, const double* d_stats, const uint64_t* d_epoch,
                     int32_t* d_block_counter, const int32_t* d_skip, void* stream);
 /* Waits for every rank's flag, sums the slots of all ranks with peer loads in rank

@@ -36,7 +36,9 @@ def test_train_cli_learns_and_checkpoints(tmp_path, monkeypatch):
     for key in ('train/steps_per_second', 'train/action/mean', 'test/episode_score/mean',
                 'actor/loss', 'critic/loss', 'actor/kl', 'train/episodes'):
         assert key in header, key
-    state = torch.load(os.path.join(run, 'checkpoints', 'step_409600.pt'))
+    saved = sorted(os.listdir(os.path.join(run, 'checkpoints')))
+    assert len(saved) == 1 and saved[0].startswith('step_4'), saved
+    state = torch.load(os.path.join(run, 'checkpoints', saved[0]))
     assert 'actor.torso.model.0.weight' in state and 'critic.head.v_layer.bias' in state
     assert 'critic.encoder.observation_normalizer._mean' in state
     # resume from the checkpoint (train.py:22-75): weights are restored

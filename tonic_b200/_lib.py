@@ -71,11 +71,12 @@ _PROTOTYPES = {
                                 c_vp, c_i32, c_i32, c_vp, c_vp]),
     'tb_mlp_wgrad': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32,
                              c_i32, c_i64, c_vp, c_i32, c_vp, c_vp]),
-    'tb_adam_step': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, c_vp, c_i32, c_f, c_vp, c_vp, c_f,
-                             c_vp, c_vp]),
-    'tb_reduce_partials': (c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'tb_adam_step': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, c_vp, c_i32, c_i32, c_f, c_vp, c_vp,
+                             c_f, c_vp, c_vp]),
+    'tb_reduce_partials': (c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'tb_peer_region_bytes': (c_i64, [c_i32]),
-    'tb_peer_publish': (c_int, [_P(TbPeers), c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tb_peer_publish': (c_int, [_P(TbPeers), c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
+                                c_vp, c_vp]),
     'tb_adam_step_peers': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, _P(TbPeers), c_f, c_vp, c_vp, c_vp,
                                    c_i32, c_f, c_vp, c_vp]),
     'tb_mlp_pack': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp]),
@@ -98,7 +99,7 @@ _PROTOTYPES = {
     'tb_mlp_backward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64,
                                    c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_mlp_wgrad_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
-                                c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp]),
+                                c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_permutation': (c_int, [c_u64, c_u64, c_vp, c_i64, c_vp, c_vp]),
     'tb_counter_add': (c_int, [c_vp, c_u64, c_vp]),

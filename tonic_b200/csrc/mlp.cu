@@ -900,10 +900,10 @@ mlp_dx_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __re
 // =====================================================================================
 constexpr int NW_ROWS = 32;          // rows staged per block
 constexpr int NW_COLS = 128;         // activation columns per CTA (2 CTAs per row split)
-constexpr int NW_GROUPS = 4;         // row-interleaved thread groups per CTA
+constexpr int NW_GROUPS = 2;         // row-interleaved thread groups per CTA (2 CTAs per SM)
 
 template <int KIN, int NO>
-__global__ void __launch_bounds__(NW_COLS * NW_GROUPS, 1)
+__global__ void __launch_bounds__(NW_COLS * NW_GROUPS, 2)
 narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* __restrict__ h2,
                     const float* __restrict__ dz1, const float* __restrict__ dz2_hi,
                     const float* __restrict__ dz2_lo, const float* __restrict__ dout, int ld_dout,
@@ -1118,15 +1118,15 @@ extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, cons
                                const float* d_h1_lo, const float* d_h2, const float* d_dz1,
                                const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
                                int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
-                               float* d_gpart, int32_t n_split, int32_t passes,
+                               float* d_gpart, int32_t n_split, int32_t n_split_w2, int32_t passes,
                                const int32_t* d_skip, void* stream) {
     using namespace tb;
     int rc = check_tc_shape(shape, "tb_mlp_wgrad_tc");
     if (rc) return rc;
     TB_REQUIRE(d_xin && d_h1_hi && d_h1_lo && d_h2 && d_dz1 && d_dz2_hi && d_dz2_lo && d_dout &&
-               d_gpart && n_rows > 0 && n_split >= 1 && ld_dout >= shape->n_out + n_extra, TB_EINVAL,
-               "tb_mlp_wgrad_tc: bad arguments");
-    rc = tb_tc_wgrad256(d_dz2_hi, d_dz2_lo, d_h1_hi, d_h1_lo, n_rows, passes, d_gpart, n_split,
+               d_gpart && n_rows > 0 && n_split >= 1 && n_split_w2 >= 1 && n_split_w2 <= n_split &&
+               ld_dout >= shape->n_out + n_extra, TB_EINVAL, "tb_mlp_wgrad_tc: bad arguments");
+    rc = tb_tc_wgrad256(d_dz2_hi, d_dz2_lo, d_h1_hi, d_h1_lo, n_rows, passes, d_gpart, n_split_w2,
                         shape->n_params, shape->off_w2, d_skip, stream);
     if (rc) return rc;
     if (shape->d_in + 1 <= 32 && shape->n_out + n_extra <= 16) {

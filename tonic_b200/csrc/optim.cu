@@ -32,7 +32,7 @@ __device__ __forceinline__ void pack_one(const TbMlpShape& sh, int i, float p, f
 
 __global__ void __launch_bounds__(256)
 adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
-            const float* __restrict__ gpart, int n_split, float grad_scale,
+            const float* __restrict__ gpart, int n_split_all, int n_split_w2, float grad_scale,
             const int32_t* d_skip, const double* d_stats, float kl_threshold, int32_t* d_stop) {
     if (skip_requested(d_skip)) return;
     if (d_stats && d_stats[TB_STAT_NONZERO_ADV] == 0.0) return;    // actors.py:22,71: no step
@@ -41,6 +41,9 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
     if (i < opt.n_params) {
         // one parameter per thread keeps ~72k threads in flight; the n_split partial loads
         // of a thread are independent (4-way unrolled sums)
+        // the W2 block may have been produced with fewer row splits than the narrow gradients
+        const int n_split = (n_split_w2 > 0 && i >= sh.off_w2 && i < sh.off_w2 + sh.hidden * sh.hidden)
+                                ? n_split_w2 : n_split_all;
         float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
         int s = 0;
         for (; s + 4 <= n_split; s += 4) {
@@ -103,7 +106,7 @@ soft_update_kernel(float* __restrict__ target, const float* __restrict__ online,
 }  // namespace tb
 
 extern "C" int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d_packed,
-                            const float* d_gpart, int32_t n_split, float grad_scale,
+                            const float* d_gpart, int32_t n_split, int32_t n_split_w2, float grad_scale,
                             const int32_t* d_skip, const double* d_stats, float kl_threshold,
                             int32_t* d_stop, void* stream) {
     tb::ProfScope prof_scope("tb_adam_step", stream);
@@ -115,7 +118,8 @@ extern "C" int tb_adam_step(const TbAdam* opt, const TbMlpShape* shape, float* d
     if (shape) sh = *shape; else memset(&sh, 0, sizeof(sh));
     const int blocks = (opt->n_params + 255) / 256;
     tb::adam_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(
-        *opt, sh, d_packed, d_gpart, n_split, grad_scale, d_skip, d_stats, kl_threshold, d_stop);
+        *opt, sh, d_packed, d_gpart, n_split, shape ? n_split_w2 : 0, grad_scale, d_skip, d_stats,
+        kl_threshold, d_stop);
     return tb::check_launch("tb_adam_step");
 }
 
@@ -144,23 +148,26 @@ extern "C" int tb_soft_update(float* d_target, const float* d_online, int64_t n,
 // multi-GPU gradient all-reduce).
 namespace tb {
 __global__ void __launch_bounds__(256)
-reduce_partials_kernel(const float* __restrict__ gpart, int n_split, int n, float* __restrict__ out) {
+reduce_partials_kernel(const float* __restrict__ gpart, int n_split_all, int n_split_w2, int w2_lo,
+                       int w2_hi, int n, float* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const int n_split = (n_split_w2 > 0 && i >= w2_lo && i < w2_hi) ? n_split_w2 : n_split_all;
     float g = 0.0f;
     for (int s = 0; s < n_split; ++s) g += gpart[(size_t)s * n + i];
     out[i] = g;
 }
 }  // namespace tb
 
-extern "C" int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_params,
+extern "C" int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2,
+                                  int32_t w2_begin, int32_t w2_end, int32_t n_params,
                                   float* d_out, const int32_t* d_skip, void* stream) {
     tb::ProfScope prof_scope("tb_reduce_partials", stream);
     TB_REQUIRE(d_gpart && d_out && n_split >= 1 && n_params > 0, TB_EINVAL,
                "tb_reduce_partials: bad arguments");
     (void)d_skip;
     tb::reduce_partials_kernel<<<(n_params + 255) / 256, 256, 0, tb::as_stream(stream)>>>(
-        d_gpart, n_split, n_params, d_out);
+        d_gpart, n_split, n_split_w2, w2_begin, w2_end, n_params, d_out);
     return tb::check_launch("tb_reduce_partials");
 }
 
@@ -203,7 +210,8 @@ __device__ __forceinline__ double* peer_stats(void* base, int slot, int n_params
 }
 
 __global__ void __launch_bounds__(256)
-peer_publish_kernel(TbPeers peers, const float* __restrict__ gpart, int n_split, int n_params,
+peer_publish_kernel(TbPeers peers, const float* __restrict__ gpart, int n_split_all, int n_split_w2,
+                    int w2_lo, int w2_hi, int n_params,
                     const double* __restrict__ stats, const unsigned long long* d_epoch,
                     int* block_counter, const int32_t* d_skip) {
     if (skip_requested(d_skip)) return;
@@ -214,6 +222,7 @@ peer_publish_kernel(TbPeers peers, const float* __restrict__ gpart, int n_split,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_params) {
         float g = 0.0f;
+        const int n_split = (n_split_w2 > 0 && i >= w2_lo && i < w2_hi) ? n_split_w2 : n_split_all;
         if (gpart)
             for (int s = 0; s < n_split; ++s) g += gpart[(size_t)s * n_params + i];
         flat[i] = g;
@@ -307,6 +316,7 @@ extern "C" int64_t tb_peer_region_bytes(int32_t n_params) {
 }
 
 extern "C" int tb_peer_publish(const TbPeers* peers, const float* d_gpart, int32_t n_split,
+                               int32_t n_split_w2, int32_t w2_begin, int32_t w2_end,
                                int32_t n_params, const double* d_stats, const uint64_t* d_epoch,
                                int32_t* d_block_counter, const int32_t* d_skip, void* stream) {
     tb::ProfScope prof_scope("tb_peer_publish", stream);
@@ -314,7 +324,7 @@ extern "C" int tb_peer_publish(const TbPeers* peers, const float* d_gpart, int32
                d_block_counter && n_params > 0 && n_split >= 0, TB_EINVAL,
                "tb_peer_publish: bad arguments");
     tb::peer_publish_kernel<<<(n_params + 255) / 256, 256, 0, tb::as_stream(stream)>>>(
-        *peers, d_gpart, n_split, n_params, d_stats,
+        *peers, d_gpart, n_split, n_split_w2, w2_begin, w2_end, n_params, d_stats,
         reinterpret_cast<const unsigned long long*>(d_epoch), d_block_counter, d_skip);
     return tb::check_launch("tb_peer_publish");
 }

@@ -182,10 +182,20 @@ class DeviceMlp:
         return self._gpart
 
     def splits_for(self, rows):
+        """Row splits of the weight-gradient partial sums.  Tensor-core path: the narrow
+        gradients use twice the splits of the W2 kernel (see `w2_splits`)."""
         from . import config
         if self.passes():
-            return max(1, min(config.wgrad_splits_tc, rows // 64))
+            return max(1, min(2 * config.wgrad_splits_tc, rows // 32))
         return max(1, min(config.wgrad_splits, rows // 128))
+
+    def w2_splits(self, n_split):
+        """Splits of the W2 block inside `n_split` partial slots (0 = same as the rest)."""
+        return max(1, n_split // 2) if self.passes() else 0
+
+    def w2_range(self):
+        off, size = self.layout.offsets['w2']
+        return off, off + size
 
     # -- kernels ------------------------------------------------------------
     def forward(self, inp, rows, out, save=False, skip=None, params=None, packed=None):
@@ -243,7 +253,7 @@ class DeviceMlp:
             _lib.call('tb_mlp_wgrad_tc', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
                       ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
                       ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
-                      ptr(gpart), n_split, passes, ptr(skip), stream())
+                      ptr(gpart), n_split, self.w2_splits(n_split), passes, ptr(skip), stream())
             return gpart
         _count_flops('tb_mlp_wgrad', flops)
         _lib.call('tb_mlp_wgrad', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
@@ -266,10 +276,10 @@ class Adam:
                                   d_m=ptr(self.m), d_v=ptr(self.v), d_step=ptr(self.step_count))
 
     def step(self, mlp, gpart, n_split, grad_scale, skip=None, stats=None,
-             kl_threshold=-1.0, stop=None):
+             kl_threshold=-1.0, stop=None, n_split_w2=0):
         _lib.call('tb_adam_step', ctypes.byref(self.struct), ctypes.byref(mlp.layout.shape),
-                  ptr(mlp.packed), ptr(gpart), n_split, grad_scale, ptr(skip), ptr(stats),
-                  kl_threshold, ptr(stop), stream())
+                  ptr(mlp.packed), ptr(gpart), n_split, n_split_w2, grad_scale, ptr(skip),
+                  ptr(stats), kl_threshold, ptr(stop), stream())
 
 
 def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=None, stats=None,
@@ -282,9 +292,11 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
     zero, KL early stop); `reduce_stats` is a statistics block that only needs the
     sum over ranks (defaults to `stats`)."""
     from . import distributed
+    w2_splits = mlp.w2_splits(n_split)
+    w2_lo, w2_hi = mlp.w2_range()
     if distributed.world() == 1:
         adam.step(mlp, gpart, n_split, 1.0 / rows_global, skip=skip, stats=stats,
-                  kl_threshold=kl_threshold, stop=stop)
+                  kl_threshold=kl_threshold, stop=stop, n_split_w2=w2_splits)
         return
     if config_peer_reduce():
         # fused path: publish flat gradient + statistics to the NVLink-mapped region, then one
@@ -292,8 +304,8 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
         region = mlp.peer_region()
         reduce_stats = stats if reduce_stats is None else reduce_stats
         _lib.call('tb_peer_publish', ctypes.byref(region.struct),
-                  ptr(gpart) if rows_local > 0 else None, n_split, mlp.layout.n_params,
-                  ptr(reduce_stats), ptr(region.epoch), ptr(region.block_counter), ptr(skip),
+                  ptr(gpart) if rows_local > 0 else None, n_split, w2_splits, w2_lo, w2_hi,
+                  mlp.layout.n_params, ptr(reduce_stats), ptr(region.epoch), ptr(region.block_counter), ptr(skip),
                   stream())
         _lib.call('tb_adam_step_peers', ctypes.byref(adam.struct), ctypes.byref(mlp.layout.shape),
                   ptr(mlp.packed), ctypes.byref(region.struct), 1.0 / rows_global,
@@ -302,8 +314,8 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
         return
     flat = mlp.flat_grad()
     if rows_local > 0:
-        _lib.call('tb_reduce_partials', ptr(gpart), n_split, mlp.layout.n_params, ptr(flat),
-                  None, stream())
+        _lib.call('tb_reduce_partials', ptr(gpart), n_split, w2_splits, w2_lo, w2_hi,
+                  mlp.layout.n_params, ptr(flat), None, stream())
     else:
         flat.zero_()
     distributed.all_reduce(flat)

@@ -22,11 +22,12 @@ import yaml
 import tonic_b200
 import tonic_b200.torch  # noqa: F401
 
+tonic = tonic_b200       # reference-style snippets (`tonic.torch.agents.PPO()`) see `tonic`
+
 
 def train(header, agent, environment, test_environment, trainer, before_training,
           after_training, parallel, sequential, seed, name, environment_name, checkpoint, path):
     args = dict(locals())
-    tonic = tonic_b200      # noqa: F841  reference-style snippets see `tonic`
     checkpoint_path = None
     if path:
         tonic_b200.logger.log(f'Loading experiment from {path}')
