@@ -29,7 +29,8 @@ def test_train_cli_learns_and_checkpoints(tmp_path, monkeypatch):
     run = os.path.join('synth', 'ppo-test', '0')
     rows = open(os.path.join(run, 'log.csv')).read().strip().splitlines()
     header = rows[0].split(',')
-    table = np.array([[float(c) for c in r.split(',')] for r in rows[1:]])
+    table = np.array([[float(c) if c != 'None' else np.nan for c in r.split(',')]
+                      for r in rows[1:]])
     assert len(table) == 4
     score = table[:, header.index('train/episode_score/mean')]
     assert score[-1] > score[0] + 5, score            # learning happens
