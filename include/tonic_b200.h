@@ -84,6 +84,23 @@ int tb_env_step(const TbEnv* env, const float* d_actions, float* d_obs,
                 float* d_next_obs, float* d_rewards, float* d_resets,
                 float* d_terminations, void* stream);
 
+/* Fused rollout of a whole on-policy segment (T vector steps) in ONE launch: per step
+ * the actor forward + Normal sample + log-prob (torch/agents/a2c.py:41-52,75-85), the
+ * environment transition with auto-reset (environments/distributed.py:28-58), the segment
+ * rows (replays/segments.py:27-36) and the normaliser sums (mean_stds.py:44-48); the
+ * caller of the reference loop is utils/trainer.py:44-50.  A CTA keeps 64 environments
+ * resident in shared memory for all T steps.  Segment buffers are [T, N, ...] float32;
+ * `shape` / d_params / d_packed describe the actor MLP (declared below); d_counter is the
+ * device-resident Philox position, advanced by the caller by T * counter_stride.       */
+struct TbMlpShape_;
+int tb_rollout_fused(const TbEnv* env, const struct TbMlpShape_* shape, const float* d_params,
+                     const float* d_packed, const float* d_log_scale, const float* d_norm_mean,
+                     const float* d_norm_std, int32_t T, float* d_seg_obs, float* d_seg_actions,
+                     float* d_seg_next_obs, float* d_seg_rewards, float* d_seg_resets,
+                     float* d_seg_terms, float* d_seg_logp, float* d_env_obs,
+                     double* d_moment_sums, uint64_t seed, uint64_t counter,
+                     uint64_t counter_stride, const uint64_t* d_counter, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Observation normaliser -- replaces torch/normalizers/mean_stds.py:44-74    */
 /* ------------------------------------------------------------------------ */
@@ -120,7 +137,7 @@ int tb_advantages(const float* d_returns, const float* d_values,
 /* ------------------------------------------------------------------------ */
 /* Two-hidden-layer MLP (torch/models/utils.py:4-23) with a linear head        */
 /* ------------------------------------------------------------------------ */
-typedef struct {
+typedef struct TbMlpShape_ {
     int32_t d_in;      /* input width (obs, or obs+act for Q critics)         */
     int32_t hidden;    /* H: both hidden layers (64, 128 or 256)              */
     int32_t n_out;     /* head rows (A, 2A for loc+scale heads, 1 for values) */

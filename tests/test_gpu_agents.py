@@ -99,10 +99,11 @@ def test_cuda_graph_sections_match_eager():
     cfg = dict(scenarios.SCENARIOS['ppo_wide'], workers=64,
                segment=dict(size=8, batch_iterations=2, batch_size=128))
     results = []
-    old = config.noise, config.indices, config.graphs
+    old = config.noise, config.indices, config.graphs, config.fused_rollout
     try:
         for use_graphs in (False, True):
             config.noise, config.indices, config.graphs = 'device', 'device', use_graphs
+            config.fused_rollout = False        # the per-step launches are what gets captured
             agent, env = product.build(cfg)
             env.start()
             for _ in range(5):          # 2 eager warm-ups, capture, 2 replays
@@ -113,6 +114,60 @@ def test_cuda_graph_sections_match_eager():
                 assert agent._update_graph.graph is not None
                 assert agent._rollout_graph.graph is not None
     finally:
-        config.noise, config.indices, config.graphs = old
+        config.noise, config.indices, config.graphs, config.fused_rollout = old
     # same kernels, same device-resident RNG streams -> bit-identical parameters
     assert torch.equal(results[0], results[1])
+
+
+@pytest.mark.parametrize('kind', ['PPO', 'A2C'])
+def test_fused_rollout_matches_per_step_launches(kind):
+    """The persistent rollout kernel (one launch per segment) against the per-step chain
+    actor forward -> gauss_sample -> env_step -> moments_record on the FFMA path: same
+    Philox streams, same tile arithmetic -> bit-identical segments, environment state and
+    episode log; normaliser sums agree to double round-off (different summation order)."""
+    import torch
+    from tonic_b200 import config
+    base = scenarios.SCENARIOS['ppo_wide' if kind == 'PPO' else 'a2c_small']
+    seg = dict(base['segment'], size=24)
+    cfg = dict(base, workers=100, max_episode_steps=9, segment=seg)     # ragged tile + many resets
+    old = config.noise, config.indices, config.graphs, config.fused_rollout, config.gemm
+    out = []
+    try:
+        for fused in (False, True):
+            config.noise, config.indices, config.graphs = 'device', 'device', False
+            config.fused_rollout, config.gemm = fused, 'ffma'
+            agent, env = product.build(cfg)
+            env.start()
+            norm = agent.model.observation_normalizer
+            sums = []
+            record = norm.update
+            norm.update = lambda: (sums.append(norm.sums.clone()), record())[1]
+            assert agent.rollout(env, seg['size']) == seg['size']
+            torch.cuda.synchronize()
+            first = {k: v.clone() for k, v in agent.replay.buffers.items()
+                     if k in ('observations', 'actions', 'next_observations', 'rewards',
+                              'resets', 'terminations', 'log_probs')}
+            n_ep = int(env.episode_count.item())
+            log = (torch.sort(env.episode_scores[:n_ep])[0].clone(),
+                   torch.sort(env.episode_lengths[:n_ep])[0].clone(), env.state.clone())
+            for _ in range(2):
+                agent.rollout(env, seg['size'])
+            torch.cuda.synchronize()
+            out.append(dict(
+                first=first, sums=sums[0], state=env.state.clone(), obs=env.observations.clone(),
+                episodes=n_ep, scores=log[0], lengths=log[1], first_state=log[2],
+                params=torch.cat([n.params for n in agent.model.networks()]).cpu()))
+    finally:
+        config.noise, config.indices, config.graphs, config.fused_rollout, config.gemm = old
+    a, b = out
+    for k in a['first']:
+        assert torch.equal(a['first'][k], b['first'][k]), k
+    assert float(a['first']['resets'].sum()) > 100       # the reset branch was exercised
+    assert torch.allclose(a['sums'], b['sums'], rtol=1e-12, atol=1e-9)
+    assert a['episodes'] == b['episodes'] and a['episodes'] > 0
+    torch.testing.assert_close(a['params'], b['params'], rtol=0, atol=1e-5)
+    # after three segments the environments are still on identical trajectories unless a
+    # 1-ulp difference of the normaliser moved an action; compare loosely
+    torch.testing.assert_close(a['state'], b['state'], rtol=0, atol=1e-3)
+    assert torch.equal(a['lengths'], b['lengths']) and torch.equal(a['scores'], b['scores'])
+    assert torch.equal(a['first_state'], b['first_state'])

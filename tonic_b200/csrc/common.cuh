@@ -136,6 +136,26 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
 }
 
+// ---- detached-scale Gaussian policy head (reference tonic/torch/models/actors.py:37-66) ----
+constexpr int kMaxAct = 64;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;     // log(sqrt(2*pi))
+constexpr float kEntropyConst = 1.41893853320467274178f;   // 0.5 + 0.5*log(2*pi)
+
+__device__ __forceinline__ float softplus_f(float x) {     // torch softplus, beta=1, threshold=20
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+// scale = clamp(softplus(log_scale) + 1e-8, 1e-4, 1)   (actors.py:63-64)
+__device__ __forceinline__ float detached_scale(float log_scale, float* dscale_dls) {
+    const float sp = softplus_f(log_scale) + 1e-8f;
+    const float sc = fminf(fmaxf(sp, 1e-4f), 1.0f);
+    if (dscale_dls) {
+        const float sig = 1.0f / (1.0f + expf(-log_scale));
+        *dscale_dls = (sp >= 1e-4f && sp <= 1.0f) ? sig : 0.0f;    // clamp passes grad inside
+    }
+    return sc;
+}
+
+
 __device__ __forceinline__ bool skip_requested(const int32_t* d_skip) {
     return d_skip != nullptr && *reinterpret_cast<const volatile int32_t*>(d_skip) != 0;
 }

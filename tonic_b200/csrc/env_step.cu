@@ -9,22 +9,9 @@
 // a CTA stages a contiguous tile of `tile_envs` rows through shared memory with
 // coalesced loads/stores; inside the tile one warp owns one env at a time
 // (lanes over observation coordinates, warp-shuffle reduction for the cost).
-#include "common.cuh"
+#include "env_dynamics.cuh"
 
 namespace tb {
-
-__device__ __forceinline__ float reset_coordinate(uint32_t key, int j) {
-    const uint32_t h = fmix32(key ^ (0x85EBCA6Bu * (uint32_t)(j + 1)));
-    return __fsub_rn(__fmul_rn((float)(h >> 8), 1.1920928955078125e-07f), 1.0f);
-}
-__device__ __forceinline__ uint32_t reset_key(uint32_t seed, uint32_t episode) {
-    return fmix32(seed + 0x9E3779B9u * (episode + 1u));
-}
-
-constexpr float kDecay = 0.9f;
-constexpr float kGain = 0.1f;
-constexpr float kTermLimit = 1.0f;
-constexpr float kCostScale = (float)(0.01 * 9.5367431640625e-07);   // 0.01 * 2^-20
 
 __global__ void __launch_bounds__(256)
 env_start_kernel(TbEnv env, float* __restrict__ obs) {
@@ -71,28 +58,12 @@ env_step_kernel(TbEnv env, const float* __restrict__ actions, float* __restrict_
         const int n = e0 + e;
         float* x = sx + (size_t)e * O;
         const float* a = sa + (size_t)e * A;
-        long long xcost = 0, acost = 0;
-        for (int j = lane; j < O; j += 32) {
-            const float drive = __fmul_rn(kGain, a[j % A]);
-            const float keep = (j == 0) ? x[0] : __fmul_rn(kDecay, x[j]);
-            const float nx = __fadd_rn(keep, drive);
-            x[j] = nx;
-            const long long q = __float2ll_rn(__fmul_rn(nx, 256.0f));
-            xcost += q * q;
-        }
-        for (int k = lane; k < A; k += 32) {
-            const long long q = __float2ll_rn(__fmul_rn(a[k], 1024.0f));
-            acost += q * q;
-        }
-        xcost = warp_sum(xcost);
-        acost = warp_sum(acost);
-        __syncwarp();
+        float reward;
+        int term;
+        env_transition_warp(x, a, O, A, lane, &reward, &term);
         int reset = 0;
         uint32_t episode = 0;
         if (lane == 0) {
-            const long long cost = 100ll * acost + 16ll * xcost;
-            const float reward = __fsub_rn(1.0f, __fmul_rn(__ll2float_rn(cost), kCostScale));
-            const int term = fabsf(x[0]) > kTermLimit;
             int length = env.d_length[n] + 1;
             // distributed.py:40 -- a time-out resets without terminating
             reset = term || (length == env.max_episode_steps);

@@ -1154,3 +1154,253 @@ extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, cons
     return launch_wgrad_jobs(shape, d_xin, d_h1_hi, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout,
                              n_extra, off_extra, n_rows, d_gpart, n_split, false, d_skip, stream);
 }
+
+// =====================================================================================
+// Fused rollout: the whole segment (T vector steps) of the on-policy collector in ONE launch.
+//
+// Reference loop being replaced (tonic/utils/trainer.py:44-50 per vector step):
+//   agent.step      actor forward + Normal sample + log-prob      torch/agents/a2c.py:41-52,75-85
+//   environment.step  dynamics, auto-reset, time-outs               environments/distributed.py:28-58
+//   agent.update    Segment.store + MeanStd.record                  a2c.py:58-69, replays/segments.py:27-36
+// The policy is constant during a segment and environments are independent, so a CTA keeps
+// its 64 environments resident (state tile in shared memory) for all T steps: per step it
+// runs the 2x256 MLP on the tile (same FFMA tile code and summation order as
+// mlp_forward_kernel), samples actions with the Philox stream of gauss_sample_kernel, advances
+// the environments (env_dynamics.cuh) and writes observation / action / log-prob /
+// next-observation / reward / reset / termination rows straight into the [T, N, ...] segment.
+// =====================================================================================
+#include "env_dynamics.cuh"
+
+namespace tb {
+
+struct RolloutArgs {
+    TbEnv env;
+    TbMlpShape sh;
+    const float* params;
+    const float* packed;
+    const float* log_scale;
+    const float* norm_mean;       // actor normaliser (NULL: reference behaviour)
+    const float* norm_std;
+    int T;
+    float* seg_obs; float* seg_actions; float* seg_next_obs; float* seg_rewards;
+    float* seg_resets; float* seg_terms; float* seg_logp;
+    float* env_obs;               // acting observations after the last step
+    double* moment_sums;          // [2 O + 1] running-normaliser sums or NULL
+    uint64_t seed, counter, counter_stride;
+    const uint64_t* d_counter;
+};
+
+template <int H, int ACT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+rollout_kernel(const RolloutArgs p) {
+    using C = Cfg<H>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* bufA = reinterpret_cast<float*>(smem_raw);
+    float* bufB = bufA + TM * C::LDH;
+    float* Bs2 = bufB + TM * C::LDH;
+    float* sx = Bs2 + 2 * KC * H;                       // [TM][O] environment state tile
+    const int O = p.env.obs_dim, A = p.env.act_dim, N = p.env.n_envs;
+    float* s_pre = sx + TM * O;                         // [TM][A] head pre-activations
+    float* s_act = s_pre + TM * A;                      // [TM][A] clipped actions
+    float* s_scale = s_act + TM * A;                    // [A]
+    int* s_len = reinterpret_cast<int*>(s_scale + kMaxAct);       // [TM]
+    uint32_t* s_epi = reinterpret_cast<uint32_t*>(s_len + TM);    // [TM]
+    double* s_score = reinterpret_cast<double*>(s_epi + TM);      // [TM] (8-byte aligned by layout)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n0 = blockIdx.x * TM;
+    const int valid = min(TM, N - n0);
+    const int kpad = (O + 3) & ~3;
+    uint64_t counter = p.counter + (p.d_counter ? *p.d_counter : 0ull);
+
+    for (int i = tid; i < valid * O; i += NTHREADS) sx[i] = p.env.d_state[(size_t)n0 * O + i];
+    if (tid < A) s_scale[tid] = detached_scale(p.log_scale[tid], nullptr);
+    if (tid < valid) {
+        s_len[tid] = p.env.d_length[n0 + tid];
+        s_epi[tid] = p.env.d_episode[n0 + tid];
+        s_score[tid] = p.env.d_score[n0 + tid];
+    }
+    double msum = 0.0, msq = 0.0;                       // thread c < O owns observation column c
+    __syncthreads();
+
+    for (int t = 0; t < p.T; ++t) {
+        const size_t row0 = (size_t)t * N + n0;         // first transition of this tile at step t
+        // ---- acting observations: segment row, normaliser statistics, layer-1 input ---------
+        for (int i = tid; i < valid * O; i += NTHREADS) p.seg_obs[row0 * O + i] = sx[i];
+        if (p.moment_sums && tid < O) {
+            for (int m = 0; m < valid; ++m) {
+                const double v = (double)sx[m * O + tid];
+                msum += v;
+                msq += v * v;
+            }
+        }
+        for (int v = tid; v < TM * kpad; v += NTHREADS) {
+            const int m = v / kpad, c = v % kpad;
+            float val = 0.0f;
+            if (m < valid && c < O) {
+                val = sx[m * O + c];
+                if (p.norm_mean) val = __fdiv_rn(__fsub_rn(val, p.norm_mean[c]), p.norm_std[c]);
+            }
+            bufB[m * C::LDH + c] = val;
+        }
+        __syncthreads();
+        // ---- actor forward (identical tile arithmetic to mlp_forward_kernel) ----------------
+        float acc[8][C::NC];
+        auto ident = [](float a, int, int) { return a; };
+        zero_acc<H>(acc);
+        gemm_acc<H>(acc, bufB, C::LDH, O, p.packed + p.sh.off_w1t, H, H, true, Bs2);
+        bias_activate<H, ACT>(acc, p.params + p.sh.off_b1);
+        store_tile<H>(acc, bufA, C::LDH, TM, ident);
+        __syncthreads();
+        zero_acc<H>(acc);
+        gemm_acc<H>(acc, bufA, C::LDH, H, p.packed + p.sh.off_w2t, H, H, true, Bs2);
+        bias_activate<H, ACT>(acc, p.params + p.sh.off_b2);
+        store_tile<H>(acc, bufB, C::LDH, TM, ident);
+        __syncthreads();
+        {
+            const float* W3 = p.params + p.sh.off_w3;
+            const float* b3 = p.params + p.sh.off_b3;
+            const int quad = tid >> 2, ql = tid & 3;
+            for (int q = quad; q < TM * A; q += NTHREADS / 4) {
+                const int m = q % TM, o = q / TM;
+                const float* hrow = bufB + m * C::LDH;
+                const float* wrow = W3 + (size_t)o * H;
+                float s = 0.0f;
+#pragma unroll 4
+                for (int i = ql; i < H / 4; i += 4) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hrow + i * 4);
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + i * 4));
+                    s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s);
+                    s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (ql == 0) s_pre[m * A + o] = s + b3[o];
+            }
+        }
+        __syncthreads();
+        // ---- Normal(loc, scale).sample() + summed log-prob (same stream as gauss_sample_kernel)
+        if (tid < valid) {
+            Philox rng(p.seed);
+            const uint64_t ctr = counter + (uint64_t)t * p.counter_stride + (uint64_t)(n0 + tid);
+            float lp = 0.0f;
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int a = 0; a < A; ++a) {
+                if ((a & 3) == 0) {
+                    const uint4 r = rng(ctr, (uint64_t)(a >> 2));
+                    const float2 u = box_muller(r.x, r.y), w = box_muller(r.z, r.w);
+                    z = make_float4(u.x, u.y, w.x, w.y);
+                }
+                const float e = (a & 3) == 0 ? z.x : (a & 3) == 1 ? z.y : (a & 3) == 2 ? z.z : z.w;
+                const float loc = tanhf(s_pre[tid * A + a]);
+                const float sc = s_scale[a];
+                const float act = __fadd_rn(__fmul_rn(e, sc), loc);
+                p.seg_actions[(row0 + tid) * A + a] = act;
+                s_act[tid * A + a] = fminf(fmaxf(act, -1.0f), 1.0f);     // wrappers.py:22
+                const float d = act - loc;
+                lp += -(d * d) / (2.0f * (sc * sc)) - logf(sc) - kLogSqrt2Pi;
+            }
+            p.seg_logp[row0 + tid] = lp;
+        }
+        __syncthreads();
+        // ---- environment transitions (one warp per environment at a time) ---------------------
+        for (int e = warp; e < valid; e += NTHREADS / 32) {
+            const int n = n0 + e;
+            float* x = sx + e * O;
+            float reward;
+            int term;
+            env_transition_warp(x, s_act + e * A, O, A, lane, &reward, &term);
+            for (int j = lane; j < O; j += 32) p.seg_next_obs[(row0 + e) * O + j] = x[j];
+            int reset = 0;
+            uint32_t episode = 0;
+            if (lane == 0) {
+                int length = s_len[e] + 1;
+                reset = term || (length == p.env.max_episode_steps);     // distributed.py:40
+                double score = s_score[e] + (double)reward;
+                episode = s_epi[e];
+                if (reset) {
+                    const unsigned long long slot = atomicAdd(p.env.d_ep_count, 1ull);
+                    if (p.env.log_cap > 0) {
+                        p.env.d_ep_scores[slot % p.env.log_cap] = score;
+                        p.env.d_ep_lengths[slot % p.env.log_cap] = length;
+                    }
+                    s_epi[e] = episode + 1u;
+                    length = 0;
+                    score = 0.0;
+                }
+                s_len[e] = length;
+                s_score[e] = score;
+                p.seg_rewards[row0 + e] = reward;
+                p.seg_resets[row0 + e] = reset ? 1.0f : 0.0f;
+                p.seg_terms[row0 + e] = term ? 1.0f : 0.0f;
+            }
+            reset = __shfl_sync(0xffffffffu, reset, 0);
+            episode = __shfl_sync(0xffffffffu, episode, 0);
+            if (reset) {                                                 // distributed.py:46-48
+                const uint32_t key = reset_key((uint32_t)(p.env.seed + p.env.first_worker + n), episode);
+                for (int j = lane; j < O; j += 32) x[j] = reset_coordinate(key, j);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- write the resident state back ----------------------------------------------------------
+    for (int i = tid; i < valid * O; i += NTHREADS) {
+        p.env.d_state[(size_t)n0 * O + i] = sx[i];
+        p.env_obs[(size_t)n0 * O + i] = sx[i];
+    }
+    if (tid < valid) {
+        p.env.d_length[n0 + tid] = s_len[tid];
+        p.env.d_episode[n0 + tid] = s_epi[tid];
+        p.env.d_score[n0 + tid] = s_score[tid];
+    }
+    if (p.moment_sums && tid < O) {
+        atomicAdd(&p.moment_sums[tid], msum);
+        atomicAdd(&p.moment_sums[O + tid], msq);
+    }
+    if (p.moment_sums && tid == 0) atomicAdd(&p.moment_sums[2 * O], (double)valid * (double)p.T);
+}
+
+}  // namespace tb
+
+extern "C" int tb_rollout_fused(const TbEnv* env, const TbMlpShape* shape, const float* d_params,
+                                const float* d_packed, const float* d_log_scale,
+                                const float* d_norm_mean, const float* d_norm_std, int32_t T,
+                                float* d_seg_obs, float* d_seg_actions, float* d_seg_next_obs,
+                                float* d_seg_rewards, float* d_seg_resets, float* d_seg_terms,
+                                float* d_seg_logp, float* d_env_obs, double* d_moment_sums,
+                                uint64_t seed, uint64_t counter, uint64_t counter_stride,
+                                const uint64_t* d_counter, void* stream) {
+    using namespace tb;
+    ProfScope prof_scope("tb_rollout_fused", stream);
+    int rc = check_shape(shape, "tb_rollout_fused");
+    if (rc) return rc;
+    TB_REQUIRE(env && d_params && d_packed && d_log_scale && d_seg_obs && d_seg_actions &&
+               d_seg_next_obs && d_seg_rewards && d_seg_resets && d_seg_terms && d_seg_logp &&
+               d_env_obs && T > 0, TB_EINVAL, "tb_rollout_fused: null pointer");
+    TB_REQUIRE(shape->d_in == env->obs_dim && shape->n_out == env->act_dim, TB_EINVAL,
+               "tb_rollout_fused: network / environment shapes differ");
+    TB_REQUIRE(env->obs_dim <= 64 && env->obs_dim <= shape->hidden && env->act_dim <= 16, TB_ENOTSUP,
+               "tb_rollout_fused: needs obs_dim <= 64 and act_dim <= 16 (got %d, %d)",
+               env->obs_dim, env->act_dim);
+    RolloutArgs a;
+    a.env = *env; a.sh = *shape; a.params = d_params; a.packed = d_packed; a.log_scale = d_log_scale;
+    a.norm_mean = d_norm_mean; a.norm_std = d_norm_std; a.T = T;
+    a.seg_obs = d_seg_obs; a.seg_actions = d_seg_actions; a.seg_next_obs = d_seg_next_obs;
+    a.seg_rewards = d_seg_rewards; a.seg_resets = d_seg_resets; a.seg_terms = d_seg_terms;
+    a.seg_logp = d_seg_logp; a.env_obs = d_env_obs; a.moment_sums = d_moment_sums;
+    a.seed = seed; a.counter = counter; a.counter_stride = counter_stride; a.d_counter = d_counter;
+    const int blocks = (env->n_envs + TM - 1) / TM;
+    const int H = shape->hidden;
+    const size_t smem = (size_t)(2 * TM * (H + 4) + 2 * KC * H + TM * env->obs_dim +
+                                 2 * TM * env->act_dim + kMaxAct) * sizeof(float) +
+                        TM * (sizeof(int) + sizeof(uint32_t) + sizeof(double)) + 16;
+    cudaStream_t s = as_stream(stream);
+#define CALL(H_, A_)                                                              \
+    {                                                                             \
+        set_smem(rollout_kernel<H_, A_>, smem);                                   \
+        rollout_kernel<H_, A_><<<blocks, NTHREADS, smem, s>>>(a);                 \
+    }
+    TB_DISPATCH_H_ACT(H, shape->act, CALL);
+#undef CALL
+    return check_launch("tb_rollout_fused");
+}

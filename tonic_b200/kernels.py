@@ -346,6 +346,19 @@ def gauss_sample(loc_pre, log_scale, actions, log_probs, eps=None, seed=0, count
               ptr(device_counter), rows, act, ptr(actions), ptr(log_probs), stream())
 
 
+def rollout_fused(env_struct, mlp, log_scale, norm_mean, norm_std, T, buffers, env_obs,
+                  moment_sums, seed, counter, counter_stride, device_counter):
+    """All T vector steps of the on-policy collector in one launch
+    (csrc/mlp.cu::rollout_kernel; reference loop utils/trainer.py:44-50)."""
+    b = buffers
+    _lib.call('tb_rollout_fused', ctypes.byref(env_struct), ctypes.byref(mlp.layout.shape),
+              ptr(mlp.params), ptr(mlp.packed), ptr(log_scale), ptr(norm_mean), ptr(norm_std),
+              int(T), ptr(b['observations']), ptr(b['actions']), ptr(b['next_observations']),
+              ptr(b['rewards']), ptr(b['resets']), ptr(b['terminations']), ptr(b['log_probs']),
+              ptr(env_obs), ptr(moment_sums), int(seed), int(counter), int(counter_stride),
+              ptr(device_counter), stream())
+
+
 def counter_add(counter, delta):
     _lib.call('tb_counter_add', ptr(counter), int(delta), stream())
 

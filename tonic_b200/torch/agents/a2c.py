@@ -129,7 +129,23 @@ class A2C(agent.Agent):
                           b['resets'][t], b['terminations'][t])
 
         done = 0
-        if self._graphable() and seg.index == 0 and vector_steps >= T:
+        if self._fusable(env) and seg.index == 0 and vector_steps >= T:
+            # whole segment in ONE persistent kernel (csrc/mlp.cu::rollout_kernel)
+            if self._noise_counter is None:
+                self._noise_counter = kernels.new_counter()
+            actor = self.model.actor
+            norm = actor.encoder.observation_normalizer
+            world, rank = distributed.world(), distributed.rank()
+            kernels.rollout_fused(
+                env.struct, actor.network.mlp, actor.network.extra('log_scale'),
+                None if norm is None else norm._mean.data,
+                None if norm is None else norm._std.data, T, b, env.observations,
+                normalizer.sums if normalizer else None, self.seed or 0, rank * N, N * world,
+                self._noise_counter)
+            kernels.counter_add(self._noise_counter, T * N * world)
+            seg.index = T
+            done = T
+        elif self._graphable() and seg.index == 0 and vector_steps >= T:
             # whole segment in one CUDA graph (tonic_b200/graphs.py)
             if self._rollout_graph is None:
                 self._rollout_graph = graphs.CapturedSection(
@@ -146,6 +162,16 @@ class A2C(agent.Agent):
         if seg.ready():
             self._update()
         return done
+
+    def _fusable(self, env):
+        """The fused rollout kernel covers the detached-scale Gaussian actor on
+        device noise with small observation / action vectors."""
+        actor = self.model.actor
+        shape = actor.network.layout.shape
+        return (config.fused_rollout and config.noise == 'device'
+                and getattr(actor.head, 'kind', None) == 'detached_gaussian'
+                and hasattr(env, 'struct') and shape.d_in <= min(64, shape.hidden)
+                and shape.n_out <= 16 and shape.hidden in (64, 128, 256))
 
     def _graphable(self):
         """Static shapes + device-resident RNG: the section can be replayed as a CUDA
