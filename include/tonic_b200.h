@@ -151,6 +151,10 @@ typedef struct TbMlpShape_ {
     /* tensor-core path (hidden == 256 only; 0 = absent): tf32 splits of W2 [H, H]
      * (B operand of the forward GEMM) and of W2^T (B operand of the backward GEMM) */
     int32_t off_w2_hi, off_w2_lo, off_w2t_hi, off_w2t_lo;
+    /* fused forward kernel (hidden == 256 and d_in <= 32; 0 = absent): W1 as the layer-1
+     * B operand, i.e. the byte image of the [256 x 32] K-major 128B-swizzled shared-memory
+     * tile (tf32 hi / lo parts, zero-padded columns), 8192 floats each, 16-byte aligned  */
+    int32_t off_w1_img_hi, off_w1_img_lo;
 } TbMlpShape;
 
 typedef struct {
@@ -218,6 +222,22 @@ int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const float* d_b_hi,
                   const float* d_aux_lo, float* d_out, float* d_out_lo,
                   const float* d_head_w, const float* d_head_b, float* d_head_out,
                   int32_t n_head, const int32_t* d_skip, void* stream);
+
+/* Whole forward pass of a 2 x 256 MLP with d_in <= 32 and n_out <= 8 as ONE tensor-core
+ * kernel (csrc/tc_mlp.cu): input gather / normalisation (encoders.py:11-30), both hidden
+ * layers (models/utils.py:15-23) and the linear head; d_xin / d_h1_hi / d_h1_lo / d_h2 may be
+ * NULL when no backward pass follows (value / action evaluation).  tb_mlp_forward_tc routes
+ * here when the shape allows it.                                                          */
+int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                      const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                      float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                      const int32_t* d_skip, void* stream);
+
+/* Profiling aid for the fused forward kernel: the first call allocates a device buffer
+ * of 64 clock64() stamps that CTA 0 of every later tb_tc_mlp_forward launch fills
+ * (slots documented in csrc/tc_mlp.cu); a non-NULL `out64` reads them back (host
+ * pointer, 64 values, synchronising copy).  Not used on the product path.               */
+int tb_tc_timeline(uint64_t* out64);
 
 /* The MLP entry points above with the two hidden-layer GEMMs (and the W2 weight
  * gradient) on the tensor cores: layer 1, the head, the head gradient and the

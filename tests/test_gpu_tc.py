@@ -127,3 +127,75 @@ def test_tc_gemm_throughput_smoke(K):
         us = start.elapsed_time(end) / 20 * 1e3
         print(f'tc_wgrad256 rows={rows} passes={passes}: {us:.1f} us, '
               f'{2 * rows * 65536 / us / 1e6:.1f} TFLOP/s (fp32-equivalent)')
+
+
+# ---- one-kernel forward pass (csrc/tc_mlp.cu) --------------------------------------------
+def _reference_forward(net, x, act):
+    L, H = net.layout, net.layout.hidden
+    p = {k: net.view(k, s).cpu().double() for k, s in
+         dict(w1=(H, L.d_in), b1=(H,), w2=(H, H), b2=(H,), w3=(L.n_out, H), b3=(L.n_out,)).items()}
+    f = torch.tanh if act == 'tanh' else torch.relu
+    h1 = f(x.double() @ p['w1'].T + p['b1'])
+    h2 = f(h1 @ p['w2'].T + p['b2'])
+    return h1, h2, h2 @ p['w3'].T + p['b3']
+
+
+@pytest.mark.parametrize('d_in,n_out,act,rows', [
+    (17, 1, 'tanh', 16384), (17, 6, 'tanh', 1000), (23, 1, 'relu', 333), (32, 8, 'relu', 128),
+    (3, 1, 'tanh', 1), (17, 6, 'tanh', 148 * 128 * 2 + 77)])
+@pytest.mark.parametrize('passes', [3, 1])
+def test_tc_mlp_forward_fused(K, d_in, n_out, act, rows, passes):
+    """tb_tc_mlp_forward (input gather + normalisation, both hidden layers and the head in one
+    tcgen05 kernel) against a float64 evaluation of the same network."""
+    import ctypes
+    from tonic_b200 import _lib
+    layout = K.MlpLayout(d_in, 256, n_out, act)
+    net = K.DeviceMlp(layout)
+    g = torch.Generator().manual_seed(rows + d_in)
+    net.params.copy_(torch.randn(layout.n_params, generator=g) * 0.15)
+    net.pack()
+    pool = torch.randn(rows + 50, d_in, generator=g)
+    idx = torch.randperm(rows + 50, generator=g)[:rows]
+    mean, std = torch.randn(d_in, generator=g) * 0.1, torch.rand(d_in, generator=g) + 0.5
+    x = (pool[idx] - mean) / std
+    h1, h2, out = _reference_forward(net, x, act)
+    inp = K.MlpInput(pool.cuda(), mean.cuda(), std.cuda(), idx=idx.cuda())
+    tol = dict(rtol=3e-5, atol=3e-5) if passes == 3 else dict(rtol=2e-2, atol=2e-2)
+    for save in (True, False):
+        got = torch.full((rows, n_out), float('nan'), device='cuda')
+        bufs = [torch.full((rows, 256), float('nan'), device='cuda') for _ in range(3)] if save else [None] * 3
+        xin = torch.full((rows, layout.ldx), float('nan'), device='cuda') if save else None
+        _lib.call('tb_tc_mlp_forward', ctypes.byref(layout.shape), K.ptr(net.params), K.ptr(net.packed),
+                  ctypes.byref(inp.struct), rows, K.ptr(got), K.ptr(xin), K.ptr(bufs[0]),
+                  K.ptr(bufs[1]), K.ptr(bufs[2]), passes, None, K.stream())
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(got.cpu(), out, **tol)
+        if save:
+            h1_hi, h1_lo, h2_got = bufs
+            np.testing.assert_allclose((h1_hi + h1_lo).cpu(), h1, **tol)
+            np.testing.assert_allclose(h2_got.cpu(), h2, **tol)
+            assert (h1_hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0
+            want = torch.cat([x, torch.ones(rows, 1), torch.zeros(rows, layout.ldx - d_in - 1)], 1)
+            np.testing.assert_allclose(xin.cpu(), want, rtol=1e-6, atol=1e-6)
+
+
+def test_tc_mlp_forward_two_inputs(K):
+    """Q-critic style input: [observations | actions] with the second part not gathered."""
+    import ctypes
+    from tonic_b200 import _lib
+    rows, d1, d2 = 500, 11, 4
+    layout = K.MlpLayout(d1 + d2, 256, 1, 'relu')
+    net = K.DeviceMlp(layout)
+    g = torch.Generator().manual_seed(5)
+    net.params.copy_(torch.randn(layout.n_params, generator=g) * 0.15)
+    net.pack()
+    pool = torch.randn(900, d1, generator=g)
+    idx = torch.randint(900, (rows,), generator=g)
+    acts = torch.randn(rows, d2, generator=g)
+    _, _, out = _reference_forward(net, torch.cat([pool[idx], acts], 1), 'relu')
+    inp = K.MlpInput(pool.cuda(), x2=acts.cuda(), gather2=False, idx=idx.cuda())
+    got = torch.empty(rows, 1, device='cuda')
+    _lib.call('tb_tc_mlp_forward', ctypes.byref(layout.shape), K.ptr(net.params), K.ptr(net.packed),
+              ctypes.byref(inp.struct), rows, K.ptr(got), None, None, None, None, 3, None, K.stream())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(got.cpu(), out, rtol=3e-5, atol=3e-5)

@@ -35,7 +35,7 @@ class TbMlpShape(ctypes.Structure):
                 ('off_w3', c_i32), ('off_b3', c_i32), ('n_params', c_i32),
                 ('off_w1t', c_i32), ('off_w2t', c_i32), ('n_packed', c_i32),
                 ('off_w2_hi', c_i32), ('off_w2_lo', c_i32), ('off_w2t_hi', c_i32),
-                ('off_w2t_lo', c_i32)]
+                ('off_w2t_lo', c_i32), ('off_w1_img_hi', c_i32), ('off_w1_img_lo', c_i32)]
 
 
 class TbMlpInput(ctypes.Structure):
@@ -97,6 +97,9 @@ _PROTOTYPES = {
     'tb_tc_gemm256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_mlp_forward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'tb_tc_timeline': (c_int, [c_vp]),
+    'tb_tc_mlp_forward': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_mlp_backward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64,
                                    c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),

@@ -14,6 +14,8 @@
 //   wgrad   : dW = dz^T [inputs | 1]   (split over rows, partial sums per split)
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tb {
@@ -1031,10 +1033,23 @@ extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
     using namespace tb;
     int rc = check_tc_shape(shape, "tb_mlp_forward_tc");
     if (rc) return rc;
-    TB_REQUIRE(d_params && d_packed && in && in->d_x1 && d_out && d_h1_hi && d_h1_lo && d_h2 &&
-               n_rows > 0, TB_EINVAL, "tb_mlp_forward_tc: null pointer");
+    TB_REQUIRE(d_params && d_packed && in && in->d_x1 && d_out && n_rows > 0, TB_EINVAL,
+               "tb_mlp_forward_tc: null pointer");
     TB_REQUIRE(in->dim1 + (in->d_x2 ? in->dim2 : 0) == shape->d_in, TB_EINVAL,
                "tb_mlp_forward_tc: input widths do not add up to d_in");
+    {
+        // narrow inputs and heads: the whole forward pass is one tensor-core kernel
+        // (csrc/tc_mlp.cu); TONIC_B200_FUSED_FWD=0 selects the three-kernel chain below
+        static const bool fused = [] {
+            const char* v = getenv("TONIC_B200_FUSED_FWD");
+            return !(v && v[0] == '0');
+        }();
+        if (fused && shape->off_w1_img_hi > 0 && shape->d_in <= 32 && shape->n_out <= 8)
+            return tb_tc_mlp_forward(shape, d_params, d_packed, in, n_rows, d_out, d_xin, d_h1_hi,
+                                     d_h1_lo, d_h2, passes, d_skip, stream);
+    }
+    TB_REQUIRE(d_h1_hi && d_h1_lo && d_h2, TB_EINVAL,
+               "tb_mlp_forward_tc: the unfused chain needs the h1 / h2 workspaces");
     const int blocks = (int)((n_rows + TM - 1) / TM);
     cudaStream_t s = as_stream(stream);
     {

@@ -16,6 +16,15 @@ __device__ __forceinline__ void pack_one(const TbMlpShape& sh, int i, float p, f
     if (i >= sh.off_w1 && i < sh.off_w1 + H * sh.d_in) {           // W1 [H, d_in] -> W1T [d_in, H]
         const int e = i - sh.off_w1, n = e / sh.d_in, k = e % sh.d_in;
         packed[sh.off_w1t + k * H + n] = p;
+        if (sh.off_w1_img_hi > 0) {
+            // layer-1 B operand of the fused forward kernel (csrc/tc_mlp.cu): element (n, k) of
+            // the K-major [256 x 32] tile with the 128-byte swizzle (8-row groups of 1024 B, 16-byte
+            // unit index XOR-ed with the row within the group); columns k >= d_in stay zero
+            const int word = (n >> 3) * 256 + (n & 7) * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
+            const float hi = __uint_as_float(__float_as_uint(p) & 0xFFFFE000u);
+            packed[sh.off_w1_img_hi + word] = hi;
+            packed[sh.off_w1_img_lo + word] = p - hi;
+        }
     } else if (i >= sh.off_w2 && i < sh.off_w2 + H * H) {          // W2 [H, H] -> W2T
         const int e = i - sh.off_w2, n = e / H, k = e % H;
         packed[sh.off_w2t + k * H + n] = p;

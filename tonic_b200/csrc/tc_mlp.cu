@@ -1,0 +1,555 @@
+// Fused forward pass of the 2 x 256 MLP on the tensor cores (sm_100a): one kernel computes
+//
+//     x   = gather / normalise / concatenate the input rows        (TbMlpInput)
+//     h1  = act(x  W1^T + b1)                                      [rows, 256]
+//     h2  = act(h1 W2^T + b2)                                      [rows, 256]
+//     out = h2 W3^T + b3                                           [rows, n_out <= 8]
+//
+// for a 128-row tile per CTA without h1 ever leaving the SM as a matmul operand; reference
+// arithmetic: tonic/torch/models/utils.py:15-23 (MLP torso), encoders.py:11-30 (normalise /
+// concatenate), critics.py:9-20 / actors.py:37-66 (linear heads).  It replaces the chain
+// mlp_layer1_kernel -> tc_gemm_kernel<.., EPI_BIAS_ACT> (csrc/mlp.cu, csrc/tc_gemm.cu); with
+// one row tile per CTA those two kernels spent most of their time on launch latency, the
+// h1 round trip through global memory and an instruction-bound FFMA first layer.
+//
+// Roles (384 threads):
+//   warp 0      producer (one thread): per tile a 1-D bulk copy of the W1 operand image
+//               (written by tb_mlp_pack in the swizzled shared-memory layout) and TMA loads of
+//               the W2 chunks (hi / lo tf32 parts, 128B swizzle);
+//   warp 1      MMA issuer (one thread): tcgen05.mma kind::tf32, M = 128, N = 256;
+//               accumulator 0 (TMEM columns 0..255) = layer 1, accumulator 1 = layer 2;
+//   warp 2      TMEM allocation;
+//   warps 4-11  "row" warps: thread (q, lane) of column half wg owns row 32 q + lane of the
+//               tile and 16 of every 32 columns (two warps share a TMEM lane quarter):
+//                 a) layer-1 A operand: gather / normalise the input row, zero-pad to K = 32,
+//                    split into tf32 hi / lo parts, store in the K-major 128B-swizzle layout
+//                    the MMA descriptor expects (and the input copy the weight gradient needs);
+//                 b) mid epilogue, per 32-column chunk c of accumulator 0: tcgen05.ld -> + b1 ->
+//                    activation -> hi / lo split -> A operand of layer-2 chunk c in shared
+//                    memory (and h1 to global memory when the backward pass needs it);
+//                 c) final epilogue on accumulator 1: + b2 -> activation -> fused linear head
+//                    (-> h2 to global memory when the backward pass needs it).
+// Shared-memory stages hold [A hi | A lo | B hi | B lo] = 96 KB (3xTF32) exactly as in
+// tc_gemm_kernel; per tile they are used 9 times: once for layer 1 and 8 times for the K
+// chunks of layer 2 (A by the row warps, B by the producer).  Measured on B200 with the
+// clock64() timeline below (16384 rows, one tile per CTA): the row warps are the critical
+// path; the activation stores of the training forward pass (h1 hi / lo, h2: 48 MB) run at
+// the chip's L2 write bandwidth.
+#include "tc_common.cuh"
+
+namespace tb {
+
+struct TcMlpParams {
+    int64_t n_rows;
+    TbMlpInput in;
+    int d_in;                   // <= 32
+    int act;
+    const float* w1_img_hi;     // W1 as the layer-1 B operand: byte image of the swizzled
+    const float* w1_img_lo;     // [256 x 32] K-major tile (hi / lo), written by tb_mlp_pack
+    const float* b1;
+    const float* b2;
+    float* xin_save;            // [n_rows, ldx] with the ones column, or NULL
+    float* h1_hi;               // [n_rows, 256] tf32 split of h1, or NULL (no backward pass)
+    float* h1_lo;
+    float* h2;                  // [n_rows, 256] or NULL
+    const float* head_w;        // [n_head, 256]
+    const float* head_b;
+    float* head_out;            // [n_rows, n_head]
+    int n_head;                 // 0..8
+    const int32_t* skip;
+    unsigned long long* timeline;   // profiling aid: 64 clock64() stamps of CTA 0, or NULL
+};
+
+constexpr int TCM_ROW_WARPS = 8;                 // two per TMEM lane quarter (column halves)
+constexpr int TCM_THREADS = (4 + TCM_ROW_WARPS) * 32;
+constexpr int TCM_STG_STRIDE = 20;               // floats per staged row (16 + pad)
+
+template <int PASSES>
+struct TcMlpCfg {
+    using G = TcCfg<PASSES>;
+    static constexpr int STAGES = 2;
+    static constexpr int STAGE_BYTES = G::STAGE_BYTES;
+    static constexpr int A_LO = TC_A_BYTES;                              // offset of A lo (3 passes)
+    static constexpr int B_HI = G::PARTS * TC_A_BYTES;
+    static constexpr int B_LO = 2 * TC_A_BYTES + TC_B_BYTES;
+    static constexpr int EPI_BYTES = TCM_ROW_WARPS * 32 * TCM_STG_STRIDE * 4;
+    static constexpr int CONST_BYTES = (TC_MAX_HEAD + 2) * TC_BN * 4;    // head weights, b1, b2
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + CONST_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ float tc_tf32_hi(float x) {
+    return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+template <int ACT>
+__device__ __forceinline__ float tc_act(float x) {
+    return ACT == TB_ACT_TANH ? tanh_fast(x) : fmaxf(x, 0.0f);
+}
+
+__device__ __forceinline__ void tc_stamp(unsigned long long* timeline, int slot) {
+    if (timeline && blockIdx.x == 0) timeline[slot] = (unsigned long long)clock64();
+}
+
+// 16 consecutive 32-bit TMEM columns of this warp's 32 lanes -> 16 registers per thread
+__device__ __forceinline__ void tcgen05_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 1-D bulk copy global -> shared memory, completing on an mbarrier (no tensor map)
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// barrier among the 8 row warps only
+__device__ __forceinline__ void row_warps_sync() {
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// write 32 consecutive K values of one operand row (as hi / lo parts) into swizzled tiles
+template <int PASSES>
+__device__ __forceinline__ void store_operand_row(unsigned char* hi_tile, unsigned char* lo_tile, int row,
+                                                  const float (&v)[32]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const uint32_t off = sw128_offset(row, u);
+        float4 h;
+        h.x = tc_tf32_hi(v[4 * u]); h.y = tc_tf32_hi(v[4 * u + 1]);
+        h.z = tc_tf32_hi(v[4 * u + 2]); h.w = tc_tf32_hi(v[4 * u + 3]);
+        *reinterpret_cast<float4*>(hi_tile + off) = h;
+        if (PASSES == 3) {
+            float4 l;
+            l.x = v[4 * u] - h.x; l.y = v[4 * u + 1] - h.y;
+            l.z = v[4 * u + 2] - h.z; l.w = v[4 * u + 3] - h.w;
+            *reinterpret_cast<float4*>(lo_tile + off) = l;
+        }
+    }
+}
+
+// write 16 consecutive K values (units 4 half .. 4 half + 3) of one operand row
+template <int PASSES>
+__device__ __forceinline__ void store_operand_half(unsigned char* hi_tile, unsigned char* lo_tile, int row,
+                                                   int half, const float (&v)[16]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const uint32_t off = sw128_offset(row, 4 * half + u);
+        float4 h;
+        h.x = tc_tf32_hi(v[4 * u]); h.y = tc_tf32_hi(v[4 * u + 1]);
+        h.z = tc_tf32_hi(v[4 * u + 2]); h.w = tc_tf32_hi(v[4 * u + 3]);
+        *reinterpret_cast<float4*>(hi_tile + off) = h;
+        if (PASSES == 3) {
+            float4 l;
+            l.x = v[4 * u] - h.x; l.y = v[4 * u + 1] - h.y;
+            l.z = v[4 * u + 2] - h.z; l.w = v[4 * u + 3] - h.w;
+            *reinterpret_cast<float4*>(lo_tile + off) = l;
+        }
+    }
+}
+
+template <int PASSES, int ACT>
+__global__ void __launch_bounds__(TCM_THREADS, 1)
+tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
+                      const __grid_constant__ CUtensorMap map_b_lo, const TcMlpParams p) {
+    using Cfg = TcMlpCfg<PASSES>;
+    if (skip_requested(p.skip)) return;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* s_head_w = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    float* s_b1 = s_head_w + TC_MAX_HEAD * TC_BN;
+    float* s_b2 = s_b1 + TC_BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
+                                                 Cfg::CONST_BYTES);
+    uint64_t* full_bar = bars;                        // [STAGES] B operand landed (TMA / bulk copy)
+    uint64_t* a_ready = bars + Cfg::STAGES;           // [STAGES] A operand written by the row warps
+    uint64_t* empty_bar = bars + 2 * Cfg::STAGES;     // [STAGES] MMAs reading the stage retired
+    uint64_t* acc_full = bars + 3 * Cfg::STAGES;      // [2] accumulator complete
+    uint64_t* x_ready = acc_full + 2;                 // layer-1 A operand written (all row warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    if (threadIdx.x == 0) tc_stamp(p.timeline, 0);
+    constexpr int USES = 1 + TC_K / TC_BK;            // stage uses per tile: layer 1 + 8 chunks
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&a_ready[s], TCM_ROW_WARPS / 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_init(x_ready, TCM_ROW_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < TC_BN; i += TCM_THREADS) {
+        s_b1[i] = p.b1[i];
+        s_b2[i] = p.b2[i];
+    }
+    for (int i = threadIdx.x; i < p.n_head * TC_BN; i += TCM_THREADS) s_head_w[i] = p.head_w[i];
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) tc_stamp(p.timeline, 1);
+    const int k_steps1 = (p.d_in + 7) >> 3;           // layer-1 MMAs (K = 8 each) per pass
+
+    if (warp == 0) {
+        // ===================== producer: W1 operand image (bulk copy), W2 chunks (TMA) ==========
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int u = 0; u < USES; ++u) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * TC_B_BYTES);
+                    if (u == 0) {
+                        bulk_load(st + Cfg::B_HI, p.w1_img_hi, TC_B_BYTES, &full_bar[stage]);
+                        if (PASSES == 3) bulk_load(st + Cfg::B_LO, p.w1_img_lo, TC_B_BYTES, &full_bar[stage]);
+                    } else {
+                        const int c = u - 1;
+                        tma_load_2d(st + Cfg::B_HI, &map_b_hi, &full_bar[stage], c * TC_BK, 0);
+                        if (PASSES == 3)
+                            tma_load_2d(st + Cfg::B_LO, &map_b_lo, &full_bar[stage], c * TC_BK, 0);
+                    }
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            uint32_t a_phase = 0;                     // bit s: parity of a_ready[s] (layer-2 uses only)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                for (int u = 0; u < USES; ++u) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_stamp(p.timeline, 40 + u);             // B operand landed
+                    if (u == 0) mbar_wait(x_ready, it & 1);
+                    else mbar_wait(&a_ready[stage], (a_phase >> stage) & 1u), a_phase ^= 1u << stage;
+                    tc_stamp(p.timeline, 50 + u);             // A operand ready -> MMAs issued
+                    tcgen05_fence_after();
+                    unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc_kmajor_sw128(st);
+                    const uint64_t a_lo = umma_desc_kmajor_sw128(st + Cfg::A_LO);
+                    const uint64_t b_hi = umma_desc_kmajor_sw128(st + Cfg::B_HI);
+                    const uint64_t b_lo = umma_desc_kmajor_sw128(st + Cfg::B_LO);
+                    const uint32_t d_tmem = tmem_base + (u == 0 ? 0u : (uint32_t)TC_BN);
+                    const int ks = u == 0 ? k_steps1 : TC_BK / 8;
+                    const bool fresh = u <= 1;                      // first chunk of an accumulator
+                    for (int k = 0; k < ks; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                        const uint32_t accumulate = (fresh && k == 0) ? 0u : 1u;
+                        if (PASSES == 3) {
+                            tcgen05_mma_tf32(d_tmem, a_lo + koff, b_hi + koff, kIdescTf32, accumulate);
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_lo + koff, kIdescTf32, 1);
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, 1);
+                        } else {
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, accumulate);
+                        }
+                    }
+                    tcgen05_commit(&empty_bar[stage]);
+                    if (u == 0) tcgen05_commit(&acc_full[0]);
+                    if (u == USES - 1) tcgen05_commit(&acc_full[1]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== row warps =====================
+        // warp 4 + rw: TMEM lane quarter q = rw % 4 (== warp % 4), group wg = rw / 4.  Thread
+        // (q, lane) owns row 32 q + lane of the tile.  The input row is split by columns between
+        // the two groups (16 each); the 32-column chunks of both epilogues alternate between
+        // them (group 0 even chunks, group 1 odd chunks), so that on every SM sub-partition one
+        // warp computes while the other waits on TMEM / shared-memory / barrier latency.
+        const int rw = warp - 4, q = rw & 3, wg = rw >> 2;
+        const int trow = q * 32 + lane;
+        const bool stamper = rw == 0 && lane == 0;
+        float* stg = epi + rw * 32 * TCM_STG_STRIDE;
+        const int d_in = p.d_in;
+        const int ldx = (d_in + 1 + 3) & ~3;
+        float* __restrict__ g_h1_hi = p.h1_hi;
+        float* __restrict__ g_h1_lo = p.h1_lo;
+        float* __restrict__ g_h2 = p.h2;
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        int it = 0;
+        if (stamper) tc_stamp(p.timeline, 31);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int64_t row0 = (int64_t)tile * TC_BM + q * 32;
+            const int64_t row = (int64_t)tile * TC_BM + trow;
+            const int g0 = it * USES;                 // stage use index of this tile's layer 1
+            // ---- a) layer-1 A operand: this thread's 16 input columns ---------------------------
+            {
+                float xv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xv[j] = 0.0f;
+                if (row < p.n_rows) {
+                    const int64_t r = p.in.d_idx ? p.in.d_idx[row] : row;
+                    const int64_t r2 = p.in.gather2 ? r : row;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = 16 * wg + j;
+                        if (c < d_in) {
+                            float val;
+                            if (c < p.in.dim1) {
+                                val = p.in.d_x1[r * p.in.dim1 + c];
+                                if (p.in.d_mean)      // mean_stds.py:36  (val - mean) / std
+                                    val = __fdiv_rn(__fsub_rn(val, p.in.d_mean[c]), p.in.d_std[c]);
+                            } else {
+                                val = p.in.d_x2[r2 * p.in.dim2 + (c - p.in.dim1)];
+                            }
+                            xv[j] = val;
+                        }
+                    }
+                    if (p.xin_save) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = 16 * wg + j;
+                            if (c < ldx) p.xin_save[row * ldx + c] = c < d_in ? xv[j] : (c == d_in ? 1.0f : 0.0f);
+                        }
+                        if (wg == 1)
+                            for (int c = 32; c < ldx; ++c) p.xin_save[row * ldx + c] = c == d_in ? 1.0f : 0.0f;
+                    }
+                }
+                const int stage = g0 & 1;
+                mbar_wait(&empty_bar[stage], ((g0 >> 1) & 1) ^ 1);
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                store_operand_half<PASSES>(st, st + Cfg::A_LO, trow, wg, xv);
+                if (stamper) tc_stamp(p.timeline, 32);        // input row loaded and stored
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_ready);
+                if (stamper) tc_stamp(p.timeline, 2);         // layer-1 A operand published
+            }
+            // ---- b) mid epilogue: h1 chunks -> layer-2 A operand -------------------------------
+            mbar_wait(&acc_full[0], it & 1);
+            tcgen05_fence_after();
+            if (stamper) tc_stamp(p.timeline, 3);             // layer-1 accumulator complete
+#pragma unroll 1
+            for (int c = wg; c < TC_K / TC_BK; c += 2) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + t_lane + (uint32_t)(c * 32), v);
+                float hv[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = b4[j / 4];
+                    hv[j] = tc_act<ACT>(__uint_as_float(v[j]) + b.x);
+                    hv[j + 1] = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+                    hv[j + 2] = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+                    hv[j + 3] = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+                }
+                if (stamper) tc_stamp(p.timeline, 4 + c);     // chunk computed
+                const int g = g0 + 1 + c, stage = g & 1;
+                mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
+                if (stamper) tc_stamp(p.timeline, 12 + c);    // stage free
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[stage]);
+                if (stamper) tc_stamp(p.timeline, 20 + c);    // operand published
+                if (g_h1_hi) {                       // saved activations (tf32 split) for backward
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float* mine = stg + lane * TCM_STG_STRIDE;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(mine + j) = make_float4(
+                                hv[16 * half + j], hv[16 * half + j + 1], hv[16 * half + j + 2],
+                                hv[16 * half + j + 3]);
+                        __syncwarp();
+                        const int col = c * 32 + half * 16 + (lane & 15);
+#pragma unroll 8
+                        for (int i = 0; i < 16; ++i) {
+                            const int r = 2 * i + (lane >> 4);
+                            if (row0 + r < p.n_rows) {
+                                const float x = stg[r * TCM_STG_STRIDE + (lane & 15)];
+                                const float hi = tc_tf32_hi(x);
+                                g_h1_hi[(row0 + r) * TC_BN + col] = hi;
+                                g_h1_lo[(row0 + r) * TC_BN + col] = x - hi;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // ---- c) final epilogue: h2, fused head ----------------------------------------------
+            if (stamper) tc_stamp(p.timeline, 28);            // mid epilogue (+ h1 stores) done
+            mbar_wait(&acc_full[1], it & 1);
+            tcgen05_fence_after();
+            if (stamper) tc_stamp(p.timeline, 29);            // layer-2 accumulator complete
+            float hacc[TC_MAX_HEAD];
+#pragma unroll
+            for (int o = 0; o < TC_MAX_HEAD; ++o) hacc[o] = 0.0f;
+#pragma unroll 1
+            for (int c = wg; c < TC_BN / 32; c += 2) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + t_lane + (uint32_t)(TC_BN + c * 32), v);
+                float hv[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = b4[j / 4];
+                    hv[j] = tc_act<ACT>(__uint_as_float(v[j]) + b.x);
+                    hv[j + 1] = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+                    hv[j + 2] = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+                    hv[j + 3] = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+                }
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o) {
+                    if (o < p.n_head) {
+                        const float4* w4 = reinterpret_cast<const float4*>(s_head_w + o * TC_BN + c * 32);
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // independent chains
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 wv = w4[j / 4];
+                            s0 = fmaf(hv[j], wv.x, s0);
+                            s1 = fmaf(hv[j + 1], wv.y, s1);
+                            s2 = fmaf(hv[j + 2], wv.z, s2);
+                            s3 = fmaf(hv[j + 3], wv.w, s3);
+                        }
+                        hacc[o] += (s0 + s1) + (s2 + s3);
+                    }
+                }
+                if (g_h2) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float* mine = stg + lane * TCM_STG_STRIDE;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            *reinterpret_cast<float4*>(mine + j) = make_float4(
+                                hv[16 * half + j], hv[16 * half + j + 1], hv[16 * half + j + 2],
+                                hv[16 * half + j + 3]);
+                        __syncwarp();
+                        const int col = c * 32 + half * 16 + (lane & 15);
+#pragma unroll 8
+                        for (int i = 0; i < 16; ++i) {
+                            const int r = 2 * i + (lane >> 4);
+                            if (row0 + r < p.n_rows)
+                                g_h2[(row0 + r) * TC_BN + col] = stg[r * TCM_STG_STRIDE + (lane & 15)];
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // the two groups' partial head sums of a row meet in shared memory: group 1 publishes
+            // its sums in its staging block, group 0 adds them (fixed order) and writes the output
+            if (p.n_head > 0) {
+                if (wg == 1) {
+#pragma unroll
+                    for (int o = 0; o < TC_MAX_HEAD; ++o) stg[lane * TCM_STG_STRIDE + o] = hacc[o];
+                }
+                row_warps_sync();
+                if (wg == 0 && row < p.n_rows) {
+                    const float* other = epi + (rw + 4) * 32 * TCM_STG_STRIDE + lane * TCM_STG_STRIDE;
+#pragma unroll
+                    for (int o = 0; o < TC_MAX_HEAD; ++o)
+                        if (o < p.n_head)
+                            p.head_out[row * p.n_head + o] = (hacc[o] + other[o]) + __ldg(p.head_b + o);
+                }
+                row_warps_sync();
+            }
+            if (stamper) tc_stamp(p.timeline, 30);            // final epilogue done
+            // TMEM reads of this tile are complete before the next tile's MMAs are released
+            // (they wait for x_ready of the next tile, arrived after this fence)
+            tcgen05_fence_before();
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
+                     : "memory");
+    }
+}
+
+template <int PASSES, int ACT>
+static int launch_tc_mlp(const CUtensorMap* maps, const TcMlpParams& p, cudaStream_t s) {
+    using Cfg = TcMlpCfg<PASSES>;
+    auto kernel = tc_mlp_forward_kernel<PASSES, ACT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        configured = true;
+    }
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], p);
+    return 0;
+}
+
+static unsigned long long* g_timeline = nullptr;     // device buffer, 64 stamps
+
+}  // namespace tb
+
+extern "C" int tb_tc_timeline(uint64_t* out64) {
+    // enable (first call) / read back the clock64() stamps CTA 0 of the last fused forward wrote
+    using namespace tb;
+    if (!g_timeline) {
+        TB_REQUIRE(cudaMalloc(&g_timeline, 64 * sizeof(unsigned long long)) == cudaSuccess, TB_ENOTSUP,
+                   "tb_tc_timeline: cudaMalloc failed");
+        cudaMemset(g_timeline, 0, 64 * sizeof(unsigned long long));
+    }
+    if (out64) {
+        TB_REQUIRE(cudaMemcpy(out64, g_timeline, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) ==
+                       cudaSuccess, TB_ENOTSUP, "tb_tc_timeline: copy failed");
+    }
+    return 0;
+}
+
+extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                                 const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                                 float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                                 const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    TB_REQUIRE(shape && d_params && d_packed && in && in->d_x1 && d_out && n_rows > 0, TB_EINVAL,
+               "tb_tc_mlp_forward: null pointer");
+    TB_REQUIRE(shape->hidden == 256 && shape->off_w2_hi > 0 && shape->off_w1_img_hi > 0 && shape->d_in >= 1 && shape->d_in <= 32 &&
+               shape->n_out >= 1 && shape->n_out <= TC_MAX_HEAD, TB_ENOTSUP,
+               "tb_tc_mlp_forward: needs hidden == 256, d_in <= 32, n_out <= 8 (got %d, %d, %d)",
+               shape->hidden, shape->d_in, shape->n_out);
+    TB_REQUIRE(in->dim1 + (in->d_x2 ? in->dim2 : 0) == shape->d_in, TB_EINVAL,
+               "tb_tc_mlp_forward: input widths do not add up to d_in");
+    TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_forward: passes must be 1 or 3");
+    TB_REQUIRE((d_h1_hi == nullptr) == (d_h1_lo == nullptr), TB_EINVAL,
+               "tb_tc_mlp_forward: h1 hi / lo must be given together");
+    CUtensorMap maps[2];
+    int rc;
+    if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, TC_BN))) return rc;
+    TcMlpParams p;
+    p.n_rows = n_rows; p.in = *in; p.d_in = shape->d_in; p.act = shape->act;
+    p.w1_img_hi = d_packed + shape->off_w1_img_hi; p.w1_img_lo = d_packed + shape->off_w1_img_lo;
+    p.b1 = d_params + shape->off_b1; p.b2 = d_params + shape->off_b2;
+    p.xin_save = d_xin; p.h1_hi = d_h1_hi; p.h1_lo = d_h1_lo; p.h2 = d_h2;
+    p.head_w = d_params + shape->off_w3; p.head_b = d_params + shape->off_b3; p.head_out = d_out;
+    p.n_head = shape->n_out; p.skip = d_skip; p.timeline = g_timeline;
+    ProfScope prof_scope("tb_tc_mlp_forward", stream);
+    const bool tanh_act = shape->act == TB_ACT_TANH;
+    if (passes == 3) {
+        if (tanh_act) launch_tc_mlp<3, TB_ACT_TANH>(maps, p, as_stream(stream));
+        else launch_tc_mlp<3, TB_ACT_RELU>(maps, p, as_stream(stream));
+    } else {
+        if (tanh_act) launch_tc_mlp<1, TB_ACT_TANH>(maps, p, as_stream(stream));
+        else launch_tc_mlp<1, TB_ACT_RELU>(maps, p, as_stream(stream));
+    }
+    return check_launch("tb_tc_mlp_forward");
+}

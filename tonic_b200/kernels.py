@@ -6,6 +6,7 @@ the CPU: every function ends in a `_lib.call(...)` into libtonic_b200.so.
 """
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -103,6 +104,13 @@ class MlpLayout:
             base = round_up(self.n_packed, 256)
             split = [base + i * H * H for i in range(4)]
             self.n_packed = base + 4 * H * H
+        # W1 as the layer-1 operand of the fused forward kernel (csrc/tc_mlp.cu): image of
+        # the swizzled [256 x 32] shared-memory tile, hi / lo parts
+        image = [0, 0]
+        self.fused_forward = self.tensor_core and d_in <= 32
+        if self.fused_forward:
+            image = [self.n_packed, self.n_packed + H * 32]
+            self.n_packed += 2 * H * 32
         self.ldx = round_up(d_in + 1, 4)
         o = self.offsets
         self.shape = _lib.TbMlpShape(
@@ -110,7 +118,8 @@ class MlpLayout:
             off_w1=o['w1'][0], off_b1=o['b1'][0], off_w2=o['w2'][0], off_b2=o['b2'][0],
             off_w3=o['w3'][0], off_b3=o['b3'][0], n_params=self.n_params,
             off_w1t=self.off_w1t, off_w2t=self.off_w2t, n_packed=self.n_packed,
-            off_w2_hi=split[0], off_w2_lo=split[1], off_w2t_hi=split[2], off_w2t_lo=split[3])
+            off_w2_hi=split[0], off_w2_lo=split[1], off_w2t_hi=split[2], off_w2t_lo=split[3],
+            off_w1_img_hi=image[0], off_w1_img_lo=image[1])
 
 
 class MlpInput:
@@ -122,6 +131,9 @@ class MlpInput:
             d_x1=ptr(x1), dim1=x1.shape[-1], d_mean=ptr(mean), d_std=ptr(std),
             d_x2=ptr(x2), dim2=0 if x2 is None else x2.shape[-1], gather2=int(gather2),
             d_idx=ptr(idx))
+
+
+_FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 
 
 class DeviceMlp:
@@ -202,9 +214,12 @@ class DeviceMlp:
         """out[rows, n_out] = head pre-activations. `params`/`packed` override the
         parameter set (target networks share the layout)."""
         passes = self.passes()
-        if save or passes:
-            self.workspace(rows)
         L = self.layout
+        # one-kernel tensor-core forward (csrc/tc_mlp.cu): no activation round trip through
+        # global memory unless a backward pass follows
+        fused = bool(passes) and L.fused_forward and L.n_out <= 8 and _FUSED_FWD
+        if save or (passes and not fused):
+            self.workspace(rows)
         params = self.params if params is None else params
         packed = self.packed if packed is None else packed
         flops = 2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out)
@@ -213,7 +228,9 @@ class DeviceMlp:
             _count_flops('tb_tc_gemm256_fwd', 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_forward_tc', ctypes.byref(L.shape), ptr(params), ptr(packed),
                       ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
-                      ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), passes, ptr(skip), stream())
+                      *((None, None, None) if fused and not save
+                        else (ptr(self.h1), ptr(self.h1_lo), ptr(self.h2))),
+                      passes, ptr(skip), stream())
             return out
         _count_flops('tb_mlp_forward', flops)
         _lib.call('tb_mlp_forward', ctypes.byref(L.shape), ptr(params), ptr(packed),
