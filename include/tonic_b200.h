@@ -233,6 +233,17 @@ int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params, const floa
                       float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
                       const int32_t* d_skip, void* stream);
 
+/* Activation gradients of the same network as ONE tensor-core kernel (csrc/tc_mlp.cu):
+ * dz2 = (dout W3) * act'(h2) and dz1 = (dz2 W2) * act'(h1), the autograd of the head and of
+ * the second hidden layer behind loss.backward() (torch/updaters/actors.py:33,104,186,
+ * critics.py:24,84); n_out <= 8.  dz2 is written as a tf32 split, dz1 as float32, both
+ * [n_rows, 256], for the weight-gradient kernels.  tb_mlp_backward_tc routes here.          */
+int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                       const float* d_dout, int32_t ld_dout, const float* d_h1_hi,
+                       const float* d_h1_lo, const float* d_h2, int64_t n_rows, float* d_dz2_hi,
+                       float* d_dz2_lo, float* d_dz1, int32_t passes, const int32_t* d_skip,
+                       void* stream);
+
 /* Profiling aid for the fused forward kernel: the first call allocates a device buffer
  * of 64 clock64() stamps that CTA 0 of every later tb_tc_mlp_forward launch fills
  * (slots documented in csrc/tc_mlp.cu); a non-NULL `out64` reads them back (host
@@ -263,11 +274,13 @@ int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, const float* d_
 
 /* Hidden-layer weight gradient on the tensor cores (MN-major tf32 operands):
  * gpart[s, off_w2 + n * 256 + k] = sum over the rows m of split s of
- * dz2[m, n] * h1[m, k]; operands as tf32 splits like tb_tc_gemm256.             */
+ * dz2[m, n] * h1[m, k]; operands as tf32 splits like tb_tc_gemm256.  With off_b2 >= 0
+ * the same pass also writes the bias gradient gpart[s, off_b2 + n] = sum_m dz2[m, n]
+ * (extra N = 16 MMAs of the dz2 operand against a block of ones).                   */
 int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const float* d_h_hi,
                    const float* d_h_lo, int64_t n_rows, int32_t passes, float* d_gpart,
-                   int32_t n_split, int32_t n_params, int32_t off_w2, const int32_t* d_skip,
-                   void* stream);
+                   int32_t n_split, int32_t n_params, int32_t off_w2, int32_t off_b2,
+                   const int32_t* d_skip, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* Optimiser -- torch.optim.Adam as constructed at updaters/actors.py:11-12,   */

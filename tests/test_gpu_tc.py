@@ -50,9 +50,10 @@ def test_tc_gemm_plain(K, rows, passes):
 @pytest.mark.parametrize('act', ['tanh', 'relu'])
 def test_tc_gemm_epilogues(K, act):
     rows = 700
-    a = torch.randn(rows, 256) * 0.3
-    w = torch.randn(256, 256) * 0.1
-    bias = torch.randn(256) * 0.1
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(rows, 256, generator=g) * 0.3
+    w = torch.randn(256, 256, generator=g) * 0.1
+    bias = torch.randn(256, generator=g) * 0.1
     f = torch.tanh if act == 'tanh' else torch.relu
     act_id = 0 if act == 'tanh' else 1
     a_hi, a_lo = split(K, a.cuda())
@@ -63,10 +64,10 @@ def test_tc_gemm_epilogues(K, act):
     K.tc_gemm256(a_hi, a_lo, w_hi, w_lo, rows, out_hi, passes=3, epilogue=0, act=act_id,
                  bias=bias.cuda(), out_lo=out_lo)
     ref = f(a @ w.T + bias)
-    np.testing.assert_allclose((out_hi + out_lo).cpu(), ref, rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose((out_hi + out_lo).cpu(), ref, rtol=2e-5, atol=3e-5)
     assert (out_hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0
     # backward: dz1 = (dz2 W) * act'(h1): B operand is W^T (rows = output index)
-    h1 = f(torch.randn(rows, 256))
+    h1 = f(torch.randn(rows, 256, generator=g))
     h_hi, h_lo = split(K, h1.cuda())
     wt_hi, wt_lo = split(K, w.T.contiguous().cuda())
     out = torch.empty(rows, 256, device='cuda')
@@ -86,7 +87,7 @@ def test_tc_wgrad(K, rows, n_split, passes):
     ref = dz.double().T @ h.double()
     dz_hi, dz_lo = split(K, dz.cuda())
     h_hi, h_lo = split(K, h.cuda())
-    n_params, off = 70000, 4352
+    n_params, off = 70400, 4352
     gpart = torch.full((n_split, n_params), float('nan'), device='cuda')
     K.tc_wgrad256(dz_hi, dz_lo, h_hi, h_lo, rows, gpart, n_split, n_params, off, passes=passes)
     got = gpart[:, off:off + 65536].sum(0).view(256, 256).cpu().double()
@@ -95,6 +96,18 @@ def test_tc_wgrad(K, rows, n_split, passes):
     assert err <= (1e-5 if passes == 3 else 5e-3) * scale, (err, scale)
     # nothing outside the W2 block is touched
     assert torch.isnan(gpart[:, :off]).all() and torch.isnan(gpart[:, off + 65536:]).all()
+    # with off_b2 the same pass also produces the bias gradient (column sums of dz) through
+    # N = 16 MMAs against a block of ones
+    gpart.fill_(float('nan'))
+    K.tc_wgrad256(dz_hi, dz_lo, h_hi, h_lo, rows, gpart, n_split, n_params, off, passes=passes,
+                  off_b2=off + 65536)
+    got = gpart[:, off:off + 65536].sum(0).view(256, 256).cpu().double()
+    assert (got - ref).abs().max().item() <= (1e-5 if passes == 3 else 5e-3) * scale
+    sums = gpart[:, off + 65536:off + 65536 + 256].sum(0).cpu().double()
+    ref_b = dz.double().sum(0)
+    tol = (1e-5 if passes == 3 else 2e-3) * max(1.0, ref_b.abs().max().item())
+    assert (sums - ref_b).abs().max().item() <= tol
+    assert torch.isnan(gpart[:, :off]).all() and torch.isnan(gpart[:, off + 65536 + 256:]).all()
 
 
 def test_tc_gemm_throughput_smoke(K):
@@ -172,7 +185,8 @@ def test_tc_mlp_forward_fused(K, d_in, n_out, act, rows, passes):
         np.testing.assert_allclose(got.cpu(), out, **tol)
         if save:
             h1_hi, h1_lo, h2_got = bufs
-            np.testing.assert_allclose((h1_hi + h1_lo).cpu(), h1, **tol)
+            # (1-pass mode stores only the tf32 part)
+            np.testing.assert_allclose((h1_hi + h1_lo if passes == 3 else h1_hi).cpu(), h1, **tol)
             np.testing.assert_allclose(h2_got.cpu(), h2, **tol)
             assert (h1_hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0
             want = torch.cat([x, torch.ones(rows, 1), torch.zeros(rows, layout.ldx - d_in - 1)], 1)
@@ -199,3 +213,41 @@ def test_tc_mlp_forward_two_inputs(K):
               ctypes.byref(inp.struct), rows, K.ptr(got), None, None, None, None, 3, None, K.stream())
     torch.cuda.synchronize()
     np.testing.assert_allclose(got.cpu(), out, rtol=3e-5, atol=3e-5)
+
+
+@pytest.mark.parametrize('n_out,act,rows', [(1, 'tanh', 16384), (6, 'tanh', 1000), (3, 'relu', 77),
+                                            (8, 'relu', 148 * 128 * 2 + 77)])
+@pytest.mark.parametrize('passes', [3, 1])
+def test_tc_mlp_backward_fused(K, n_out, act, rows, passes):
+    """tb_tc_mlp_backward (head gradient, hidden-layer GEMM and both activation gradients in
+    one tcgen05 kernel) against float64."""
+    import ctypes
+    from tonic_b200 import _lib
+    layout = K.MlpLayout(17, 256, n_out, act)
+    net = K.DeviceMlp(layout)
+    g = torch.Generator().manual_seed(rows + n_out)
+    net.params.copy_(torch.randn(layout.n_params, generator=g) * 0.15)
+    net.pack()
+    f = torch.tanh if act == 'tanh' else torch.relu
+    h1 = f(torch.randn(rows, 256, generator=g))
+    h2 = f(torch.randn(rows, 256, generator=g))
+    dout = torch.randn(rows, n_out + 2, generator=g)          # wider rows: ld_dout > n_out
+    w2 = net.view('w2', (256, 256)).cpu().double()
+    w3 = net.view('w3', (n_out, 256)).cpu().double()
+    grad = (lambda h: 1 - h * h) if act == 'tanh' else (lambda h: (h > 0).double())
+    dz2 = (dout[:, :n_out].double() @ w3) * grad(h2.double())
+    dz1 = (dz2 @ w2) * grad(h1.double())
+    h1_hi, h1_lo = split(K, h1.cuda())
+    out = [torch.full((rows, 256), float('nan'), device='cuda') for _ in range(3)]
+    d_dout, d_h2 = dout.cuda(), h2.cuda()        # keep the device copies alive across the call
+    _lib.call('tb_tc_mlp_backward', ctypes.byref(layout.shape), K.ptr(net.params), K.ptr(net.packed),
+              K.ptr(d_dout), n_out + 2, K.ptr(h1_hi), K.ptr(h1_lo), K.ptr(d_h2), rows,
+              K.ptr(out[0]), K.ptr(out[1]), K.ptr(out[2]), passes, None, K.stream())
+    torch.cuda.synchronize()
+    # 1-pass mode keeps only the tf32 part of dz2 (2^-11 truncation), 3-pass mode the exact split
+    t2 = 1e-5 if passes == 3 else 1e-3
+    np.testing.assert_allclose((out[0] + out[1] if passes == 3 else out[0]).cpu(), dz2, rtol=t2, atol=t2)
+    assert (out[0].view(torch.int32) & 0x1FFF).abs().max().item() == 0
+    tol = 1e-5 if passes == 3 else 5e-3
+    err = (out[2].cpu().double() - dz1).abs().max().item()
+    assert err <= tol * dz1.abs().max().item(), (err, dz1.abs().max().item())

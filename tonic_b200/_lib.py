@@ -99,13 +99,16 @@ _PROTOTYPES = {
     'tb_mlp_forward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_tc_timeline': (c_int, [c_vp]),
+    'tb_tc_mlp_backward': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64,
+                                   c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_tc_mlp_forward': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_mlp_backward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64,
                                    c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_mlp_wgrad_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                 c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp,
+                               c_vp]),
     'tb_permutation': (c_int, [c_u64, c_u64, c_vp, c_i64, c_vp, c_vp]),
     'tb_counter_add': (c_int, [c_vp, c_u64, c_vp]),
     'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),

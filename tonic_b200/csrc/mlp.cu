@@ -635,6 +635,7 @@ static int launch_wgrad_jobs(const TbMlpShape* shape, const float* d_xin, const 
                              const float* d_dz2_lo, const float* d_dout, int32_t ld_dout,
                              int32_t n_extra, int32_t off_extra, int64_t n_rows, float* d_gpart,
                              int32_t n_split, bool include_w2, const int32_t* d_skip, void* stream) {
+    // include_w2 == false: W2 and b2 come from the tensor-core kernel (tb_tc_wgrad256)
     using namespace tb;
     const int H = shape->hidden, d_in = shape->d_in, n_out = shape->n_out;
     const int ldx = (d_in + 1 + 3) & ~3;
@@ -671,8 +672,9 @@ static int launch_wgrad_jobs(const TbMlpShape* shape, const float* d_xin, const 
                       shape->off_b1 + tn * 128, tkw == 32 ? 1 : 0);
         }
         // db2[n] = sum_m dz2[m][n]  (ones column of xin)
-        ok &= add(d_dz2, d_dz2_lo, H, tn * 128, an, d_xin, ldx, d_in, 1, 0, 1, d_in,
-                  shape->off_b2 + tn * 128, 1);
+        if (include_w2)
+            ok &= add(d_dz2, d_dz2_lo, H, tn * 128, an, d_xin, ldx, d_in, 1, 0, 1, d_in,
+                      shape->off_b2 + tn * 128, 1);
     }
     // dW3[o][k] = sum_m dout[m][o] h2[m][k]
     for (int o0 = 0; o0 < n_out; o0 += 16)
@@ -893,8 +895,8 @@ mlp_dx_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __re
 // =====================================================================================
 // Narrow weight gradients in one streaming pass (tensor-core path companion):
 //   dW1[n][j] = sum_m dz1[m][n] xin[m][j]  (j <= d_in: the ones column gives db1)
-//   db2[n]    = sum_m (dz2_hi + dz2_lo)[m][n]
 //   dW3[o][n] = sum_m dout[m][o] h2[m][n],   db3[o] / extras = column sums of dout
+// (db2 = column sums of dz2 comes out of the tensor-core kernel, csrc/tc_gemm.cu)
 // One CTA per row split; thread (g, n): column n of the 256-wide activations, rows of
 // parity g.  Every activation element is read exactly once, coalesced; xin / dout rows are
 // staged in shared memory and broadcast.  Replaces the generic tile jobs when
@@ -907,8 +909,7 @@ constexpr int NW_GROUPS = 2;         // row-interleaved thread groups per CTA (2
 template <int KIN, int NO>
 __global__ void __launch_bounds__(NW_COLS * NW_GROUPS, 2)
 narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* __restrict__ h2,
-                    const float* __restrict__ dz1, const float* __restrict__ dz2_hi,
-                    const float* __restrict__ dz2_lo, const float* __restrict__ dout, int ld_dout,
+                    const float* __restrict__ dz1, const float* __restrict__ dout, int ld_dout,
                     int n_extra, int off_extra, int64_t n_rows, int64_t rows_per_split,
                     float* __restrict__ gpart, const int32_t* d_skip) {
     if (skip_requested(d_skip)) return;
@@ -923,7 +924,7 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
     const int ldx = (d_in + 1 + 3) & ~3;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_split;
     const int64_t r1 = min(n_rows, r0 + rows_per_split);
-    float w1[KIN], w3[NO], b2 = 0.0f, dsum = 0.0f;
+    float w1[KIN], w3[NO], dsum = 0.0f;
 #pragma unroll
     for (int j = 0; j < KIN; ++j) w1[j] = 0.0f;
 #pragma unroll
@@ -944,20 +945,18 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
         if (half == 0 && threadIdx.x < nd)
             for (int r = 0; r < rows; ++r) dsum += ds[r][threadIdx.x];
         // 8 rows per group and block: all 32 loads are issued before the first use
-        float a1[NW_ROWS / NW_GROUPS], hv[NW_ROWS / NW_GROUPS], a2[NW_ROWS / NW_GROUPS];
+        float a1[NW_ROWS / NW_GROUPS], hv[NW_ROWS / NW_GROUPS];
 #pragma unroll
         for (int q = 0; q < NW_ROWS / NW_GROUPS; ++q) {
             const int r = g + q * NW_GROUPS;
             const int64_t e = (base + min(r, rows - 1)) * H + n;
             a1[q] = __ldg(dz1 + e);
             hv[q] = __ldg(h2 + e);
-            a2[q] = __ldg(dz2_hi + e) + __ldg(dz2_lo + e);
         }
 #pragma unroll
         for (int q = 0; q < NW_ROWS / NW_GROUPS; ++q) {
             const int r = g + q * NW_GROUPS;
             if (r < rows) {
-                b2 += a2[q];
 #pragma unroll
                 for (int j = 0; j < KIN; ++j) w1[j] = fmaf(a1[q], xs[r][j], w1[j]);
 #pragma unroll
@@ -966,7 +965,7 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
         }
     }
     // combine the row groups (fixed order), then write this split's partial sums
-    constexpr int LDC = KIN + NO + 1;
+    constexpr int LDC = KIN + NO;
     const int c = threadIdx.x & (NW_COLS - 1);
     __syncthreads();
     if (g > 0) {
@@ -975,7 +974,6 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
         for (int j = 0; j < KIN; ++j) dst[j] = w1[j];
 #pragma unroll
         for (int o = 0; o < NO; ++o) dst[KIN + o] = w3[o];
-        dst[KIN + NO] = b2;
     }
     __syncthreads();
     if (g == 0) {
@@ -985,7 +983,6 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
             for (int j = 0; j < KIN; ++j) w1[j] += src[j];
 #pragma unroll
             for (int o = 0; o < NO; ++o) w3[o] += src[KIN + o];
-            b2 += src[KIN + NO];
         }
         float* out = gpart + (size_t)blockIdx.x * sh.n_params;
 #pragma unroll
@@ -996,7 +993,6 @@ narrow_wgrad_kernel(TbMlpShape sh, const float* __restrict__ xin, const float* _
 #pragma unroll
         for (int o = 0; o < NO; ++o)
             if (o < n_out) out[sh.off_w3 + o * H + n] = w3[o];
-        out[sh.off_b2 + n] = b2;
         if (half == 0) {
             if ((int)threadIdx.x < n_out) out[sh.off_b3 + threadIdx.x] = dsum;
             else if ((int)threadIdx.x < nd) out[off_extra + (threadIdx.x - n_out)] = dsum;
@@ -1100,6 +1096,15 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
                "tb_mlp_backward_tc: dx column range invalid");
     const int blocks = (int)((n_rows + TM - 1) / TM);
     cudaStream_t s = as_stream(stream);
+    static const bool fused_bwd = [] {
+        const char* v = getenv("TONIC_B200_FUSED_BWD");
+        return !(v && v[0] == '0');
+    }();
+    if (fused_bwd && shape->n_out <= 8) {
+        // head gradient + hidden-layer GEMM + activation gradient in one kernel (csrc/tc_mlp.cu)
+        rc = tb_tc_mlp_backward(shape, d_params, d_packed, d_dout, ld_dout, d_h1_hi, d_h1_lo, d_h2, n_rows,
+                                d_dz2_hi, d_dz2_lo, d_dz1, passes, d_skip, stream);
+    } else {
     {
         const size_t smem = head_backward_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_head_backward", stream);
@@ -1117,6 +1122,7 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
     rc = tb_tc_gemm256(d_dz2_hi, d_dz2_lo, d_packed + shape->off_w2t_hi, d_packed + shape->off_w2t_lo,
                        n_rows, passes, 1, shape->act, nullptr, d_h1_hi, d_h1_lo, d_dz1, nullptr, nullptr,
                        nullptr, nullptr, 0, d_skip, stream);
+    }
     if (rc || !d_dx) return rc;
     {
         const size_t smem = dx_smem_bytes<256>();
@@ -1141,21 +1147,43 @@ extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, cons
     TB_REQUIRE(d_xin && d_h1_hi && d_h1_lo && d_h2 && d_dz1 && d_dz2_hi && d_dz2_lo && d_dout &&
                d_gpart && n_rows > 0 && n_split >= 1 && n_split_w2 >= 1 && n_split_w2 <= n_split &&
                ld_dout >= shape->n_out + n_extra, TB_EINVAL, "tb_mlp_wgrad_tc: bad arguments");
+    // The tensor-core kernel (dW2, db2) and the narrow-gradient kernel (dW1, db1, dW3, db3) are
+    // independent: the second one runs on a side stream between two events, so that inside a
+    // captured graph (and in eager mode) both are resident on the SMs at the same time.
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    static const bool overlap = [] {
+        const char* v = getenv("TONIC_B200_WGRAD_OVERLAP");
+        return !(v && v[0] == '0');
+    }();
+    const bool narrow = shape->d_in + 1 <= 32 && shape->n_out + n_extra <= 16;
+    void* narrow_stream = stream;
+    if (overlap && narrow) {
+        if (!side) {
+            TB_REQUIRE(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+                           cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+                           cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming) == cudaSuccess,
+                       TB_ENOTSUP, "tb_mlp_wgrad_tc: cannot create the side stream");
+        }
+        cudaEventRecord(fork_ev, as_stream(stream));
+        cudaStreamWaitEvent(side, fork_ev, 0);
+        narrow_stream = side;
+    }
     rc = tb_tc_wgrad256(d_dz2_hi, d_dz2_lo, d_h1_hi, d_h1_lo, n_rows, passes, d_gpart, n_split_w2,
-                        shape->n_params, shape->off_w2, d_skip, stream);
+                        shape->n_params, shape->off_w2, shape->off_b2, d_skip, stream);
     if (rc) return rc;
-    if (shape->d_in + 1 <= 32 && shape->n_out + n_extra <= 16) {
+    if (narrow) {
         // streaming single-pass kernel for the narrow gradients
-        ProfScope prof_scope("tb_mlp_wgrad_narrow", stream);
+        ProfScope prof_scope("tb_mlp_wgrad_narrow", narrow_stream);
         int64_t rows_per_split = ((n_rows + n_split - 1) / n_split + NW_ROWS - 1) / NW_ROWS * NW_ROWS;
         const bool small_in = shape->d_in + 1 <= 20, small_out = shape->n_out + n_extra <= 8;
 #define TB_NARROW(KIN_, NO_)                                                                       \
     {                                                                                             \
-        const size_t smem = (size_t)(NW_GROUPS - 1) * NW_COLS * (KIN_ + NO_ + 1) * sizeof(float); \
+        const size_t smem = (size_t)(NW_GROUPS - 1) * NW_COLS * (KIN_ + NO_) * sizeof(float); \
         set_smem(narrow_wgrad_kernel<KIN_, NO_>, smem);                                           \
         narrow_wgrad_kernel<KIN_, NO_><<<dim3(n_split, 256 / NW_COLS), NW_COLS * NW_GROUPS, smem, \
-                                         as_stream(stream)>>>(                                    \
-            *shape, d_xin, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout, n_extra, off_extra,  \
+                                         as_stream(narrow_stream)>>>(                             \
+            *shape, d_xin, d_h2, d_dz1, d_dout, ld_dout, n_extra, off_extra,                      \
             n_rows, rows_per_split, d_gpart, d_skip);                                             \
     }
         if (small_in && small_out) TB_NARROW(20, 8)
@@ -1163,7 +1191,12 @@ extern "C" int tb_mlp_wgrad_tc(const TbMlpShape* shape, const float* d_xin, cons
         else if (small_out) TB_NARROW(32, 8)
         else TB_NARROW(32, 16)
 #undef TB_NARROW
-        return check_launch("tb_mlp_wgrad_tc/narrow");
+        rc = check_launch("tb_mlp_wgrad_tc/narrow");
+        if (narrow_stream != stream) {
+            cudaEventRecord(join_ev, side);
+            cudaStreamWaitEvent(as_stream(stream), join_ev, 0);
+        }
+        return rc;
     }
     ProfScope prof_scope("tb_mlp_wgrad_small", stream);
     return launch_wgrad_jobs(shape, d_xin, d_h1_hi, d_h2, d_dz1, d_dz2_hi, d_dz2_lo, d_dout, ld_dout,

@@ -51,8 +51,9 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
         // one parameter per thread keeps ~72k threads in flight; the n_split partial loads
         // of a thread are independent (4-way unrolled sums)
         // the W2 block may have been produced with fewer row splits than the narrow gradients
-        const int n_split = (n_split_w2 > 0 && i >= sh.off_w2 && i < sh.off_w2 + sh.hidden * sh.hidden)
-                                ? n_split_w2 : n_split_all;
+        // (W2 and, with the tensor-core kernel, b2 right behind it: tb_tc_wgrad256)
+        const int w2_end = sh.off_w2 + sh.hidden * sh.hidden + (sh.off_w2_hi > 0 ? sh.hidden : 0);
+        const int n_split = (n_split_w2 > 0 && i >= sh.off_w2 && i < w2_end) ? n_split_w2 : n_split_all;
         float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
         int s = 0;
         for (; s + 4 <= n_split; s += 4) {

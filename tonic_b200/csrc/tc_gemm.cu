@@ -308,6 +308,7 @@ struct TcWgradParams {
     float* gpart;               // [n_split, n_params]
     int n_params;
     int off_w2;                 // offset of W2 [256, 256] in the flat layout
+    int off_b2;                 // offset of b2 [256] (column sums of dz2), or -1
     const int32_t* skip;
     int dbg_lbo, dbg_sbo, dbg_kstep, dbg_idesc_xor;   // bring-up knobs (0 = defaults)
 };
@@ -322,7 +323,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    // [8 x 32] block of ones: B operand of the bias-gradient MMAs (any layout of ones is ones)
+    float* ones = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
+                                                 Cfg::HEAD_BYTES);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::STAGES;
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -340,10 +344,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == 2) {       // 256 columns for dW2 + 16 for the column sums (power of two: 512)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(tmem_slot)), "n"(256) : "memory");
+                         smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (p.off_b2 >= 0) {
+        for (int i = threadIdx.x; i < 1024; i += TC_THREADS) ones[i] = 1.0f;
+        fence_proxy_async_smem();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -402,6 +410,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
                     } else {
                         tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
                     }
+                    if (p.off_b2 >= 0) {
+                        // db2[n] = sum_m dz2[m, n]: the same A operand against a block of ones,
+                        // N = 16 accumulator columns 256..271 (all 16 columns hold the sum)
+                        const uint32_t idesc16 = (kIdescTf32MN & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
+                        const uint64_t b_ones = umma_desc_mnmajor_sw128(ones, lbo, sbo);
+                        tcgen05_mma_tf32(tmem_base + TC_BN, a_hi + koff, b_ones, idesc16, (c | k) != 0);
+                        if (PASSES == 3) tcgen05_mma_tf32(tmem_base + TC_BN, a_lo + koff, b_ones, idesc16, 1);
+                    }
                 }
                 tcgen05_commit(&empty_bar[stage]);
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -434,11 +450,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
                 out[(size_t)r * TC_BN + c * 32 + lane] = n_chunks > 0 ? stg[r * TC_STAGE_ROWSTRIDE + lane] : 0.0f;
             __syncwarp();
         }
+        if (p.off_b2 >= 0) {
+            float sum = 0.0f;
+            if (n_chunks > 0) {
+                uint32_t v[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                      "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+                      "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)TC_BN) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                sum = __uint_as_float(v[0]);
+            }
+            p.gpart[(size_t)split * p.n_params + p.off_b2 + tile * TC_BM + w * 32 + lane] = sum;
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
                      : "memory");
     }
 }
@@ -522,7 +554,7 @@ extern "C" int tb_tc_gemm256(const float* d_a_hi, const float* d_a_lo, const flo
 
 extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const float* d_h_hi,
                               const float* d_h_lo, int64_t n_rows, int32_t passes, float* d_gpart,
-                              int32_t n_split, int32_t n_params, int32_t off_w2,
+                              int32_t n_split, int32_t n_params, int32_t off_w2, int32_t off_b2,
                               const int32_t* d_skip, void* stream) {
     using namespace tb;
     TB_REQUIRE(d_dz_hi && d_h_hi && d_gpart && n_rows > 0 && n_split >= 1, TB_EINVAL,
@@ -538,7 +570,7 @@ extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const 
     TcWgradParams p;
     p.n_rows = n_rows;
     p.rows_per_split = ((n_rows + n_split - 1) / n_split + TCW_ROWS - 1) / TCW_ROWS * TCW_ROWS;
-    p.gpart = d_gpart; p.n_params = n_params; p.off_w2 = off_w2; p.skip = d_skip;
+    p.gpart = d_gpart; p.n_params = n_params; p.off_w2 = off_w2; p.off_b2 = off_b2; p.skip = d_skip;
     auto knob = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     p.dbg_lbo = knob("TB_TCW_LBO"); p.dbg_sbo = knob("TB_TCW_SBO"); p.dbg_kstep = knob("TB_TCW_KSTEP");
     p.dbg_idesc_xor = knob("TB_TCW_IDESC_XOR");

@@ -109,6 +109,32 @@ __device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t
         ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// TMA store of a [128 x 32]-float swizzled shared-memory tile (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent store groups of this thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// barrier among the 4 warps of one row-warp group
+__device__ __forceinline__ void group_sync(int wg) {
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory");
+}
+
+// 32 consecutive float32 values of one row into a swizzled [128 x 32] staging tile (TMA store source)
+__device__ __forceinline__ void store_plain_row(unsigned char* tile, int row, const float (&v)[32]) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(tile + sw128_offset(row, u)) =
+            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+}
+
 // barrier among the 8 row warps only
 __device__ __forceinline__ void row_warps_sync() {
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -157,7 +183,10 @@ __device__ __forceinline__ void store_operand_half(unsigned char* hi_tile, unsig
 template <int PASSES, int ACT>
 __global__ void __launch_bounds__(TCM_THREADS, 1)
 tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
-                      const __grid_constant__ CUtensorMap map_b_lo, const TcMlpParams p) {
+                      const __grid_constant__ CUtensorMap map_b_lo,
+                      const __grid_constant__ CUtensorMap map_h1_hi,
+                      const __grid_constant__ CUtensorMap map_h1_lo,
+                      const __grid_constant__ CUtensorMap map_h2, const TcMlpParams p) {
     using Cfg = TcMlpCfg<PASSES>;
     if (skip_requested(p.skip)) return;
     extern __shared__ unsigned char smem_raw[];
@@ -281,12 +310,11 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         const int rw = warp - 4, q = rw & 3, wg = rw >> 2;
         const int trow = q * 32 + lane;
         const bool stamper = rw == 0 && lane == 0;
+        const bool issuer = q == 0 && lane == 0;            // this group's TMA-store thread
         float* stg = epi + rw * 32 * TCM_STG_STRIDE;
         const int d_in = p.d_in;
         const int ldx = (d_in + 1 + 3) & ~3;
-        float* __restrict__ g_h1_hi = p.h1_hi;
-        float* __restrict__ g_h1_lo = p.h1_lo;
-        float* __restrict__ g_h2 = p.h2;
+        const bool save_h1 = p.h1_hi != nullptr, save_h2 = p.h2 != nullptr;
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         int it = 0;
         if (stamper) tc_stamp(p.timeline, 31);
@@ -361,33 +389,24 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                 mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
                 if (stamper) tc_stamp(p.timeline, 12 + c);    // stage free
                 unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                if (save_h1) {        // the TMA stores of this group's previous chunk have left the stage
+                    if (issuer) bulk_wait_read<0>();
+                    group_sync(wg);
+                }
                 store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
                 if (stamper) tc_stamp(p.timeline, 20 + c);    // operand published
-                if (g_h1_hi) {                       // saved activations (tf32 split) for backward
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float* mine = stg + lane * TCM_STG_STRIDE;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(mine + j) = make_float4(
-                                hv[16 * half + j], hv[16 * half + j + 1], hv[16 * half + j + 2],
-                                hv[16 * half + j + 3]);
-                        __syncwarp();
-                        const int col = c * 32 + half * 16 + (lane & 15);
-#pragma unroll 8
-                        for (int i = 0; i < 16; ++i) {
-                            const int r = 2 * i + (lane >> 4);
-                            if (row0 + r < p.n_rows) {
-                                const float x = stg[r * TCM_STG_STRIDE + (lane & 15)];
-                                const float hi = tc_tf32_hi(x);
-                                g_h1_hi[(row0 + r) * TC_BN + col] = hi;
-                                g_h1_lo[(row0 + r) * TC_BN + col] = x - hi;
-                            }
-                        }
-                        __syncwarp();
+                if (save_h1) {
+                    // saved activations for backward: the operand tile IS the tf32 split of h1 in
+                    // the layout TMA expects -> one thread stores it asynchronously (the MMA and
+                    // the store only read the tile; this group rewrites it two chunks later)
+                    group_sync(wg);
+                    if (issuer) {
+                        tma_store_2d(&map_h1_hi, st, c * TC_BK, tile * TC_BM);
+                        if (PASSES == 3) tma_store_2d(&map_h1_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                        bulk_commit();
                     }
                 }
             }
@@ -399,6 +418,12 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
             float hacc[TC_MAX_HEAD];
 #pragma unroll
             for (int o = 0; o < TC_MAX_HEAD; ++o) hacc[o] = 0.0f;
+            unsigned char* own_stage = smem + ((g0 + 1 + wg) & 1) * Cfg::STAGE_BYTES;
+            int n_staged = 0;
+            if (save_h2 && save_h1) {      // the h1 stores have left this group's operand buffers
+                if (issuer) bulk_wait_read<0>();
+                group_sync(wg);
+            }
 #pragma unroll 1
             for (int c = wg; c < TC_BN / 32; c += 2) {
                 uint32_t v[32];
@@ -429,25 +454,23 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                         hacc[o] += (s0 + s1) + (s2 + s3);
                     }
                 }
-                if (g_h2) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        float* mine = stg + lane * TCM_STG_STRIDE;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            *reinterpret_cast<float4*>(mine + j) = make_float4(
-                                hv[16 * half + j], hv[16 * half + j + 1], hv[16 * half + j + 2],
-                                hv[16 * half + j + 3]);
-                        __syncwarp();
-                        const int col = c * 32 + half * 16 + (lane & 15);
-#pragma unroll 8
-                        for (int i = 0; i < 16; ++i) {
-                            const int r = 2 * i + (lane >> 4);
-                            if (row0 + r < p.n_rows)
-                                g_h2[(row0 + r) * TC_BN + col] = stg[r * TCM_STG_STRIDE + (lane & 15)];
-                        }
-                        __syncwarp();
+                if (save_h2) {
+                    // h2 for the backward pass: staged in this group's (now idle) operand buffers
+                    // in the TMA layout, stored asynchronously
+                    constexpr int NBUF = PASSES == 3 ? 2 : 1;
+                    unsigned char* buf = own_stage + (n_staged % NBUF) * TC_A_BYTES;
+                    if (n_staged >= NBUF) {
+                        if (issuer) bulk_wait_read<NBUF - 1>();
+                        group_sync(wg);
                     }
+                    store_plain_row(buf, trow, hv);
+                    fence_proxy_async_smem();
+                    group_sync(wg);
+                    if (issuer) {
+                        tma_store_2d(&map_h2, buf, c * TC_BK, tile * TC_BM);
+                        bulk_commit();
+                    }
+                    ++n_staged;
                 }
             }
             // the two groups' partial head sums of a row meet in shared memory: group 1 publishes
@@ -469,9 +492,16 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
             }
             if (stamper) tc_stamp(p.timeline, 30);            // final epilogue done
             // TMEM reads of this tile are complete before the next tile's MMAs are released
-            // (they wait for x_ready of the next tile, arrived after this fence)
+            // (they wait for x_ready of the next tile, arrived after this fence); the barrier
+            // keeps the next tile's input rows out of a stage the other group still reads back
             tcgen05_fence_before();
+            if ((save_h1 || save_h2) && tile + (int)gridDim.x < n_tiles) {
+                // the next tile's input rows go into operand buffers the stores may still read
+                if (issuer) bulk_wait_read<0>();
+                row_warps_sync();
+            }
         }
+        if (issuer) bulk_wait_all();
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -479,6 +509,325 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
                      : "memory");
     }
+}
+
+// =====================================================================================
+// Fused backward pass (activation gradients) on the tensor cores:
+//
+//     dz2 = (dout W3) * act'(h2)            [rows, 256]   (row warps, from global h2)
+//     dz1 = (dz2 W2)  * act'(h1)            [rows, 256]   (tcgen05 GEMM + epilogue)
+//
+// i.e. the autograd of the head and of the second hidden layer (reference: loss.backward()
+// in torch/updaters/actors.py:33,104,186 / critics.py:24,84 through models/utils.py:15-23).
+// It replaces mlp_head_backward_kernel -> tc_gemm_kernel<.., EPI_ACT_GRAD>; dz2 (as a tf32
+// split) and dz1 still go to global memory because the weight-gradient kernels consume them.
+// Same structure as the forward kernel: the row warps build the A operand chunk by chunk
+// (even chunks group 0, odd chunks group 1), the producer streams W2^T chunks by TMA, one
+// thread issues the MMAs, and the row warps run the epilogue.
+// =====================================================================================
+struct TcMlpBwdParams {
+    int64_t n_rows;
+    const float* dout;          // [n_rows, ld_dout], columns 0..n_head-1
+    int ld_dout;
+    int n_head;                 // <= 8
+    const float* head_w;        // W3 [n_head, 256]
+    const float* h2;            // [n_rows, 256]
+    const float* h1_hi;         // [n_rows, 256] tf32 split of h1
+    const float* h1_lo;
+    float* dz2_hi;              // [n_rows, 256] tf32 split of dz2
+    float* dz2_lo;
+    float* dz1;                 // [n_rows, 256]
+    const int32_t* skip;
+    unsigned long long* timeline;   // profiling aid (see TcMlpParams)
+};
+
+template <int ACT>
+__device__ __forceinline__ float tc_act_grad(float h) {     // act'(z) written in terms of h = act(z)
+    return ACT == TB_ACT_TANH ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f);
+}
+
+template <int PASSES, int ACT>
+__global__ void __launch_bounds__(TCM_THREADS, 1)
+tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
+                       const __grid_constant__ CUtensorMap map_b_lo,
+                       const __grid_constant__ CUtensorMap map_dz2_hi,
+                       const __grid_constant__ CUtensorMap map_dz2_lo,
+                       const __grid_constant__ CUtensorMap map_dz1, const TcMlpBwdParams p) {
+    using Cfg = TcMlpCfg<PASSES>;
+    if (skip_requested(p.skip)) return;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* s_head_w = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
+                                                 Cfg::CONST_BYTES);
+    uint64_t* full_bar = bars;                        // [STAGES] W2^T chunk landed
+    uint64_t* a_ready = bars + Cfg::STAGES;           // [STAGES] dz2 chunk written by a row-warp group
+    uint64_t* empty_bar = bars + 2 * Cfg::STAGES;     // [STAGES] MMAs reading the stage retired
+    uint64_t* acc_full = bars + 3 * Cfg::STAGES;      // accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    if (threadIdx.x == 0) tc_stamp(p.timeline, 0);
+    constexpr int CHUNKS = TC_K / TC_BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&a_ready[s], TCM_ROW_WARPS / 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < TC_MAX_HEAD * TC_BN; i += TCM_THREADS)
+        s_head_w[i] = i < p.n_head * TC_BN ? p.head_w[i] : 0.0f;
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) tc_stamp(p.timeline, 1);
+
+    if (warp == 0) {
+        // ===================== producer: W2^T chunks (TMA) =====================
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < CHUNKS; ++c, ++g) {
+                    const int stage = g & 1;
+                    mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
+                    unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * TC_B_BYTES);
+                    tma_load_2d(st + Cfg::B_HI, &map_b_hi, &full_bar[stage], c * TC_BK, 0);
+                    if (PASSES == 3) tma_load_2d(st + Cfg::B_LO, &map_b_lo, &full_bar[stage], c * TC_BK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int c = 0; c < CHUNKS; ++c, ++g) {
+                    const int stage = g & 1;
+                    const uint32_t parity = (g >> 1) & 1;
+                    mbar_wait(&full_bar[stage], parity);
+                    tc_stamp(p.timeline, 40 + c);
+                    mbar_wait(&a_ready[stage], parity);
+                    tc_stamp(p.timeline, 50 + c);
+                    tcgen05_fence_after();
+                    unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc_kmajor_sw128(st);
+                    const uint64_t a_lo = umma_desc_kmajor_sw128(st + Cfg::A_LO);
+                    const uint64_t b_hi = umma_desc_kmajor_sw128(st + Cfg::B_HI);
+                    const uint64_t b_lo = umma_desc_kmajor_sw128(st + Cfg::B_LO);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                        const uint32_t accumulate = (c | k) != 0;
+                        if (PASSES == 3) {
+                            tcgen05_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, kIdescTf32, accumulate);
+                            tcgen05_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, kIdescTf32, 1);
+                            tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32, 1);
+                        } else {
+                            tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32, accumulate);
+                        }
+                    }
+                    tcgen05_commit(&empty_bar[stage]);
+                    if (c == CHUNKS - 1) tcgen05_commit(acc_full);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== row warps =====================
+        const int rw = warp - 4, q = rw & 3, wg = rw >> 2;
+        const int trow = q * 32 + lane;
+        float* stg = epi + rw * 32 * TCM_STG_STRIDE;
+        const bool issuer = q == 0 && lane == 0;            // this group's TMA-store thread
+        const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+        const bool stamper = (rw == 0 || rw == 4) && lane == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int64_t row0 = (int64_t)tile * TC_BM + q * 32;
+            const int64_t row = (int64_t)tile * TC_BM + trow;
+            const bool live = row < p.n_rows;
+            float dv[TC_MAX_HEAD];
+#pragma unroll
+            for (int o = 0; o < TC_MAX_HEAD; ++o)
+                dv[o] = (live && o < p.n_head) ? __ldg(p.dout + row * p.ld_dout + o) : 0.0f;
+            // ---- a) dz2 chunks: A operand of the GEMM + tf32 split to global memory -------------
+            // h2 is read with coalesced 64-byte row segments (lane -> 2 rows x 16 columns; row-wise
+            // 16-byte loads would pull every sector through the small L1 twice) and transposed to
+            // the row-per-thread layout through the warp's staging block; the loads of the group's
+            // next chunk are in flight while the current one is computed and published
+            float z[32], t[32];
+            auto load_h2 = [&](int c) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int64_t r = row0 + 2 * i + (lane >> 4);
+                        t[16 * half + i] = r < p.n_rows
+                            ? __ldg(p.h2 + r * TC_BN + c * 32 + half * 16 + (lane & 15)) : 0.0f;
+                    }
+            };
+            load_h2(wg);
+#pragma unroll 1
+            for (int c = wg; c < CHUNKS; c += 2) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        stg[(2 * i + (lane >> 4)) * TCM_STG_STRIDE + (lane & 15)] = t[16 * half + i];
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 h = *reinterpret_cast<const float4*>(stg + lane * TCM_STG_STRIDE + j);
+                        z[16 * half + j] = h.x; z[16 * half + j + 1] = h.y;
+                        z[16 * half + j + 2] = h.z; z[16 * half + j + 3] = h.w;
+                    }
+                    __syncwarp();
+                }
+                if (c + 2 < CHUNKS) load_h2(c + 2);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int o = 0; o < TC_MAX_HEAD; ++o) {
+                        if (o < p.n_head) {
+                            const float4 wv = *reinterpret_cast<const float4*>(s_head_w + o * TC_BN + c * 32 + j);
+                            s0 = fmaf(dv[o], wv.x, s0);
+                            s1 = fmaf(dv[o], wv.y, s1);
+                            s2 = fmaf(dv[o], wv.z, s2);
+                            s3 = fmaf(dv[o], wv.w, s3);
+                        }
+                    }
+                    z[j] = s0 * tc_act_grad<ACT>(z[j]);
+                    z[j + 1] = s1 * tc_act_grad<ACT>(z[j + 1]);
+                    z[j + 2] = s2 * tc_act_grad<ACT>(z[j + 2]);
+                    z[j + 3] = s3 * tc_act_grad<ACT>(z[j + 3]);
+                }
+                if (stamper) tc_stamp(p.timeline, 4 + c);      // chunk computed
+                const int g = it * CHUNKS + c, stage = g & 1;     // == wg: a group owns one stage
+                mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
+                if (stamper) tc_stamp(p.timeline, 12 + c);     // stage free
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
+                group_sync(wg);
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z);
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[stage]);
+                if (stamper) tc_stamp(p.timeline, 20 + c);     // published
+                // dz2 (tf32 split) for the weight-gradient kernels: the operand tile is already in
+                // the TMA layout -> asynchronous store by one thread
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
+                    if (PASSES == 3) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
+                }
+            }
+            // ---- b) epilogue: dz1 = acc * act'(h1).  h1 (hi + lo) is read with coalesced 64-byte
+            // row segments, the accumulator half chunk goes through the staging block into the same
+            // lane -> (2 rows x 16 columns) layout, the products are written into the group's idle
+            // operand buffers in the TMA layout and stored by TMA; the h1 loads of the next half
+            // chunk are in flight while the current one is processed ------------------------------
+            float ua[16], ub[16];
+            auto load_h1 = [&](int c, int half) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int64_t r = row0 + 2 * i + (lane >> 4);
+                    const int64_t e = r * TC_BN + c * 32 + half * 16 + (lane & 15);
+                    ua[i] = r < p.n_rows ? __ldg(p.h1_hi + e) : 0.0f;
+                    ub[i] = (PASSES == 3 && r < p.n_rows) ? __ldg(p.h1_lo + e) : 0.0f;
+                }
+            };
+            load_h1(wg, 0);
+            if (stamper) tc_stamp(p.timeline, 28 + wg * 4);    // dz2 phase done
+            mbar_wait(acc_full, it & 1);
+            tcgen05_fence_after();
+            if (stamper) tc_stamp(p.timeline, 29 + wg * 4);    // accumulator complete
+            if (issuer) bulk_wait_read<0>();        // dz2 stores have left this group's buffers
+            group_sync(wg);
+            unsigned char* own_stage = smem + wg * Cfg::STAGE_BYTES;
+            int n_staged = 0;
+#pragma unroll 1
+            for (int c = wg; c < CHUNKS; c += 2) {
+                constexpr int NBUF = PASSES == 3 ? 2 : 1;
+                unsigned char* buf = own_stage + (n_staged % NBUF) * TC_A_BYTES;
+                if (n_staged >= NBUF) {
+                    if (issuer) bulk_wait_read<NBUF - 1>();
+                    group_sync(wg);
+                }
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[16];
+                    tcgen05_ld_32x16(tmem_base + t_lane + (uint32_t)(c * 32 + half * 16), v);
+                    float* mine = stg + lane * TCM_STG_STRIDE;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(mine + j) = make_float4(
+                            __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+                    __syncwarp();
+                    const int cc = half * 16 + (lane & 15);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = 2 * i + (lane >> 4);
+                        const float gval = tc_act_grad<ACT>(ua[i] + ub[i]) * stg[r * TCM_STG_STRIDE + (lane & 15)];
+                        *reinterpret_cast<float*>(buf + sw128_offset(q * 32 + r, cc >> 2) + ((cc & 3) << 2)) = gval;
+                    }
+                    __syncwarp();
+                    if (half == 0) load_h1(c, 1);
+                    else if (c + 2 < CHUNKS) load_h1(c + 2, 0);
+                }
+                fence_proxy_async_smem();
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_dz1, buf, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
+                }
+                ++n_staged;
+            }
+            if (stamper) tc_stamp(p.timeline, 30 + wg * 4);    // epilogue done
+            // this tile's TMEM reads (both groups) are complete before the next tile's first MMA
+            // overwrites the accumulator: that MMA waits for a_ready of chunk 0, which group 0
+            // arrives only after this fence and barrier
+            tcgen05_fence_before();
+            if (issuer) bulk_wait_read<0>();        // dz1 stores have left the operand buffers
+            row_warps_sync();
+        }
+        if (issuer) bulk_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256)
+                     : "memory");
+    }
+}
+
+template <int PASSES, int ACT>
+static int launch_tc_mlp_bwd(const CUtensorMap* maps, const TcMlpBwdParams& p, cudaStream_t s) {
+    using Cfg = TcMlpCfg<PASSES>;
+    auto kernel = tc_mlp_backward_kernel<PASSES, ACT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        configured = true;
+    }
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    return 0;
 }
 
 template <int PASSES, int ACT>
@@ -492,7 +841,7 @@ static int launch_tc_mlp(const CUtensorMap* maps, const TcMlpParams& p, cudaStre
     }
     const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], p);
+    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
     return 0;
 }
 
@@ -531,10 +880,16 @@ extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params,
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_forward: passes must be 1 or 3");
     TB_REQUIRE((d_h1_hi == nullptr) == (d_h1_lo == nullptr), TB_EINVAL,
                "tb_tc_mlp_forward: h1 hi / lo must be given together");
-    CUtensorMap maps[2];
+    CUtensorMap maps[5];
     int rc;
     if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, TC_BN))) return rc;
     if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, TC_BN))) return rc;
+    maps[2] = maps[3] = maps[4] = maps[0];       // placeholders when nothing is saved
+    if (d_h1_hi) {
+        if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TC_BM))) return rc;
+        if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TC_BM))) return rc;
+    }
+    if (d_h2 && (rc = make_map(&maps[4], d_h2, n_rows, TC_BM))) return rc;
     TcMlpParams p;
     p.n_rows = n_rows; p.in = *in; p.d_in = shape->d_in; p.act = shape->act;
     p.w1_img_hi = d_packed + shape->off_w1_img_hi; p.w1_img_lo = d_packed + shape->off_w1_img_lo;
@@ -552,4 +907,40 @@ extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params,
         else launch_tc_mlp<1, TB_ACT_RELU>(maps, p, as_stream(stream));
     }
     return check_launch("tb_tc_mlp_forward");
+}
+
+extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                                  const float* d_dout, int32_t ld_dout, const float* d_h1_hi,
+                                  const float* d_h1_lo, const float* d_h2, int64_t n_rows,
+                                  float* d_dz2_hi, float* d_dz2_lo, float* d_dz1, int32_t passes,
+                                  const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    TB_REQUIRE(shape && d_params && d_packed && d_dout && d_h1_hi && d_h1_lo && d_h2 && d_dz2_hi &&
+               d_dz2_lo && d_dz1 && n_rows > 0, TB_EINVAL, "tb_tc_mlp_backward: null pointer");
+    TB_REQUIRE(shape->hidden == 256 && shape->off_w2t_hi > 0 && shape->n_out >= 1 &&
+               shape->n_out <= TC_MAX_HEAD && ld_dout >= shape->n_out, TB_ENOTSUP,
+               "tb_tc_mlp_backward: needs hidden == 256 and n_out <= 8 (got %d, %d)", shape->hidden,
+               shape->n_out);
+    TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_backward: passes must be 1 or 3");
+    CUtensorMap maps[5];
+    int rc;
+    if ((rc = make_map(&maps[0], d_packed + shape->off_w2t_hi, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[1], d_packed + shape->off_w2t_lo, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[2], d_dz2_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[3], d_dz2_lo, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[4], d_dz1, n_rows, TC_BM))) return rc;
+    TcMlpBwdParams p;
+    p.n_rows = n_rows; p.dout = d_dout; p.ld_dout = ld_dout; p.n_head = shape->n_out;
+    p.head_w = d_params + shape->off_w3; p.h2 = d_h2; p.h1_hi = d_h1_hi; p.h1_lo = d_h1_lo;
+    p.dz2_hi = d_dz2_hi; p.dz2_lo = d_dz2_lo; p.dz1 = d_dz1; p.skip = d_skip; p.timeline = g_timeline;
+    ProfScope prof_scope("tb_tc_mlp_backward", stream);
+    const bool tanh_act = shape->act == TB_ACT_TANH;
+    if (passes == 3) {
+        if (tanh_act) launch_tc_mlp_bwd<3, TB_ACT_TANH>(maps, p, as_stream(stream));
+        else launch_tc_mlp_bwd<3, TB_ACT_RELU>(maps, p, as_stream(stream));
+    } else {
+        if (tanh_act) launch_tc_mlp_bwd<1, TB_ACT_TANH>(maps, p, as_stream(stream));
+        else launch_tc_mlp_bwd<1, TB_ACT_RELU>(maps, p, as_stream(stream));
+    }
+    return check_launch("tb_tc_mlp_backward");
 }

@@ -206,7 +206,12 @@ class DeviceMlp:
         return max(1, n_split // 2) if self.passes() else 0
 
     def w2_range(self):
+        """Parameters whose partial gradients come from the tensor-core weight-gradient kernel
+        (its own split count): W2 and, right behind it in the layout, b2."""
         off, size = self.layout.offsets['w2']
+        if self.passes():
+            assert self.layout.offsets['b2'][0] == off + size
+            size += self.layout.hidden
         return off, off + size
 
     # -- kernels ------------------------------------------------------------
@@ -538,8 +543,8 @@ def tc_gemm256(a_hi, a_lo, b_hi, b_lo, rows, out, passes=3, epilogue=2, act=0, b
 
 
 def tc_wgrad256(dz_hi, dz_lo, h_hi, h_lo, rows, gpart, n_split, n_params, off_w2, passes=3,
-                skip=None):
+                skip=None, off_b2=-1):
     """gpart[s, off_w2 + n*256 + k] = sum_m dz[m, n] h[m, k] over the rows of split s."""
     _count_flops('tb_tc_wgrad256', 2.0 * rows * 256 * 256)
     _lib.call('tb_tc_wgrad256', ptr(dz_hi), ptr(dz_lo), ptr(h_hi), ptr(h_lo), rows, passes,
-              ptr(gpart), n_split, n_params, off_w2, ptr(skip), stream())
+              ptr(gpart), n_split, n_params, off_w2, off_b2, ptr(skip), stream())
