@@ -35,7 +35,8 @@ sys.path.insert(0, ROOT)
 OBS, ACT, ENVS_PER_GPU, SEGMENT, EPOCHS, MINIBATCHES, HIDDEN = 17, 6, 4096, 128, 10, 32, 256
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (16384 rows) from the committed
 # `ncu --set full` captures under profiles/ (cold cache, serialised)
-NCU_TRAFFIC = {'tb_tc_gemm256_bwd': 70.8e6, 'tb_tc_gemm256_fwd': None, 'tb_tc_wgrad256': None}
+NCU_TRAFFIC = {'tb_tc_gemm256_bwd': 70.8e6, 'tb_tc_gemm256_fwd': None, 'tb_tc_wgrad256': None,
+               'tb_tc_mlp_forward': None, 'tb_tc_mlp_backward': None}
 MAX_EPISODE_STEPS = 1000
 
 
@@ -194,13 +195,17 @@ def run_ours(args):
     skipped = profiled_iterations['critic'] - timed_iterations['critic'] - (
         profiled_iterations['actor'] - timed_iterations['actor'])
     rows_local = batch // world
-    gemm_names = ('tb_tc_gemm256_fwd', 'tb_tc_gemm256_bwd', 'tb_tc_wgrad256',
-                  'tb_mlp_forward', 'tb_mlp_backward', 'tb_mlp_wgrad')
+    gemm_names = ('tb_tc_mlp_forward', 'tb_tc_mlp_backward', 'tb_tc_gemm256_fwd', 'tb_tc_gemm256_bwd',
+                  'tb_tc_wgrad256', 'tb_mlp_forward', 'tb_mlp_backward', 'tb_mlp_wgrad')
+    # algorithmic FLOPs of ONE skipped launch (they are actor-minibatch launches)
+    actor_launch_flops = {
+        'tb_tc_mlp_forward': 2.0 * rows_local * (OBS * HIDDEN + HIDDEN * HIDDEN + HIDDEN * ACT),
+        'tb_tc_mlp_backward': 2.0 * rows_local * HIDDEN * (ACT + HIDDEN)}
 
     def executed_flops(name):
         total = kernels.flops.get(name, 0.0)
         if name in gemm_names:
-            per_launch = 2.0 * rows_local * HIDDEN * HIDDEN
+            per_launch = actor_launch_flops.get(name, 2.0 * rows_local * HIDDEN * HIDDEN)
             if name in ('tb_mlp_forward', 'tb_mlp_backward', 'tb_mlp_wgrad'):
                 per_launch = total / max(prof.get(name, (1, 0))[0], 1)
             total -= skipped * per_launch
@@ -218,11 +223,12 @@ def run_ours(args):
         executed_launches=top_count - (skipped if top in gemm_names else 0),
         avg_launch_us=round(top_ms / max(top_count - skipped, 1) * 1e3, 2),
         share_of_kernel_time=round(top_ms / total_kernel_ms, 4),
-        flops_per_launch=2.0 * rows_local * HIDDEN * HIDDEN,
+        flops_per_launch=round(top_flops / max(top_count - skipped, 1), 1),
         tensor_pipe_tflops=round(achieved * max(passes, 1), 3),
         note=('dominant GEMM entry point by CUDA-event time in an eager (graphs off) pass of the '
-              'same K steps; achieved = algorithmic fp32-equivalent FLOPs (2*rows*256*256 per '
-              'executed launch) / event time; ' +
+              'same K steps; achieved = algorithmic fp32-equivalent FLOPs of the executed launches '
+              '(fused forward: 2*rows*(d_in*256 + 256*256 + 256*n_out); fused backward: '
+              '2*rows*256*(n_out + 256); weight gradient: 2*rows*256*256) / event time; ' +
               ('FP32 FFMA kernels' if passes == 0 else
                f'tcgen05 kind::tf32 with {passes} MMA pass(es) per product, so the tensor pipe '
                f'itself runs {passes}x the achieved figure (tensor_pipe_tflops)') +

@@ -134,6 +134,7 @@ class MlpInput:
 
 
 _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
+_FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
 
 
 class DeviceMlp:
@@ -230,7 +231,8 @@ class DeviceMlp:
         flops = 2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out)
         if passes:
             _count_flops('tb_mlp_forward_tc', flops)
-            _count_flops('tb_tc_gemm256_fwd', 2.0 * rows * L.hidden * L.hidden)
+            _count_flops('tb_tc_mlp_forward' if fused else 'tb_tc_gemm256_fwd',
+                         flops if fused else 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_forward_tc', ctypes.byref(L.shape), ptr(params), ptr(packed),
                       ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
                       *((None, None, None) if fused and not save
@@ -251,7 +253,10 @@ class DeviceMlp:
         passes = self.passes()
         if passes:
             _count_flops('tb_mlp_backward_tc', flops)
-            _count_flops('tb_tc_gemm256_bwd', 2.0 * rows * L.hidden * L.hidden)
+            if L.n_out <= 8 and _FUSED_BWD:      # one kernel: head gradient + hidden-layer GEMM
+                _count_flops('tb_tc_mlp_backward', 2.0 * rows * L.hidden * (L.n_out + L.hidden))
+            else:
+                _count_flops('tb_tc_gemm256_bwd', 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_backward_tc', ctypes.byref(L.shape), ptr(params),
                       ptr(self.packed if packed is None else packed), ptr(dout), dout.shape[-1],
                       ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), rows, ptr(self.dz2),
