@@ -121,7 +121,7 @@ def run_ours(args):
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    from tonic_b200 import _lib, config, kernels
+    from tonic_b200 import _lib, config, graphs, kernels
     from tonic_b200.utils import logger
     iterations = dict(actor=0, critic=0)          # statistics are still read back every update
 
@@ -152,7 +152,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + graphs.replayed_launches
     iterations.update(actor=0, critic=0)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -166,7 +166,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     elapsed_ms = float(elapsed_ms.item())
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + graphs.replayed_launches - launches0
     timed_iterations = dict(iterations)
     env_steps = args.steps * SEGMENT * total_envs
     value = env_steps / (elapsed_ms / 1e3)
@@ -240,15 +240,7 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing protocol with HOST arrays ------------------------
     e2e = None
-    if world == 1:
-        config.noise = 'host'     # noise drawn from torch's CPU generator like the reference
-        config.indices = 'host'   # numpy-compatible permutations generated on the host
-        kernels.transfers['h2d'] = kernels.transfers['d2h'] = 0
-        agent.replay.index = 0
-        observations = env.start(host=True)
-        steps_count = 0
-        e2e_iters = max(1, min(args.steps, 2))
-
+    if True:
         def host_iteration(observations, steps_count):
             for _ in range(SEGMENT):
                 actions = agent.step(observations, steps_count)
@@ -256,21 +248,45 @@ def run_ours(args):
                 agent.update(**infos, steps=steps_count)
                 steps_count += ENVS_PER_GPU
             return observations, steps_count
-        observations, steps_count = host_iteration(observations, steps_count)   # warm-up
-        torch.cuda.synchronize()
-        kernels.transfers['h2d'] = kernels.transfers['d2h'] = 0
-        t0 = time.time()
-        for _ in range(e2e_iters):
-            observations, steps_count = host_iteration(observations, steps_count)
-        torch.cuda.synchronize()
-        dt = time.time() - t0
-        e2e = dict(value=round(e2e_iters * SEGMENT * ENVS_PER_GPU / dt, 1), unit='env-steps/s',
-                   h2d_bytes_per_step=kernels.transfers['h2d'] // e2e_iters,
-                   d2h_bytes_per_step=kernels.transfers['d2h'] // e2e_iters,
-                   steps=e2e_iters,
+
+        def measure(iters, warm):
+            """The reference's protocol with numpy arrays crossing the boundary every vector step."""
+            agent.replay.index = 0
+            observations = env.start(host=True)
+            steps_count = 0
+            for _ in range(warm):
+                observations, steps_count = host_iteration(observations, steps_count)
+            torch.cuda.synchronize()
+            barrier()
+            kernels.transfers['h2d'] = kernels.transfers['d2h'] = 0
+            t0 = time.time()
+            for _ in range(iters):
+                observations, steps_count = host_iteration(observations, steps_count)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.time() - t0], device='cuda', dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)      # slowest rank
+            dt = float(dt.item())
+            return (iters * SEGMENT * total_envs / dt, kernels.transfers['h2d'] // iters,
+                    kernels.transfers['d2h'] // iters)
+        # product configuration: device Philox noise + device permutations, update replayed as a
+        # CUDA graph (3 warm iterations: 2 eager executions size the workspaces, 1 captures)
+        e2e_iters = max(1, min(args.steps, 3))
+        fast, h2d, d2h = measure(e2e_iters, 3)
+        # parity configuration: host torch RNG noise + numpy-compatible MT19937 permutations
+        parity = None
+        if world == 1:
+            config.noise = config.indices = 'host'
+            parity, _, _ = measure(1, 1)
+            config.noise, config.indices = 'device', args.indices
+            parity = round(parity, 1)
+        e2e = dict(value=round(fast, 1), unit='env-steps/s', h2d_bytes_per_step=h2d,
+                   d2h_bytes_per_step=d2h, steps=e2e_iters, parity_mode_value=parity,
                    note='agent.step / environment.step / agent.update called with numpy arrays '
-                        'every vector step (pinned staging), host torch RNG noise, host MT19937 '
-                        'minibatch permutations')
+                        'every vector step (pinned staging, copies inside the timed region; bytes '
+                        'are per rank and per PPO iteration of 128 vector steps); value = product configuration '
+                        '(device noise and permutations, graph-replayed update), parity_mode_value '
+                        '= host torch RNG noise + host MT19937 permutations (bit-compatible streams)')
 
     if rank != 0:
         return

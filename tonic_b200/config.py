@@ -26,11 +26,13 @@ graphs  True     : sections with static shapes (PPO / A2C rollout of a whole seg
 peer_reduce True : with several ranks the gradient all-reduce is fused into the Adam
                    kernel over NVLink peer memory (symmetric memory); False = NCCL
                    all-reduce of the flat gradient + statistics, then Adam.
-fused_rollout True : with device noise the whole on-policy segment (T vector steps of
-                   actor forward + sampling + environment step + segment store +
-                   normaliser record) is ONE persistent kernel (csrc/mlp.cu
-                   rollout_kernel, FP32 FFMA arithmetic, 64 environments resident per
-                   CTA); False = one launch per stage per step.
+fused_rollout 'auto' : with device noise the whole on-policy segment (T vector steps of actor
+                   forward + sampling + environment step + segment store + normaliser record)
+                   can run as ONE persistent kernel (csrc/mlp.cu rollout_kernel, FP32 FFMA
+                   arithmetic, 64 environments resident per CTA = 64 CTAs at 4096 envs).  'auto'
+                   uses it unless the per-step chain can be replayed as a CUDA graph on the
+                   tensor-core path (then the chain is faster: measured 4.9 vs 6.5 ms per
+                   128-step segment of 4096 envs on B200); True = always, False = never.
 wgrad_splits     : number of row splits of the weight-gradient kernel.
 """
 
@@ -42,6 +44,6 @@ indices = 'host'
 graphs = os.environ.get('TONIC_B200_GRAPHS', '1') != '0'
 peer_reduce = os.environ.get('TONIC_B200_PEER_REDUCE', '1') != '0'   # fused NVLink reduce + Adam
 graphs_multi_gpu = os.environ.get('TONIC_B200_GRAPHS_MULTI', '1') != '0'   # capture NCCL too
-fused_rollout = os.environ.get('TONIC_B200_FUSED_ROLLOUT', '1') != '0'
+fused_rollout = {'0': False, '1': True}.get(os.environ.get('TONIC_B200_FUSED_ROLLOUT', 'auto'), 'auto')
 wgrad_splits = 37      # FFMA: 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
 wgrad_splits_tc = 74   # tensor cores: 2 row tiles x 74 splits = 148 CTAs

@@ -56,6 +56,14 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
         const int n_split = (n_split_w2 > 0 && i >= sh.off_w2 && i < w2_end) ? n_split_w2 : n_split_all;
         float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
         int s = 0;
+        // 16 independent loads in flight per thread (the sum order stays s mod 4 -> g0..g3)
+        for (; s + 16 <= n_split; s += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldg(gpart + (size_t)(s + u) * opt.n_params + i);
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) { g0 += v[u]; g1 += v[u + 1]; g2 += v[u + 2]; g3 += v[u + 3]; }
+        }
         for (; s + 4 <= n_split; s += 4) {
             g0 += gpart[(size_t)(s + 0) * opt.n_params + i];
             g1 += gpart[(size_t)(s + 1) * opt.n_params + i];

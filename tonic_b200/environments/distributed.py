@@ -92,12 +92,13 @@ class DeviceVectorEnvironment:
         self.step_into(actions, self.observations, self.next_observations, self.rewards,
                        self.resets, self.terminations)
         if host:
-            infos = dict(
-                observations=kernels.to_host(self.next_observations),
-                rewards=kernels.to_host(self.rewards),
-                resets=kernels.to_host(self.resets).astype(np.bool_),
-                terminations=kernels.to_host(self.terminations).astype(np.bool_))
-            return kernels.to_host(self.observations), infos
+            # one synchronisation for the five result arrays (pinned staging)
+            obs, next_obs, rewards, resets, terminations = kernels.to_host(
+                self.observations, self.next_observations, self.rewards, self.resets,
+                self.terminations)
+            infos = dict(observations=next_obs, rewards=rewards, resets=resets.astype(np.bool_),
+                         terminations=terminations.astype(np.bool_))
+            return obs, infos
         infos = dict(observations=self.next_observations, rewards=self.rewards,
                      resets=self.resets, terminations=self.terminations)
         return self.observations, infos

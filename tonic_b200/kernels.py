@@ -34,32 +34,65 @@ flops = {}
 _pinned = {}
 
 
-def to_device(x, dtype=F32):
-    """numpy / torch (host or device) -> contiguous device tensor of `dtype`.
-    Host arrays are staged through a cached pinned buffer."""
+_RING = 8        # pinned staging buffers per (shape, dtype): a copy out of one may still be in flight
+
+
+def to_device(x, dtype=F32, out=None):
+    """numpy / torch (host or device) -> contiguous device tensor of `dtype` (`out`: write into
+    this device tensor instead of a new one).  Host arrays are staged through a small ring of
+    cached pinned buffers; a buffer is reused only after the copy out of it has completed (its
+    own event, not a stream-wide synchronisation)."""
     if isinstance(x, torch.Tensor) and x.is_cuda:
-        return x.to(dtype=dtype).contiguous()
+        x = x.to(dtype=dtype).contiguous()
+        if out is None:
+            return x
+        out.copy_(x)
+        return out
     arr = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
     target = {torch.float32: np.float32, torch.float64: np.float64,
               torch.int64: np.int64, torch.int32: np.int32}[dtype]
     arr = np.ascontiguousarray(arr, dtype=target)
     key = (arr.shape, arr.dtype.str)
-    stage = _pinned.get(key)
-    if stage is None:
-        stage = _pinned[key] = torch.empty(arr.shape, dtype=dtype).pin_memory()
-    out = torch.empty(arr.shape, dtype=dtype, device=device())
-    # the staging buffer is reused: wait for the previous copy out of it
-    torch.cuda.current_stream().synchronize()
+    ring = _pinned.get(key)
+    if ring is None:
+        ring = _pinned[key] = dict(next=0, slots=[])
+    if len(ring['slots']) < _RING:
+        ring['slots'].append((torch.empty(arr.shape, dtype=dtype).pin_memory(), torch.cuda.Event()))
+        stage, event = ring['slots'][-1]
+    else:
+        stage, event = ring['slots'][ring['next']]
+        ring['next'] = (ring['next'] + 1) % _RING
+        event.synchronize()
+    if out is None:
+        out = torch.empty(arr.shape, dtype=dtype, device=device())
     stage.numpy()[...] = arr
     out.copy_(stage, non_blocking=True)
+    event.record()
     transfers['h2d'] += arr.nbytes
     return out
 
 
-def to_host(t):
-    """Device tensor -> numpy (synchronises)."""
-    transfers['d2h'] += t.numel() * t.element_size()
-    return t.detach().cpu().numpy()
+_host_stage = {}
+
+
+def to_host(*tensors):
+    """Device tensor(s) -> fresh numpy array(s): asynchronous copies into cached pinned buffers,
+    ONE synchronisation for the whole group, then a host copy (the caller owns the result, like
+    the fresh arrays the reference returns: environments/distributed.py:52-58)."""
+    stages = []
+    for i, t in enumerate(tensors):
+        key = (i, tuple(t.shape), t.dtype)       # one staging buffer per position in the group
+        stage = _host_stage.get(key)
+        if stage is None:
+            if len(_host_stage) > 64:       # shapes that vary (episode logs): keep the cache small
+                _host_stage.clear()
+            stage = _host_stage[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        stage.copy_(t.detach(), non_blocking=True)
+        transfers['d2h'] += t.numel() * t.element_size()
+        stages.append(stage)
+    torch.cuda.current_stream().synchronize()
+    out = [st.numpy().copy() for st in stages]
+    return out[0] if len(out) == 1 else out
 
 
 def _count_flops(name, value):

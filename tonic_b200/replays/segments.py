@@ -48,8 +48,8 @@ class Segment:
         if self.buffers is None:
             self.allocate(**{k: tuple(np.shape(v)) if not isinstance(v, torch.Tensor)
                              else tuple(v.shape) for k, v in kwargs.items()})
-        for key, val in kwargs.items():
-            self.buffers[key][self.index].copy_(kernels.to_device(val))
+        for key, val in kwargs.items():     # host arrays go straight into the segment row
+            kernels.to_device(val, out=self.buffers[key][self.index])
         self.index += 1
 
     def advance(self):

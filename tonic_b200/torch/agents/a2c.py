@@ -168,7 +168,9 @@ class A2C(agent.Agent):
         device noise with small observation / action vectors."""
         actor = self.model.actor
         shape = actor.network.layout.shape
-        return (config.fused_rollout and config.noise == 'device'
+        if config.fused_rollout == 'auto' and self._graphable() and actor.network.mlp.passes():
+            return False        # graph replay of the tensor-core per-step chain is faster
+        return (bool(config.fused_rollout) and config.noise == 'device'
                 and getattr(actor.head, 'kind', None) == 'detached_gaussian'
                 and hasattr(env, 'struct') and shape.d_in <= min(64, shape.hidden)
                 and shape.n_out <= 16 and shape.hidden in (64, 128, 256))
