@@ -233,6 +233,17 @@ int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params, const floa
                       float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
                       const int32_t* d_skip, void* stream);
 
+/* tb_tc_mlp_forward for a single-output value head with the squared-error loss of
+ * VRegression (torch/updaters/critics.py:18-28) fused into its epilogue: the arguments of
+ * tb_mse_loss (targets gathered by d_idx, dout = 2 (v - target), sums into the TB_STAT_*
+ * block) in addition to those of tb_tc_mlp_forward; n_out must be 1.                     */
+int tb_tc_mlp_forward_vloss(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                            const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                            float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                            const float* d_targets, const int64_t* d_idx, float* d_dout,
+                            int32_t ld_dout, double* d_stats, int32_t stat_slot,
+                            int32_t count_rows, const int32_t* d_skip, void* stream);
+
 /* Activation gradients of the same network as ONE tensor-core kernel (csrc/tc_mlp.cu):
  * dz2 = (dout W3) * act'(h2) and dz1 = (dz2 W2) * act'(h1), the autograd of the head and of
  * the second hidden layer behind loss.backward() (torch/updaters/actors.py:33,104,186,

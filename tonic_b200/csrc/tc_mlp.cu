@@ -58,6 +58,15 @@ struct TcMlpParams {
     int n_head;                 // 0..8
     const int32_t* skip;
     unsigned long long* timeline;   // profiling aid: 64 clock64() stamps of CTA 0, or NULL
+    // optional fused squared-error loss on the single head output (value regression,
+    // torch/updaters/critics.py:18-28): dout = 2 (v - target), sums into the statistics block
+    const float* loss_targets;      // [.] indexed by loss_idx[row] (or row), or NULL
+    const int64_t* loss_idx;
+    float* loss_dout;               // [n_rows, loss_ld]
+    int loss_ld;
+    double* loss_stats;             // TB_STAT_* block
+    int loss_stat_slot;             // slot receiving the sum of values
+    int loss_count_rows;
 };
 
 constexpr int TCM_ROW_WARPS = 8;                 // two per TMEM lane quarter (column halves)
@@ -481,14 +490,44 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                     for (int o = 0; o < TC_MAX_HEAD; ++o) stg[lane * TCM_STG_STRIDE + o] = hacc[o];
                 }
                 row_warps_sync();
+                double st_loss = 0.0, st_val = 0.0, st_rows = 0.0;
                 if (wg == 0 && row < p.n_rows) {
                     const float* other = epi + (rw + 4) * 32 * TCM_STG_STRIDE + lane * TCM_STG_STRIDE;
 #pragma unroll
                     for (int o = 0; o < TC_MAX_HEAD; ++o)
                         if (o < p.n_head)
                             p.head_out[row * p.n_head + o] = (hacc[o] + other[o]) + __ldg(p.head_b + o);
+                    if (p.loss_targets) {
+                        // same arithmetic as mse_loss_kernel (csrc/heads.cu)
+                        const float v = (hacc[0] + other[0]) + __ldg(p.head_b);
+                        const float t = p.loss_targets[p.loss_idx ? p.loss_idx[row] : row];
+                        const float d = v - t;
+                        p.loss_dout[row * p.loss_ld] = 2.0f * d;
+                        st_loss = (double)d * (double)d;
+                        st_val = v;
+                        st_rows = 1.0;
+                    }
+                }
+                if (p.loss_targets && wg == 0) {
+                    st_loss = warp_sum(st_loss);
+                    st_val = warp_sum(st_val);
+                    st_rows = warp_sum(st_rows);
+                    if (lane == 0) {       // group 0's staging blocks are idle here
+                        double* mine = reinterpret_cast<double*>(stg);
+                        mine[0] = st_loss; mine[1] = st_val; mine[2] = st_rows;
+                    }
                 }
                 row_warps_sync();
+                if (p.loss_targets && rw == 0 && lane == 0) {
+                    double tl = 0.0, tv = 0.0, tr = 0.0;
+                    for (int k = 0; k < 4; ++k) {          // fixed order over the 4 warps of group 0
+                        const double* part = reinterpret_cast<const double*>(epi + k * 32 * TCM_STG_STRIDE);
+                        tl += part[0]; tv += part[1]; tr += part[2];
+                    }
+                    atomicAdd(&p.loss_stats[TB_STAT_LOSS], tl);
+                    atomicAdd(&p.loss_stats[p.loss_stat_slot], tv);
+                    if (p.loss_count_rows) atomicAdd(&p.loss_stats[TB_STAT_ROWS], tr);
+                }
             }
             if (stamper) tc_stamp(p.timeline, 30);            // final epilogue done
             // TMEM reads of this tile are complete before the next tile's MMAs are released
@@ -864,10 +903,16 @@ extern "C" int tb_tc_timeline(uint64_t* out64) {
     return 0;
 }
 
-extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params, const float* d_packed,
-                                 const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
-                                 float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
-                                 const int32_t* d_skip, void* stream) {
+namespace tb {
+struct VLoss {
+    const float* targets; const int64_t* idx; float* dout; int ld; double* stats; int slot; int count_rows;
+};
+}  // namespace tb
+
+static int tc_mlp_forward_impl(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                               const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                               float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                               const tb::VLoss* loss, const int32_t* d_skip, void* stream) {
     using namespace tb;
     TB_REQUIRE(shape && d_params && d_packed && in && in->d_x1 && d_out && n_rows > 0, TB_EINVAL,
                "tb_tc_mlp_forward: null pointer");
@@ -897,6 +942,16 @@ extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params,
     p.xin_save = d_xin; p.h1_hi = d_h1_hi; p.h1_lo = d_h1_lo; p.h2 = d_h2;
     p.head_w = d_params + shape->off_w3; p.head_b = d_params + shape->off_b3; p.head_out = d_out;
     p.n_head = shape->n_out; p.skip = d_skip; p.timeline = g_timeline;
+    p.loss_targets = nullptr; p.loss_idx = nullptr; p.loss_dout = nullptr; p.loss_ld = 1;
+    p.loss_stats = nullptr; p.loss_stat_slot = 0; p.loss_count_rows = 0;
+    if (loss) {
+        TB_REQUIRE(shape->n_out == 1 && loss->targets && loss->dout && loss->stats && loss->ld >= 1 &&
+                   loss->slot >= 0 && loss->slot < TB_STAT_COUNT, TB_EINVAL,
+                   "tb_tc_mlp_forward_vloss: needs a single-output head, targets, dout and stats");
+        p.loss_targets = loss->targets; p.loss_idx = loss->idx; p.loss_dout = loss->dout;
+        p.loss_ld = loss->ld; p.loss_stats = loss->stats; p.loss_stat_slot = loss->slot;
+        p.loss_count_rows = loss->count_rows;
+    }
     ProfScope prof_scope("tb_tc_mlp_forward", stream);
     const bool tanh_act = shape->act == TB_ACT_TANH;
     if (passes == 3) {
@@ -907,6 +962,25 @@ extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params,
         else launch_tc_mlp<1, TB_ACT_RELU>(maps, p, as_stream(stream));
     }
     return check_launch("tb_tc_mlp_forward");
+}
+
+extern "C" int tb_tc_mlp_forward(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                                 const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                                 float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                                 const int32_t* d_skip, void* stream) {
+    return tc_mlp_forward_impl(shape, d_params, d_packed, in, n_rows, d_out, d_xin, d_h1_hi, d_h1_lo, d_h2,
+                               passes, nullptr, d_skip, stream);
+}
+
+extern "C" int tb_tc_mlp_forward_vloss(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                                       const TbMlpInput* in, int64_t n_rows, float* d_out, float* d_xin,
+                                       float* d_h1_hi, float* d_h1_lo, float* d_h2, int32_t passes,
+                                       const float* d_targets, const int64_t* d_idx, float* d_dout,
+                                       int32_t ld_dout, double* d_stats, int32_t stat_slot,
+                                       int32_t count_rows, const int32_t* d_skip, void* stream) {
+    tb::VLoss loss{d_targets, d_idx, d_dout, ld_dout, d_stats, stat_slot, count_rows};
+    return tc_mlp_forward_impl(shape, d_params, d_packed, in, n_rows, d_out, d_xin, d_h1_hi, d_h1_lo, d_h2,
+                               passes, &loss, d_skip, stream);
 }
 
 extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params, const float* d_packed,

@@ -249,9 +249,12 @@ class DeviceMlp:
         return off, off + size
 
     # -- kernels ------------------------------------------------------------
-    def forward(self, inp, rows, out, save=False, skip=None, params=None, packed=None):
+    def forward(self, inp, rows, out, save=False, skip=None, params=None, packed=None, vloss=None):
         """out[rows, n_out] = head pre-activations. `params`/`packed` override the
-        parameter set (target networks share the layout)."""
+        parameter set (target networks share the layout).  `vloss` = (targets, idx, dout, stats):
+        squared-error loss of a single-output head; `self.vloss_fused` tells the caller whether
+        the forward kernel computed it (otherwise kernels.mse_loss has to be launched)."""
+        self.vloss_fused = False
         passes = self.passes()
         L = self.layout
         # one-kernel tensor-core forward (csrc/tc_mlp.cu): no activation round trip through
@@ -266,6 +269,17 @@ class DeviceMlp:
             _count_flops('tb_mlp_forward_tc', flops)
             _count_flops('tb_tc_mlp_forward' if fused else 'tb_tc_gemm256_fwd',
                          flops if fused else 2.0 * rows * L.hidden * L.hidden)
+            if fused and vloss is not None and L.n_out == 1:
+                targets, idx, dout, stats = vloss
+                self.vloss_fused = True
+                _lib.call('tb_tc_mlp_forward_vloss', ctypes.byref(L.shape), ptr(params), ptr(packed),
+                          ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
+                          *((None, None, None) if not save
+                            else (ptr(self.h1), ptr(self.h1_lo), ptr(self.h2))),
+                          passes, ptr(targets), ptr(idx), ptr(dout),
+                          dout.shape[-1] if dout.dim() > 1 else 1, ptr(stats), _lib.STAT_VALUE, 1,
+                          ptr(skip), stream())
+                return out
             _lib.call('tb_mlp_forward_tc', ctypes.byref(L.shape), ptr(params), ptr(packed),
                       ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
                       *((None, None, None) if fused and not save

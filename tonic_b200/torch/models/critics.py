@@ -50,13 +50,13 @@ class Critic(torch.nn.Module):
                                 gather2=gather_actions and idx is not None, idx=idx)
 
     def values(self, observations, actions=None, out=None, idx=None, rows=None,
-               gather_actions=True, save=False, skip=None, params=None, packed=None):
+               gather_actions=True, save=False, skip=None, params=None, packed=None, vloss=None):
         rows = observations.shape[0] if rows is None else rows
         if out is None:
             out = network.scratch(rows, 1, observations)
         inp = self.input(observations, actions, idx, gather_actions)
         return self.network.mlp.forward(inp, rows, out, save=save, skip=skip, params=params,
-                                        packed=packed)
+                                        packed=packed, vloss=vloss)
 
     def forward(self, observations, actions=None):
         observations = kernels.to_device(observations)

@@ -40,8 +40,11 @@ class VRegression:
         gpart = None
         if rows > 0:
             values, dout = self._scratch(rows)
-            critic.values(observations, out=values, idx=idx, rows=rows, save=True)
-            kernels.mse_loss(values, returns, idx, rows, dout, stats)
+            # the tensor-core forward kernel evaluates the squared-error loss in its epilogue
+            critic.values(observations, out=values, idx=idx, rows=rows, save=True,
+                          vloss=(returns, idx, dout, stats))
+            if not net.mlp.vloss_fused:
+                kernels.mse_loss(values, returns, idx, rows, dout, stats)
             net.mlp.backward(dout, rows)
             gpart = net.mlp.wgrad(dout, rows, n_split)
         kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
