@@ -35,8 +35,10 @@ sys.path.insert(0, ROOT)
 OBS, ACT, ENVS_PER_GPU, SEGMENT, EPOCHS, MINIBATCHES, HIDDEN = 17, 6, 4096, 128, 10, 32, 256
 # dram__bytes_read.sum + dram__bytes_write.sum per launch (16384 rows) from the committed
 # `ncu --set full` captures under profiles/ (cold cache, serialised)
-NCU_TRAFFIC = {'tb_tc_gemm256_bwd': 70.8e6, 'tb_tc_gemm256_fwd': None, 'tb_tc_wgrad256': None,
-               'tb_tc_mlp_forward': None, 'tb_tc_mlp_backward': None}
+# dram__bytes_read.sum + dram__bytes_write.sum of one 16384-row critic-minibatch launch, from the committed
+# `ncu --set full` captures (profiles/r1_ncu_full_fused_raw.csv, profiles/r1_ncu_full_*_raw.csv)
+NCU_TRAFFIC = {'tb_tc_gemm256_bwd': 70.8e6, 'tb_tc_gemm256_fwd': None, 'tb_tc_wgrad256': 69.4e6,
+               'tb_tc_mlp_forward': 3.45e6, 'tb_tc_mlp_backward': 60.2e6}
 MAX_EPISODE_STEPS = 1000
 
 
