@@ -89,6 +89,9 @@ def reference_agent(cfg):
     replay = tonic.replays.Buffer(**cfg['buffer'])
     if kind == 'SAC':
         exploration = tonic.explorations.NoActionNoise(cfg['start_steps'])
+    elif cfg.get('exploration') == 'ou':
+        exploration = tonic.explorations.OrnsteinUhlenbeckActionNoise(
+            start_steps=cfg['start_steps'])
     else:
         exploration = tonic.explorations.NormalActionNoise(
             start_steps=cfg['start_steps'])

@@ -523,8 +523,9 @@ class OffPolicyOracle:
 
     def __init__(self, kind, hidden, buffer, start_steps=20000, log=None,
                  target_coeff=0.005, noise_scale=0.1, delay_steps=2,
-                 entropy_coeff=0.2, target_noise=(0.2, 0.5)):
+                 entropy_coeff=0.2, target_noise=(0.2, 0.5), exploration='normal'):
         self.kind, self.hidden = kind, tuple(hidden)
+        self.exploration, self.ou_noises = exploration, None   # 'ou': noisy.py:53-88
         self.replay = RingStore(**buffer)
         self.start_steps, self.noise_scale = start_steps, noise_scale
         self.log = log or (lambda *a, **k: None)
@@ -594,7 +595,16 @@ class OffPolicyOracle:
     def step(self, observations, steps):              # ddpg.py:45-53 + noisy.py:15-22,38-47
         if steps > self.start_steps:
             actions = self._policy(observations)
-            if self.kind != 'SAC':
+            if self.exploration == 'ou':              # noisy.py:71-81
+                scale, clip, theta, dt = 0.1, 2, .15, 1e-2          # defaults noisy.py:55
+                if self.ou_noises is None:
+                    self.ou_noises = np.zeros_like(actions)
+                noises = self.noise_rng.normal(size=actions.shape)
+                noises = np.clip(noises, -clip, clip)
+                self.ou_noises -= theta * self.ou_noises * dt
+                self.ou_noises += scale * np.sqrt(dt) * noises
+                actions = (actions + self.ou_noises).astype(np.float32)
+            elif self.kind != 'SAC':
                 noises = self.noise_scale * self.noise_rng.normal(size=actions.shape)
                 actions = (actions + noises).astype(np.float32)
             actions = np.clip(actions, -1, 1)
@@ -617,6 +627,8 @@ class OffPolicyOracle:
         self.norm.record(self.last_observations)
         if self.replay.ready(steps):
             self._update(steps)
+        if self.exploration == 'ou' and self.ou_noises is not None:   # ddpg.py:76 + noisy.py:86-88
+            self.ou_noises *= (1. - resets)[:, None]
 
     def _q(self, net, observations, actions):
         return value_critic_forward(net, self.norm, torch.relu, observations, actions)
@@ -708,6 +720,7 @@ def build(cfg, log=None):
         agent = OnPolicyOracle(cfg['agent'], cfg['hidden'], cfg['segment'], log=log)
     else:
         agent = OffPolicyOracle(cfg['agent'], cfg['hidden'], cfg['buffer'],
-                                start_steps=cfg['start_steps'], log=log)
+                                start_steps=cfg['start_steps'], log=log,
+                                exploration=cfg.get('exploration', 'normal'))
     agent.initialize(env.observation_space, env.action_space, seed=cfg['seed'])
     return agent, env

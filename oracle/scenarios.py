@@ -48,6 +48,11 @@ SCENARIOS = {
         hidden=(256, 256), vector_steps=40, start_steps=60,
         buffer=dict(size=400, batch_iterations=4, batch_size=16,
                     steps_before_batches=48, steps_between_batches=16)),
+    'ddpg_ou': dict(      # OrnsteinUhlenbeckActionNoise (explorations/noisy.py:53-88), SURVEY 8f rank 2
+        agent='DDPG', obs=9, act=2, workers=4, max_episode_steps=7, seed=5, exploration='ou',
+        hidden=(64, 64), vector_steps=40, start_steps=40,
+        buffer=dict(size=400, batch_iterations=3, batch_size=16,
+                    steps_before_batches=48, steps_between_batches=16)),
     'td3_small': dict(
         agent='TD3', obs=11, act=3, workers=4, max_episode_steps=13, seed=4,
         hidden=(256, 256), vector_steps=40, start_steps=60,

@@ -43,6 +43,9 @@ def build(cfg, log=None):
         replay = tonic_b200.replays.Buffer(**cfg['buffer'])
         if kind == 'SAC':
             exploration = tonic_b200.explorations.NoActionNoise(cfg['start_steps'])
+        elif cfg.get('exploration') == 'ou':
+            exploration = tonic_b200.explorations.OrnsteinUhlenbeckActionNoise(
+                start_steps=cfg['start_steps'])
         else:
             exploration = tonic_b200.explorations.NormalActionNoise(
                 start_steps=cfg['start_steps'])

@@ -1,3 +1,3 @@
-from .noisy import NoActionNoise, NormalActionNoise
+from .noisy import NoActionNoise, NormalActionNoise, OrnsteinUhlenbeckActionNoise
 
-__all__ = [NoActionNoise, NormalActionNoise]
+__all__ = [NoActionNoise, NormalActionNoise, OrnsteinUhlenbeckActionNoise]

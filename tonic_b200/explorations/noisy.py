@@ -8,7 +8,8 @@ stream.  With `config.noise == 'host'` the numbers come from the native
 numpy-compatible `RandomState(seed)` (bit-identical to the reference's stream:
 float64 uniform warm-up actions, float64 normal noise added to float32 actions);
 with 'device' they are drawn by Philox inside the action kernel.
-The OU process (noisy.py:53-88) is a "next" row.
+The OU process (noisy.py:53-88) keeps its state on the host (numpy float32 arithmetic of the
+reference, numpy-compatible normal stream) and hands the policy an additive float32 noise block.
 """
 
 import numpy as np
@@ -73,3 +74,40 @@ class NormalActionNoise(NoActionNoise):
                 self.np_random.normal((workers * distributed.world(), self.action_size)),
                 workers), dtype=torch.float64)
         return None
+
+
+class OrnsteinUhlenbeckActionNoise(NoActionNoise):
+    """Reference: explorations/noisy.py:53-88.  `noise()` advances the process exactly like the
+    reference (`noises -= theta * noises * dt; noises += scale * sqrt(dt) * clip(N(0,1), +-clip)`,
+    float32 state updated in place with numpy's casting rules) and returns the rows of this rank
+    as an ADDITIVE float32 block; `update(resets)` clears the state of finished episodes.  The
+    normal draws always come from the host stream (the state is host-resident)."""
+
+    additive = True
+
+    def __init__(self, scale=0.1, clip=2, theta=.15, dt=1e-2, start_steps=20000):
+        self.scale, self.clip, self.theta, self.dt = scale, clip, theta, dt
+        self.start_steps = start_steps
+
+    def initialize(self, policy, action_space, seed=None):
+        super().initialize(policy, action_space, seed)
+        self.noises = None
+
+    def warmup_actions(self, workers):      # uniform(-1, 1) from the host stream (noisy.py:82-84)
+        return kernels.to_device(self._own(
+            self.np_random.uniform(-1, 1, (workers * distributed.world(), self.action_size)), workers))
+
+    def noise(self, workers):
+        if self.noises is None:
+            self.noises = np.zeros((workers, self.action_size), np.float32)     # zeros_like(actions)
+        draws = self._own(self.np_random.normal((workers * distributed.world(), self.action_size)),
+                          workers)
+        draws = np.clip(draws, -self.clip, self.clip)
+        self.noises -= self.theta * self.noises * self.dt
+        self.noises += self.scale * np.sqrt(self.dt) * draws
+        return kernels.to_device(self.noises)
+
+    def update(self, resets):
+        if self.noises is not None:
+            resets = kernels.to_host(resets) if isinstance(resets, torch.Tensor) else np.asarray(resets)
+            self.noises *= (1. - resets.astype(np.float64))[:, None]

@@ -63,6 +63,10 @@ class DDPG(agent.Agent):
             return self._greedy_actions(observations)
         pre = self.model.actor.pre_activations(observations)
         out = self._new_actions(observations)
+        if getattr(self.exploration, 'additive', False):
+            # OU process: float32 noise state added as is (noisy.py:78-80)
+            kernels.tanh_action(pre, out, mode=1, noise32=noise, noise_scale=1.0)
+            return out
         kernels.tanh_action(pre, out, mode=1, noise64=noise, seed=(self.seed or 0) ^ 0xdd9,
                             counter=self._noise_counter, noise_scale=scale)
         self._noise_counter += observations.shape[0]
