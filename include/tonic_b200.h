@@ -448,6 +448,21 @@ int tb_q_target(const float* d_rewards, const float* d_terminations, const int64
                 const float* d_log_probs, double entropy_coeff, int64_t n_rows,
                 float* d_targets, void* stream);
 
+/* Same with the replay's stored discounts column (n-step returns: the product of the
+ * per-step discounts, replays/buffers.py:58-79) instead of (1 - termination) * gamma. */
+int tb_q_target_discounts(const float* d_rewards, const float* d_discounts, const int64_t* d_idx,
+                          const float* d_q1, const float* d_q2, const float* d_log_probs,
+                          double entropy_coeff, int64_t n_rows, float* d_targets, void* stream);
+
+/* Buffer.accumulate_n_steps (replays/buffers.py:58-79), called after row `index` of the ring
+ * [max_size, N, ...] was written and before `size` is incremented: back-fills rewards /
+ * discounts / next_observations of the previous min(size, return_steps - 1) rows while no
+ * reset separates them from the new transition.                                         */
+int tb_replay_accumulate_n_steps(float* d_rewards, float* d_discounts, float* d_next_obs,
+                                 const float* d_resets, int32_t index, int32_t size,
+                                 int32_t max_size, int32_t n_workers, int32_t obs_dim,
+                                 int32_t return_steps, void* stream);
+
 /* Actor losses through the critics: loss_i = alpha * log_prob_i - min(q1_i, q2_i)
  * (DPG actors.py:177-179 with q2 = log_prob = NULL; soft DPG :254-257).  Writes
  * d loss_i / d q_k into d_dout1 / d_dout2 and accumulates TB_STAT_LOSS / ROWS.  */

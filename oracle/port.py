@@ -159,12 +159,12 @@ class SegmentStore:
 
 
 class RingStore:
-    """replays/buffers.py:4-91 (return_steps == 1 path)."""
+    """replays/buffers.py:4-91 (n-step accumulation: :58-79)."""
 
     def __init__(self, size=int(1e6), return_steps=1, batch_iterations=50,
                  batch_size=100, discount_factor=0.99,
                  steps_before_batches=int(1e4), steps_between_batches=50):
-        assert return_steps == 1, 'n-step accumulation is a "next" row (SURVEY 8f)'
+        self.return_steps = return_steps
         self.full_size, self.iterations, self.batch_size = size, batch_iterations, batch_size
         self.gamma = discount_factor
         self.before, self.between = steps_before_batches, steps_between_batches
@@ -186,6 +186,20 @@ class RingStore:
                          for k, v in kw.items()}
         for k, v in kw.items():
             self.data[k][self.index] = v
+        if self.return_steps > 1:                    # buffers.py:58-79
+            rewards, next_obs, discounts = kw['rewards'], kw['next_observations'], kw['discounts']
+            masks = np.ones(self.workers, F32)
+            for i in range(min(self.count, self.return_steps - 1)):
+                index = (self.index - i - 1) % self.rows
+                masks *= (1 - self.data['resets'][index])
+                new_rewards = self.data['rewards'][index] + self.data['discounts'][index] * rewards
+                self.data['rewards'][index] = (1 - masks) * self.data['rewards'][index] + masks * new_rewards
+                new_discounts = self.data['discounts'][index] * discounts
+                self.data['discounts'][index] = ((1 - masks) * self.data['discounts'][index]
+                                                 + masks * new_discounts)
+                self.data['next_observations'][index] = (
+                    (1 - masks)[:, None] * self.data['next_observations'][index]
+                    + masks[:, None] * next_obs)
         self.index = (self.index + 1) % self.rows
         self.count = min(self.count + 1, self.rows)
 

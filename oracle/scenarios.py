@@ -53,6 +53,11 @@ SCENARIOS = {
         hidden=(64, 64), vector_steps=40, start_steps=40,
         buffer=dict(size=400, batch_iterations=3, batch_size=16,
                     steps_before_batches=48, steps_between_batches=16)),
+    'ddpg_nstep': dict(   # Buffer(return_steps=3): n-step accumulation (replays/buffers.py:58-79)
+        agent='DDPG', obs=6, act=2, workers=4, max_episode_steps=5, seed=12,
+        hidden=(64, 64), vector_steps=40, start_steps=60,
+        buffer=dict(size=400, return_steps=3, batch_iterations=3, batch_size=16,
+                    steps_before_batches=48, steps_between_batches=16)),
     'td3_small': dict(
         agent='TD3', obs=11, act=3, workers=4, max_episode_steps=13, seed=4,
         hidden=(256, 256), vector_steps=40, start_steps=60,

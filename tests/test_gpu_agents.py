@@ -72,7 +72,7 @@ def test_on_policy_scenario_matches_reference(golden, name):
     check_weights(agent, g)
 
 
-OFF_POLICY = ['ddpg_small', 'ddpg_ou', 'td3_small', 'sac_small', 'sac_wrap']
+OFF_POLICY = ['ddpg_small', 'ddpg_ou', 'ddpg_nstep', 'td3_small', 'sac_small', 'sac_wrap']
 
 
 @pytest.mark.parametrize('name', OFF_POLICY)

@@ -101,7 +101,8 @@ q_target_kernel(const float* __restrict__ rewards, const float* __restrict__ ter
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t r = idx ? idx[i] : i;
-    const float disc = __fmul_rn(__fsub_rn(1.0f, terminations[r]), gamma);
+    // gamma < 0: `terminations` is the replay's stored (n-step) discounts column
+    const float disc = gamma < 0.0f ? terminations[r] : __fmul_rn(__fsub_rn(1.0f, terminations[r]), gamma);
     float v = q1[i];
     if (q2) v = fminf(v, q2[i]);
     if (logp) v = __fsub_rn(v, __fmul_rn(alpha, logp[i]));
@@ -241,4 +242,68 @@ extern "C" int tb_sac_head_grad(const float* d_pre, const float* d_eps, const fl
     tb::sac_head_grad_kernel<<<tb::blocks_for(total), 256, 0, tb::as_stream(stream)>>>(
         d_pre, d_eps, d_actions, d_dqda1, d_dqda2, (float)entropy_coeff, total, act_dim, d_dout);
     return tb::check_launch("tb_sac_head_grad");
+}
+
+// ---- n-step returns of the ring replay (replays/buffers.py:58-79) -------------------------
+// Called after row `index` was written: for the previous min(size, return_steps - 1) rows, while
+// no reset separates them from the new transition, rewards += discounts * new_rewards,
+// discounts *= new_discounts, next_observations = new next_observations (float32, every product
+// and sum rounded separately like the numpy expressions).  Thread (worker, coordinate).
+namespace tb {
+__global__ void __launch_bounds__(256)
+accumulate_n_steps_kernel(float* __restrict__ rewards, float* __restrict__ discounts,
+                          float* __restrict__ next_obs, const float* __restrict__ resets,
+                          int index, int count, int max_size, int N, int O) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)N * O) return;
+    const int w = (int)(t / O), j = (int)(t % O);
+    const float new_reward = rewards[(size_t)index * N + w];
+    const float new_discount = discounts[(size_t)index * N + w];
+    const float new_obs = next_obs[((size_t)index * N + w) * O + j];
+    float mask = 1.0f;
+    for (int i = 0; i < count; ++i) {
+        const int row = ((index - i - 1) % max_size + max_size) % max_size;
+        const size_t e = (size_t)row * N + w;
+        mask = __fmul_rn(mask, __fsub_rn(1.0f, resets[e]));
+        const float keep = __fsub_rn(1.0f, mask);
+        if (j == 0) {
+            const float r_old = rewards[e], d_old = discounts[e];
+            const float r_new = __fadd_rn(r_old, __fmul_rn(d_old, new_reward));
+            rewards[e] = __fadd_rn(__fmul_rn(keep, r_old), __fmul_rn(mask, r_new));
+            const float d_new = __fmul_rn(d_old, new_discount);
+            discounts[e] = __fadd_rn(__fmul_rn(keep, d_old), __fmul_rn(mask, d_new));
+        }
+        const size_t eo = e * O + j;
+        next_obs[eo] = __fadd_rn(__fmul_rn(keep, next_obs[eo]), __fmul_rn(mask, new_obs));
+    }
+}
+}  // namespace tb
+
+extern "C" int tb_replay_accumulate_n_steps(float* d_rewards, float* d_discounts, float* d_next_obs,
+                                            const float* d_resets, int32_t index, int32_t size,
+                                            int32_t max_size, int32_t n_workers, int32_t obs_dim,
+                                            int32_t return_steps, void* stream) {
+    tb::ProfScope prof_scope("tb_replay_accumulate_n_steps", stream);
+    TB_REQUIRE(d_rewards && d_discounts && d_next_obs && d_resets && index >= 0 && index < max_size &&
+               size >= 0 && n_workers > 0 && obs_dim > 0 && return_steps >= 1, TB_EINVAL,
+               "tb_replay_accumulate_n_steps: bad arguments");
+    const int count = size < return_steps - 1 ? size : return_steps - 1;
+    TB_REQUIRE(count < max_size, TB_EINVAL, "tb_replay_accumulate_n_steps: return_steps exceeds the ring");
+    if (count <= 0) return 0;
+    const int64_t total = (int64_t)n_workers * obs_dim;
+    tb::accumulate_n_steps_kernel<<<tb::blocks_for(total), 256, 0, tb::as_stream(stream)>>>(
+        d_rewards, d_discounts, d_next_obs, d_resets, index, count, max_size, n_workers, obs_dim);
+    return tb::check_launch("tb_replay_accumulate_n_steps");
+}
+
+extern "C" int tb_q_target_discounts(const float* d_rewards, const float* d_discounts, const int64_t* d_idx,
+                                     const float* d_q1, const float* d_q2, const float* d_log_probs,
+                                     double entropy_coeff, int64_t n_rows, float* d_targets, void* stream) {
+    tb::ProfScope prof_scope("tb_q_target", stream);
+    TB_REQUIRE(d_rewards && d_discounts && d_q1 && d_targets && n_rows > 0, TB_EINVAL,
+               "tb_q_target_discounts: bad arguments");
+    tb::q_target_kernel<<<tb::blocks_for(n_rows), 256, 0, tb::as_stream(stream)>>>(
+        d_rewards, d_discounts, d_idx, -1.0f, d_q1, d_q2, d_log_probs, (float)entropy_coeff, n_rows,
+        d_targets);
+    return tb::check_launch("tb_q_target_discounts");
 }

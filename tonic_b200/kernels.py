@@ -548,9 +548,23 @@ def squashed_sample(pre, actions, log_probs=None, eps=None, eps_out=None, seed=0
 
 
 def q_target(rewards, terminations, idx, discount_factor, q1, q2, log_probs, entropy_coeff,
-             rows, targets):
+             rows, targets, discounts=None):
+    """`discounts`: the replay's stored discounts column (n-step returns) instead of
+    (1 - terminations) * discount_factor."""
+    if discounts is not None:
+        _lib.call('tb_q_target_discounts', ptr(rewards), ptr(discounts), ptr(idx), ptr(q1), ptr(q2),
+                  ptr(log_probs), entropy_coeff, rows, ptr(targets), stream())
+        return
     _lib.call('tb_q_target', ptr(rewards), ptr(terminations), ptr(idx), discount_factor, ptr(q1),
               ptr(q2), ptr(log_probs), entropy_coeff, rows, ptr(targets), stream())
+
+
+def replay_accumulate_n_steps(rewards, discounts, next_observations, resets, index, size,
+                              return_steps):
+    max_size, workers = rewards.shape[:2]
+    _lib.call('tb_replay_accumulate_n_steps', ptr(rewards), ptr(discounts), ptr(next_observations),
+              ptr(resets), index, size, max_size, workers, next_observations.shape[-1],
+              return_steps, stream())
 
 
 def q_actor_loss(q1, q2, log_probs, entropy_coeff, rows, dout1, dout2, stats):

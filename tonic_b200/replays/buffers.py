@@ -7,8 +7,8 @@ the same transitions (buffers.py:84-89).  Batches are not materialised: the upda
 kernels gather rows through the index vector.  `discounts = (1 - terminations) *
 discount_factor` (buffers.py:34-36) is recomputed inside the target kernel from
 the stored terminations (bit-identical float32 arithmetic).
-n-step returns (`return_steps > 1`, buffers.py:58-79) are a "next" row
- and raise.
+With n-step returns (`return_steps > 1`, buffers.py:58-79) the discounts column is
+stored too and `tb_replay_accumulate_n_steps` back-fills the previous rows at every store.
 """
 
 import numpy as np
@@ -21,8 +21,6 @@ from ..utils.random_state import RandomState
 class Buffer:
     def __init__(self, size=int(1e6), return_steps=1, batch_iterations=50, batch_size=100,
                  discount_factor=0.99, steps_before_batches=int(1e4), steps_between_batches=50):
-        if return_steps != 1:
-            raise NotImplementedError('n-step returns are not implemented on the device')
         self.full_max_size = size
         self.return_steps = return_steps
         self.batch_iterations = batch_iterations
@@ -59,8 +57,20 @@ class Buffer:
             self.allocate(**{k: tuple(v.shape) if isinstance(v, torch.Tensor) else np.shape(v)
                              for k, v in kwargs.items()})
         for key, val in kwargs.items():
-            self.buffers[key][self.index].copy_(kernels.to_device(val))
+            kernels.to_device(val, out=self.buffers[key][self.index])
+        if self.return_steps > 1:
+            self.accumulate_n_steps()
         self.advance()
+
+    def accumulate_n_steps(self):
+        """buffers.py:34-36,58-79: discounts = float32(1 - terminations) * discount_factor for the
+        row just written, then the n-step back-fill of the previous rows."""
+        b = self.buffers
+        if 'discounts' not in b:
+            b['discounts'] = torch.full_like(b['rewards'], float('nan'))
+        b['discounts'][self.index] = (1 - b['terminations'][self.index]) * np.float32(self.discount_factor)
+        kernels.replay_accumulate_n_steps(b['rewards'], b['discounts'], b['next_observations'],
+                                          b['resets'], self.index, self.size, self.return_steps)
 
     def row(self, key):
         """Row `index` of a buffer, for producers that write it in place."""

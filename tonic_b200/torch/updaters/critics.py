@@ -140,7 +140,8 @@ class _QLearning:
         q2 = self._next_q[1] if len(self.target_critics) > 1 else None
         kernels.q_target(replay.flat('rewards'), replay.flat('terminations'), idx,
                          replay.discount_factor, self._next_q[0], q2, next_logp,
-                         self.entropy_coeff, rows, self._targets)
+                         self.entropy_coeff, rows, self._targets,
+                         discounts=replay.flat('discounts') if replay.return_steps > 1 else None)
         for k, critic in enumerate(self.critics):               # critics.py:77-84,169-179
             net = critic.network
             n_split = net.mlp.splits_for(rows)
