@@ -71,9 +71,15 @@ typedef struct {
     int32_t* d_ep_lengths;     /* [log_cap]                                   */
     unsigned long long* d_ep_count; /* [1] total finished episodes            */
     int32_t log_cap;
+    /* TimeFeature wrapper (environments/wrappers.py:25-54): observation rows get one
+     * more column, low + (high - low) * episode_steps / max_episode_steps (low after
+     * a reset); 0 = off.  Observation arrays are then [N, obs_dim + 1].             */
+    int32_t time_feature;
+    float time_low, time_high;
 } TbEnv;
 
-/* Sequential.start (:22-26): reset every env, lengths=0, writes obs [N,O].   */
+/* Sequential.start (:22-26): reset every env, lengths=0, writes obs [N,O]
+ * ([N,O+1] with the time feature).                                           */
 int tb_env_start(const TbEnv* env, float* d_obs, void* stream);
 
 /* Sequential.step (:28-58).  d_actions [N,A].  Outputs: d_obs [N,O] = acting

@@ -41,10 +41,14 @@ def reference_environment(cfg):
             cfg['obs'], cfg['act'], cfg['max_episode_steps'], name=name)
         high = np.ones(cfg['act'], np.float32)
         env.action_space = gym.spaces.Box(-high, high)
+        if cfg.get('time_feature'):      # TimeFeature reads observation_space.low / high / dtype
+            bound = np.full(cfg['obs'], np.inf, np.float32)
+            env.observation_space = gym.spaces.Box(-bound, bound)
         return gym.wrappers.TimeLimit(env, cfg['max_episode_steps'])
 
     def builder():
-        return tonic.environments.builders.build_environment(raw, 'synth')
+        return tonic.environments.builders.build_environment(
+            raw, 'synth', time_feature=bool(cfg.get('time_feature', False)))
 
     env = tonic.environments.distribute(builder, 1, cfg['workers'])
     env.initialize(seed=cfg['seed'])

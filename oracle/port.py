@@ -33,13 +33,23 @@ F32 = np.float32
 class VectorEnv:
     """M environments stepped in sequence inside one process."""
 
-    def __init__(self, obs, act, workers, max_episode_steps, first_worker=0):
+    def __init__(self, obs, act, workers, max_episode_steps, first_worker=0, time_feature=False):
         self.envs = [synth_env.SynthControlEnv(obs, act, max_episode_steps)
                      for _ in range(workers)]
         self.max_episode_steps = max_episode_steps
         self.observation_space = self.envs[0].observation_space
+        if time_feature:       # environments/wrappers.py:25-54 (low = -1, high = 1)
+            self.observation_space = synth_env.Space(obs + 1)
+        self.time_feature = time_feature
         self.action_space = self.envs[0].action_space
         self.first_worker = first_worker
+
+    def _timed(self, ob, steps):
+        """TimeFeature.reset / step (wrappers.py:40-54): append low + (high - low) * steps / max."""
+        if not self.time_feature:
+            return ob
+        v = -1 + (1 - -1) * (steps / self.max_episode_steps) if steps else -1
+        return np.append(ob, v)
 
     def initialize(self, seed):
         # distributed.py:18-20: env i is seeded seed + i.
@@ -49,7 +59,7 @@ class VectorEnv:
     def start(self):
         # distributed.py:22-26
         self.lengths = np.zeros(len(self.envs), int)
-        return np.array([env.reset() for env in self.envs], F32)
+        return np.array([self._timed(env.reset(), 0) for env in self.envs], F32)
 
     def step(self, actions):
         # distributed.py:28-58.  ActionRescaler with unit bounds
@@ -59,6 +69,7 @@ class VectorEnv:
         for i, env in enumerate(self.envs):
             ob, rew, term, _ = env.step(actions[i])
             self.lengths[i] += 1
+            ob = self._timed(ob, self.lengths[i])
             # distributed.py:39-40: a time-out resets but is not a termination.
             reset = term or self.lengths[i] == self.max_episode_steps
             trans_obs.append(ob)
@@ -66,7 +77,7 @@ class VectorEnv:
             resets.append(reset)
             terms.append(term)
             if reset:
-                ob = env.reset()
+                ob = self._timed(env.reset(), 0)
                 self.lengths[i] = 0
             acting_obs.append(ob)
         infos = dict(observations=np.array(trans_obs, F32),
@@ -728,7 +739,8 @@ class OffPolicyOracle:
 
 def build(cfg, log=None):
     """Scenario config (oracle/scenarios.py) -> (agent, environment)."""
-    env = VectorEnv(cfg['obs'], cfg['act'], cfg['workers'], cfg['max_episode_steps'])
+    env = VectorEnv(cfg['obs'], cfg['act'], cfg['workers'], cfg['max_episode_steps'],
+                    time_feature=cfg.get('time_feature', False))
     env.initialize(cfg['seed'])
     if cfg['agent'] in ('PPO', 'A2C'):
         agent = OnPolicyOracle(cfg['agent'], cfg['hidden'], cfg['segment'], log=log)

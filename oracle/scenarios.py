@@ -39,6 +39,10 @@ SCENARIOS = {
         agent='PPO', obs=17, act=6, workers=4, max_episode_steps=9, seed=5,
         hidden=(64, 64), vector_steps=26,
         segment=dict(size=12, batch_iterations=5, batch_size=None)),
+    'ppo_timefeature': dict(   # build_environment(time_feature=True): wrappers.py:25-54
+        agent='PPO', obs=5, act=2, workers=6, max_episode_steps=9, seed=21, time_feature=True,
+        hidden=(64, 64), vector_steps=36,
+        segment=dict(size=12, batch_iterations=3, batch_size=24)),
     'a2c_small': dict(
         agent='A2C', obs=17, act=6, workers=8, max_episode_steps=11, seed=1,
         hidden=(64, 64), vector_steps=40,

@@ -14,7 +14,8 @@ def build(cfg, log=None):
     if log is not None:
         logger.store = log
     spec = tonic_b200.environments.SynthControl(
-        'synth', cfg['obs'], cfg['act'], cfg['max_episode_steps'])
+        'synth', cfg['obs'], cfg['act'], cfg['max_episode_steps'],
+        time_feature=cfg.get('time_feature', False))
     env = tonic_b200.environments.distribute(lambda: spec, 1, cfg['workers'])
     env.initialize(seed=cfg['seed'])
     hidden = tuple(cfg['hidden'])

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 from oracle import scenarios  # noqa: E402  (checker only)
 from tests import product  # noqa: E402
 
-ON_POLICY = ['ppo_small', 'ppo_wide', 'ppo_ragged', 'ppo_fullbatch', 'a2c_small']
+ON_POLICY = ['ppo_small', 'ppo_wide', 'ppo_ragged', 'ppo_fullbatch', 'ppo_timefeature', 'a2c_small']
 
 
 def by_key(keys, values):

@@ -26,7 +26,8 @@ class TbEnv(ctypes.Structure):
                 ('max_episode_steps', c_i32), ('seed', c_i64), ('first_worker', c_i64),
                 ('d_state', c_vp), ('d_length', c_vp), ('d_episode', c_vp),
                 ('d_score', c_vp), ('d_ep_scores', c_vp), ('d_ep_lengths', c_vp),
-                ('d_ep_count', c_vp), ('log_cap', c_i32)]
+                ('d_ep_count', c_vp), ('log_cap', c_i32), ('time_feature', c_i32),
+                ('time_low', c_f), ('time_high', c_f)]
 
 
 class TbMlpShape(ctypes.Structure):

@@ -16,13 +16,15 @@ namespace tb {
 __global__ void __launch_bounds__(256)
 env_start_kernel(TbEnv env, float* __restrict__ obs) {
     const int64_t total = (int64_t)env.n_envs * env.obs_dim;
+    const int OW = env.obs_dim + (env.time_feature ? 1 : 0);       // observation row width
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int n = (int)(i / env.obs_dim), j = (int)(i % env.obs_dim);
         const uint32_t seed = (uint32_t)(env.seed + env.first_worker + n);
         const float v = reset_coordinate(reset_key(seed, 0u), j);
         env.d_state[i] = v;
-        obs[i] = v;
+        obs[(size_t)n * OW + j] = v;
+        if (j == 0 && env.time_feature) obs[(size_t)n * OW + env.obs_dim] = env.time_low;   // wrappers.py:43
         if (j == 0) {
             env.d_length[n] = 0;
             env.d_episode[n] = 1u;
@@ -41,6 +43,7 @@ env_step_kernel(TbEnv env, const float* __restrict__ actions, float* __restrict_
     float* sx = smem;                          // [tile, O] state -> transition obs
     float* so = sx + (size_t)tile_envs * O;    // [tile, O] acting obs (post reset)
     float* sa = so + (size_t)tile_envs * O;    // [tile, A] clipped actions
+    float* stf = sa + (size_t)tile_envs * A;   // [tile, 2] time feature of next_obs / acting obs
 
     const int e0 = blockIdx.x * tile_envs;
     const int count = min(tile_envs, env.n_envs - e0);
@@ -67,6 +70,13 @@ env_step_kernel(TbEnv env, const float* __restrict__ actions, float* __restrict_
             int length = env.d_length[n] + 1;
             // distributed.py:40 -- a time-out resets without terminating
             reset = term || (length == env.max_episode_steps);
+            if (env.time_feature) {     // wrappers.py:49-52 in float64, cast like np.array(.., float32)
+                const double prop = (double)length / (double)env.max_episode_steps;
+                const float v = (float)((double)env.time_low +
+                                        ((double)env.time_high - (double)env.time_low) * prop);
+                stf[2 * e] = v;
+                stf[2 * e + 1] = reset ? env.time_low : v;
+            }
             double score = env.d_score[n] + (double)reward;    // trainer.py:52
             episode = env.d_episode[n];
             if (reset) {                                        // trainer.py:64-71
@@ -98,18 +108,19 @@ env_step_kernel(TbEnv env, const float* __restrict__ actions, float* __restrict_
     __syncthreads();
 
     float* gs = env.d_state + (size_t)e0 * O;
-    float* go = obs + (size_t)e0 * O;
-    float* gn = next_obs + (size_t)e0 * O;
-    for (int i = tid; i < count * O; i += blockDim.x) {
-        const float v = so[i];
-        gs[i] = v;
-        go[i] = v;
-        gn[i] = sx[i];
+    for (int i = tid; i < count * O; i += blockDim.x) gs[i] = so[i];
+    const int OW = O + (env.time_feature ? 1 : 0);
+    float* go = obs + (size_t)e0 * OW;
+    float* gn = next_obs + (size_t)e0 * OW;
+    for (int i = tid; i < count * OW; i += blockDim.x) {
+        const int e = i / OW, j = i % OW;
+        go[i] = j < O ? so[e * O + j] : stf[2 * e + 1];
+        gn[i] = j < O ? sx[e * O + j] : stf[2 * e];
     }
 }
 
 static int pick_tile(const TbEnv* env, size_t* smem_bytes) {
-    const size_t per_env = (size_t)(2 * env->obs_dim + env->act_dim) * sizeof(float);
+    const size_t per_env = (size_t)(2 * env->obs_dim + env->act_dim + 2) * sizeof(float);
     int tile = 256;
     while (tile > 8 && ((size_t)tile * per_env > 96 * 1024 ||
                         (int64_t)tile * kNumSMs > (int64_t)env->n_envs))

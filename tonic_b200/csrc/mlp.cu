@@ -1425,6 +1425,7 @@ extern "C" int tb_rollout_fused(const TbEnv* env, const TbMlpShape* shape, const
     TB_REQUIRE(env && d_params && d_packed && d_log_scale && d_seg_obs && d_seg_actions &&
                d_seg_next_obs && d_seg_rewards && d_seg_resets && d_seg_terms && d_seg_logp &&
                d_env_obs && T > 0, TB_EINVAL, "tb_rollout_fused: null pointer");
+    TB_REQUIRE(!env->time_feature, TB_ENOTSUP, "tb_rollout_fused: the time feature is not supported");
     TB_REQUIRE(shape->d_in == env->obs_dim && shape->n_out == env->act_dim, TB_EINVAL,
                "tb_rollout_fused: network / environment shapes differ");
     TB_REQUIRE(env->obs_dim <= 64 && env->obs_dim <= shape->hidden && env->act_dim <= 16, TB_ENOTSUP,

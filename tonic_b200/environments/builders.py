@@ -35,12 +35,15 @@ class SynthControl:
                'Pendulum': (3, 1)}
 
     def __init__(self, name='HalfCheetah', observation_size=None, action_size=None,
-                 max_episode_steps=1000):
+                 max_episode_steps=1000, time_feature=False):
         if observation_size is None or action_size is None:
             observation_size, action_size = self.PRESETS[name]
         self.name = f'SynthControl-{name}' if name in self.PRESETS else str(name)
         self.observation_size = int(observation_size)
         self.action_size = int(action_size)
-        self.observation_space = Space(observation_size, -np.inf, np.inf)
+        # time_feature: what build_environment(time_feature=True) adds (reference
+        # environments/builders.py:65-68, wrappers.py:25-54): one more observation column
+        self.time_feature = bool(time_feature)
+        self.observation_space = Space(observation_size + int(self.time_feature), -np.inf, np.inf)
         self.action_space = Space(action_size)          # wrappers.py:14-15: [-1, 1]^n
         self.max_episode_steps = int(max_episode_steps)

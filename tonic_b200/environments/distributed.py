@@ -56,8 +56,10 @@ class DeviceVectorEnvironment:
         self.episode_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self._episodes_read = 0
         # output buffers (views handed to the caller)
-        self.observations = torch.zeros(N, O, dtype=torch.float32, device=dev)
-        self.next_observations = torch.zeros(N, O, dtype=torch.float32, device=dev)
+        tf = bool(getattr(self.spec, 'time_feature', False))
+        self.time_feature = tf
+        self.observations = torch.zeros(N, O + tf, dtype=torch.float32, device=dev)
+        self.next_observations = torch.zeros(N, O + tf, dtype=torch.float32, device=dev)
         self.rewards = torch.zeros(N, dtype=torch.float32, device=dev)
         self.resets = torch.zeros(N, dtype=torch.float32, device=dev)
         self.terminations = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -67,7 +69,8 @@ class DeviceVectorEnvironment:
             first_worker=self.first_worker, d_state=ptr(self.state),
             d_length=ptr(self.lengths), d_episode=ptr(self.episodes), d_score=ptr(self.scores),
             d_ep_scores=ptr(self.episode_scores), d_ep_lengths=ptr(self.episode_lengths),
-            d_ep_count=ptr(self.episode_count), log_cap=cap)
+            d_ep_count=ptr(self.episode_count), log_cap=cap, time_feature=int(tf),
+            time_low=-1.0, time_high=1.0)
 
     def start(self, host=False):
         """Resets every environment; returns the first observations [N, O]."""

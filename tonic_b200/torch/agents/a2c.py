@@ -172,7 +172,8 @@ class A2C(agent.Agent):
             return False        # graph replay of the tensor-core per-step chain is faster
         return (bool(config.fused_rollout) and config.noise == 'device'
                 and getattr(actor.head, 'kind', None) == 'detached_gaussian'
-                and hasattr(env, 'struct') and shape.d_in <= min(64, shape.hidden)
+                and hasattr(env, 'struct') and not getattr(env, 'time_feature', False)
+                and shape.d_in <= min(64, shape.hidden)
                 and shape.n_out <= 16 and shape.hidden in (64, 128, 256))
 
     def _graphable(self):
