@@ -124,6 +124,34 @@ constexpr uint32_t kIdescTf32 =
 
 constexpr int TC_MAX_HEAD = 8;
 
+// ---- thread-block cluster helpers (experimental 2-CTA variant of the fused kernels) ----------
+// TMA load with multicast: the box lands at the same shared-memory offset of every CTA in
+// `cta_mask` and completes the transaction count of the mbarrier at the same offset in each.
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                                      int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void bulk_load_multicast(void* smem, const void* gmem, uint32_t bytes,
+                                                    uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)),
+        "h"(cta_mask) : "memory");
+}
+// commit: arrive on the mbarrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tcgen05_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // generic-proxy writes to shared memory (st.shared) -> visible to the async proxy
 // (tcgen05.mma / TMA reading shared memory)
 __device__ __forceinline__ void fence_proxy_async_smem() {

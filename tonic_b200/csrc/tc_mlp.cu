@@ -189,7 +189,11 @@ __device__ __forceinline__ void store_operand_half(unsigned char* hi_tile, unsig
     }
 }
 
-template <int PASSES, int ACT>
+// CLUSTER = 2 (experimental, TONIC_B200_CLUSTER=2): the two CTAs of a thread-block cluster each
+// fetch half of every weight-operand chunk and multicast it to both, which halves the L2 -> SM
+// traffic of the operand that bounds this kernel; the shared-memory stages are then released
+// by both MMA threads (multicast commit).
+template <int PASSES, int ACT, int CLUSTER>
 __global__ void __launch_bounds__(TCM_THREADS, 1)
 tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                       const __grid_constant__ CUtensorMap map_b_lo,
@@ -222,7 +226,7 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&a_ready[s], TCM_ROW_WARPS / 2);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CLUSTER);      // released by the MMA thread of every CTA that multicasts into it
         }
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
@@ -242,6 +246,8 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    if (CLUSTER == 2) cluster_sync_all();            // the peer's barriers exist before anything targets them
+    const int crank = CLUSTER == 2 ? (int)(blockIdx.x & 1) : 0;
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) tc_stamp(p.timeline, 1);
     const int k_steps1 = (p.d_in + 7) >> 3;           // layer-1 MMAs (K = 8 each) per pass
@@ -251,12 +257,30 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x) {
                 for (int u = 0; u < USES; ++u) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * TC_B_BYTES);
-                    if (u == 0) {
+                    if (CLUSTER == 2) {
+                        // this CTA fetches rows [128 crank, 128 crank + 128) of the operand (half of
+                        // the bytes) and multicasts them; the other half arrives from the peer
+                        const int half = crank * (TC_B_BYTES / 2);
+                        if (u == 0) {
+                            bulk_load_multicast(st + Cfg::B_HI + half, reinterpret_cast<const unsigned char*>(p.w1_img_hi) + half,
+                                                TC_B_BYTES / 2, &full_bar[stage], 3);
+                            if (PASSES == 3)
+                                bulk_load_multicast(st + Cfg::B_LO + half, reinterpret_cast<const unsigned char*>(p.w1_img_lo) + half,
+                                                    TC_B_BYTES / 2, &full_bar[stage], 3);
+                        } else {
+                            const int c = u - 1;
+                            tma_load_2d_multicast(st + Cfg::B_HI + half, &map_b_hi, &full_bar[stage], c * TC_BK,
+                                                  crank * (TC_BN / 2), 3);
+                            if (PASSES == 3)
+                                tma_load_2d_multicast(st + Cfg::B_LO + half, &map_b_lo, &full_bar[stage], c * TC_BK,
+                                                      crank * (TC_BN / 2), 3);
+                        }
+                    } else if (u == 0) {
                         bulk_load(st + Cfg::B_HI, p.w1_img_hi, TC_B_BYTES, &full_bar[stage]);
                         if (PASSES == 3) bulk_load(st + Cfg::B_LO, p.w1_img_lo, TC_B_BYTES, &full_bar[stage]);
                     } else {
@@ -275,7 +299,7 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
             int stage = 0, it = 0;
             uint32_t phase = 0;
             uint32_t a_phase = 0;                     // bit s: parity of a_ready[s] (layer-2 uses only)
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x, ++it) {
                 for (int u = 0; u < USES; ++u) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_stamp(p.timeline, 40 + u);             // B operand landed
@@ -302,7 +326,8 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                             tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, accumulate);
                         }
                     }
-                    tcgen05_commit(&empty_bar[stage]);
+                    if (CLUSTER == 2) tcgen05_commit_multicast(&empty_bar[stage], 3);
+                    else tcgen05_commit(&empty_bar[stage]);
                     if (u == 0) tcgen05_commit(&acc_full[0]);
                     if (u == USES - 1) tcgen05_commit(&acc_full[1]);
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -327,7 +352,7 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         int it = 0;
         if (stamper) tc_stamp(p.timeline, 31);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x, ++it) {
             const int64_t row0 = (int64_t)tile * TC_BM + q * 32;
             const int64_t row = (int64_t)tile * TC_BM + trow;
             const int g0 = it * USES;                 // stage use index of this tile's layer 1
@@ -544,6 +569,7 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER == 2) cluster_sync_all();            // no CTA leaves while the peer may still write into it
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
                      : "memory");
@@ -869,18 +895,37 @@ static int launch_tc_mlp_bwd(const CUtensorMap* maps, const TcMlpBwdParams& p, c
     return 0;
 }
 
-template <int PASSES, int ACT>
+template <int PASSES, int ACT, int CLUSTER>
 static int launch_tc_mlp(const CUtensorMap* maps, const TcMlpParams& p, cudaStream_t s) {
     using Cfg = TcMlpCfg<PASSES>;
-    auto kernel = tc_mlp_forward_kernel<PASSES, ACT>;
+    auto kernel = tc_mlp_forward_kernel<PASSES, ACT, CLUSTER>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         configured = true;
     }
     const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
-    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    if (CLUSTER == 1) {
+        const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+        kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+        return 0;
+    }
+    // clusters of 2 CTAs: an even grid, both CTAs of a cluster run the same number of tiles
+    int grid = (n_tiles + 1) & ~1;
+    if (grid > (kNumSMs & ~1)) grid = kNumSMs & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TCM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, maps[0], maps[1], maps[2], maps[3], maps[4], p);
     return 0;
 }
 
@@ -925,10 +970,18 @@ static int tc_mlp_forward_impl(const TbMlpShape* shape, const float* d_params, c
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_forward: passes must be 1 or 3");
     TB_REQUIRE((d_h1_hi == nullptr) == (d_h1_lo == nullptr), TB_EINVAL,
                "tb_tc_mlp_forward: h1 hi / lo must be given together");
+    // experimental: 2-CTA clusters with multicast of the weight-operand chunks (3-pass mode only;
+    // written and compiled in round 1, not yet validated on hardware -> off unless requested)
+    static const bool cluster_env = [] {
+        const char* v = getenv("TONIC_B200_CLUSTER");
+        return v && v[0] == '2';
+    }();
+    const bool cluster2 = cluster_env && passes == 3;
     CUtensorMap maps[5];
     int rc;
-    if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, TC_BN))) return rc;
-    if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, TC_BN))) return rc;
+    const int b_box_rows = cluster2 ? TC_BN / 2 : TC_BN;       // each CTA of a cluster loads half the rows
+    if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, b_box_rows))) return rc;
+    if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, b_box_rows))) return rc;
     maps[2] = maps[3] = maps[4] = maps[0];       // placeholders when nothing is saved
     if (d_h1_hi) {
         if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TC_BM))) return rc;
@@ -954,12 +1007,15 @@ static int tc_mlp_forward_impl(const TbMlpShape* shape, const float* d_params, c
     }
     ProfScope prof_scope("tb_tc_mlp_forward", stream);
     const bool tanh_act = shape->act == TB_ACT_TANH;
-    if (passes == 3) {
-        if (tanh_act) launch_tc_mlp<3, TB_ACT_TANH>(maps, p, as_stream(stream));
-        else launch_tc_mlp<3, TB_ACT_RELU>(maps, p, as_stream(stream));
+    if (passes == 3 && cluster2) {
+        if (tanh_act) launch_tc_mlp<3, TB_ACT_TANH, 2>(maps, p, as_stream(stream));
+        else launch_tc_mlp<3, TB_ACT_RELU, 2>(maps, p, as_stream(stream));
+    } else if (passes == 3) {
+        if (tanh_act) launch_tc_mlp<3, TB_ACT_TANH, 1>(maps, p, as_stream(stream));
+        else launch_tc_mlp<3, TB_ACT_RELU, 1>(maps, p, as_stream(stream));
     } else {
-        if (tanh_act) launch_tc_mlp<1, TB_ACT_TANH>(maps, p, as_stream(stream));
-        else launch_tc_mlp<1, TB_ACT_RELU>(maps, p, as_stream(stream));
+        if (tanh_act) launch_tc_mlp<1, TB_ACT_TANH, 1>(maps, p, as_stream(stream));
+        else launch_tc_mlp<1, TB_ACT_RELU, 1>(maps, p, as_stream(stream));
     }
     return check_launch("tb_tc_mlp_forward");
 }
