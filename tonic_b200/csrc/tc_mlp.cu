@@ -611,7 +611,7 @@ __device__ __forceinline__ float tc_act_grad(float h) {     // act'(z) written i
     return ACT == TB_ACT_TANH ? (1.0f - h * h) : (h > 0.0f ? 1.0f : 0.0f);
 }
 
-template <int PASSES, int ACT>
+template <int PASSES, int ACT, int CLUSTER>      // CLUSTER: see tc_mlp_forward_kernel
 __global__ void __launch_bounds__(TCM_THREADS, 1)
 tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                        const __grid_constant__ CUtensorMap map_b_lo,
@@ -641,7 +641,7 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         for (int s = 0; s < Cfg::STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&a_ready[s], TCM_ROW_WARPS / 2);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CLUSTER);
         }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -656,6 +656,8 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    if (CLUSTER == 2) cluster_sync_all();
+    const int crank = CLUSTER == 2 ? (int)(blockIdx.x & 1) : 0;
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) tc_stamp(p.timeline, 1);
 
@@ -663,14 +665,23 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         // ===================== producer: W2^T chunks (TMA) =====================
         if (lane == 0) {
             int g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < CHUNKS; ++c, ++g) {
                     const int stage = g & 1;
                     mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
                     unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * TC_B_BYTES);
-                    tma_load_2d(st + Cfg::B_HI, &map_b_hi, &full_bar[stage], c * TC_BK, 0);
-                    if (PASSES == 3) tma_load_2d(st + Cfg::B_LO, &map_b_lo, &full_bar[stage], c * TC_BK, 0);
+                    if (CLUSTER == 2) {      // half of the rows each, multicast to both CTAs
+                        const int half = crank * (TC_B_BYTES / 2);
+                        tma_load_2d_multicast(st + Cfg::B_HI + half, &map_b_hi, &full_bar[stage], c * TC_BK,
+                                              crank * (TC_BN / 2), 3);
+                        if (PASSES == 3)
+                            tma_load_2d_multicast(st + Cfg::B_LO + half, &map_b_lo, &full_bar[stage], c * TC_BK,
+                                                  crank * (TC_BN / 2), 3);
+                    } else {
+                        tma_load_2d(st + Cfg::B_HI, &map_b_hi, &full_bar[stage], c * TC_BK, 0);
+                        if (PASSES == 3) tma_load_2d(st + Cfg::B_LO, &map_b_lo, &full_bar[stage], c * TC_BK, 0);
+                    }
                 }
             }
         }
@@ -678,7 +689,7 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         // ===================== MMA issuer =====================
         if (lane == 0) {
             int g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x) {
                 for (int c = 0; c < CHUNKS; ++c, ++g) {
                     const int stage = g & 1;
                     const uint32_t parity = (g >> 1) & 1;
@@ -704,7 +715,8 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                             tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32, accumulate);
                         }
                     }
-                    tcgen05_commit(&empty_bar[stage]);
+                    if (CLUSTER == 2) tcgen05_commit_multicast(&empty_bar[stage], 3);
+                    else tcgen05_commit(&empty_bar[stage]);
                     if (c == CHUNKS - 1) tcgen05_commit(acc_full);
                 }
             }
@@ -718,7 +730,7 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         const bool stamper = (rw == 0 || rw == 4) && lane == 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x, ++it) {
             const int64_t row0 = (int64_t)tile * TC_BM + q * 32;
             const int64_t row = (int64_t)tile * TC_BM + trow;
             const bool live = row < p.n_rows;
@@ -874,24 +886,43 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CLUSTER == 2) cluster_sync_all();
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256)
                      : "memory");
     }
 }
 
-template <int PASSES, int ACT>
+template <int PASSES, int ACT, int CLUSTER>
 static int launch_tc_mlp_bwd(const CUtensorMap* maps, const TcMlpBwdParams& p, cudaStream_t s) {
     using Cfg = TcMlpCfg<PASSES>;
-    auto kernel = tc_mlp_backward_kernel<PASSES, ACT>;
+    auto kernel = tc_mlp_backward_kernel<PASSES, ACT, CLUSTER>;
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         configured = true;
     }
     const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
-    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+    if (CLUSTER == 1) {
+        const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+        kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+        return 0;
+    }
+    int grid = (n_tiles + 1) & ~1;
+    if (grid > (kNumSMs & ~1)) grid = kNumSMs & ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TCM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, maps[0], maps[1], maps[2], maps[3], maps[4], p);
     return 0;
 }
 
@@ -1052,10 +1083,16 @@ extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params
                "tb_tc_mlp_backward: needs hidden == 256 and n_out <= 8 (got %d, %d)", shape->hidden,
                shape->n_out);
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_backward: passes must be 1 or 3");
+    static const bool cluster_env = [] {        // experimental, see tb_tc_mlp_forward
+        const char* v = getenv("TONIC_B200_CLUSTER");
+        return v && v[0] == '2';
+    }();
+    const bool cluster2 = cluster_env && passes == 3;
+    const int b_box_rows = cluster2 ? TC_BN / 2 : TC_BN;
     CUtensorMap maps[5];
     int rc;
-    if ((rc = make_map(&maps[0], d_packed + shape->off_w2t_hi, TC_BN, TC_BN))) return rc;
-    if ((rc = make_map(&maps[1], d_packed + shape->off_w2t_lo, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[0], d_packed + shape->off_w2t_hi, TC_BN, b_box_rows))) return rc;
+    if ((rc = make_map(&maps[1], d_packed + shape->off_w2t_lo, TC_BN, b_box_rows))) return rc;
     if ((rc = make_map(&maps[2], d_dz2_hi, n_rows, TC_BM))) return rc;
     if ((rc = make_map(&maps[3], d_dz2_lo, n_rows, TC_BM))) return rc;
     if ((rc = make_map(&maps[4], d_dz1, n_rows, TC_BM))) return rc;
@@ -1065,12 +1102,15 @@ extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params
     p.dz2_hi = d_dz2_hi; p.dz2_lo = d_dz2_lo; p.dz1 = d_dz1; p.skip = d_skip; p.timeline = g_timeline;
     ProfScope prof_scope("tb_tc_mlp_backward", stream);
     const bool tanh_act = shape->act == TB_ACT_TANH;
-    if (passes == 3) {
-        if (tanh_act) launch_tc_mlp_bwd<3, TB_ACT_TANH>(maps, p, as_stream(stream));
-        else launch_tc_mlp_bwd<3, TB_ACT_RELU>(maps, p, as_stream(stream));
+    if (passes == 3 && cluster2) {
+        if (tanh_act) launch_tc_mlp_bwd<3, TB_ACT_TANH, 2>(maps, p, as_stream(stream));
+        else launch_tc_mlp_bwd<3, TB_ACT_RELU, 2>(maps, p, as_stream(stream));
+    } else if (passes == 3) {
+        if (tanh_act) launch_tc_mlp_bwd<3, TB_ACT_TANH, 1>(maps, p, as_stream(stream));
+        else launch_tc_mlp_bwd<3, TB_ACT_RELU, 1>(maps, p, as_stream(stream));
     } else {
-        if (tanh_act) launch_tc_mlp_bwd<1, TB_ACT_TANH>(maps, p, as_stream(stream));
-        else launch_tc_mlp_bwd<1, TB_ACT_RELU>(maps, p, as_stream(stream));
+        if (tanh_act) launch_tc_mlp_bwd<1, TB_ACT_TANH, 1>(maps, p, as_stream(stream));
+        else launch_tc_mlp_bwd<1, TB_ACT_RELU, 1>(maps, p, as_stream(stream));
     }
     return check_launch("tb_tc_mlp_backward");
 }
