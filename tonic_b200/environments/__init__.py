@@ -1,4 +1,6 @@
 from .builders import SynthControl, Space
 from .distributed import DeviceVectorEnvironment, distribute
+from .host import HostParallel, HostSequential, distribute_host
 
-__all__ = [SynthControl, Space, DeviceVectorEnvironment, distribute]
+__all__ = [SynthControl, Space, DeviceVectorEnvironment, distribute, HostSequential, HostParallel,
+           distribute_host]

@@ -132,10 +132,10 @@ def distribute(environment_builder, worker_groups=1, workers_per_group=1):
     sharded contiguously over the ranks (one GPU each)."""
     spec = environment_builder()
     if not hasattr(spec, 'observation_size'):
-        raise NotImplementedError(
-            'tonic_b200 steps device-resident synthetic environments only '
-            '(tonic_b200.environments.SynthControl); host Gym/dm_control '
-            'environments are outside the hot path (SURVEY.md section 2, row 14)')
+        # a host environment (Gym / dm_control / user code): the reference's worker grid on the
+        # host, feeding the device learner through numpy arrays (tonic_b200/environments/host.py)
+        from . import host
+        return host.distribute_host(environment_builder, worker_groups, workers_per_group)
     total = int(worker_groups) * int(workers_per_group)
     rank, world = 0, 1
     if torch.distributed.is_available() and torch.distributed.is_initialized():
