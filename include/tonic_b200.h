@@ -334,6 +334,20 @@ int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2
                        int32_t w2_begin, int32_t w2_end, int32_t n_params, float* d_out,
                        const int32_t* d_skip, void* stream);
 
+/* ---- global-norm gradient clipping ---------------------------------------------
+ * Reference: torch.nn.utils.clip_grad_norm_(self.variables, self.gradient_clip) between
+ * loss.backward() and optimizer.step() (tonic/torch/updaters/actors.py:37-38,96-98,
+ * 176-177,256-257; critics.py:24-25,82-83,177-178,230-231).
+ * tb_grad_sqnorm: *d_sumsq += sum_i d_grad[i]^2 (float64, fixed order) -- called once
+ *                 per network whose variables the updater's optimizer owns.
+ * tb_grad_clip:   d_grad[i] *= min(1, max_norm / (sqrt(*d_sumsq) * grad_scale + 1e-6)),
+ *                 grad_scale = 1 / (rows of the global minibatch): the flat gradient
+ *                 holds SUMS over rows, the reference clips the MEAN gradient.       */
+int tb_grad_sqnorm(const float* d_grad, int32_t n, double* d_sumsq, const int32_t* d_skip,
+                   void* stream);
+int tb_grad_clip(float* d_grad, int32_t n, const double* d_sumsq, float grad_scale,
+                 float max_norm, const int32_t* d_skip, void* stream);
+
 /* ---- fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU) ---- */
 /* base[r] = address, in THIS process, of rank r's symmetric region of
  * tb_peer_region_bytes(n_params) bytes (zero-initialised; obtained from

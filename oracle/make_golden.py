@@ -26,7 +26,7 @@ import gym  # noqa: E402  (the shim)
 import tonic  # noqa: E402  (the reference)
 import tonic.torch  # noqa: E402
 
-from oracle import scenarios, synth_env  # noqa: E402
+from oracle import bench_shape, scenarios, synth_env  # noqa: E402
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
 
@@ -72,6 +72,12 @@ def reference_agent(cfg):
             observation_normalizer=n.MeanStd())
         replay = tonic.replays.Segment(**cfg['segment'])
         cls = getattr(tonic.torch.agents, kind)
+        clip = cfg.get('gradient_clip', 0)
+        if clip:
+            actor_updater = (u.ClippedRatio if kind == 'PPO' else u.StochasticPolicyGradient)(
+                gradient_clip=clip)
+            return cls(model=model, replay=replay, actor_updater=actor_updater,
+                       critic_updater=u.VRegression(gradient_clip=clip))
         return cls(model=model, replay=replay)
 
     critic = m.Critic(
@@ -100,6 +106,15 @@ def reference_agent(cfg):
         exploration = tonic.explorations.NormalActionNoise(
             start_steps=cfg['start_steps'])
     cls = getattr(tonic.torch.agents, kind)
+    clip = cfg.get('gradient_clip', 0)
+    if clip:
+        actor_cls = dict(DDPG=u.DeterministicPolicyGradient, TD3=u.DeterministicPolicyGradient,
+                         SAC=u.TwinCriticSoftDeterministicPolicyGradient)[kind]
+        critic_cls = dict(DDPG=u.DeterministicQLearning, TD3=u.TwinCriticDeterministicQLearning,
+                          SAC=u.TwinCriticSoftQLearning)[kind]
+        return cls(model=model, replay=replay, exploration=exploration,
+                   actor_updater=actor_cls(gradient_clip=clip),
+                   critic_updater=critic_cls(gradient_clip=clip))
     return cls(model=model, replay=replay, exploration=exploration)
 
 
@@ -241,11 +256,40 @@ def unit_vectors():
     return out
 
 
+def run_reference_bench_shape():
+    """One PPO iteration of the unmodified reference at the benched shape
+    (oracle/bench_shape.py): digests + strided samples."""
+    import time
+    cfg = bench_shape.CFG
+    t0 = time.time()
+    env = reference_environment(cfg)
+    agent = reference_agent(cfg)
+    agent.initialize(env.observation_space, env.action_space, seed=cfg['seed'])
+    out = bench_shape.weight_digests(agent.model.state_dict(), 'digest_w0/')
+    rec = scenarios.InfoRecorder()
+    tonic.utils.logger.store = rec
+    out.update(bench_shape.drive(agent, env, cfg))
+    out.update(rec.arrays())
+    out.update(bench_shape.weight_digests(agent.model.state_dict(), 'digest_w/'))
+    out['torch_threads'] = np.array([torch.get_num_threads()])
+    print(f'ppo_bench: {time.time() - t0:.1f} s,',
+          sum(k == 'critic/loss' for k in rec.keys), 'critic updates,',
+          sum(k == 'actor/loss' for k in rec.keys), 'actor updates')
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    np.savez_compressed(os.path.join(OUT, 'units.npz'), **unit_vectors())
-    print('units.npz')
-    for name in scenarios.SCENARIOS:
+    only = [a for a in sys.argv[1:]]
+    if 'ppo_bench' in only:
+        np.savez_compressed(os.path.join(OUT, 'ppo_bench.npz'), **run_reference_bench_shape())
+        only.remove('ppo_bench')
+        if not only:
+            return
+    if not only:
+        np.savez_compressed(os.path.join(OUT, 'units.npz'), **unit_vectors())
+        print('units.npz')
+    for name in (only or scenarios.SCENARIOS):
         data = run_reference_scenario(name)
         if max(scenarios.SCENARIOS[name]['hidden']) > 64:
             # keep wide-model fixtures small: final weights as float16-free

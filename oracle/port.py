@@ -397,7 +397,8 @@ class OnPolicyOracle:
 
     def __init__(self, kind, hidden, segment, log=None, actor_lr=3e-4,
                  critic_lr=1e-3, ratio_clip=0.2, kl_threshold=0.015,
-                 entropy_coeff=0.0):
+                 entropy_coeff=0.0, gradient_clip=0):
+        self.gradient_clip = gradient_clip            # actors.py:37-38,96-98; critics.py:24-25
         self.kind, self.hidden = kind, tuple(hidden)
         self.replay = SegmentStore(**segment)
         self.log = log or (lambda *a, **k: None)
@@ -466,6 +467,8 @@ class OnPolicyOracle:
         values = self._values(observations)
         loss = F.mse_loss(values, returns)
         loss.backward()
+        if self.gradient_clip > 0:                    # critics.py:24-25
+            torch.nn.utils.clip_grad_norm_(list(self.critic.parameters()), self.gradient_clip)
         self.critic_opt.step()
         return dict(loss=loss.detach(), v=values.detach())
 
@@ -497,6 +500,8 @@ class OnPolicyOracle:
         if self.entropy_coeff != 0:
             loss -= self.entropy_coeff * entropy
         loss.backward()
+        if self.gradient_clip > 0:                    # actors.py:37-38,96-98
+            torch.nn.utils.clip_grad_norm_(list(self.actor.parameters()), self.gradient_clip)
         self.actor_opt.step()
         with torch.no_grad():
             kl = (log_probs - new_log_probs).mean()
@@ -548,7 +553,9 @@ class OffPolicyOracle:
 
     def __init__(self, kind, hidden, buffer, start_steps=20000, log=None,
                  target_coeff=0.005, noise_scale=0.1, delay_steps=2,
-                 entropy_coeff=0.2, target_noise=(0.2, 0.5), exploration='normal'):
+                 entropy_coeff=0.2, target_noise=(0.2, 0.5), exploration='normal',
+                 gradient_clip=0):
+        self.gradient_clip = gradient_clip            # actors.py:176-177,256-257; critics.py:82-83,177-178,230-231
         self.kind, self.hidden = kind, tuple(hidden)
         self.exploration, self.ou_noises = exploration, None   # 'ou': noisy.py:53-88
         self.replay = RingStore(**buffer)
@@ -684,6 +691,9 @@ class OffPolicyOracle:
         losses = [F.mse_loss(v, returns) for v in values]
         loss = losses[0] if len(losses) == 1 else losses[0] + losses[1]
         loss.backward()
+        if self.gradient_clip > 0:                    # joint norm over all critics' variables
+            torch.nn.utils.clip_grad_norm_(
+                [p for c in self.critics for p in c.parameters()], self.gradient_clip)
         self.critic_opt.step()
         out = dict(loss=loss.detach())
         if len(values) == 1:
@@ -710,6 +720,8 @@ class OffPolicyOracle:
             actions = deterministic_actor_forward(self.actor, observations)
             loss = -self._q(self.critics[0], observations, actions).mean()
         loss.backward()
+        if self.gradient_clip > 0:
+            torch.nn.utils.clip_grad_norm_(list(self.actor.parameters()), self.gradient_clip)
         self.actor_opt.step()
         for p in critic_params:
             p.requires_grad = True
@@ -743,10 +755,12 @@ def build(cfg, log=None):
                     time_feature=cfg.get('time_feature', False))
     env.initialize(cfg['seed'])
     if cfg['agent'] in ('PPO', 'A2C'):
-        agent = OnPolicyOracle(cfg['agent'], cfg['hidden'], cfg['segment'], log=log)
+        agent = OnPolicyOracle(cfg['agent'], cfg['hidden'], cfg['segment'], log=log,
+                               gradient_clip=cfg.get('gradient_clip', 0))
     else:
         agent = OffPolicyOracle(cfg['agent'], cfg['hidden'], cfg['buffer'],
                                 start_steps=cfg['start_steps'], log=log,
-                                exploration=cfg.get('exploration', 'normal'))
+                                exploration=cfg.get('exploration', 'normal'),
+                                gradient_clip=cfg.get('gradient_clip', 0))
     agent.initialize(env.observation_space, env.action_space, seed=cfg['seed'])
     return agent, env

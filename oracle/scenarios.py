@@ -43,6 +43,10 @@ SCENARIOS = {
         agent='PPO', obs=5, act=2, workers=6, max_episode_steps=9, seed=21, time_feature=True,
         hidden=(64, 64), vector_steps=36,
         segment=dict(size=12, batch_iterations=3, batch_size=24)),
+    'ppo_clip': dict(     # gradient_clip > 0 in both updaters (actors.py:96-98, critics.py:24-25)
+        agent='PPO', obs=9, act=3, workers=8, max_episode_steps=11, seed=7, gradient_clip=0.05,
+        hidden=(256, 256), vector_steps=34,
+        segment=dict(size=16, batch_iterations=3, batch_size=32)),
     'a2c_small': dict(
         agent='A2C', obs=17, act=6, workers=8, max_episode_steps=11, seed=1,
         hidden=(64, 64), vector_steps=40,
@@ -65,6 +69,11 @@ SCENARIOS = {
     'td3_small': dict(
         agent='TD3', obs=11, act=3, workers=4, max_episode_steps=13, seed=4,
         hidden=(256, 256), vector_steps=40, start_steps=60,
+        buffer=dict(size=400, batch_iterations=4, batch_size=16,
+                    steps_before_batches=48, steps_between_batches=16)),
+    'td3_clip': dict(     # joint-norm clip over both critics (critics.py:177-178) + actor clip
+        agent='TD3', obs=7, act=2, workers=4, max_episode_steps=9, seed=9, gradient_clip=0.1,
+        hidden=(64, 64), vector_steps=40, start_steps=60,
         buffer=dict(size=400, batch_iterations=4, batch_size=16,
                     steps_before_batches=48, steps_between_batches=16)),
     'sac_small': dict(

@@ -28,7 +28,15 @@ def build(cfg, log=None):
                             head=m.ValueHead()),
             observation_normalizer=n.MeanStd())
         replay = tonic_b200.replays.Segment(**cfg['segment'])
-        agent = getattr(tonic_b200.torch.agents, kind)(model=model, replay=replay)
+        extra = {}
+        clip = cfg.get('gradient_clip', 0)
+        if clip:
+            u = tonic_b200.torch.updaters
+            extra = dict(
+                actor_updater=(u.ClippedRatio if kind == 'PPO' else u.StochasticPolicyGradient)(
+                    gradient_clip=clip),
+                critic_updater=u.VRegression(gradient_clip=clip))
+        agent = getattr(tonic_b200.torch.agents, kind)(model=model, replay=replay, **extra)
     else:
         critic = m.Critic(encoder=m.ObservationActionEncoder(),
                           torso=m.MLP(hidden, torch.nn.ReLU), head=m.ValueHead())
@@ -50,8 +58,18 @@ def build(cfg, log=None):
         else:
             exploration = tonic_b200.explorations.NormalActionNoise(
                 start_steps=cfg['start_steps'])
+        extra = {}
+        clip = cfg.get('gradient_clip', 0)
+        if clip:
+            u = tonic_b200.torch.updaters
+            actor_cls = dict(DDPG=u.DeterministicPolicyGradient, TD3=u.DeterministicPolicyGradient,
+                             SAC=u.TwinCriticSoftDeterministicPolicyGradient)[kind]
+            critic_cls = dict(DDPG=u.DeterministicQLearning, TD3=u.TwinCriticDeterministicQLearning,
+                              SAC=u.TwinCriticSoftQLearning)[kind]
+            extra = dict(actor_updater=actor_cls(gradient_clip=clip),
+                         critic_updater=critic_cls(gradient_clip=clip))
         agent = getattr(tonic_b200.torch.agents, kind)(
-            model=model, replay=replay, exploration=exploration)
+            model=model, replay=replay, exploration=exploration, **extra)
     agent.initialize(env.observation_space, env.action_space, seed=cfg['seed'])
     return agent, env
 

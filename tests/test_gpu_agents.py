@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 from oracle import scenarios  # noqa: E402  (checker only)
 from tests import product  # noqa: E402
 
-ON_POLICY = ['ppo_small', 'ppo_wide', 'ppo_ragged', 'ppo_fullbatch', 'ppo_timefeature', 'a2c_small']
+ON_POLICY = ['ppo_small', 'ppo_wide', 'ppo_ragged', 'ppo_fullbatch', 'ppo_timefeature', 'ppo_clip',
+             'a2c_small']
 
 
 def by_key(keys, values):
@@ -72,7 +73,7 @@ def test_on_policy_scenario_matches_reference(golden, name):
     check_weights(agent, g)
 
 
-OFF_POLICY = ['ddpg_small', 'ddpg_ou', 'ddpg_nstep', 'td3_small', 'sac_small', 'sac_wrap']
+OFF_POLICY = ['ddpg_small', 'ddpg_ou', 'ddpg_nstep', 'td3_small', 'td3_clip', 'sac_small', 'sac_wrap']
 
 
 @pytest.mark.parametrize('name', OFF_POLICY)
@@ -93,6 +94,92 @@ def test_off_policy_scenario_matches_reference(golden, name):
     np.testing.assert_allclose(actions, g['actions'], rtol=1e-5, atol=5e-5)
     check_infos(rec, g)
     check_weights(agent, g)
+
+
+def test_ppo_iteration_at_the_benched_shape_matches_reference(golden):
+    """One PPO iteration at BASELINE.json configs[1]'s shape -- 4096 environments x 128
+    steps, 2 x 256 tanh MLPs, 10 epochs x 32 minibatches of 16384 -- against digests of the
+    UNMODIFIED reference (tests/golden/ppo_bench.npz, oracle/bench_shape.py).  Host-RNG
+    parity mode: torch CPU noise stream, numpy-compatible MT19937 permutations."""
+    from oracle import bench_shape
+    from tonic_b200 import kernels
+    g = golden('ppo_bench')
+    cfg = bench_shape.CFG
+    rec = scenarios.InfoRecorder()
+    agent, env = product.build(cfg, log=rec)
+    w0 = bench_shape.weight_digests(agent.model.state_dict(), 'digest_w0/')
+    for k, v in w0.items():
+        np.testing.assert_allclose(v, g[k], rtol=1e-12, atol=0, err_msg=k)     # same init stream
+
+    class HostEnv:      # numpy protocol on top of the device environment
+        def start(self):
+            return env.start(host=True)
+
+        def step(self, actions):
+            return env.step(np.asarray(actions, np.float32))
+    out = bench_shape.drive(agent, HostEnv(), cfg)
+    # environment trajectory: bit-exact -> identical float64 digests and counts
+    for k in ('observation_digest', 'reward_digest', 'reset_count', 'termination_count'):
+        np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+    assert g['termination_count'].sum() > 0
+    # sampled actions: same eps stream, float32 round-off of the 2 x 256 MLP
+    np.testing.assert_allclose(out['action_sample'], g['action_sample'], rtol=1e-5, atol=5e-5)
+    np.testing.assert_allclose(out['action_digest'], g['action_digest'], rtol=1e-5)
+    check_infos(rec, g)
+    got = by_key(rec.keys, rec.means)
+    assert len(got['critic/loss']) == 320 and len(got['actor/loss']) == int(got['actor/iterations'][0])
+    # final weights (320 Adam steps per network at B = 16384)
+    w = bench_shape.weight_digests(agent.model.state_dict(), 'digest_w/')
+    assert set(w) == {k for k in g if k.startswith('digest_w/')}
+    for k, v in w.items():
+        np.testing.assert_allclose(v[2:], g[k][2:], rtol=1e-3, atol=2e-4, err_msg=k)
+        np.testing.assert_allclose(v[1], g[k][1], rtol=1e-3, err_msg=k)
+
+
+def test_greedy_and_test_time_actions_match_reference_kats():
+    """SURVEY.md 8(c) KAT2 / KAT5 on the GPU (a29b): default PPO / DDPG, seed 0, O=17, A=6:
+    first stochastic step, the DDPG warm-up uniform actions and the greedy test-time action."""
+    import tonic_b200
+    import tonic_b200.torch
+
+    class Space:
+        def __init__(self, n):
+            self.shape = (n,)
+    ppo = tonic_b200.torch.agents.PPO()
+    ppo.initialize(Space(17), Space(6), seed=0)
+    actions = ppo.step(np.zeros((2, 17), np.float32), 0)
+    np.testing.assert_allclose(actions[0, :3], [-0.7685214, -0.05233827, -0.05380505], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(np.asarray(ppo.last_log_probs.cpu()), [-5.1127973, -5.57454], rtol=1e-5)
+    # the PPO / A2C test-time action is a fresh stochastic sample (a2c.py:87-90): next
+    # draw of the same torch CPU stream
+    ddpg = tonic_b200.torch.agents.DDPG()
+    ddpg.initialize(Space(17), Space(6), seed=0)
+    warm = ddpg.step(np.zeros((2, 17), np.float32), 0)
+    np.testing.assert_allclose(warm[0, :3], [0.09762701, 0.43037873, 0.20552675], rtol=1e-6)
+    greedy = ddpg.test_step(np.zeros((1, 17), np.float32), 0)
+    np.testing.assert_allclose(np.asarray(greedy)[0, :3], [0.0708199, 0.0229248, 0.05138565],
+                               rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['ppo_wide', 'ddpg_small', 'sac_small'])
+def test_test_time_actions_match_oracle(golden, name):
+    """a29b: after a teacher-forced scenario the product's `test_step` (stochastic sample for
+    PPO, greedy / tanh(mean) for DDPG / SAC; a2c.py:87-90, ddpg.py:78-81, sac.py:48-51) agrees
+    with the oracle port that ran the same scenario on the CPU."""
+    import torch
+    from oracle import port
+    g = golden(name)
+    cfg = scenarios.SCENARIOS[name]
+    agent, env = product.build(cfg)
+    product.teacher_forced(agent, env, g, cfg['vector_steps'])
+    oagent, oenv = port.build(cfg)
+    scenarios.drive(oagent, oenv, cfg['vector_steps'])
+    obs = np.asarray(g['observations'][-1][:1], np.float32)
+    torch.manual_seed(1234)
+    ours = np.asarray(agent.test_step(obs, 0))
+    torch.manual_seed(1234)
+    theirs = np.asarray(oagent.test_step(obs, 0))
+    np.testing.assert_allclose(ours, theirs, rtol=1e-4, atol=5e-5)
 
 
 def test_cuda_graph_sections_match_eager():

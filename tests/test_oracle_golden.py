@@ -131,3 +131,36 @@ def test_oracle_reproduces_reference_scenario(golden, name):
                 if k.startswith(('w/', 'w0/', 'digest_w/', 'digest_w0/'))}
     assert ref_keys == set(w)
     assert checked == len(ref_keys)
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('TONIC_B200_SLOW_TESTS'),
+                    reason='takes ~1-2 CPU minutes: set TONIC_B200_SLOW_TESTS=1')
+def test_oracle_reproduces_reference_at_the_benched_shape(golden):
+    """Oracle port vs the unmodified reference at BASELINE configs[1]'s shape (digests)."""
+    from oracle import bench_shape
+    g = golden('ppo_bench')
+    cfg = bench_shape.CFG
+    rec = scenarios.InfoRecorder()
+    agent, env = port.build(cfg, log=rec)
+    out = bench_shape.drive(agent, env, cfg)
+    for k in ('observation_digest', 'reward_digest', 'reset_count', 'termination_count'):
+        np.testing.assert_array_equal(out[k], g[k], err_msg=k)
+    np.testing.assert_allclose(out['action_sample'], g['action_sample'], rtol=1e-6, atol=1e-6)
+    assert list(rec.keys) == list(g['info_keys'])
+    np.testing.assert_allclose(rec.means, g['info_mean'], rtol=1e-5, atol=1e-6)
+    w = bench_shape.weight_digests(agent.state_dict(), 'digest_w/')
+    for k, v in w.items():
+        np.testing.assert_allclose(v, g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+
+
+def test_benched_shape_fixture_is_the_benchmark_configuration(golden):
+    from oracle import bench_shape
+    g = golden('ppo_bench')
+    cfg = bench_shape.CFG
+    assert (cfg['workers'], cfg['segment']['size'], cfg['segment']['batch_size'],
+            cfg['segment']['batch_iterations'], cfg['hidden']) == (4096, 128, 16384, 10, (256, 256))
+    assert g['action_digest'].shape == (128, 2) and g['action_sample'].shape == (128, 32, 6)
+    keys = list(g['info_keys'])
+    assert keys.count('critic/loss') == 320
+    a = bench_shape.driving_actions(3, 4096, 6)
+    assert a.dtype == np.float32 and a.min() >= -1.25 and a.max() < 1.25 and (np.abs(a) > 1).any()

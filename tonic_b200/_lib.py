@@ -77,6 +77,8 @@ _PROTOTYPES = {
     'tb_adam_step': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, c_vp, c_i32, c_i32, c_f, c_vp, c_vp,
                              c_f, c_vp, c_vp]),
     'tb_reduce_partials': (c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'tb_grad_sqnorm': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'tb_grad_clip': (c_int, [c_vp, c_i32, c_vp, c_f, c_f, c_vp, c_vp]),
     'tb_peer_region_bytes': (c_i64, [c_i32]),
     'tb_peer_publish': (c_int, [_P(TbPeers), c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
                                 c_vp, c_vp]),

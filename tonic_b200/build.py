@@ -35,16 +35,25 @@ def build(force=False, verbose=False):
     nvcc = find_nvcc()
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
-    objects = []
-    logs = []
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(objdir, src.rsplit('.', 1)[0] + '.o')
         cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        # an object newer than its own source and every header is reused
+        deps = [os.path.join(CSRC, src), os.path.join(os.path.dirname(HERE), 'include', 'tonic_b200.h')]
+        deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(map(os.path.getmtime, deps)):
+            return obj, f'$ (up to date) {obj}\n', 0
         res = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(f'$ {" ".join(cmd)}\n{res.stdout}{res.stderr}')
-        if res.returncode != 0:
-            raise RuntimeError('nvcc failed:\n' + logs[-1])
-        objects.append(obj)
+        return obj, f'$ {" ".join(cmd)}\n{res.stdout}{res.stderr}', res.returncode
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    objects = [r[0] for r in results]
+    logs = [r[1] for r in results]
+    for obj, log, rc in results:
+        if rc != 0:
+            raise RuntimeError('nvcc failed:\n' + log)
     cmd = [nvcc, '-shared', '-o', LIB] + objects + ['-lcudart']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

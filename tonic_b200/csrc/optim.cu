@@ -190,6 +190,53 @@ extern "C" int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t
 }
 
 // =====================================================================================
+// Global-norm gradient clipping (torch.nn.utils.clip_grad_norm_ at
+// tonic/torch/updaters/actors.py:37-38,96-98,176-177,256-257 and critics.py:24-25,82-83,
+// 177-178,230-231): the flat (summed) gradient of every network of an updater adds its
+// sum of squares to one double; the coefficient min(1, max_norm / (norm + 1e-6)) then
+// scales each flat gradient before the Adam step.  One block, fixed summation order.
+// =====================================================================================
+namespace tb {
+__global__ void __launch_bounds__(1024)
+grad_sqnorm_kernel(const float* __restrict__ g, int n, double* __restrict__ sumsq, const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)g[i] * (double)g[i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) *sumsq += acc;
+}
+
+__global__ void __launch_bounds__(256)
+grad_clip_kernel(float* __restrict__ g, int n, const double* __restrict__ sumsq, float grad_scale,
+                 float max_norm, const int32_t* d_skip) {
+    if (skip_requested(d_skip)) return;
+    // the norm of the MEAN gradient (the partial sums are scaled by grad_scale in the Adam kernel)
+    const float total_norm = (float)(sqrt(*sumsq) * (double)grad_scale);
+    const float coef = fminf(max_norm / (total_norm + 1e-6f), 1.0f);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] *= coef;
+}
+}  // namespace tb
+
+extern "C" int tb_grad_sqnorm(const float* d_grad, int32_t n, double* d_sumsq, const int32_t* d_skip,
+                              void* stream) {
+    tb::ProfScope prof_scope("tb_grad_sqnorm", stream);
+    TB_REQUIRE(d_grad && d_sumsq && n > 0, TB_EINVAL, "tb_grad_sqnorm: bad arguments");
+    tb::grad_sqnorm_kernel<<<1, 1024, 0, tb::as_stream(stream)>>>(d_grad, n, d_sumsq, d_skip);
+    return tb::check_launch("tb_grad_sqnorm");
+}
+
+extern "C" int tb_grad_clip(float* d_grad, int32_t n, const double* d_sumsq, float grad_scale,
+                            float max_norm, const int32_t* d_skip, void* stream) {
+    tb::ProfScope prof_scope("tb_grad_clip", stream);
+    TB_REQUIRE(d_grad && d_sumsq && n > 0 && max_norm > 0.0f, TB_EINVAL, "tb_grad_clip: bad arguments");
+    tb::grad_clip_kernel<<<(n + 255) / 256, 256, 0, tb::as_stream(stream)>>>(d_grad, n, d_sumsq, grad_scale,
+                                                                             max_norm, d_skip);
+    return tb::check_launch("tb_grad_clip");
+}
+
+// =====================================================================================
 // Fused gradient all-reduce + Adam over NVLink peer memory (SURVEY.md section 8e, K9+K10).
 //
 // Every rank owns a "symmetric" region (same layout on every GPU, mapped into every

@@ -125,17 +125,23 @@ class DeviceVectorEnvironment:
         raise NotImplementedError('synthetic device environments have no renderer')
 
 
-def distribute(environment_builder, worker_groups=1, workers_per_group=1):
+def distribute(environment_builder, worker_groups=1, workers_per_group=1, single=False):
     """Same signature as the reference's `distribute`
     (tonic/environments/distributed.py:158-172).  `worker_groups *
     workers_per_group` environments are created in total; under torchrun they are
-    sharded contiguously over the ranks (one GPU each)."""
+    sharded contiguously over the ranks (one GPU each).  `single=True` builds ONE
+    environment per process whatever the number of ranks (the test environment of
+    train.py:88-91)."""
     spec = environment_builder()
     if not hasattr(spec, 'observation_size'):
         # a host environment (Gym / dm_control / user code): the reference's worker grid on the
         # host, feeding the device learner through numpy arrays (tonic_b200/environments/host.py)
         from . import host
+        if single:
+            worker_groups = workers_per_group = 1
         return host.distribute_host(environment_builder, worker_groups, workers_per_group)
+    if single:
+        return DeviceVectorEnvironment(spec, 1)
     total = int(worker_groups) * int(workers_per_group)
     rank, world = 0, 1
     if torch.distributed.is_available() and torch.distributed.is_initialized():

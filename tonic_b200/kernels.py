@@ -356,8 +356,58 @@ class Adam:
                   ptr(stats), kl_threshold, ptr(stop), stream())
 
 
+class GradientClipper:
+    """torch.nn.utils.clip_grad_norm_ over ALL variables of one updater's optimizer
+    (reference: updaters/actors.py:37-38,96-98; critics.py:24-25,177-178 -- the twin-critic
+    updaters clip the joint norm of both critics).  `add` turns one network's split partial
+    sums into its flat (all-reduced) gradient and accumulates the squared norm on the
+    device; `finish` scales every pending gradient by min(1, max_norm / (norm + 1e-6)) and
+    runs the Adam steps.  `deferred` = the caller adds several networks before `finish`."""
+
+    def __init__(self, max_norm):
+        self.max_norm = float(max_norm)
+        self.sumsq = None
+        self.pending = []
+        self.deferred = False
+
+    def add(self, adam, mlp, gpart, n_split, rows_local, rows_global, skip, stats, kl_threshold,
+            stop, reduce_stats):
+        from . import distributed
+        if self.sumsq is None:
+            self.sumsq = torch.zeros(1, dtype=torch.float64, device=device())
+        if not self.pending:
+            self.sumsq.zero_()
+        n = mlp.layout.n_params
+        flat = mlp.flat_grad()
+        if rows_local > 0:
+            w2_lo, w2_hi = mlp.w2_range()
+            _lib.call('tb_reduce_partials', ptr(gpart), n_split, mlp.w2_splits(n_split), w2_lo,
+                      w2_hi, n, ptr(flat), None, stream())
+        else:
+            flat.zero_()
+        if distributed.world() > 1:
+            distributed.all_reduce(flat)
+            reduce_stats = stats if reduce_stats is None else reduce_stats
+            if reduce_stats is not None:
+                distributed.all_reduce(reduce_stats)
+        _lib.call('tb_grad_sqnorm', ptr(flat), n, ptr(self.sumsq), ptr(skip), stream())
+        self.pending.append((adam, mlp, flat, 1.0 / rows_global, skip, stats, kl_threshold, stop))
+
+    def finish(self):
+        for adam, mlp, flat, scale, skip, stats, kl_threshold, stop in self.pending:
+            _lib.call('tb_grad_clip', ptr(flat), mlp.layout.n_params, ptr(self.sumsq), scale,
+                      self.max_norm, ptr(skip), stream())
+            adam.step(mlp, flat, 1, scale, skip=skip, stats=stats, kl_threshold=kl_threshold,
+                      stop=stop)
+        self.pending.clear()
+
+
+def make_clipper(gradient_clip):
+    return GradientClipper(gradient_clip) if gradient_clip and gradient_clip > 0 else None
+
+
 def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=None, stats=None,
-                    kl_threshold=-1.0, stop=None, reduce_stats=None):
+                    kl_threshold=-1.0, stop=None, reduce_stats=None, clip=None):
     """Adam step from the split weight gradients of this rank.  Single process:
     the partial sums are reduced inside the Adam kernel.  Several ranks: partial
     sums -> flat gradient -> all-reduce (and the statistics block) -> Adam with
@@ -366,6 +416,12 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
     zero, KL early stop); `reduce_stats` is a statistics block that only needs the
     sum over ranks (defaults to `stats`)."""
     from . import distributed
+    if clip is not None:
+        clip.add(adam, mlp, gpart, n_split, rows_local, rows_global, skip, stats, kl_threshold,
+                 stop, reduce_stats)
+        if not clip.deferred:
+            clip.finish()
+        return
     w2_splits = mlp.w2_splits(n_split)
     w2_lo, w2_hi = mlp.w2_range()
     if distributed.world() == 1:

@@ -118,7 +118,9 @@ class Buffer:
         for idx, _, _, _ in self.index_batches(steps):
             out = {}
             for k in keys:
-                if k == 'discounts':
+                if k == 'discounts' and self.return_steps == 1:
+                    # buffers.py:34-36: (1 - terminations) * discount_factor; with n-step
+                    # returns the stored column holds the accumulated discounts (:58-79)
                     out[k] = (1 - self.flat('terminations')[idx]) * np.float32(self.discount_factor)
                 else:
                     out[k] = self.flat(k)[idx]

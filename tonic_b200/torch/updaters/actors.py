@@ -35,6 +35,7 @@ class _GaussianPolicyUpdater:
         self.variables = [p for p in actor.parameters() if p.requires_grad]
         self.adam = kernels.Adam(actor.network.params,
                                  **optimizers.adam_hyperparameters(self.optimizer, 3e-4))
+        self.clipper = kernels.make_clipper(self.gradient_clip)
         self._rows = 0
 
     def _scratch(self, rows):
@@ -63,7 +64,8 @@ class _GaussianPolicyUpdater:
             gpart = net.mlp.wgrad(dout, rows, n_split, n_extra=A,
                                   off_extra=net.extra_offset('log_scale'), skip=stop)
         kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
-                                skip=stop, stats=stats, kl_threshold=self.kl_threshold, stop=stop)
+                                skip=stop, stats=stats, kl_threshold=self.kl_threshold, stop=stop,
+                                clip=self.clipper)
 
     def infos(self, s):
         """Statistics block (host copy) -> the reference's info dict (python floats)."""
@@ -94,9 +96,8 @@ class StochasticPolicyGradient(_GaussianPolicyUpdater):
     (reference: updaters/actors.py:9-50)."""
 
     def __init__(self, optimizer=None, entropy_coeff=0, gradient_clip=0):
-        if gradient_clip:
-            raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer, self.entropy_coeff = optimizer, entropy_coeff
+        self.gradient_clip = gradient_clip
 
 
 class ClippedRatio(_GaussianPolicyUpdater):
@@ -106,11 +107,10 @@ class ClippedRatio(_GaussianPolicyUpdater):
 
     def __init__(self, optimizer=None, ratio_clip=0.2, kl_threshold=0.015, entropy_coeff=0,
                  gradient_clip=0):
-        if gradient_clip:
-            raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer = optimizer
         self.ratio_clip, self.kl_threshold = ratio_clip, kl_threshold
         self.entropy_coeff = entropy_coeff
+        self.gradient_clip = gradient_clip
 
 
 class _CriticGradientUpdater:
@@ -126,6 +126,7 @@ class _CriticGradientUpdater:
         self.variables = [p for p in self.actor.parameters() if p.requires_grad]
         self.adam = kernels.Adam(self.actor.network.params,
                                  **optimizers.adam_hyperparameters(self.optimizer, self.default_lr))
+        self.clipper = kernels.make_clipper(self.gradient_clip)
         self.obs_size = self.actor.network.layout.d_in
         self.seed, self._counter, self._rows = 0, 0, 0
 
@@ -149,7 +150,7 @@ class _CriticGradientUpdater:
             net.mlp.backward(self._dout, rows)
             gpart = net.mlp.wgrad(self._dout, rows, n_split)
         kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
-                                reduce_stats=stats)
+                                reduce_stats=stats, clip=self.clipper)
 
     @staticmethod
     def infos(s):
@@ -160,9 +161,7 @@ class DeterministicPolicyGradient(_CriticGradientUpdater):
     """loss = -mean Q(s, mu(s)) (reference: updaters/actors.py:159-189)."""
 
     def __init__(self, optimizer=None, gradient_clip=0):
-        if gradient_clip:
-            raise NotImplementedError('gradient clipping is not implemented')
-        self.optimizer = optimizer
+        self.optimizer, self.gradient_clip = optimizer, gradient_clip
 
     def launch(self, observations, idx, rows, stats, rows_global=None, mine=None):
         if rows == 0:
@@ -194,9 +193,8 @@ class TwinCriticSoftDeterministicPolicyGradient(_CriticGradientUpdater):
     default_lr = 3e-4
 
     def __init__(self, optimizer=None, entropy_coeff=0.2, gradient_clip=0):
-        if gradient_clip:
-            raise NotImplementedError('gradient clipping is not implemented')
         self.optimizer, self.entropy_coeff = optimizer, entropy_coeff
+        self.gradient_clip = gradient_clip
 
     def launch(self, observations, idx, rows, stats, rows_global=None, mine=None):
         A = self.actor.action_size

@@ -14,12 +14,11 @@ class VRegression:
     def __init__(self, loss=None, optimizer=None, gradient_clip=0):
         if loss is not None and not isinstance(loss, torch.nn.MSELoss):
             raise NotImplementedError('only the MSE loss has a kernel')
-        if gradient_clip:
-            raise NotImplementedError('gradient clipping is not implemented')
-        self.optimizer = optimizer
+        self.optimizer, self.gradient_clip = optimizer, gradient_clip
 
     def initialize(self, model):
         self.model = model
+        self.clipper = kernels.make_clipper(self.gradient_clip)
         self.critic = model.critic
         self.variables = [p for p in self.critic.parameters() if p.requires_grad]
         self.adam = kernels.Adam(self.critic.network.params,
@@ -48,7 +47,7 @@ class VRegression:
             net.mlp.backward(dout, rows)
             gpart = net.mlp.wgrad(dout, rows, n_split)
         kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
-                                reduce_stats=stats)
+                                reduce_stats=stats, clip=self.clipper)
 
     @staticmethod
     def infos(s):
@@ -74,9 +73,7 @@ class _QLearning:
     def __init__(self, loss=None, optimizer=None, gradient_clip=0):
         if loss is not None and not isinstance(loss, torch.nn.MSELoss):
             raise NotImplementedError('only the MSE loss has a kernel')
-        if gradient_clip:
-            raise NotImplementedError('gradient clipping is not implemented')
-        self.optimizer = optimizer
+        self.optimizer, self.gradient_clip = optimizer, gradient_clip
 
     def _critics(self, model):
         raise NotImplementedError
@@ -88,6 +85,10 @@ class _QLearning:
         hyper = optimizers.adam_hyperparameters(self.optimizer, self.default_lr)
         # one torch Adam over both critics == one Adam per critic with equal step counts
         self.adams = [kernels.Adam(c.network.params, **hyper) for c in self.critics]
+        # one optimizer over the variables of all critics: the clip norm is their JOINT norm
+        self.clipper = kernels.make_clipper(self.gradient_clip)
+        if self.clipper:
+            self.clipper.deferred = True
         self.action_size = model.actor.action_size
         self.seed, self._counter, self._rows = 0, 0, 0
 
@@ -128,7 +129,10 @@ class _QLearning:
             for k, critic in enumerate(self.critics):
                 kernels.apply_gradients(self.adams[k], critic.network.mlp, None, 1, 0,
                                         rows_global,
-                                        reduce_stats=stats if k == len(self.critics) - 1 else None)
+                                        reduce_stats=stats if k == len(self.critics) - 1 else None,
+                                        clip=self.clipper)
+            if self.clipper:
+                self.clipper.finish()
             return
         self._scratch(rows)
         obs, acts = replay.flat('observations'), replay.flat('actions')
@@ -154,7 +158,10 @@ class _QLearning:
             # the statistics block is all-reduced once (with the last critic)
             kernels.apply_gradients(self.adams[k], net.mlp, gpart, n_split, rows,
                                     rows_global or rows,
-                                    reduce_stats=stats if k == len(self.critics) - 1 else None)
+                                    reduce_stats=stats if k == len(self.critics) - 1 else None,
+                                    clip=self.clipper)
+        if self.clipper:
+            self.clipper.finish()
 
     def infos(self, s):
         rows = s[_lib.STAT_ROWS]

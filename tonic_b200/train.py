@@ -59,8 +59,10 @@ def train(header, agent, environment, test_environment, trainer, before_training
     environment.initialize(seed=seed)
 
     _test_environment = test_environment if test_environment else _environment
-    test_environment = tonic_b200.environments.DeviceVectorEnvironment(
-        eval(_test_environment), 1)
+    # a single test environment built the way the reference builds it (train.py:88-91):
+    # distribute() picks the device grid or the host grid from what the builder returns
+    test_environment = tonic_b200.environments.distribute(
+        lambda: eval(_test_environment), single=True)
     test_environment.initialize(seed=seed + 10000)
 
     if not agent:

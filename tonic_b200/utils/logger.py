@@ -22,13 +22,14 @@ current_logger = None
 
 
 class _Aggregate:
-    __slots__ = ('count', 'total', 'total_sq', 'low', 'high', 'stats', 'items')
+    __slots__ = ('count', 'total', 'total_sq', 'low', 'high', 'stats', 'items', 'integral')
 
     def __init__(self, stats):
         self.count, self.total, self.total_sq = 0, 0.0, 0.0
         self.low, self.high = np.inf, -np.inf
         self.stats = stats
-        self.items = 0          # number of store() calls (reference '/size')
+        self.items = 0          # number of stored values (reference '/size')
+        self.integral = True    # every stored value was a Python / numpy integer
 
     def add(self, count, total, total_sq, low, high, items=1):
         self.count += count
@@ -74,18 +75,23 @@ class Logger:
         self.rows_written = 0
 
     # -- collecting -----------------------------------------------------------
-    def store(self, key, value, stats=False):
+    def store(self, key, value, stats=False, items=1):
+        """`items`: how many values of the reference's per-call list this call stands for
+        (the reference stores one value per call and reports the list length as '/size')."""
+        integral = isinstance(value, (int, np.integer)) and not isinstance(value, bool)
         v = _host(value).ravel()
         if v.size == 0:
             return
         self.store_aggregate(key, v.size, v.sum(), np.square(v).sum(), v.min(), v.max(),
-                             stats=stats)
+                             stats=stats, items=items, integral=integral)
 
-    def store_aggregate(self, key, count, total, total_sq, low, high, stats=False, items=1):
+    def store_aggregate(self, key, count, total, total_sq, low, high, stats=False, items=1,
+                        integral=False):
         agg = self.epoch.get(key)
         if agg is None:
             agg = self.epoch[key] = _Aggregate(stats)
         agg.add(count, float(total), float(total_sq), float(low), float(high), items)
+        agg.integral = agg.integral and integral
 
     # -- reporting --------------------------------------------------------------
     def _row(self):
@@ -99,6 +105,8 @@ class Logger:
                 row[key + '/size'] = agg.items
             else:
                 row[key] = agg.mean()
+                if agg.integral and row[key] == int(row[key]):    # train/steps, episodes, epochs
+                    row[key] = int(row[key])
         return row
 
     def dump(self):

@@ -53,8 +53,12 @@ class Trainer:
         workers = env.workers
         stats = kernels.ArrayStats()
         while True:
-            to_epoch = self.epoch_steps - self.epoch_step_count
-            budget = max(1, -(-to_epoch // workers))
+            # vector steps until the next epoch end, checkpoint or the end of training,
+            # whichever comes first (trainer.py:73-112 checks all three after every step)
+            to_go = min(self.epoch_steps - self.epoch_step_count,
+                        self.max_steps - self.steps,
+                        self.save_steps - self.steps_since_save)
+            budget = max(1, -(-to_go // workers))
             done = agent.rollout(env, budget, steps=self.steps, action_stats=stats)
             self._advance(done * workers)
             if self.show_progress:
@@ -67,9 +71,9 @@ class Trainer:
                 stats.reset()
                 scores, lengths = env.finished_episodes()
                 self.episodes += len(scores)
-                if len(scores):
-                    logger.store('train/episode_score', scores, stats=True)
-                    logger.store('train/episode_length', lengths, stats=True)
+                if len(scores):       # one value per finished episode (trainer.py:66-68)
+                    logger.store('train/episode_score', scores, stats=True, items=len(scores))
+                    logger.store('train/episode_length', lengths, stats=True, items=len(lengths))
                 self._end_epoch(workers)
             if self._checkpoint_and_stop():
                 break
@@ -97,8 +101,10 @@ class Trainer:
                 logger.show_progress(self.steps, self.epoch_steps, self.max_steps)
             finished = np.flatnonzero(resets)
             if len(finished):
-                logger.store('train/episode_score', scores[finished], stats=True)
-                logger.store('train/episode_length', lengths[finished], stats=True)
+                logger.store('train/episode_score', scores[finished], stats=True,
+                             items=len(finished))
+                logger.store('train/episode_length', lengths[finished], stats=True,
+                             items=len(finished))
                 scores[finished] = 0
                 lengths[finished] = 0
                 self.episodes += len(finished)
@@ -127,13 +133,23 @@ class Trainer:
         logger.store('train/steps', self.steps)
         logger.store('train/worker_steps', self.steps // workers)
         logger.store('train/steps_per_second', self.epoch_step_count / epoch_time)
-        self.last_row = logger.dump()
+        self.last_row = logger.dump() if self._writer() else logger.get_current_logger()._row()
+        if not self._writer():
+            logger.get_current_logger().epoch.clear()
         self.last_epoch_time = time.time()
         self.epoch_step_count = 0
 
+    @staticmethod
+    def _writer():
+        """Under torchrun the replicas are identical: only rank 0 writes logs / checkpoints."""
+        import torch.distributed as dist
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
     def _checkpoint_and_stop(self):
         stop = self.steps >= self.max_steps
-        if stop or self.steps_since_save >= self.save_steps:
+        if (stop or self.steps_since_save >= self.save_steps) and not self._writer():
+            self.steps_since_save = self.steps % self.save_steps
+        elif stop or self.steps_since_save >= self.save_steps:
             path = os.path.join(logger.get_path(), 'checkpoints')
             if os.path.isdir(path) and self.replace_checkpoint:
                 for name in os.listdir(path):
