@@ -334,6 +334,23 @@ int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2
                        int32_t w2_begin, int32_t w2_end, int32_t n_params, float* d_out,
                        const int32_t* d_skip, void* stream);
 
+/* ALL weight gradients of one network-minibatch in one launch, reduced to the flat gradient
+ * (reference: loss.backward() filling .grad of every variable, torch/updaters/actors.py:33,95,
+ * critics.py:23,81).  dW2 / db2 run on the tensor cores (tcgen05, 3xTF32), the narrow
+ * gradients dW1 / db1 / dW3 / db3 / extras on the FFMA pipe of the same CTAs at the same time;
+ * after a grid-wide barrier (2 * n_split <= 148 CTAs, all resident) every CTA sums the
+ * n_split partial slots of its slice of the parameter vector in a fixed order into
+ * d_flat[n_params] (sums over rows: the caller scales by 1 / rows in tb_adam_step with
+ * n_split = 1).  d_gpart: [n_split, n_params] scratch; d_sync: one zero-initialised uint64
+ * per network (grid-barrier counter).  Needs hidden == 256, d_in <= 31, n_out <= 8,
+ * n_out + n_extra <= 16.                                                                  */
+int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float* d_h1_hi,
+                       const float* d_h1_lo, const float* d_h2, const float* d_dz1,
+                       const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
+                       int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
+                       float* d_gpart, int32_t n_split, float* d_flat, uint64_t* d_sync,
+                       int32_t passes, const int32_t* d_skip, void* stream);
+
 /* ---- global-norm gradient clipping ---------------------------------------------
  * Reference: torch.nn.utils.clip_grad_norm_(self.variables, self.gradient_clip) between
  * loss.backward() and optimizer.step() (tonic/torch/updaters/actors.py:37-38,96-98,

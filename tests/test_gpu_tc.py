@@ -251,3 +251,65 @@ def test_tc_mlp_backward_fused(K, n_out, act, rows, passes):
     tol = 1e-5 if passes == 3 else 5e-3
     err = (out[2].cpu().double() - dz1).abs().max().item()
     assert err <= tol * dz1.abs().max().item(), (err, dz1.abs().max().item())
+
+
+@pytest.mark.parametrize('d_in,n_out,n_extra,rows,n_split', [
+    (17, 1, 0, 16384, 74), (17, 6, 6, 16384, 74), (23, 8, 0, 1000, 31), (31, 3, 2, 77, 2),
+    (3, 1, 0, 33, 1), (17, 6, 6, 148 * 128 + 5, 74)])
+@pytest.mark.parametrize('passes', [3, 1])
+def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_split, passes):
+    """tb_mlp_wgrad_fused (tcgen05 dW2 / db2 + FFMA narrow gradients in the same CTAs + grid
+    barrier + fixed-order reduction to the flat gradient) against float64 sums; two launches
+    give bit-identical results (deterministic reduction order)."""
+    import ctypes
+    from tonic_b200 import _lib
+    layout = K.MlpLayout(d_in, 256, n_out, 'tanh', [('log_scale', n_extra)] if n_extra else ())
+    sh = layout.shape
+    g = torch.Generator().manual_seed(rows + d_in)
+    xin = torch.zeros(rows, layout.ldx)
+    xin[:, :d_in] = torch.randn(rows, d_in, generator=g)
+    xin[:, d_in] = 1.0
+    h1, h2 = torch.tanh(torch.randn(rows, 256, generator=g)), torch.tanh(torch.randn(rows, 256, generator=g))
+    dz1, dz2 = torch.randn(rows, 256, generator=g) * 0.1, torch.randn(rows, 256, generator=g) * 0.1
+    ld = n_out + n_extra + 1
+    dout = torch.randn(rows, ld, generator=g)
+    ref = torch.zeros(layout.n_params, dtype=torch.float64)
+    o = layout.offsets
+    d = lambda t: t.double()      # noqa: E731
+    ref[o['w1'][0]:o['w1'][0] + 256 * d_in] = (d(dz1).T @ d(xin[:, :d_in])).reshape(-1)
+    ref[o['b1'][0]:o['b1'][0] + 256] = d(dz1).sum(0)
+    ref[o['w2'][0]:o['w2'][0] + 65536] = (d(dz2).T @ d(h1)).reshape(-1)
+    ref[o['b2'][0]:o['b2'][0] + 256] = d(dz2).sum(0)
+    ref[o['w3'][0]:o['w3'][0] + n_out * 256] = (d(dout[:, :n_out]).T @ d(h2)).reshape(-1)
+    ref[o['b3'][0]:o['b3'][0] + n_out] = d(dout[:, :n_out]).sum(0)
+    off_extra = 0
+    if n_extra:
+        off_extra = o['log_scale'][0]
+        ref[off_extra:off_extra + n_extra] = d(dout[:, n_out:n_out + n_extra]).sum(0)
+    dev = [t.cuda() for t in (xin, h2, dz1, dout)]
+    h1_hi, h1_lo = split(K, h1.cuda())
+    dz2_hi, dz2_lo = split(K, dz2.cuda())
+    gpart = torch.zeros(n_split, layout.n_params, device='cuda')
+    sync = torch.zeros(1, dtype=torch.int64, device='cuda')
+    outs = []
+    for _ in range(2):
+        flat = torch.full((layout.n_params,), float('nan'), device='cuda')
+        _lib.call('tb_mlp_wgrad_fused', ctypes.byref(sh), K.ptr(dev[0]), K.ptr(h1_hi), K.ptr(h1_lo),
+                  K.ptr(dev[1]), K.ptr(dev[2]), K.ptr(dz2_hi), K.ptr(dz2_lo), K.ptr(dev[3]), ld, n_extra,
+                  off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), passes, None, K.stream())
+        torch.cuda.synchronize()
+        outs.append(flat.cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert int(sync.item()) == 2 * 2 * n_split          # two barriers of 2 * n_split CTAs
+    got = outs[0].double()
+    used = torch.zeros(layout.n_params, dtype=torch.bool)
+    for name, (off, size) in o.items():
+        used[off:off + size] = True
+    scale = ref.abs().max().item()
+    tol = 2e-6 * scale * (rows ** 0.5) if passes == 3 else 2e-3 * scale
+    narrow = torch.ones(layout.n_params, dtype=torch.bool)
+    narrow[o['w2'][0]:o['w2'][0] + 65536 + 256] = False
+    err_n = (got - ref)[used & narrow].abs().max().item()
+    err_w = (got - ref)[used & ~narrow].abs().max().item()
+    assert err_n <= 2e-6 * scale * (rows ** 0.5) + 1e-5, (err_n, scale)       # FFMA part: fp32 in any mode
+    assert err_w <= tol + 1e-5, (err_w, scale)

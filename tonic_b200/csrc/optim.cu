@@ -47,6 +47,16 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
     if (d_stats && d_stats[TB_STAT_NONZERO_ADV] == 0.0) return;    // actors.py:22,71: no step
     const int t = opt.d_step[0] + 1;                               // incremented by the last block
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // bias corrections once per block (two double-precision pow() per thread were a third of
+    // this kernel's instructions)
+    __shared__ float s_step_size, s_bc2_sqrt;
+    if (threadIdx.x == 0) {
+        const double bc1 = 1.0 - pow(opt.beta1, (double)t);
+        const double bc2 = 1.0 - pow(opt.beta2, (double)t);
+        s_step_size = (float)(opt.lr / bc1);
+        s_bc2_sqrt = (float)sqrt(bc2);
+    }
+    __syncthreads();
     if (i < opt.n_params) {
         // one parameter per thread keeps ~72k threads in flight; the n_split partial loads
         // of a thread are independent (4-way unrolled sums)
@@ -76,10 +86,7 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
         const float w1 = (float)(1.0 - opt.beta1), w2 = (float)(1.0 - opt.beta2);
         const float m = opt.d_m[i] + w1 * (g - opt.d_m[i]);                          // lerp_
         const float v = opt.d_v[i] * (float)opt.beta2 + w2 * g * g;                  // mul_.addcmul_
-        const double bc1 = 1.0 - pow(opt.beta1, (double)t);
-        const double bc2 = 1.0 - pow(opt.beta2, (double)t);
-        const float step_size = (float)(opt.lr / bc1);
-        const float bc2_sqrt = (float)sqrt(bc2);
+        const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
         const float denom = sqrtf(v) / bc2_sqrt + (float)opt.eps;
         const float p = opt.d_params[i] - step_size * (m / denom);                   // addcdiv_
         opt.d_m[i] = m;

@@ -475,6 +475,349 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
     }
 }
 
+
+// =====================================================================================
+// ALL weight gradients of one network-minibatch in ONE launch, reduced inside the kernel:
+//
+//   warps 0-7   the tensor-core kernel above: dW2 (3xTF32 tcgen05, MN-major operands) and
+//               db2 (ones-MMA) for output rows [128 tile, +128) over the rows of split s;
+//   warps 8-15  at the same time, on the FFMA pipe the tensor-core mainloop leaves idle:
+//               the narrow gradients of the same (tile, split) block
+//                   dW1[n][j] = sum_m dz1[m][n] xin[m][j]   (ones column of xin: db1)
+//                   dW3[o][n] = sum_m dout[m][o] h2[m][n],  db3 / extras = column sums of dout
+//               (autograd of models/utils.py:15-23 and the heads, as narrow_wgrad_kernel in
+//               csrc/mlp.cu, which this replaces together with its side stream);
+//   all warps   after a grid-wide barrier (all 2 x n_split <= 148 CTAs are resident: one per
+//               SM) CTA b sums the n_split partial slots of its slice of the flat parameter
+//               vector in a FIXED order ((s%4==0) + (s%4==1)) + ((s%4==2) + (s%4==3)) --
+//               the order the Adam kernel used -- and writes the flat gradient, so that the
+//               optimizer step (or the multi-GPU exchange) reads ONE vector instead of
+//               74-148 partial slots (19 MB -> 0.3 MB per minibatch).
+// =====================================================================================
+constexpr int TCA_THREADS = 512;
+constexpr int TCA_NARROW_WARP0 = 8;          // warps 8..15
+constexpr int TCA_NO = 8;                    // head outputs with a dW3 row (n_out <= 8)
+constexpr int TCA_ND = 16;                   // dout columns with a column sum (n_out + extras <= 16)
+
+struct TcWgradAllParams {
+    TcWgradParams w;            // tensor-core part (gpart, n_params, off_w2, off_b2, rows_per_split)
+    TbMlpShape sh;
+    const float* xin;           // [n_rows, ldx] with the ones column
+    const float* h2;            // [n_rows, 256]
+    const float* dz1;           // [n_rows, 256]
+    const float* dout;          // [n_rows, ld_dout]
+    int ld_dout, n_extra, off_extra;
+    int n_split;
+    float* flat;                // [n_params] reduced gradient (sum over rows)
+    unsigned long long* sync;   // grid-barrier counter (monotonic)
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned int n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(counter, 1ULL);
+        const unsigned long long target = (old / n_ctas + 1ULL) * n_ctas;
+        unsigned long long seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+            if (seen < target) __nanosleep(40);
+        } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int PASSES, int KIN>
+__global__ void __launch_bounds__(TCA_THREADS, 1)
+tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
+                    const __grid_constant__ CUtensorMap map_h_hi, const __grid_constant__ CUtensorMap map_h_lo,
+                    const TcWgradAllParams q) {
+    using Cfg = TcCfg<PASSES>;
+    const TcWgradParams& p = q.w;
+    if (skip_requested(p.skip)) return;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    // HEAD_BYTES region (9 KB): [8 x 32] ones block, then the narrow warps' staging
+    float* ones = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    float* xs = ones + 256;                              // [2][32][KIN]   <= 2 * 32 * 32 * 4 = 8 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
+                                                 Cfg::HEAD_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + Cfg::STAGES;
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    __shared__ float ds[2][TCW_ROWS][TCA_ND];            // dout rows of the chunk (4 KB)
+    // row-group 1 -> row-group 0 exchange of the narrow sums: lives in the epilogue warps'
+    // staging block (18 KB), which they only touch after named barrier 2 (see below)
+    float (*comb)[KIN] = reinterpret_cast<float (*)[KIN]>(epi);          // [128][KIN] <= 16 KB
+    static_assert(128 * KIN * 4 <= Cfg::EPI_BYTES && 128 * TCA_NO * 4 <= Cfg::EPI_BYTES, "exchange block too large");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;                                 // 0 / 1: columns 128*tile..
+    const int split = blockIdx.y;
+    const int64_t m_begin = (int64_t)split * p.rows_per_split;
+    const int64_t m_end = min(p.n_rows, m_begin + p.rows_per_split);
+    const int n_chunks = m_end > m_begin ? (int)((m_end - m_begin + TCW_ROWS - 1) / TCW_ROWS) : 0;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 256; i += TCA_THREADS) ones[i] = 1.0f;
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                const int m0 = (int)(m_begin + (int64_t)c * TCW_ROWS);
+                for (int b = 0; b < TC_BM / 32; ++b)
+                    tma_load_2d(st + b * 4096, &map_dz_hi, &full_bar[stage], tile * TC_BM + b * 32, m0);
+                unsigned char* bh = st + Cfg::PARTS * TCW_A_BYTES;
+                for (int b = 0; b < TC_BN / 32; ++b)
+                    tma_load_2d(bh + b * 4096, &map_h_hi, &full_bar[stage], b * 32, m0);
+                if (PASSES == 3) {
+                    for (int b = 0; b < TC_BM / 32; ++b)
+                        tma_load_2d(st + TCW_A_BYTES + b * 4096, &map_dz_lo, &full_bar[stage],
+                                    tile * TC_BM + b * 32, m0);
+                    unsigned char* bl = st + 2 * TCW_A_BYTES + TCW_B_BYTES;
+                    for (int b = 0; b < TC_BN / 32; ++b)
+                        tma_load_2d(bl + b * 4096, &map_h_lo, &full_bar[stage], b * 32, m0);
+                }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t idesc16 = (kIdescTf32MN & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
+            const uint64_t b_ones = umma_desc_mnmajor_sw128(ones);
+            for (int c = 0; c < n_chunks; ++c) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                const uint64_t a_hi = umma_desc_mnmajor_sw128(st);
+                const uint64_t a_lo = umma_desc_mnmajor_sw128(st + TCW_A_BYTES);
+                const uint64_t b_hi = umma_desc_mnmajor_sw128(st + Cfg::PARTS * TCW_A_BYTES);
+                const uint64_t b_lo = umma_desc_mnmajor_sw128(st + 2 * TCW_A_BYTES + TCW_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TCW_ROWS / 8; ++k) {
+                    const uint64_t koff = (uint64_t)(k * 1024 >> 4);     // next 8-row group
+                    if (PASSES == 3) {
+                        tcgen05_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
+                        tcgen05_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, kIdescTf32MN, 1);
+                        tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32MN, 1);
+                    } else {
+                        tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
+                    }
+                    // db2[n] = sum_m dz2[m, n]: the A operand against a block of ones (N = 16)
+                    tcgen05_mma_tf32(tmem_base + TC_BN, a_hi + koff, b_ones, idesc16, (c | k) != 0);
+                    if (PASSES == 3) tcgen05_mma_tf32(tmem_base + TC_BN, a_lo + koff, b_ones, idesc16, 1);
+                }
+                tcgen05_commit(&empty_bar[stage]);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            tcgen05_commit(tmem_full);
+        }
+    } else if (warp >= 4 && warp < TCA_NARROW_WARP0) {
+        // ---- epilogue: accumulator -> this split's partial slot (dW2 rows, db2) ----------------
+        const int w = warp - 4;
+        float* stg = epi + w * 32 * TC_STAGE_ROWSTRIDE;
+        float* out = p.gpart + (size_t)split * p.n_params + p.off_w2 + (size_t)(tile * TC_BM + w * 32) * TC_BN;
+        if (n_chunks > 0) {
+            mbar_wait(tmem_full, 0);
+            tcgen05_fence_after();
+        }
+        // the staging block doubles as the narrow warps' exchange buffer: wait until they left it
+        asm volatile("bar.sync 2, 384;" ::: "memory");
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; ++c) {
+            if (n_chunks > 0) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)(c * 32), v);
+                float* mine = stg + lane * TC_STAGE_ROWSTRIDE;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(mine + j) =
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                    __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                __syncwarp();
+            }
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r)
+                out[(size_t)r * TC_BN + c * 32 + lane] = n_chunks > 0 ? stg[r * TC_STAGE_ROWSTRIDE + lane] : 0.0f;
+            __syncwarp();
+        }
+        float sum = 0.0f;
+        if (n_chunks > 0) {
+            uint32_t v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                  "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+                  "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(tmem_base + ((uint32_t)(w * 32) << 16) + (uint32_t)TC_BN) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            sum = __uint_as_float(v[0]);
+        }
+        p.gpart[(size_t)split * p.n_params + p.off_b2 + tile * TC_BM + w * 32 + lane] = sum;
+    } else if (warp >= TCA_NARROW_WARP0) {
+        // ---- narrow gradients on the FFMA pipe: thread (g, c): column n = 128 tile + c, rows of
+        // parity g; 16 rows per chunk and thread, the loads of the next chunk are issued before
+        // the current one is consumed -------------------------------------------------------------
+        const int t = threadIdx.x - TCA_NARROW_WARP0 * 32;       // 0..255
+        const int c = t & 127, g = t >> 7;
+        const int n = tile * 128 + c;
+        const TbMlpShape& sh = q.sh;
+        const int d_in = sh.d_in, n_out = sh.n_out, nd = n_out + q.n_extra;
+        const int ldx = (d_in + 1 + 3) & ~3;
+        float w1[KIN], w3[TCA_NO], dsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KIN; ++j) w1[j] = 0.0f;
+#pragma unroll
+        for (int o = 0; o < TCA_NO; ++o) w3[o] = 0.0f;
+        float a1[16], hv[16], na1[16], nhv[16];
+        auto load_rows = [&](int chunk, float (&da)[16], float (&dh)[16]) {
+            const int64_t base = m_begin + (int64_t)chunk * TCW_ROWS;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int64_t r = min(base + g + 2 * u, m_end - 1);
+                da[u] = ldg_nc_volatile(q.dz1 + r * 256 + n);
+                dh[u] = ldg_nc_volatile(q.h2 + r * 256 + n);
+            }
+        };
+        auto stage_rows = [&](int chunk) {
+            const int64_t base = m_begin + (int64_t)chunk * TCW_ROWS;
+            float* x = xs + (chunk & 1) * TCW_ROWS * KIN;
+            for (int v = t; v < TCW_ROWS * KIN; v += 256) {
+                const int r = v / KIN, j = v % KIN;
+                x[v] = (base + r < m_end && j <= d_in) ? q.xin[(base + r) * ldx + j] : 0.0f;
+            }
+            for (int v = t; v < TCW_ROWS * TCA_ND; v += 256) {
+                const int r = v / TCA_ND, o = v % TCA_ND;
+                ds[chunk & 1][r][o] = (base + r < m_end && o < nd) ? q.dout[(base + r) * q.ld_dout + o] : 0.0f;
+            }
+        };
+        if (n_chunks > 0) {
+            load_rows(0, a1, hv);
+            stage_rows(0);
+        }
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // staging of chunk ch visible; buffer of ch+1 free
+            if (ch + 1 < n_chunks) {
+                load_rows(ch + 1, na1, nhv);
+                stage_rows(ch + 1);
+            }
+            const int rows = (int)min((int64_t)TCW_ROWS, m_end - (m_begin + (int64_t)ch * TCW_ROWS));
+            const float* x = xs + (ch & 1) * TCW_ROWS * KIN;
+            if (tile == 0 && t < nd)
+                for (int r = 0; r < rows; ++r) dsum += ds[ch & 1][r][t];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int r = g + 2 * u;
+                if (r < rows) {
+#pragma unroll
+                    for (int j = 0; j < KIN; ++j) w1[j] = fmaf(a1[u], x[r * KIN + j], w1[j]);
+#pragma unroll
+                    for (int o = 0; o < TCA_NO; ++o) w3[o] = fmaf(ds[ch & 1][r][o], hv[u], w3[o]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { a1[u] = na1[u]; hv[u] = nhv[u]; }
+        }
+        // combine the two row groups (fixed order: group 0 + group 1) in two rounds through the
+        // exchange block, then write this split's partial slot
+        if (g == 1) {
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) comb[c][j] = w1[j];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (g == 0) {
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) w1[j] += comb[c][j];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float (*comb3)[TCA_NO] = reinterpret_cast<float (*)[TCA_NO]>(epi);
+        if (g == 1) {
+#pragma unroll
+            for (int o = 0; o < TCA_NO; ++o) comb3[c][o] = w3[o];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (g == 0) {
+#pragma unroll
+            for (int o = 0; o < TCA_NO; ++o) w3[o] += comb3[c][o];
+        }
+        asm volatile("bar.arrive 2, 384;" ::: "memory");       // exchange block released to the epilogue warps
+        if (g == 0) {
+            float* out = p.gpart + (size_t)split * p.n_params;
+#pragma unroll
+            for (int j = 0; j < KIN; ++j) {
+                if (j < d_in) out[sh.off_w1 + n * d_in + j] = w1[j];
+                else if (j == d_in) out[sh.off_b1 + n] = w1[j];
+            }
+#pragma unroll
+            for (int o = 0; o < TCA_NO; ++o)
+                if (o < n_out) out[sh.off_w3 + o * 256 + n] = w3[o];
+            if (tile == 0) {
+                if (t < n_out) out[sh.off_b3 + t] = dsum;
+                else if (t < nd) out[q.off_extra + (t - n_out)] = dsum;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
+                     : "memory");
+    }
+    // ---- grid-wide barrier, then the fixed-order reduction of this CTA's parameter slice -------
+    const unsigned int n_ctas = gridDim.x * gridDim.y;
+    grid_barrier(q.sync, n_ctas);
+    const int b = blockIdx.y * gridDim.x + blockIdx.x;
+    const int per = (((p.n_params + (int)n_ctas - 1) / (int)n_ctas) + 127) & ~127;     // multiple of 128
+    const int lo = b * per, hi = min(p.n_params, lo + per);
+    float* red = reinterpret_cast<float*>(smem);          // [3][128] partial sums of lanes 1..3 (stages are idle)
+    const int qd = threadIdx.x >> 7, e = threadIdx.x & 127;       // 4 quarter-sums x 128 parameters per pass
+    for (int i0 = lo; i0 < hi; i0 += 128) {
+        const int i = i0 + e;
+        float acc = 0.0f;
+        if (i < hi) {
+            const float* src = p.gpart + i;
+            int s = qd;
+            for (; s + 12 < q.n_split; s += 16) {       // 4 independent loads in flight
+                const float v0 = __ldcg(src + (size_t)s * p.n_params);
+                const float v1 = __ldcg(src + (size_t)(s + 4) * p.n_params);
+                const float v2 = __ldcg(src + (size_t)(s + 8) * p.n_params);
+                const float v3 = __ldcg(src + (size_t)(s + 12) * p.n_params);
+                acc += v0; acc += v1; acc += v2; acc += v3;
+            }
+            for (; s < q.n_split; s += 4) acc += __ldcg(src + (size_t)s * p.n_params);
+        }
+        __syncthreads();
+        if (qd > 0) red[(qd - 1) * 128 + e] = acc;
+        __syncthreads();
+        if (qd == 0 && i < hi) q.flat[i] = (acc + red[e]) + (red[128 + e] + red[256 + e]);
+    }
+}
+
 // ---- split helper: hi = x with the low 13 mantissa bits cleared, lo = x - hi -------------
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
@@ -595,4 +938,61 @@ extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const 
         tc_wgrad_kernel<1><<<grid, TC_THREADS, TcCfg<1>::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], p);
     }
     return check_launch("tb_tc_wgrad256");
+}
+
+// All weight gradients of one minibatch in one launch, reduced to the flat gradient
+// (see tc_wgrad_all_kernel).  d_sync: one uint64 (zero-initialised once), the grid-barrier
+// counter of this network.
+extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float* d_h1_hi,
+                                  const float* d_h1_lo, const float* d_h2, const float* d_dz1,
+                                  const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
+                                  int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
+                                  float* d_gpart, int32_t n_split, float* d_flat, uint64_t* d_sync,
+                                  int32_t passes, const int32_t* d_skip, void* stream) {
+    using namespace tb;
+    TB_REQUIRE(shape && d_xin && d_h1_hi && d_h1_lo && d_h2 && d_dz1 && d_dz2_hi && d_dz2_lo && d_dout &&
+               d_gpart && d_flat && d_sync && n_rows > 0, TB_EINVAL, "tb_mlp_wgrad_fused: null pointer");
+    TB_REQUIRE(shape->hidden == 256 && shape->off_w2_hi > 0 && shape->d_in + 1 <= 32 &&
+               shape->n_out >= 1 && shape->n_out <= TCA_NO && shape->n_out + n_extra <= TCA_ND &&
+               ld_dout >= shape->n_out + n_extra, TB_ENOTSUP,
+               "tb_mlp_wgrad_fused: needs hidden == 256, d_in <= 31, n_out <= 8, n_out + extras <= 16");
+    TB_REQUIRE(n_split >= 1 && 2 * n_split <= kNumSMs, TB_EINVAL,
+               "tb_mlp_wgrad_fused: 2 * n_split CTAs must be resident together (<= %d)", kNumSMs);
+    TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_mlp_wgrad_fused: passes must be 1 or 3");
+    TB_REQUIRE(shape->off_b2 == shape->off_w2 + 256 * 256, TB_EINVAL,
+               "tb_mlp_wgrad_fused: b2 must follow W2 in the flat layout");
+    CUtensorMap maps[4];
+    int rc;
+    if ((rc = make_map(&maps[0], d_dz2_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[1], d_dz2_lo, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    TcWgradAllParams q;
+    q.w.n_rows = n_rows;
+    q.w.rows_per_split = ((n_rows + n_split - 1) / n_split + TCW_ROWS - 1) / TCW_ROWS * TCW_ROWS;
+    q.w.gpart = d_gpart; q.w.n_params = shape->n_params; q.w.off_w2 = shape->off_w2;
+    q.w.off_b2 = shape->off_b2; q.w.skip = d_skip;
+    q.w.dbg_lbo = q.w.dbg_sbo = q.w.dbg_kstep = q.w.dbg_idesc_xor = 0;
+    q.sh = *shape; q.xin = d_xin; q.h2 = d_h2; q.dz1 = d_dz1; q.dout = d_dout; q.ld_dout = ld_dout;
+    q.n_extra = n_extra; q.off_extra = off_extra; q.n_split = n_split; q.flat = d_flat;
+    q.sync = reinterpret_cast<unsigned long long*>(d_sync);
+    dim3 grid(TC_BN / TC_BM, n_split);
+    cudaStream_t s = as_stream(stream);
+    ProfScope prof_scope("tb_mlp_wgrad_fused", stream);
+    const bool small_in = shape->d_in + 1 <= 20;
+#define TB_WGRAD_ALL(P_, K_)                                                                         \
+    {                                                                                                \
+        static bool configured = false;                                                              \
+        if (!configured) {                                                                           \
+            cudaFuncSetAttribute(tc_wgrad_all_kernel<P_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 TcCfg<P_>::SMEM_BYTES);                                             \
+            configured = true;                                                                       \
+        }                                                                                            \
+        tc_wgrad_all_kernel<P_, K_><<<grid, TCA_THREADS, TcCfg<P_>::SMEM_BYTES, s>>>(                \
+            maps[0], maps[1], maps[2], maps[3], q);                                                  \
+    }
+    if (passes == 3) { if (small_in) TB_WGRAD_ALL(3, 20) else TB_WGRAD_ALL(3, 32) }
+    else { if (small_in) TB_WGRAD_ALL(1, 20) else TB_WGRAD_ALL(1, 32) }
+#undef TB_WGRAD_ALL
+    return check_launch("tb_mlp_wgrad_fused");
 }

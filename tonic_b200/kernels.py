@@ -168,6 +168,7 @@ class MlpInput:
 
 _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 _FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
+_FUSED_WGRAD = os.environ.get('TONIC_B200_FUSED_WGRAD', '1') != '0'
 
 
 class DeviceMlp:
@@ -227,10 +228,20 @@ class DeviceMlp:
             self._gpart = torch.zeros(n_split, self.layout.n_params, dtype=F32, device=device())
         return self._gpart
 
-    def splits_for(self, rows):
-        """Row splits of the weight-gradient partial sums.  Tensor-core path: the narrow
-        gradients use twice the splits of the W2 kernel (see `w2_splits`)."""
+    def fused_wgrad(self, n_extra=0):
+        """All weight gradients in one launch, reduced in the kernel to ONE flat gradient
+        (csrc/tc_gemm.cu::tc_wgrad_all_kernel)."""
+        L = self.layout
+        return (bool(self.passes()) and _FUSED_WGRAD and L.d_in + 1 <= 32 and L.n_out <= 8
+                and L.n_out + n_extra <= 16)
+
+    def splits_for(self, rows, n_extra=0):
+        """Row splits of the weight-gradient partial sums.  Tensor-core path: 2 column tiles x
+        splits CTAs; the fused kernel needs all of them resident (<= 148).  Unfused chain: the
+        narrow gradients use twice the splits of the W2 kernel (see `w2_splits`)."""
         from . import config
+        if self.fused_wgrad(n_extra):
+            return max(1, min(config.wgrad_splits_tc, rows // 32))
         if self.passes():
             return max(1, min(2 * config.wgrad_splits_tc, rows // 32))
         return max(1, min(config.wgrad_splits, rows // 128))
@@ -321,6 +332,21 @@ class DeviceMlp:
         flops = 2.0 * rows * (L.hidden * L.hidden + L.hidden * (L.d_in + 2)
                               + (L.n_out + n_extra) * (L.hidden + 1))
         passes = self.passes()
+        if self.fused_wgrad(n_extra):
+            # one launch: tensor-core dW2 + FFMA narrow gradients + in-kernel reduction; the
+            # result is the flat gradient (n_split = 1 for the optimizer / the exchange)
+            _count_flops('tb_mlp_wgrad_fused', flops)
+            if getattr(self, '_wgrad_sync', None) is None:
+                self._wgrad_sync = torch.zeros(1, dtype=torch.int64, device=device())
+            flat = self.flat_grad()
+            _lib.call('tb_mlp_wgrad_fused', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
+                      ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
+                      ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
+                      ptr(gpart), n_split, ptr(flat), ptr(self._wgrad_sync), passes, ptr(skip),
+                      stream())
+            self.reduced = True
+            return flat
+        self.reduced = False
         if passes:
             _count_flops('tb_mlp_wgrad_tc', flops)
             _count_flops('tb_tc_wgrad256', 2.0 * rows * L.hidden * L.hidden)
@@ -379,11 +405,12 @@ class GradientClipper:
             self.sumsq.zero_()
         n = mlp.layout.n_params
         flat = mlp.flat_grad()
-        if rows_local > 0:
+        if rows_local > 0 and gpart.data_ptr() != flat.data_ptr():
             w2_lo, w2_hi = mlp.w2_range()
-            _lib.call('tb_reduce_partials', ptr(gpart), n_split, mlp.w2_splits(n_split), w2_lo,
+            _lib.call('tb_reduce_partials', ptr(gpart), n_split,
+                      mlp.w2_splits(n_split) if n_split > 1 else 0, w2_lo,
                       w2_hi, n, ptr(flat), None, stream())
-        else:
+        elif rows_local == 0:
             flat.zero_()
         if distributed.world() > 1:
             distributed.all_reduce(flat)
@@ -416,13 +443,15 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
     zero, KL early stop); `reduce_stats` is a statistics block that only needs the
     sum over ranks (defaults to `stats`)."""
     from . import distributed
+    if gpart is not None and getattr(mlp, 'reduced', False) and rows_local > 0:
+        n_split = 1         # `gpart` is the flat gradient the fused weight-gradient kernel reduced
     if clip is not None:
         clip.add(adam, mlp, gpart, n_split, rows_local, rows_global, skip, stats, kl_threshold,
                  stop, reduce_stats)
         if not clip.deferred:
             clip.finish()
         return
-    w2_splits = mlp.w2_splits(n_split)
+    w2_splits = mlp.w2_splits(n_split) if n_split > 1 else 0
     w2_lo, w2_hi = mlp.w2_range()
     if distributed.world() == 1:
         adam.step(mlp, gpart, n_split, 1.0 / rows_global, skip=skip, stats=stats,
@@ -443,10 +472,10 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
                   kl_threshold, ptr(stop), stream())
         return
     flat = mlp.flat_grad()
-    if rows_local > 0:
+    if rows_local > 0 and gpart.data_ptr() != flat.data_ptr():
         _lib.call('tb_reduce_partials', ptr(gpart), n_split, w2_splits, w2_lo, w2_hi,
                   mlp.layout.n_params, ptr(flat), None, stream())
-    else:
+    elif rows_local == 0:
         flat.zero_()
     distributed.all_reduce(flat)
     reduce_stats = stats if reduce_stats is None else reduce_stats
