@@ -87,6 +87,68 @@ class VectorEnv:
         return np.array(acting_obs, F32), infos
 
 
+class ParallelVectorEnv:
+    """P forked worker groups of M sequential environments each, synchronous scatter / gather
+    over a pipe per group and one result queue (environments/distributed.py:69-155): worker
+    j = g * M + i is seeded seed + j, actions are split group-major (`np.split`, :137)."""
+
+    def __init__(self, obs, act, groups, per_group, max_episode_steps):
+        self.shape = (obs, act, max_episode_steps)
+        self.groups, self.per_group = groups, per_group
+        probe = VectorEnv(obs, act, 1, max_episode_steps)
+        self.observation_space, self.action_space = probe.observation_space, probe.action_space
+        self.max_episode_steps = max_episode_steps
+
+    def initialize(self, seed):
+        import multiprocessing
+        ctx = multiprocessing.get_context('fork')
+        self.queue = ctx.Queue()
+        self.pipes, self.procs = [], []
+
+        def proc(pipe, index, group_seed):
+            envs = VectorEnv(*self.shape[:2], self.per_group, self.shape[2])
+            envs.initialize(group_seed)
+            self.queue.put((index, envs.start()))
+            while True:
+                actions = pipe.recv()
+                if actions is None:
+                    return
+                self.queue.put((index, envs.step(actions)))
+
+        for i in range(self.groups):
+            pipe, worker_end = ctx.Pipe()
+            self.pipes.append(pipe)
+            p = ctx.Process(target=proc, args=(worker_end, i, seed + i * self.per_group))
+            p.daemon = True
+            p.start()
+            self.procs.append(p)
+
+    def start(self):
+        parts = [None] * self.groups
+        for _ in range(self.groups):
+            index, observations = self.queue.get()
+            parts[index] = observations
+        return np.concatenate(parts)
+
+    def step(self, actions):
+        for part, pipe in zip(np.split(np.asarray(actions), self.groups), self.pipes):
+            pipe.send(part)
+        outs = [None] * self.groups
+        for _ in range(self.groups):
+            index, out = self.queue.get()
+            outs[index] = out
+        observations = np.concatenate([o[0] for o in outs])
+        infos = {k: np.concatenate([o[1][k] for o in outs])
+                 for k in ('observations', 'rewards', 'resets', 'terminations')}
+        return observations, infos
+
+    def close(self):
+        for pipe in self.pipes:
+            pipe.send(None)
+        for p in self.procs:
+            p.join(timeout=5)
+
+
 # ---------------------------------------------------------------------------
 # Replays
 # ---------------------------------------------------------------------------

@@ -21,11 +21,29 @@ from oracle import scenarios  # noqa: E402
 from tests import product, test_gpu_agents  # noqa: E402
 
 
+def check_all():
+    """Every golden scenario whose workers split over the ranks of the initialised process
+    group (bench.py --gpus N > 1 runs this before timing: `multi_rank_parity`)."""
+    world = dist.get_world_size()
+    names = [n for n in ('ppo_small', 'ppo_wide', 'ppo_ragged', 'a2c_small', 'td3_small', 'sac_small',
+                         'ddpg_small') if scenarios.SCENARIOS[n]['workers'] % world == 0]
+    assert names, f'no golden scenario splits over {world} ranks'
+    check(names, verbose=False)
+    return names
+
+
 def main(names):
     local_rank = int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local_rank)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    check(names)
+    dist.destroy_process_group()
+
+
+def check(names, verbose=True):
     rank, world = dist.get_rank(), dist.get_world_size()
+    from tonic_b200.utils import logger
+    saved = {k: getattr(logger, k) for k in ('store', 'store_aggregate')}
     for name in names:
         cfg = scenarios.SCENARIOS[name]
         g = dict(np.load(os.path.join(ROOT, 'tests', 'golden', name + '.npz')))
@@ -48,9 +66,10 @@ def main(names):
         ref = flat.clone()
         dist.broadcast(ref, 0)
         assert torch.equal(flat, ref), 'replica weights diverged'
-        if rank == 0:
+        if rank == 0 and verbose:
             print(f'{name}: {world} ranks reproduce the single-process reference', flush=True)
-    dist.destroy_process_group()
+    for k, v in saved.items():
+        setattr(logger, k, v)
 
 
 if __name__ == '__main__':

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_prints_one_contract_line():
     res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
                           '--steps', '1', '--warmup', '0'], capture_output=True, text=True,
-                         timeout=900, cwd=ROOT)
+                         timeout=900, cwd=ROOT,
+                         env=dict(os.environ, TB_BENCH_CPU_ENVS='32'))   # small sample: this is a format check
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.strip().splitlines() if l.startswith('{')]
     assert len(lines) == 1, res.stdout
@@ -25,3 +26,6 @@ def test_reference_arm_prints_one_contract_line():
     e2e = line['e2e']
     assert e2e['value'] == line['value'] and e2e['h2d_bytes_per_step'] == 0 == e2e['d2h_bytes_per_step']
     assert 'workload' in line['config']
+    # thread-pinned sweep incl. the forked --parallel C --sequential N/C grid
+    grid = base['grid']
+    assert any(not g['mode'].startswith('--parallel 1 ') for g in grid) and all(g['torch_threads'] >= 1 for g in grid)

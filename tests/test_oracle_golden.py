@@ -164,3 +164,24 @@ def test_benched_shape_fixture_is_the_benchmark_configuration(golden):
     assert keys.count('critic/loss') == 320
     a = bench_shape.driving_actions(3, 4096, 6)
     assert a.dtype == np.float32 and a.min() >= -1.25 and a.max() < 1.25 and (np.abs(a) > 1).any()
+
+
+def test_parallel_worker_grid_equals_sequential():
+    """The forked P x M grid (distributed.py:69-155) returns what one sequential group of
+    P * M environments returns: same seeds (seed + j), group-major order."""
+    seq = port.VectorEnv(5, 2, 6, 7)
+    par = port.ParallelVectorEnv(5, 2, 3, 2, 7)
+    seq.initialize(11)
+    par.initialize(11)
+    try:
+        np.testing.assert_array_equal(seq.start(), par.start())
+        rs = np.random.RandomState(0)
+        for _ in range(20):
+            a = rs.normal(size=(6, 2)).astype(np.float32)
+            o1, i1 = seq.step(a)
+            o2, i2 = par.step(a)
+            np.testing.assert_array_equal(o1, o2)
+            for k in i1:
+                np.testing.assert_array_equal(i1[k], i2[k], err_msg=k)
+    finally:
+        par.close()
