@@ -343,13 +343,19 @@ int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2
  * d_flat[n_params] (sums over rows: the caller scales by 1 / rows in tb_adam_step with
  * n_split = 1).  d_gpart: [n_split, n_params] scratch; d_sync: one zero-initialised uint64
  * per network (grid-barrier counter).  Needs hidden == 256, d_in <= 31, n_out <= 8,
- * n_out + n_extra <= 16.                                                                  */
+ * n_out + n_extra <= 12.
+ * opt != NULL (single process, no gradient clipping): the reduction phase also performs the
+ * optimizer step of tb_adam_step on its slice -- g = grad_scale * flat[i], Adam, refresh of
+ * d_packed, and the same device-side controls (d_stats / kl_threshold / d_stop) -- so the
+ * chain forward -> backward -> weight gradients + Adam is three launches.                   */
 int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float* d_h1_hi,
                        const float* d_h1_lo, const float* d_h2, const float* d_dz1,
                        const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
                        int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
                        float* d_gpart, int32_t n_split, float* d_flat, uint64_t* d_sync,
-                       int32_t passes, const int32_t* d_skip, void* stream);
+                       int32_t passes, const TbAdam* opt, float* d_packed, float grad_scale,
+                       const double* d_stats, float kl_threshold, int32_t* d_stop,
+                       const int32_t* d_skip, void* stream);
 
 /* ---- global-norm gradient clipping ---------------------------------------------
  * Reference: torch.nn.utils.clip_grad_norm_(self.variables, self.gradient_clip) between

@@ -296,7 +296,8 @@ def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_s
         flat = torch.full((layout.n_params,), float('nan'), device='cuda')
         _lib.call('tb_mlp_wgrad_fused', ctypes.byref(sh), K.ptr(dev[0]), K.ptr(h1_hi), K.ptr(h1_lo),
                   K.ptr(dev[1]), K.ptr(dev[2]), K.ptr(dz2_hi), K.ptr(dz2_lo), K.ptr(dev[3]), ld, n_extra,
-                  off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), passes, None, K.stream())
+                  off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), passes,
+                  None, None, 0.0, None, -1.0, None, None, K.stream())
         torch.cuda.synchronize()
         outs.append(flat.cpu())
     assert torch.equal(outs[0], outs[1])
@@ -313,3 +314,68 @@ def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_s
     err_w = (got - ref)[used & ~narrow].abs().max().item()
     assert err_n <= 2e-6 * scale * (rows ** 0.5) + 1e-5, (err_n, scale)       # FFMA part: fp32 in any mode
     assert err_w <= tol + 1e-5, (err_w, scale)
+
+
+@pytest.mark.parametrize('n_out,n_extra,with_stats', [(1, 0, False), (6, 6, True)])
+def test_wgrad_fused_adam_equals_separate_step(K, n_out, n_extra, with_stats):
+    """The optimizer step inside tb_mlp_wgrad_fused (reduction phase) is bit-identical to
+    tb_adam_step on the flat gradient: parameters, moments, packed operands, step counter and
+    the device-side PPO controls (zero-advantage skip, KL stop flag)."""
+    import ctypes
+    from tonic_b200 import _lib
+    rows, n_split, d_in = 4096, 74, 17
+    extras = [('log_scale', n_extra)] if n_extra else ()
+    g = torch.Generator().manual_seed(7)
+    data = dict(xin=torch.randn(rows, 20, generator=g), h2=torch.randn(rows, 256, generator=g),
+                dz1=torch.randn(rows, 256, generator=g) * 0.1, dout=torch.randn(rows, n_out + n_extra, generator=g),
+                h1=torch.tanh(torch.randn(rows, 256, generator=g)), dz2=torch.randn(rows, 256, generator=g) * 0.1)
+    dev = {k: v.cuda() for k, v in data.items()}
+    h1_hi, h1_lo = split(K, dev['h1'])
+    dz2_hi, dz2_lo = split(K, dev['dz2'])
+    init = torch.randn(K.MlpLayout(d_in, 256, n_out, 'tanh', extras).n_params, generator=g) * 0.1
+
+    def run(fused, stats_vec):
+        layout = K.MlpLayout(d_in, 256, n_out, 'tanh', extras)
+        net = K.DeviceMlp(layout)
+        net.params.copy_(init)
+        net.pack()
+        adam = K.Adam(net.params, lr=1e-3)
+        adam.m.copy_(init * 0.01)
+        adam.v.copy_(init.abs() * 0.001)
+        gpart = torch.zeros(n_split, layout.n_params, device='cuda')
+        flat = torch.zeros(layout.n_params, device='cuda')
+        sync = torch.zeros(1, dtype=torch.int64, device='cuda')
+        stats = None if stats_vec is None else torch.tensor(stats_vec, dtype=torch.float64, device='cuda')
+        stop = torch.zeros(1, dtype=torch.int32, device='cuda')
+        off_extra = layout.offsets['log_scale'][0] if n_extra else 0
+        for _ in range(2):        # two steps: the step counter advances
+            opt = ctypes.byref(adam.struct) if fused else None
+            _lib.call('tb_mlp_wgrad_fused', ctypes.byref(layout.shape), K.ptr(dev['xin']), K.ptr(h1_hi),
+                      K.ptr(h1_lo), K.ptr(dev['h2']), K.ptr(dev['dz1']), K.ptr(dz2_hi), K.ptr(dz2_lo),
+                      K.ptr(dev['dout']), n_out + n_extra, n_extra, off_extra, rows, K.ptr(gpart), n_split,
+                      K.ptr(flat), K.ptr(sync), 3, opt, K.ptr(net.packed) if fused else None,
+                      1.0 / rows if fused else 0.0, K.ptr(stats) if fused else None,
+                      0.015 if fused and stats is not None else -1.0, K.ptr(stop) if fused else None,
+                      None, K.stream())
+            if not fused:
+                adam.step(net, flat, 1, 1.0 / rows, stats=stats, kl_threshold=0.015 if stats is not None else -1.0,
+                          stop=stop)
+        torch.cuda.synchronize()
+        return [t.cpu().clone() for t in (net.params, adam.m, adam.v, net.packed, adam.step_count, stop)]
+
+    cases = [None]
+    if with_stats:
+        live = [0.0] * _lib.STAT_COUNT
+        live[_lib.STAT_ROWS], live[_lib.STAT_NONZERO_ADV], live[_lib.STAT_KL] = rows, rows, 0.02 * rows
+        dead = list(live)
+        dead[_lib.STAT_NONZERO_ADV] = 0.0
+        cases = [live, dead]
+    for stats_vec in cases:
+        a, b = run(True, stats_vec), run(False, stats_vec)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        if stats_vec is None or stats_vec[_lib.STAT_NONZERO_ADV] > 0:
+            assert int(a[4][0]) == 2 and not torch.equal(a[0], init)
+            assert int(a[5][0]) == (1 if stats_vec is not None else 0)       # kl 0.02 > 0.015 -> stop
+        else:
+            assert int(a[4][0]) == 0 and torch.equal(a[0], init) and int(a[5][0]) == 0

@@ -117,7 +117,8 @@ _PROTOTYPES = {
     'tb_mlp_wgrad_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                 c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_mlp_wgrad_fused': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
-                                   c_i32, c_i32, c_i64, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+                                   c_i32, c_i32, c_i64, c_vp, c_i32, c_vp, c_vp, c_i32, _P(TbAdam), c_vp,
+                                   c_f, c_vp, c_f, c_vp, c_vp, c_vp]),
     'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp,
                                c_vp]),
     'tb_permutation': (c_int, [c_u64, c_u64, c_vp, c_i64, c_vp, c_vp]),

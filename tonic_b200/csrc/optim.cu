@@ -7,37 +7,9 @@
 // tonic/torch/updaters/critics.py:9-10,59-60,143-144,190-191 (betas 0.9/0.999,
 // eps 1e-8, no weight decay); early stop tonic/torch/agents/ppo.py:45-46 with
 // updaters/actors.py:103,112; soft update models/actor_critics.py:68-72,126-130.
-#include "common.cuh"
+#include "adam.cuh"
 
 namespace tb {
-
-__device__ __forceinline__ void pack_one(const TbMlpShape& sh, int i, float p, float* packed) {
-    const int H = sh.hidden;
-    if (i >= sh.off_w1 && i < sh.off_w1 + H * sh.d_in) {           // W1 [H, d_in] -> W1T [d_in, H]
-        const int e = i - sh.off_w1, n = e / sh.d_in, k = e % sh.d_in;
-        packed[sh.off_w1t + k * H + n] = p;
-        if (sh.off_w1_img_hi > 0) {
-            // layer-1 B operand of the fused forward kernel (csrc/tc_mlp.cu): element (n, k) of
-            // the K-major [256 x 32] tile with the 128-byte swizzle (8-row groups of 1024 B, 16-byte
-            // unit index XOR-ed with the row within the group); columns k >= d_in stay zero
-            const int word = (n >> 3) * 256 + (n & 7) * 32 + (((k >> 2) ^ (n & 7)) << 2) + (k & 3);
-            const float hi = __uint_as_float(__float_as_uint(p) & 0xFFFFE000u);
-            packed[sh.off_w1_img_hi + word] = hi;
-            packed[sh.off_w1_img_lo + word] = p - hi;
-        }
-    } else if (i >= sh.off_w2 && i < sh.off_w2 + H * H) {          // W2 [H, H] -> W2T
-        const int e = i - sh.off_w2, n = e / H, k = e % H;
-        packed[sh.off_w2t + k * H + n] = p;
-        if (sh.off_w2_hi > 0) {      // tf32 splits for the tensor-core path (csrc/tc_gemm.cu)
-            const float hi = __uint_as_float(__float_as_uint(p) & 0xFFFFE000u);
-            const float lo = p - hi;
-            packed[sh.off_w2_hi + e] = hi;
-            packed[sh.off_w2_lo + e] = lo;
-            packed[sh.off_w2t_hi + k * H + n] = hi;
-            packed[sh.off_w2t_lo + k * H + n] = lo;
-        }
-    }
-}
 
 __global__ void __launch_bounds__(256)
 adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
@@ -50,12 +22,7 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
     // bias corrections once per block (two double-precision pow() per thread were a third of
     // this kernel's instructions)
     __shared__ float s_step_size, s_bc2_sqrt;
-    if (threadIdx.x == 0) {
-        const double bc1 = 1.0 - pow(opt.beta1, (double)t);
-        const double bc2 = 1.0 - pow(opt.beta2, (double)t);
-        s_step_size = (float)(opt.lr / bc1);
-        s_bc2_sqrt = (float)sqrt(bc2);
-    }
+    if (threadIdx.x == 0) adam_corrections(opt, t, &s_step_size, &s_bc2_sqrt);
     __syncthreads();
     if (i < opt.n_params) {
         // one parameter per thread keeps ~72k threads in flight; the n_split partial loads
@@ -82,17 +49,7 @@ adam_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed,
         }
         for (; s < n_split; ++s) g0 += gpart[(size_t)s * opt.n_params + i];
         const float g = ((g0 + g1) + (g2 + g3)) * grad_scale;
-        // torch/optim/adam.py::_single_tensor_adam
-        const float w1 = (float)(1.0 - opt.beta1), w2 = (float)(1.0 - opt.beta2);
-        const float m = opt.d_m[i] + w1 * (g - opt.d_m[i]);                          // lerp_
-        const float v = opt.d_v[i] * (float)opt.beta2 + w2 * g * g;                  // mul_.addcmul_
-        const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
-        const float denom = sqrtf(v) / bc2_sqrt + (float)opt.eps;
-        const float p = opt.d_params[i] - step_size * (m / denom);                   // addcdiv_
-        opt.d_m[i] = m;
-        opt.d_v[i] = v;
-        opt.d_params[i] = p;
-        if (packed) pack_one(sh, i, p, packed);
+        adam_apply(opt, sh, packed, i, g, s_step_size, s_bc2_sqrt);
     }
     // last block to finish publishes the new step count and the KL early-stop flag
     __shared__ bool is_last;
@@ -343,27 +300,17 @@ adam_peers_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed, TbPeers
         s_stats[threadIdx.x] = s;
         if (blockIdx.x == 0 && d_stats) d_stats[threadIdx.x] = s;      // global statistics
     }
+    __shared__ float s_step_size, s_bc2_sqrt;
+    const int t = opt.d_step[0] + 1;
+    if (threadIdx.x == 0) adam_corrections(opt, t, &s_step_size, &s_bc2_sqrt);
     __syncthreads();
     const bool do_step = !(use_stats && s_stats[TB_STAT_NONZERO_ADV] == 0.0);   // actors.py:22,71
-    const int t = opt.d_step[0] + 1;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (do_step && i < n_params) {
         float g = 0.0f;
         for (int r = 0; r < peers.world; ++r) g += __ldcv(peer_grad(peers.base[r], slot, n_params) + i);
         g *= grad_scale;
-        const float w1 = (float)(1.0 - opt.beta1), w2 = (float)(1.0 - opt.beta2);
-        const float m = opt.d_m[i] + w1 * (g - opt.d_m[i]);
-        const float v = opt.d_v[i] * (float)opt.beta2 + w2 * g * g;
-        const double bc1 = 1.0 - pow(opt.beta1, (double)t);
-        const double bc2 = 1.0 - pow(opt.beta2, (double)t);
-        const float step_size = (float)(opt.lr / bc1);
-        const float bc2_sqrt = (float)sqrt(bc2);
-        const float denom = sqrtf(v) / bc2_sqrt + (float)opt.eps;
-        const float p = opt.d_params[i] - step_size * (m / denom);
-        opt.d_m[i] = m;
-        opt.d_v[i] = v;
-        opt.d_params[i] = p;
-        if (packed) pack_one(sh, i, p, packed);
+        adam_apply(opt, sh, packed, i, g, s_step_size, s_bc2_sqrt);
     }
     __shared__ bool is_last;
     __threadfence();

@@ -27,6 +27,7 @@
 // grade, which keeps the 1e-4 loss parity with the reference's fp32 CPU path.
 // PASSES = 1 is plain TF32 (fast mode).
 #include "tc_common.cuh"
+#include "adam.cuh"
 
 namespace tb {
 
@@ -497,7 +498,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_cons
 constexpr int TCA_THREADS = 512;
 constexpr int TCA_NARROW_WARP0 = 8;          // warps 8..15
 constexpr int TCA_NO = 8;                    // head outputs with a dW3 row (n_out <= 8)
-constexpr int TCA_ND = 16;                   // dout columns with a column sum (n_out + extras <= 16)
+constexpr int TCA_ND = 12;                   // dout columns with a column sum (n_out + extras <= 12)
+// dynamic shared memory: operand stages | epilogue staging / exchange block | ones block (4 KB)
+// | xin rows of two chunks | alignment slack + barriers
+template <int PASSES, int KIN>
+constexpr int tca_smem_bytes() {
+    return TcCfg<PASSES>::STAGES * TcCfg<PASSES>::STAGE_BYTES + TcCfg<PASSES>::EPI_BYTES + 4096 +
+           2 * 32 * KIN * 4 + 1024 + 256;
+}
 
 struct TcWgradAllParams {
     TcWgradParams w;            // tensor-core part (gpart, n_params, off_w2, off_b2, rows_per_split)
@@ -510,6 +518,15 @@ struct TcWgradAllParams {
     int n_split;
     float* flat;                // [n_params] reduced gradient (sum over rows)
     unsigned long long* sync;   // grid-barrier counter (monotonic)
+    // optional fused optimizer step (single process, no gradient clipping): the reduction phase
+    // applies Adam to its slice right away -- same arithmetic and device-side controls as adam_kernel
+    int fuse_adam;
+    TbAdam opt;
+    float* packed;
+    float grad_scale;
+    const double* stats;        // minibatch statistics (PPO controls) or NULL
+    float kl_threshold;
+    int32_t* stop;
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned int n_ctas) {
@@ -539,11 +556,10 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    // HEAD_BYTES region (9 KB): [8 x 32] ones block, then the narrow warps' staging
+    // [8 x 32] block of ones (B operand of the bias-gradient MMAs), then the narrow warps' xin rows
     float* ones = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
-    float* xs = ones + 256;                              // [2][32][KIN]   <= 2 * 32 * 32 * 4 = 8 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
-                                                 Cfg::HEAD_BYTES);
+    float* xs = ones + 1024;                             // [2][32][KIN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * 32 * KIN);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + Cfg::STAGES;
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
@@ -571,7 +587,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                          smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < 256; i += TCA_THREADS) ones[i] = 1.0f;
+    for (int i = threadIdx.x; i < 1024; i += TCA_THREADS) ones[i] = 1.0f;
     fence_proxy_async_smem();
     tcgen05_fence_before();
     __syncthreads();
@@ -796,6 +812,11 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     const int lo = b * per, hi = min(p.n_params, lo + per);
     float* red = reinterpret_cast<float*>(smem);          // [3][128] partial sums of lanes 1..3 (stages are idle)
     const int qd = threadIdx.x >> 7, e = threadIdx.x & 127;       // 4 quarter-sums x 128 parameters per pass
+    // fused Adam (updaters/actors.py:22,71: no step when every advantage of the minibatch is zero)
+    const bool do_step = q.fuse_adam && !(q.stats && q.stats[TB_STAT_NONZERO_ADV] == 0.0);
+    const int t_step = q.fuse_adam ? q.opt.d_step[0] + 1 : 0;
+    float* s_corr = red + 3 * 128;                        // step_size, bc2_sqrt
+    if (do_step && threadIdx.x == 0) adam_corrections(q.opt, t_step, &s_corr[0], &s_corr[1]);
     for (int i0 = lo; i0 < hi; i0 += 128) {
         const int i = i0 + e;
         float acc = 0.0f;
@@ -814,7 +835,30 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         __syncthreads();
         if (qd > 0) red[(qd - 1) * 128 + e] = acc;
         __syncthreads();
-        if (qd == 0 && i < hi) q.flat[i] = (acc + red[e]) + (red[128 + e] + red[256 + e]);
+        if (qd == 0 && i < hi) {
+            const float g = (acc + red[e]) + (red[128 + e] + red[256 + e]);
+            q.flat[i] = g;
+            if (do_step) adam_apply(q.opt, q.sh, q.packed, i, g * q.grad_scale, s_corr[0], s_corr[1]);
+        }
+    }
+    if (q.fuse_adam) {
+        // last CTA to finish publishes the new step count and the KL early-stop flag
+        // (ppo.py:45-46 with updaters/actors.py:103,112), exactly like adam_kernel
+        __shared__ bool is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(&q.opt.d_step[1], 1) == (int)n_ctas - 1;
+        __syncthreads();
+        if (is_last && threadIdx.x == 0) {
+            q.opt.d_step[1] = 0;
+            if (do_step) {
+                q.opt.d_step[0] = t_step;
+                if (q.stop && q.stats && q.kl_threshold >= 0.0f) {
+                    const float kl = (float)(q.stats[TB_STAT_KL] / q.stats[TB_STAT_ROWS]);
+                    if (kl > q.kl_threshold) *q.stop = 1;
+                }
+            }
+        }
     }
 }
 
@@ -948,14 +992,19 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
                                   const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
                                   int32_t ld_dout, int32_t n_extra, int32_t off_extra, int64_t n_rows,
                                   float* d_gpart, int32_t n_split, float* d_flat, uint64_t* d_sync,
-                                  int32_t passes, const int32_t* d_skip, void* stream) {
+                                  int32_t passes, const TbAdam* opt, float* d_packed, float grad_scale,
+                                  const double* d_stats, float kl_threshold, int32_t* d_stop,
+                                  const int32_t* d_skip, void* stream) {
     using namespace tb;
+    TB_REQUIRE(!opt || (opt->d_params && opt->d_m && opt->d_v && opt->d_step && shape &&
+                        opt->n_params == shape->n_params), TB_EINVAL,
+               "tb_mlp_wgrad_fused: optimizer / shape mismatch");
     TB_REQUIRE(shape && d_xin && d_h1_hi && d_h1_lo && d_h2 && d_dz1 && d_dz2_hi && d_dz2_lo && d_dout &&
                d_gpart && d_flat && d_sync && n_rows > 0, TB_EINVAL, "tb_mlp_wgrad_fused: null pointer");
     TB_REQUIRE(shape->hidden == 256 && shape->off_w2_hi > 0 && shape->d_in + 1 <= 32 &&
                shape->n_out >= 1 && shape->n_out <= TCA_NO && shape->n_out + n_extra <= TCA_ND &&
                ld_dout >= shape->n_out + n_extra, TB_ENOTSUP,
-               "tb_mlp_wgrad_fused: needs hidden == 256, d_in <= 31, n_out <= 8, n_out + extras <= 16");
+               "tb_mlp_wgrad_fused: needs hidden == 256, d_in <= 31, n_out <= 8, n_out + extras <= 12");
     TB_REQUIRE(n_split >= 1 && 2 * n_split <= kNumSMs, TB_EINVAL,
                "tb_mlp_wgrad_fused: 2 * n_split CTAs must be resident together (<= %d)", kNumSMs);
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_mlp_wgrad_fused: passes must be 1 or 3");
@@ -976,6 +1025,10 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     q.sh = *shape; q.xin = d_xin; q.h2 = d_h2; q.dz1 = d_dz1; q.dout = d_dout; q.ld_dout = ld_dout;
     q.n_extra = n_extra; q.off_extra = off_extra; q.n_split = n_split; q.flat = d_flat;
     q.sync = reinterpret_cast<unsigned long long*>(d_sync);
+    q.fuse_adam = opt != nullptr;
+    if (opt) q.opt = *opt; else memset(&q.opt, 0, sizeof(q.opt));
+    q.packed = d_packed; q.grad_scale = grad_scale; q.stats = d_stats; q.kl_threshold = kl_threshold;
+    q.stop = d_stop;
     dim3 grid(TC_BN / TC_BM, n_split);
     cudaStream_t s = as_stream(stream);
     ProfScope prof_scope("tb_mlp_wgrad_fused", stream);
@@ -985,10 +1038,10 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
         static bool configured = false;                                                              \
         if (!configured) {                                                                           \
             cudaFuncSetAttribute(tc_wgrad_all_kernel<P_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 TcCfg<P_>::SMEM_BYTES);                                             \
+                                 tca_smem_bytes<P_, K_>());                                          \
             configured = true;                                                                       \
         }                                                                                            \
-        tc_wgrad_all_kernel<P_, K_><<<grid, TCA_THREADS, TcCfg<P_>::SMEM_BYTES, s>>>(                \
+        tc_wgrad_all_kernel<P_, K_><<<grid, TCA_THREADS, tca_smem_bytes<P_, K_>(), s>>>(             \
             maps[0], maps[1], maps[2], maps[3], q);                                                  \
     }
     if (passes == 3) { if (small_in) TB_WGRAD_ALL(3, 20) else TB_WGRAD_ALL(3, 32) }

@@ -169,6 +169,7 @@ class MlpInput:
 _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 _FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
 _FUSED_WGRAD = os.environ.get('TONIC_B200_FUSED_WGRAD', '1') != '0'
+_FUSED_ADAM = os.environ.get('TONIC_B200_FUSED_ADAM', '1') != '0'
 
 
 class DeviceMlp:
@@ -233,7 +234,7 @@ class DeviceMlp:
         (csrc/tc_gemm.cu::tc_wgrad_all_kernel)."""
         L = self.layout
         return (bool(self.passes()) and _FUSED_WGRAD and L.d_in + 1 <= 32 and L.n_out <= 8
-                and L.n_out + n_extra <= 16)
+                and L.n_out + n_extra <= 12)
 
     def splits_for(self, rows, n_extra=0):
         """Row splits of the weight-gradient partial sums.  Tensor-core path: 2 column tiles x
@@ -326,7 +327,10 @@ class DeviceMlp:
                   ptr(self.h1), ptr(self.h2), rows, ptr(self.dz2), ptr(self.dz1), ptr(dx),
                   dx_col0, 0 if dx is None else dx.shape[-1], ptr(skip), stream())
 
-    def wgrad(self, dout, rows, n_split, n_extra=0, off_extra=0, skip=None):
+    def wgrad(self, dout, rows, n_split, n_extra=0, off_extra=0, skip=None, fuse=None):
+        """`fuse` = (adam, grad_scale, stats, kl_threshold, stop): the fused kernel also runs the
+        optimizer step (single process, no clipping); `self.applied` tells the caller."""
+        self.applied = False
         gpart = self.gpart(n_split)
         L = self.layout
         flops = 2.0 * rows * (L.hidden * L.hidden + L.hidden * (L.d_in + 2)
@@ -339,12 +343,18 @@ class DeviceMlp:
             if getattr(self, '_wgrad_sync', None) is None:
                 self._wgrad_sync = torch.zeros(1, dtype=torch.int64, device=device())
             flat = self.flat_grad()
+            opt = packed = stats = stop = None
+            scale, kl = 0.0, -1.0
+            if fuse is not None:
+                adam, scale, stats, kl, stop = fuse
+                opt, packed = ctypes.byref(adam.struct), self.packed
             _lib.call('tb_mlp_wgrad_fused', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
                       ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
                       ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
-                      ptr(gpart), n_split, ptr(flat), ptr(self._wgrad_sync), passes, ptr(skip),
-                      stream())
+                      ptr(gpart), n_split, ptr(flat), ptr(self._wgrad_sync), passes, opt,
+                      ptr(packed), scale, ptr(stats), kl, ptr(stop), ptr(skip), stream())
             self.reduced = True
+            self.applied = fuse is not None
             return flat
         self.reduced = False
         if passes:
@@ -431,6 +441,27 @@ class GradientClipper:
 
 def make_clipper(gradient_clip):
     return GradientClipper(gradient_clip) if gradient_clip and gradient_clip > 0 else None
+
+
+def wgrad_and_apply(adam, mlp, dout, rows, rows_global, n_extra=0, off_extra=0, skip=None,
+                    stats=None, kl_threshold=-1.0, stop=None, reduce_stats=None, clip=None):
+    """Weight gradients of the minibatch whose activations `mlp` holds, then the optimizer step
+    (loss.backward() ... optimizer.step(), e.g. updaters/critics.py:23-26).  Single process without
+    gradient clipping on the tensor-core path: ONE launch (weight gradients, in-kernel reduction
+    and Adam).  Otherwise weight gradients -> [clip] -> [exchange] -> Adam (`apply_gradients`)."""
+    from . import distributed
+    n_split = mlp.splits_for(rows, n_extra)
+    gpart = None
+    if rows > 0:
+        fuse = None
+        if (_FUSED_ADAM and clip is None and distributed.world() == 1 and mlp.fused_wgrad(n_extra)):
+            fuse = (adam, 1.0 / rows_global, stats, kl_threshold, stop)
+        gpart = mlp.wgrad(dout, rows, n_split, n_extra=n_extra, off_extra=off_extra, skip=skip,
+                          fuse=fuse)
+        if mlp.applied:
+            return
+    apply_gradients(adam, mlp, gpart, n_split, rows, rows_global, skip=skip, stats=stats,
+                    kl_threshold=kl_threshold, stop=stop, reduce_stats=reduce_stats, clip=clip)
 
 
 def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=None, stats=None,

@@ -52,8 +52,7 @@ class _GaussianPolicyUpdater:
         size of the whole minibatch (the mean's denominator)."""
         actor, net = self.actor, self.actor.network
         A = actor.action_size
-        n_split = net.mlp.splits_for(rows)
-        gpart = None
+        dout = None
         if rows > 0:
             pre, dout = self._scratch(rows)
             actor.pre_activations(observations, out=pre, idx=idx, rows=rows, save=True, skip=stop)
@@ -61,11 +60,9 @@ class _GaussianPolicyUpdater:
                                       log_probs, idx, rows, dout, stats, self.ratio_clip,
                                       self.entropy_coeff, skip=stop)
             net.mlp.backward(dout, rows, skip=stop)
-            gpart = net.mlp.wgrad(dout, rows, n_split, n_extra=A,
-                                  off_extra=net.extra_offset('log_scale'), skip=stop)
-        kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
-                                skip=stop, stats=stats, kl_threshold=self.kl_threshold, stop=stop,
-                                clip=self.clipper)
+        kernels.wgrad_and_apply(self.adam, net.mlp, dout, rows, rows_global or rows, n_extra=A,
+                                off_extra=net.extra_offset('log_scale'), skip=stop, stats=stats,
+                                kl_threshold=self.kl_threshold, stop=stop, clip=self.clipper)
 
     def infos(self, s):
         """Statistics block (host copy) -> the reference's info dict (python floats)."""
@@ -144,13 +141,10 @@ class _CriticGradientUpdater:
 
     def _finish(self, rows, stats, rows_global=None):
         net = self.actor.network
-        n_split = net.mlp.splits_for(rows)
-        gpart = None
         if rows > 0:
             net.mlp.backward(self._dout, rows)
-            gpart = net.mlp.wgrad(self._dout, rows, n_split)
-        kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
-                                reduce_stats=stats, clip=self.clipper)
+        kernels.wgrad_and_apply(self.adam, net.mlp, self._dout if rows > 0 else None, rows,
+                                rows_global or rows, reduce_stats=stats, clip=self.clipper)
 
     @staticmethod
     def infos(s):

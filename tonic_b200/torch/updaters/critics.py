@@ -35,8 +35,7 @@ class VRegression:
 
     def launch(self, observations, returns, idx, rows, stats, rows_global=None):
         critic, net = self.critic, self.critic.network
-        n_split = net.mlp.splits_for(rows)
-        gpart = None
+        dout = None
         if rows > 0:
             values, dout = self._scratch(rows)
             # the tensor-core forward kernel evaluates the squared-error loss in its epilogue
@@ -45,8 +44,7 @@ class VRegression:
             if not net.mlp.vloss_fused:
                 kernels.mse_loss(values, returns, idx, rows, dout, stats)
             net.mlp.backward(dout, rows)
-            gpart = net.mlp.wgrad(dout, rows, n_split)
-        kernels.apply_gradients(self.adam, net.mlp, gpart, n_split, rows, rows_global or rows,
+        kernels.wgrad_and_apply(self.adam, net.mlp, dout, rows, rows_global or rows,
                                 reduce_stats=stats, clip=self.clipper)
 
     @staticmethod
@@ -148,16 +146,13 @@ class _QLearning:
                          discounts=replay.flat('discounts') if replay.return_steps > 1 else None)
         for k, critic in enumerate(self.critics):               # critics.py:77-84,169-179
             net = critic.network
-            n_split = net.mlp.splits_for(rows)
             critic.values(obs, acts, out=self._values[k][:rows], idx=idx, rows=rows, save=True)
             kernels.mse_loss(self._values[k], self._targets, None, rows, self._dout, stats,
                              stat_slot=_lib.STAT_VALUE if k == 0 else _lib.STAT_VALUE2,
                              count_rows=(k == 0))
             net.mlp.backward(self._dout, rows)
-            gpart = net.mlp.wgrad(self._dout, rows, n_split)
             # the statistics block is all-reduced once (with the last critic)
-            kernels.apply_gradients(self.adams[k], net.mlp, gpart, n_split, rows,
-                                    rows_global or rows,
+            kernels.wgrad_and_apply(self.adams[k], net.mlp, self._dout, rows, rows_global or rows,
                                     reduce_stats=stats if k == len(self.critics) - 1 else None,
                                     clip=self.clipper)
         if self.clipper:
