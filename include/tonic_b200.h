@@ -76,7 +76,15 @@ typedef struct {
      * a reset); 0 = off.  Observation arrays are then [N, obs_dim + 1].             */
     int32_t time_feature;
     float time_low, time_high;
+    /* Task: TB_TASK_SYNTH = SynthControl(O, A) (d_state, float32 [N, O]); the closed-form
+     * classic-control tasks behind Gym(name) (environments/builders.py:12-16) keep a float64
+     * state [N, 2] in d_state64: TB_TASK_PENDULUM (theta, theta_dot; obs 3, act 1),
+     * TB_TASK_MOUNTAIN_CAR (position, velocity; obs 2, act 1).  Their ActionRescaler bounds
+     * (wrappers.py:7-22) are part of the task.                                            */
+    int32_t task;
+    double* d_state64;
 } TbEnv;
+enum { TB_TASK_SYNTH = 0, TB_TASK_PENDULUM = 1, TB_TASK_MOUNTAIN_CAR = 2 };
 
 /* Sequential.start (:22-26): reset every env, lengths=0, writes obs [N,O]
  * ([N,O+1] with the time feature).                                           */

@@ -425,3 +425,38 @@ def test_device_permutation_is_a_bijection(K):
             # minibatch slices cover the index range evenly
             chunk = host[:n // 8]
             assert abs(chunk.mean() / n - 0.5) < 0.05
+
+
+@pytest.mark.parametrize('name,steps', [('Pendulum-v1', 450), ('MountainCarContinuous-v0', 1200)])
+@pytest.mark.parametrize('time_feature', [False, True])
+def test_classic_control_device_env_is_bit_exact_vs_numpy(name, steps, time_feature):
+    """Gym(name) as a device kernel (csrc/classic_env.cu) against the numpy
+    restatement (environments/classic.py) under the reference's Sequential semantics
+    (distributed.py:28-58): observations, rewards, resets, terminations bit-exact, including
+    time-outs, terminations and the counter-based reset stream."""
+    import tonic_b200
+    from tonic_b200.environments import classic, host
+    N, seed = 37, 11
+    build = lambda: classic.Gym(name, time_feature=time_feature)     # noqa: E731
+    dev = tonic_b200.environments.distribute(build, 1, N)
+    assert isinstance(dev, tonic_b200.environments.DeviceVectorEnvironment)
+    ref = host.distribute_host(build, 1, N)
+    dev.initialize(seed=seed)
+    ref.initialize(seed=seed)
+    assert dev.max_episode_steps == ref.max_episode_steps
+    np.testing.assert_array_equal(dev.start(host=True), ref.start())
+    rs = np.random.RandomState(3)
+    resets = terms = 0
+    for t in range(steps):
+        # a slowly varying push (MountainCar needs a consistent strategy to reach the goal)
+        a = (np.sin(0.05 * t + np.arange(N))[:, None] * 1.3 + 0.2 * rs.normal(size=(N, 1))).astype(np.float32)
+        o1, i1 = dev.step(a)
+        o2, i2 = ref.step(a)
+        np.testing.assert_array_equal(o1, o2, err_msg=f'step {t}')
+        for k in ('observations', 'rewards', 'resets', 'terminations'):
+            np.testing.assert_array_equal(i1[k], i2[k], err_msg=f'{k} step {t}')
+        resets += int(i1['resets'].sum())
+        terms += int(i1['terminations'].sum())
+    assert resets >= N                        # every environment hit its time limit / goal at least once
+    if name.startswith('MountainCar'):
+        assert terms > 0                      # true terminations were exercised

@@ -48,3 +48,66 @@ def test_train_cli_learns_and_checkpoints(tmp_path, monkeypatch):
                                    'save_steps=int(1e6), test_episodes=1, show_progress=False)',
                            path=run, **common2)
     assert trainer2.steps >= int(1e5)
+
+
+def _reward_curve(seed, fast, iterations=20):
+    """Mean per-step reward of every collected segment of one PPO run (2 x 256 tanh MLPs, 256
+    environments, T = 64, 4 epochs x 8 minibatches of 2048) in parity mode (host torch / numpy
+    RNG streams, eager launches) or in the benchmarked fast mode (device Philox noise, device
+    Feistel permutations, CUDA-graph replay)."""
+    import tonic_b200
+    import tonic_b200.torch
+    from tonic_b200 import config
+    from tonic_b200.utils import logger
+    m, n = tonic_b200.torch.models, tonic_b200.torch.normalizers
+    config.noise = config.indices = 'device' if fast else 'host'
+    logger.store = lambda *a, **k: None
+    spec = tonic_b200.environments.SynthControl('HalfCheetah', max_episode_steps=100)
+    env = tonic_b200.environments.distribute(lambda: spec, 1, 256)
+    env.initialize(seed=seed)
+    model = m.ActorCritic(
+        actor=m.Actor(encoder=m.ObservationEncoder(), torso=m.MLP((256, 256), torch.nn.Tanh),
+                      head=m.DetachedScaleGaussianPolicyHead()),
+        critic=m.Critic(encoder=m.ObservationEncoder(), torso=m.MLP((256, 256), torch.nn.Tanh),
+                        head=m.ValueHead()),
+        observation_normalizer=n.MeanStd())
+    agent = tonic_b200.torch.agents.PPO(
+        model=model, replay=tonic_b200.replays.Segment(size=64, batch_iterations=4, batch_size=2048))
+    agent.initialize(env.observation_space, env.action_space, seed=seed)
+    env.start()
+    curve = []
+    inner = agent._update
+
+    def record_then_update():
+        curve.append(float(agent.replay.buffers['rewards'].mean().item()))
+        inner()
+    agent._update = record_then_update
+    for _ in range(iterations):
+        assert agent.rollout(env, 64) == 64
+    return np.array(curve)
+
+
+def test_fast_mode_returns_stay_in_the_parity_mode_band():
+    """north_star: "returns matching reference within tolerance" for the BENCHED configuration.
+    The parity mode is pinned to the reference step by step (tests/test_gpu_agents.py); here the
+    fast mode's learning curves (5 seeds) must be statistically indistinguishable from the
+    parity mode's: same start, same improvement, final level within the seed-to-seed band."""
+    from tonic_b200 import config
+    saved = config.noise, config.indices
+    try:
+        parity = np.array([_reward_curve(s, fast=False) for s in range(5)])
+        fast = np.array([_reward_curve(s, fast=True) for s in range(5)])
+    finally:
+        config.noise, config.indices = saved
+    assert parity.shape == fast.shape == (5, 20)
+    # first segment: same initial policy and environments, only the noise stream differs
+    np.testing.assert_allclose(fast[:, 0].mean(), parity[:, 0].mean(), atol=0.15 * abs(parity[:, 0].mean()) + 0.05)
+    p_end, f_end = parity[:, -5:].mean(1), fast[:, -5:].mean(1)
+    gain_p, gain_f = p_end.mean() - parity[:, 0].mean(), f_end.mean() - fast[:, 0].mean()
+    assert gain_p > 0 and gain_f > 0, (gain_p, gain_f)            # both learn
+    band = 3.0 * (p_end.std() + f_end.std()) / np.sqrt(5) + 0.1 * abs(gain_p)
+    assert abs(f_end.mean() - p_end.mean()) <= band, (f_end, p_end, band)
+    # the whole curve of the fast mode lies inside the parity envelope widened by the same band
+    lo, hi = parity.min(0) - band, parity.max(0) + band
+    inside = ((fast.mean(0) >= lo) & (fast.mean(0) <= hi)).mean()
+    assert inside >= 0.9, (inside, fast.mean(0), lo, hi)

@@ -27,7 +27,7 @@ class TbEnv(ctypes.Structure):
                 ('d_state', c_vp), ('d_length', c_vp), ('d_episode', c_vp),
                 ('d_score', c_vp), ('d_ep_scores', c_vp), ('d_ep_lengths', c_vp),
                 ('d_ep_count', c_vp), ('log_cap', c_i32), ('time_feature', c_i32),
-                ('time_low', c_f), ('time_high', c_f)]
+                ('time_low', c_f), ('time_high', c_f), ('task', c_i32), ('d_state64', c_vp)]
 
 
 class TbMlpShape(ctypes.Structure):

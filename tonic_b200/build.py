@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libtonic_b200.so')
-SOURCES = ['api.cu', 'env_step.cu', 'returns.cu', 'moments.cu', 'mlp.cu', 'optim.cu',
+SOURCES = ['api.cu', 'env_step.cu', 'classic_env.cu', 'returns.cu', 'moments.cu', 'mlp.cu', 'optim.cu',
            'heads.cu', 'offpolicy.cu', 'tc_gemm.cu', 'tc_mlp.cu', 'host_rng.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']

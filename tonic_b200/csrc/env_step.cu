@@ -129,12 +129,29 @@ static int pick_tile(const TbEnv* env, size_t* smem_bytes) {
     return tile;
 }
 
+// closed-form classic-control tasks (csrc/classic_env.cu)
+int classic_env_start(const TbEnv* env, float* d_obs, cudaStream_t s);
+int classic_env_step(const TbEnv* env, const float* d_actions, float* d_obs, float* d_next_obs,
+                     float* d_rewards, float* d_resets, float* d_terminations, cudaStream_t s);
+
+static int check_task(const TbEnv* env, const char* who) {
+    if (env->task == TB_TASK_SYNTH) return 0;
+    TB_REQUIRE(env->task == TB_TASK_PENDULUM || env->task == TB_TASK_MOUNTAIN_CAR, TB_EINVAL,
+               "%s: unknown task %d", who, env->task);
+    TB_REQUIRE(env->d_state64 && env->act_dim == 1 &&
+               env->obs_dim == (env->task == TB_TASK_PENDULUM ? 3 : 2), TB_EINVAL,
+               "%s: classic task %d needs d_state64, act_dim 1 and its observation size", who, env->task);
+    return 0;
+}
+
 }  // namespace tb
 
 extern "C" int tb_env_start(const TbEnv* env, float* d_obs, void* stream) {
     tb::ProfScope prof_scope("tb_env_start", stream);
     TB_REQUIRE(env && d_obs && env->n_envs > 0 && env->obs_dim > 0 && env->act_dim > 0,
                TB_EINVAL, "tb_env_start: bad arguments");
+    if (int rc = tb::check_task(env, "tb_env_start")) return rc;
+    if (env->task != TB_TASK_SYNTH) return tb::classic_env_start(env, d_obs, tb::as_stream(stream));
     const int64_t total = (int64_t)env->n_envs * env->obs_dim;
     const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     cudaMemsetAsync(env->d_ep_count, 0, sizeof(unsigned long long), tb::as_stream(stream));
@@ -148,6 +165,10 @@ extern "C" int tb_env_step(const TbEnv* env, const float* d_actions, float* d_ob
     tb::ProfScope prof_scope("tb_env_step", stream);
     TB_REQUIRE(env && d_actions && d_obs && d_next_obs && d_rewards && d_resets && d_terminations,
                TB_EINVAL, "tb_env_step: null pointer");
+    if (int rc = tb::check_task(env, "tb_env_step")) return rc;
+    if (env->task != TB_TASK_SYNTH)
+        return tb::classic_env_step(env, d_actions, d_obs, d_next_obs, d_rewards, d_resets, d_terminations,
+                                    tb::as_stream(stream));
     size_t smem = 0;
     const int tile = tb::pick_tile(env, &smem);
     TB_REQUIRE(smem <= 200 * 1024, TB_ENOTSUP, "tb_env_step: obs_dim %d too large", env->obs_dim);

@@ -58,6 +58,8 @@ class DeviceVectorEnvironment:
         # output buffers (views handed to the caller)
         tf = bool(getattr(self.spec, 'time_feature', False))
         self.time_feature = tf
+        task = int(getattr(self.spec, 'task_id', 0))
+        self.state64 = torch.zeros(N, 2, dtype=torch.float64, device=dev) if task else None
         self.observations = torch.zeros(N, O + tf, dtype=torch.float32, device=dev)
         self.next_observations = torch.zeros(N, O + tf, dtype=torch.float32, device=dev)
         self.rewards = torch.zeros(N, dtype=torch.float32, device=dev)
@@ -70,7 +72,7 @@ class DeviceVectorEnvironment:
             d_length=ptr(self.lengths), d_episode=ptr(self.episodes), d_score=ptr(self.scores),
             d_ep_scores=ptr(self.episode_scores), d_ep_lengths=ptr(self.episode_lengths),
             d_ep_count=ptr(self.episode_count), log_cap=cap, time_feature=int(tf),
-            time_low=-1.0, time_high=1.0)
+            time_low=-1.0, time_high=1.0, task=task, d_state64=ptr(self.state64))
 
     def start(self, host=False):
         """Resets every environment; returns the first observations [N, O]."""
@@ -125,6 +127,28 @@ class DeviceVectorEnvironment:
         raise NotImplementedError('synthetic device environments have no renderer')
 
 
+class ClassicSpec:
+    """Device description of a closed-form classic-control task built by
+    `environments.Gym(name)` (environments/classic.py): same spaces / name / time limit, the
+    dynamics run in csrc/classic_env.cu (bit-identical to the numpy classes)."""
+
+    def __init__(self, wrapped):
+        self.task_id = int(wrapped.task_id)
+        self.name = wrapped.name
+        self.max_episode_steps = int(wrapped.max_episode_steps)
+        self.time_feature = bool(wrapped.time_feature)
+        self.observation_space = wrapped.observation_space
+        self.action_space = wrapped.action_space
+        self.observation_size = wrapped.environment.observation_space.shape[0]
+        self.action_size = wrapped.action_space.shape[0]
+
+
+def _classic_on_device():
+    """TONIC_B200_CLASSIC=host keeps Gym(name) tasks on the host worker grid."""
+    import os
+    return os.environ.get('TONIC_B200_CLASSIC', 'device') != 'host' and torch.cuda.is_available()
+
+
 def distribute(environment_builder, worker_groups=1, workers_per_group=1, single=False):
     """Same signature as the reference's `distribute`
     (tonic/environments/distributed.py:158-172).  `worker_groups *
@@ -133,6 +157,9 @@ def distribute(environment_builder, worker_groups=1, workers_per_group=1, single
     environment per process whatever the number of ranks (the test environment of
     train.py:88-91)."""
     spec = environment_builder()
+    if getattr(spec, 'task_id', 0) and _classic_on_device():
+        # Gym(name) for a closed-form task: stepped by the device kernel (csrc/classic_env.cu)
+        spec = ClassicSpec(spec)
     if not hasattr(spec, 'observation_size'):
         # a host environment (Gym / dm_control / user code): the reference's worker grid on the
         # host, feeding the device learner through numpy arrays (tonic_b200/environments/host.py)

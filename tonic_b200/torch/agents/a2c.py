@@ -173,6 +173,7 @@ class A2C(agent.Agent):
         return (bool(config.fused_rollout) and config.noise == 'device'
                 and getattr(actor.head, 'kind', None) == 'detached_gaussian'
                 and hasattr(env, 'struct') and not getattr(env, 'time_feature', False)
+                and not getattr(env.spec, 'task_id', 0)      # the kernel steps SynthControl only
                 and shape.d_in <= min(64, shape.hidden)
                 and shape.n_out <= 16 and shape.hidden in (64, 128, 256))
 
