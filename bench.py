@@ -499,39 +499,42 @@ def measure_offpolicy(run, name, steps, warmup, batch):
     from tonic_b200.utils import logger
     kind, preset, obs, act, envs = OFF_POLICY[name]
     world = run.world
+    batch = batch * world                    # GLOBAL batch (every rank contributes `batch` rows)
     config.noise, config.indices = 'device', 'device'
     saved = logger.store, logger.store_aggregate
     logger.store = lambda *a, **k: None
     logger.store_aggregate = lambda *a, **k: None
+    from tonic_b200 import graphs
     agent, env = build_offpolicy(name, envs, envs * world, batch)
-    timer = UpdateTimer(agent)
-    state = dict(obs=env.start(), steps=1)
+    env.start()
+    state = dict(steps=1)
 
     def vector_step():
-        actions = agent.step(state['obs'], state['steps'])
-        state['obs'], infos = env.step(actions)
-        agent.update(**infos, steps=state['steps'])
+        # the fused driver of tonic_b200.Trainer: act -> environment -> store -> record -> update,
+        # device resident, replayed as a CUDA graph once captured
+        agent.rollout(env, 1, steps=state['steps'])
         state['steps'] += envs * world
 
     fill = -(-REPLAY_SIZE // envs)           # vector steps that fill the ring (no update yet)
     for _ in range(fill):
         vector_step()
     assert agent.replay.size == agent.replay.max_size
+    collect_ms = run.timed(vector_step, steps) / steps       # collector only (ring full, no update)
     agent.replay.steps_before_batches = 0    # from here on: one update per vector step
-    for _ in range(warmup):
+    for _ in range(max(warmup, 3)):          # 2 eager executions size the workspaces, 1 captures
         vector_step()
-    timer.reset()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + graphs.replayed_launches
     ms = run.timed(vector_step, steps)
-    launches = _lib.launch_count() - launches0
-    update_ms = run.max_over_ranks(timer.mean_ms() or 0.0)
-    assert len(timer.events) == steps, (len(timer.events), steps)
-    # instrumented pass (per-launch events)
+    launches = _lib.launch_count() + graphs.replayed_launches - launches0
+    update_ms = ms / steps - collect_ms      # device time added by the update to one vector step
+    # instrumented pass (graphs off: per-launch events)
+    config.graphs = False
     kernels.flops.clear()
     kernels.profile_begin()
     for _ in range(min(steps, 5)):
         vector_step()
     prof = kernels.profile_end()
+    config.graphs = True
     n_prof = min(steps, 5)
     pk = peaks()
     nets = agent.model.networks()
@@ -539,7 +542,7 @@ def measure_offpolicy(run, name, steps, warmup, batch):
     row_bytes = 4 * (2 * obs + act + 2)        # gathered bytes per sampled transition
     hbm = hbm_table(prof, {
         'tb_env_step': (8 * obs + 4 * (2 * obs + act + 4)) * envs,
-        'tb_q_target': (4 * 5 + 8) * batch,
+        'tb_q_target': (4 * 5 + 8) * (batch // world),
         'tb_soft_update': 12 * P_total / max(len(nets) // 2, 1),
         'tb_adam_step': 28 * P_total / max(len(nets), 1),
         'tb_moments_record': 4 * obs * envs,
@@ -555,6 +558,7 @@ def measure_offpolicy(run, name, steps, warmup, batch):
                  'vector step',
         value=round(steps * envs * world / (ms / 1e3), 1), unit='env-steps/s',
         ms_per_vector_step=round(ms / steps, 3), update_ms=round(update_ms, 3),
+        collect_ms=round(collect_ms, 4), cuda_graphs=bool(config.graphs),
         update_iterations=50, batch=batch, gpu_launches_per_step=launches // steps,
         replay_bytes=int(agent.replay.max_size * envs * 4 * (2 * obs + act + 3)),
         sampled_bytes_per_update=50 * batch * row_bytes,

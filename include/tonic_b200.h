@@ -545,6 +545,25 @@ int tb_permutation(uint64_t seed, uint64_t stream_id, const uint64_t* d_counter,
 /* *d_counter += delta (device-resident RNG stream positions).                  */
 int tb_counter_add(uint64_t* d_counter, uint64_t delta, void* stream);
 
+/* ---- device-resident off-policy collection / sampling (fast mode, CUDA-graph safe) ------
+ * tb_set_noise_base: base pointer (device uint64, or NULL) that tb_tanh_action and
+ *   tb_squashed_sample add to their by-value `counter`: a captured update draws fresh
+ *   Philox numbers at every replay (advance the base with tb_counter_add).
+ * tb_randint: d_out[i] uniform in [0, *d_total) -- the sample indices of
+ *   replays/buffers.py:84-88 (np_random.randint(size * N, size=batch)) for all
+ *   batch_iterations at once; Philox stream (seed, stream_id, *d_counter + i).
+ * Ring state (device int64[3]): {index, size, size * n_workers}.
+ * tb_ring_store: Buffer.store (replays/buffers.py:47-56): for each of n_keys (<= 8) host-listed
+ *   keys, row *d_ring_state[0] of h_dst[k] ([max_size, row_elems] float32) <- h_src[k]
+ *   (the staged rows of this vector step: h_row_elems[k] floats).
+ * tb_ring_advance: index = (index + 1) % max_size, size = min(size + 1, max_size).          */
+int tb_set_noise_base(const uint64_t* d_base);
+int tb_randint(uint64_t seed, uint64_t stream_id, const uint64_t* d_counter, const int64_t* d_total,
+               int64_t n, int64_t* d_out, void* stream);
+int tb_ring_store(const float* const* h_src, float* const* h_dst, const int64_t* h_row_elems,
+                  int32_t n_keys, const int64_t* d_ring_state, void* stream);
+int tb_ring_advance(int64_t* d_ring_state, int64_t max_size, int64_t n_workers, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Host-side numpy-compatible MT19937 streams (legacy numpy.random.RandomState)*/
 /* used for bit-exact minibatch / replay indices and exploration noise:        */

@@ -262,3 +262,48 @@ def test_fused_rollout_matches_per_step_launches(kind):
     torch.testing.assert_close(a['state'], b['state'], rtol=0, atol=1e-3)
     assert torch.equal(a['lengths'], b['lengths']) and torch.equal(a['scores'], b['scores'])
     assert torch.equal(a['first_state'], b['first_state'])
+
+
+@pytest.mark.parametrize('kind', ['DDPG', 'TD3', 'SAC'])
+def test_off_policy_fast_path_graph_replay_matches_eager(kind):
+    """Fast mode of the off-policy agents (device Philox noise, device-drawn replay indices, ring
+    state on the device): `rollout()` -- act -> environment -> ring store -> record -> update per
+    vector step -- replayed as CUDA graphs gives bit-identical parameters and replay contents to
+    issuing the same kernels one by one; warm-up (uniform actions), collection without updates
+    and collection with updates are all exercised."""
+    import torch
+    from tonic_b200 import config
+    cfg = dict(agent=kind, obs=11, act=3, workers=64, max_episode_steps=13, seed=4, hidden=(256, 256),
+               start_steps=64 * 4,
+               buffer=dict(size=64 * 40, batch_iterations=3, batch_size=32,
+                           steps_before_batches=64 * 8, steps_between_batches=50))
+    old = config.noise, config.indices, config.graphs
+    out = []
+    try:
+        for use_graphs in (False, True):
+            config.noise, config.indices, config.graphs = 'device', 'device', use_graphs
+            agent, env = product.build(cfg)
+            env.start()
+            assert agent.can_rollout(env)
+            steps = 0
+            for _ in range(9):                       # 4 vector steps per call
+                assert agent.rollout(env, 4, steps=steps) == 4
+                steps += 4 * 64
+            torch.cuda.synchronize()
+            if use_graphs:
+                assert any(sec.graph is not None for sec in agent._sections.values())
+            params = torch.cat([n.params for n in agent.model.networks()]).cpu()
+            ring = {k: v.clone().cpu() for k, v in agent.replay.buffers.items()}
+            out.append((params, ring, agent.replay.index, agent.replay.size,
+                        agent.replay._ring.cpu().tolist()))
+    finally:
+        config.noise, config.indices, config.graphs = old
+    (p0, r0, i0, s0, d0), (p1, r1, i1, s1, d1) = out
+    assert torch.isfinite(p0).all() and (i0, s0, d0) == (i1, s1, d1)
+    assert d0 == [36 % 40, 36, 36 * 64]              # device ring state = host mirror
+    for k in r0:
+        assert torch.equal(torch.nan_to_num(r0[k]), torch.nan_to_num(r1[k])), k
+    assert torch.equal(p0, p1)
+    # the agents did train: online and target networks differ from each other
+    nets = agent.model.networks()
+    assert not torch.equal(nets[0].params, nets[-1].params)

@@ -124,6 +124,10 @@ _PROTOTYPES = {
     'tb_permutation': (c_int, [c_u64, c_u64, c_vp, c_i64, c_vp, c_vp]),
     'tb_counter_add': (c_int, [c_vp, c_u64, c_vp]),
     'tb_array_stats': (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'tb_set_noise_base': (c_int, [c_vp]),
+    'tb_randint': (c_int, [c_u64, c_u64, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    'tb_ring_store': (c_int, [_P(c_vp), _P(c_vp), _P(c_i64), c_i32, c_vp, c_vp]),
+    'tb_ring_advance': (c_int, [c_vp, c_i64, c_i64, c_vp]),
     'tb_profile_begin': (c_int, []),
     'tb_profile_end': (c_int, [ctypes.c_char_p, c_i32]),
     'tb_rs_create': (c_vp, [c_u32]),

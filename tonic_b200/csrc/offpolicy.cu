@@ -24,6 +24,15 @@ __device__ __forceinline__ float sac_scale(float pre, float* dscale) {
     return sc;
 }
 
+// Device-resident base of the Philox stream positions (tb_set_noise_base): when set, every noise
+// kernel below adds *base to its by-value counter, so a captured CUDA graph draws fresh numbers
+// at every replay (the caller advances the base with tb_counter_add inside the graph).
+static const uint64_t* g_noise_base = nullptr;
+
+__device__ __forceinline__ uint64_t noise_position(uint64_t counter, const uint64_t* base) {
+    return counter + (base ? *base : 0ull);
+}
+
 __device__ __forceinline__ float philox_normal(const Philox& rng, uint64_t row, int a, uint64_t counter) {
     const uint4 r = rng(counter + row, (uint64_t)(a >> 2));
     const float2 p = (a & 2) ? box_muller(r.z, r.w) : box_muller(r.x, r.y);
@@ -35,10 +44,11 @@ __device__ __forceinline__ float philox_normal(const Philox& rng, uint64_t row, 
 __global__ void __launch_bounds__(256)
 tanh_action_kernel(const float* __restrict__ pre, int64_t total, int A, int mode,
                    const float* __restrict__ noise32, const double* __restrict__ noise64,
-                   uint64_t seed, uint64_t counter, float noise_scale, float noise_clip,
-                   float* __restrict__ out) {
+                   uint64_t seed, uint64_t counter0, const uint64_t* __restrict__ base,
+                   float noise_scale, float noise_clip, float* __restrict__ out) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= total) return;
+    const uint64_t counter = noise_position(counter0, base);
     const int64_t row = i / A;
     const int a = (int)(i % A);
     Philox rng(seed);
@@ -66,11 +76,12 @@ tanh_action_kernel(const float* __restrict__ pre, int64_t total, int A, int mode
 // log_prob = sum_j Normal(loc, scale).log_prob(raw) - log(1 - action^2 + 1e-6)
 __global__ void __launch_bounds__(256)
 squashed_sample_kernel(const float* __restrict__ pre, const float* __restrict__ eps_in,
-                       uint64_t seed, uint64_t counter, int64_t n, int A, int greedy,
-                       float* __restrict__ actions, float* __restrict__ log_probs,
+                       uint64_t seed, uint64_t counter0, const uint64_t* __restrict__ base, int64_t n,
+                       int A, int greedy, float* __restrict__ actions, float* __restrict__ log_probs,
                        float* __restrict__ eps_out) {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (row >= n) return;
+    const uint64_t counter = noise_position(counter0, base);
     Philox rng(seed);
     float lp = 0.0f;
     for (int a = 0; a < A; ++a) {
@@ -169,7 +180,92 @@ sac_head_grad_kernel(const float* __restrict__ pre, const float* __restrict__ ep
 
 inline int blocks_for(int64_t n) { return (int)((n + 255) / 256); }
 
+// ---- device-resident ring replay (fast mode) ---------------------------------------------------
+// out[i] uniform in [0, *d_total): Philox word x 64-bit multiply-high (replays/buffers.py:86
+// draws np_random.randint(size * N, size=batch); here the stream is Philox, the support identical)
+__global__ void __launch_bounds__(256)
+randint_kernel(uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ d_counter,
+               const int64_t* __restrict__ d_total, int64_t n, int64_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Philox rng(seed);
+    const uint4 r = rng((d_counter ? *d_counter : 0ull) + (uint64_t)i, stream_id);
+    const unsigned long long u = ((unsigned long long)r.x << 32) | r.y;
+    out[i] = (int64_t)__umul64hi(u, (unsigned long long)*d_total);
+}
+
+struct RingCopy {
+    const float* src[8];
+    float* dst[8];
+    int64_t elems[8];       // floats per row of each key
+    int n;
+};
+
+// row *d_index of every key <- the staged vector-step rows (replays/buffers.py:47-56 store)
+__global__ void __launch_bounds__(256)
+ring_store_kernel(RingCopy c, const int64_t* __restrict__ d_index) {
+    const int64_t row = *d_index;
+    const int k = blockIdx.y;
+    if (k >= c.n) return;
+    float* dst = c.dst[k] + row * c.elems[k];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < c.elems[k];
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = c.src[k][i];
+}
+
+// index = (index + 1) % max_size; size = min(size + 1, max_size); total = size * n_workers
+__global__ void ring_advance_kernel(int64_t* state, int64_t max_size, int64_t n_workers) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        state[0] = (state[0] + 1) % max_size;
+        state[1] = min(state[1] + 1, max_size);
+        state[2] = state[1] * n_workers;
+    }
+}
+
 }  // namespace tb
+
+extern "C" int tb_set_noise_base(const uint64_t* d_base) {
+    tb::g_noise_base = d_base;
+    return 0;
+}
+
+extern "C" int tb_randint(uint64_t seed, uint64_t stream_id, const uint64_t* d_counter,
+                          const int64_t* d_total, int64_t n, int64_t* d_out, void* stream) {
+    tb::ProfScope prof_scope("tb_randint", stream);
+    TB_REQUIRE(d_total && d_out && n > 0, TB_EINVAL, "tb_randint: bad arguments");
+    tb::randint_kernel<<<tb::blocks_for(n), 256, 0, tb::as_stream(stream)>>>(seed, stream_id, d_counter,
+                                                                            d_total, n, d_out);
+    return tb::check_launch("tb_randint");
+}
+
+extern "C" int tb_ring_store(const float* const* h_src, float* const* h_dst, const int64_t* h_row_elems,
+                             int32_t n_keys, const int64_t* d_ring_state, void* stream) {
+    tb::ProfScope prof_scope("tb_ring_store", stream);
+    TB_REQUIRE(h_src && h_dst && h_row_elems && d_ring_state && n_keys >= 1 && n_keys <= 8, TB_EINVAL,
+               "tb_ring_store: bad arguments (1..8 keys)");
+    tb::RingCopy c;
+    int64_t largest = 0;
+    for (int k = 0; k < 8; ++k) {
+        c.src[k] = k < n_keys ? h_src[k] : nullptr;
+        c.dst[k] = k < n_keys ? h_dst[k] : nullptr;
+        c.elems[k] = k < n_keys ? h_row_elems[k] : 0;
+        TB_REQUIRE(k >= n_keys || (c.src[k] && c.dst[k] && c.elems[k] > 0), TB_EINVAL,
+                   "tb_ring_store: key %d is incomplete", k);
+        if (c.elems[k] > largest) largest = c.elems[k];
+    }
+    c.n = n_keys;
+    int bx = (int)((largest + 255) / 256);
+    if (bx > 2 * tb::kNumSMs) bx = 2 * tb::kNumSMs;
+    tb::ring_store_kernel<<<dim3(bx, n_keys), 256, 0, tb::as_stream(stream)>>>(c, d_ring_state);
+    return tb::check_launch("tb_ring_store");
+}
+
+extern "C" int tb_ring_advance(int64_t* d_ring_state, int64_t max_size, int64_t n_workers, void* stream) {
+    tb::ProfScope prof_scope("tb_ring_advance", stream);
+    TB_REQUIRE(d_ring_state && max_size > 0 && n_workers > 0, TB_EINVAL, "tb_ring_advance: bad arguments");
+    tb::ring_advance_kernel<<<1, 32, 0, tb::as_stream(stream)>>>(d_ring_state, max_size, n_workers);
+    return tb::check_launch("tb_ring_advance");
+}
 
 extern "C" int tb_tanh_action(const float* d_pre, int64_t n_rows, int32_t act_dim, int32_t mode,
                               const float* d_noise32, const double* d_noise64, uint64_t seed,
@@ -180,8 +276,8 @@ extern "C" int tb_tanh_action(const float* d_pre, int64_t n_rows, int32_t act_di
                TB_EINVAL, "tb_tanh_action: bad arguments");
     const int64_t total = n_rows * act_dim;
     tb::tanh_action_kernel<<<tb::blocks_for(total), 256, 0, tb::as_stream(stream)>>>(
-        d_pre, total, act_dim, mode, d_noise32, d_noise64, seed, counter, noise_scale, noise_clip,
-        d_out);
+        d_pre, total, act_dim, mode, d_noise32, d_noise64, seed, counter, tb::g_noise_base, noise_scale,
+        noise_clip, d_out);
     return tb::check_launch("tb_tanh_action");
 }
 
@@ -193,7 +289,8 @@ extern "C" int tb_squashed_sample(const float* d_pre, const float* d_eps, uint64
     TB_REQUIRE(d_pre && d_actions && n_rows > 0 && act_dim > 0, TB_EINVAL,
                "tb_squashed_sample: bad arguments");
     tb::squashed_sample_kernel<<<tb::blocks_for(n_rows), 256, 0, tb::as_stream(stream)>>>(
-        d_pre, d_eps, seed, counter, n_rows, act_dim, greedy, d_actions, d_log_probs, d_eps_out);
+        d_pre, d_eps, seed, counter, tb::g_noise_base, n_rows, act_dim, greedy, d_actions, d_log_probs,
+        d_eps_out);
     return tb::check_launch("tb_squashed_sample");
 }
 

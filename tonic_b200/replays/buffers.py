@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from .. import distributed, kernels
+from .._lib import ptr
 from ..utils.random_state import RandomState
 
 
@@ -51,6 +52,10 @@ class Buffer:
         E, B = self.batch_iterations, self.batch_size
         self._host_idx = torch.empty(E, B, dtype=torch.int64).pin_memory()
         self._dev_idx = torch.empty(E, B, dtype=torch.int64, device=dev)
+        # device mirror of (index, size, size * workers) for the graph-safe fast path
+        self._ring = torch.zeros(3, dtype=torch.int64, device=dev)
+        self._ring_tables = {}
+        self._index_counter = kernels.new_counter()
 
     def store(self, **kwargs):
         if self.buffers is None:
@@ -72,13 +77,59 @@ class Buffer:
         kernels.replay_accumulate_n_steps(b['rewards'], b['discounts'], b['next_observations'],
                                           b['resets'], self.index, self.size, self.return_steps)
 
+    # -- device-resident fast path (config.noise == config.indices == 'device') ---------------
+    def sync_ring(self):
+        """Host -> device copy of the ring position (after host-side stores)."""
+        self._ring.copy_(torch.tensor([self.index, self.size, self.size * self.num_workers]))
+
+    def store_device(self, **staged):
+        """Buffer.store (buffers.py:47-56) of this vector step's rows, given as device tensors
+        with FIXED addresses, at the row the device ring state points to (CUDA-graph safe:
+        nothing here depends on the host's copy of `index`)."""
+        import ctypes
+        keys = tuple(staged)
+        table = self._ring_tables.get(keys)
+        if table is None or any(staged[k].data_ptr() != p for k, p in zip(keys, table[3])):
+            n = len(keys)
+            src = (ctypes.c_void_p * n)(*[staged[k].data_ptr() for k in keys])
+            dst = (ctypes.c_void_p * n)(*[self.buffers[k].data_ptr() for k in keys])
+            elems = (ctypes.c_int64 * n)(*[self.buffers[k][0].numel() for k in keys])
+            for k in keys:
+                assert staged[k].numel() == self.buffers[k][0].numel() and staged[k].is_contiguous(), k
+            table = self._ring_tables[keys] = (src, dst, elems, [staged[k].data_ptr() for k in keys])
+        from .. import _lib
+        _lib.call('tb_ring_store', table[0], table[1], table[2], len(keys), ptr(self._ring),
+                  kernels.stream())
+
+    def advance_device(self):
+        from .. import _lib
+        _lib.call('tb_ring_advance', ptr(self._ring), self.max_size, self.num_workers, kernels.stream())
+
+    def index_batches_device(self, seed):
+        """`batch_iterations` index vectors drawn on the device (Philox) from the filled part of
+        THIS rank's ring (each rank contributes batch_size / world rows, like the on-policy
+        device mode); yields the tuples of `index_batches`."""
+        from .. import _lib
+        world = distributed.world()
+        rows = self.batch_size // world
+        assert rows * world == self.batch_size, 'batch_size must split over the ranks'
+        E = self.batch_iterations
+        _lib.call('tb_randint', int(seed or 0) ^ 0x1d8, distributed.rank(), ptr(self._index_counter),
+                  ptr(self._ring[2:]), E * rows, ptr(self._dev_idx), kernels.stream())
+        kernels.counter_add(self._index_counter, E * rows)
+        flat = self._dev_idx.view(-1)
+        for e in range(E):
+            yield flat[e * rows:(e + 1) * rows], rows, self.batch_size, None
+
     def row(self, key):
         """Row `index` of a buffer, for producers that write it in place."""
         return self.buffers[key][self.index]
 
-    def advance(self):
+    def advance(self, mirror_only=False):
+        """`mirror_only`: the device ring state was advanced by `advance_device` (fast path)."""
         self.index = (self.index + 1) % self.max_size
         self.size = min(self.size + 1, self.max_size)
+        self._ring_stale = not mirror_only
 
     def flat(self, key):
         b = self.buffers[key]

@@ -4,7 +4,7 @@ tonic/torch/agents/ddpg.py:20-112)."""
 import numpy as np
 import torch
 
-from ... import _lib, explorations, kernels, replays
+from ... import _lib, config, distributed, explorations, graphs, kernels, replays
 from ...utils import logger
 from .. import models, normalizers, updaters
 from . import agent
@@ -42,6 +42,9 @@ class DDPG(agent.Agent):
         self.actor_updater.seed = self.critic_updater.seed = seed or 0
         self.action_size = action_space.shape[0]
         self._noise_counter = 0
+        self._noise_base = None          # device-resident Philox position (fast path)
+        self._sections = {}              # captured (warm, updating) vector-step graphs
+        self._update_stats = None
 
     # -- acting -----------------------------------------------------------------
     def _new_actions(self, observations):
@@ -100,10 +103,16 @@ class DDPG(agent.Agent):
     def _actor_turn(self, iteration):
         return True
 
-    def _update(self, steps):
-        batches = list(self.replay.index_batches(steps))
-        stats = torch.zeros(len(batches), 2, _lib.STAT_COUNT, dtype=torch.float64,
-                            device=kernels.device())
+    def _stats_block(self):
+        n = self.replay.batch_iterations
+        if self._update_stats is None or self._update_stats.shape[0] != n:
+            self._update_stats = torch.zeros(n, 2, _lib.STAT_COUNT, dtype=torch.float64,
+                                             device=kernels.device())
+        return self._update_stats
+
+    def _enqueue_update(self, batches, stats):
+        """All kernels of one update (ddpg.py:86-112), no host synchronisation."""
+        stats.zero_()
         obs = self.replay.flat('observations')
         for i, (idx, rows, rows_global, mine) in enumerate(batches):  # ddpg.py:105-112, td3.py:41-46
             self.critic_updater.launch(self.replay, idx, rows, stats[i, 0],
@@ -112,12 +121,109 @@ class DDPG(agent.Agent):
                 self.actor_updater.launch(obs, idx, rows, stats[i, 1], rows_global=rows_global,
                                           mine=mine)
                 self.model.update_targets()
-        host = kernels.to_host(stats)
-        for i in range(len(batches)):
+        if self.model.observation_normalizer:
+            self.model.observation_normalizer.update()
+
+    def _report(self, host):
+        for i in range(host.shape[0]):
             for k, v in self.critic_updater.infos(host[i, 0]).items():
                 logger.store('critic/' + k, v)
             if self._actor_turn(i):
                 for k, v in self.actor_updater.infos(host[i, 1]).items():
                     logger.store('actor/' + k, v)
-        if self.model.observation_normalizer:
-            self.model.observation_normalizer.update()
+
+    def _update(self, steps):
+        stats = self._stats_block()
+        self._enqueue_update(list(self.replay.index_batches(steps)), stats)
+        self._report(kernels.to_host(stats))
+
+    # -- fused collection (device environments, fast mode) ----------------------------------
+    def _graphable(self):
+        """Device-resident RNG streams and ring state: a whole vector step (act -> environment
+        -> store -> record [-> update]) can be replayed as a CUDA graph."""
+        return (config.graphs and self._device_mode()
+                and (distributed.world() == 1 or config.graphs_multi_gpu))
+
+    def _device_mode(self):
+        return (config.noise == 'device' and config.indices == 'device'
+                and not getattr(self.exploration, 'additive', False))
+
+    def can_rollout(self, environment):
+        """The fused trainer path (utils/trainer.py) needs the device-resident streams."""
+        return self._device_mode() and self.replay.return_steps == 1
+
+    def _reset_noise_offsets(self):
+        """Offsets inside one vector step (the device base advances between steps)."""
+        self._noise_counter = 0
+        self.exploration._counter = 0
+        self.actor_updater._counter = self.critic_updater._counter = 0
+
+    def _enqueue_step(self, env, warm, updating):
+        """agent.step -> environment.step -> agent.update of trainer.py:44-50 for one vector
+        step, entirely on the device: the transition goes from fixed staging buffers into the
+        ring row the DEVICE ring state points to."""
+        rep = self.replay
+        _lib.call('tb_set_noise_base', _lib.ptr(self._noise_base))
+        try:
+            self._reset_noise_offsets()
+            obs = self._staged_obs
+            obs.copy_(env.observations)                      # a2c/ddpg keep a copy of the acting observations
+            if warm:
+                actions = self._policy(obs, self.exploration.noise(obs.shape[0]))
+            else:
+                actions = self.exploration.warmup_actions(obs.shape[0])
+            self._staged_actions.copy_(actions)
+            env.step_into(self._staged_actions, env.observations, env.next_observations, env.rewards,
+                          env.resets, env.terminations)
+            rep.store_device(observations=obs, actions=self._staged_actions,
+                             next_observations=env.next_observations, rewards=env.rewards,
+                             resets=env.resets, terminations=env.terminations)
+            rep.advance_device()
+            if self.model.observation_normalizer:
+                self.model.observation_normalizer.record(obs)
+            if updating:
+                self._enqueue_update(list(rep.index_batches_device(self.seed)), self._stats_block())
+            kernels.counter_add(self._noise_base, 1 << 24)
+        finally:
+            _lib.call('tb_set_noise_base', None)
+
+    def rollout(self, environment, vector_steps, steps=0, action_stats=None):
+        """Runs `vector_steps` iterations of the training loop's body (trainer.py:44-55) without
+        leaving the device; every iteration that `replay.ready` is followed by the update.
+        Fast mode only (device noise and indices); returns the number of vector steps done."""
+        if not self._device_mode() or self.replay.return_steps > 1:
+            raise NotImplementedError('rollout() needs config.noise == config.indices == "device", '
+                                      'a non-OU exploration and return_steps == 1; use step/update')
+        env, rep = environment, self.replay
+        N, A, world = env.workers, self.action_size, distributed.world()
+        O = env.observation_space.shape[0]
+        if rep.buffers is None:
+            rep.allocate(observations=(N, O), actions=(N, A), next_observations=(N, O),
+                         rewards=(N,), resets=(N,), terminations=(N,))
+        if self._noise_base is None:
+            dev = kernels.device()
+            self._noise_base = kernels.new_counter()
+            self._staged_obs = torch.empty(N, O, dtype=torch.float32, device=dev)
+            self._staged_actions = torch.empty(N, A, dtype=torch.float32, device=dev)
+        if getattr(rep, '_ring_stale', True):
+            rep.sync_ring()
+            rep._ring_stale = False
+        for done in range(vector_steps):
+            now = steps + done * N * world
+            updating = rep.ready(now)
+            warm = now > self.exploration.start_steps
+            key = (warm, updating, id(env))
+            if self._graphable():
+                if key not in self._sections:
+                    self._sections[key] = graphs.CapturedSection(
+                        lambda w=warm, u=updating: self._enqueue_step(env, w, u))
+                self._sections[key]()
+            else:
+                self._enqueue_step(env, warm, updating)
+            rep.advance(mirror_only=True)
+            if action_stats is not None:
+                action_stats.add(self._staged_actions)
+            if updating:
+                rep.last_steps = now
+                self._report(kernels.to_host(self._stats_block()))
+        return vector_steps

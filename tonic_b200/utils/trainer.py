@@ -41,7 +41,8 @@ class Trainer:
 
     # ------------------------------------------------------------------ run
     def run(self):
-        fused = hasattr(self.agent, 'rollout') and hasattr(self.environment, 'step_into')
+        fused = (hasattr(self.agent, 'rollout') and hasattr(self.environment, 'step_into')
+                 and getattr(self.agent, 'can_rollout', lambda env: True)(self.environment))
         self.start_time = self.last_epoch_time = time.time()
         self.steps = self.epoch_step_count = self.epochs = self.episodes = 0
         self.steps_since_save = 0
