@@ -307,3 +307,48 @@ def test_off_policy_fast_path_graph_replay_matches_eager(kind):
     # the agents did train: online and target networks differ from each other
     nets = agent.model.networks()
     assert not torch.equal(nets[0].params, nets[-1].params)
+
+
+def test_host_protocol_fast_path_matches_plain_path():
+    """The reference protocol with numpy arrays (agent.step / environment.step / agent.update)
+    in the product configuration: every call is one captured graph over pinned staging buffers
+    (kernels.HostBridge).  Same kernels, same device RNG streams as the call-by-call path ->
+    identical actions, observations, segment contents and parameters after the updates."""
+    import torch
+    from tonic_b200 import config
+    cfg = dict(scenarios.SCENARIOS['ppo_wide'], workers=48, max_episode_steps=7,
+               segment=dict(size=6, batch_iterations=2, batch_size=96))
+    old = config.noise, config.indices, config.graphs
+    out = []
+    try:
+        for use_graphs in (False, True):
+            config.noise, config.indices, config.graphs = 'device', 'device', use_graphs
+            agent, env = product.build(cfg)
+            obs = env.start(host=True)
+            trace, steps = [], 0
+            for t in range(20):                      # three updates (T = 6) + a partial segment
+                actions = agent.step(obs, steps)
+                assert isinstance(actions, np.ndarray) and actions.dtype == np.float32
+                obs, infos = env.step(actions)
+                assert infos['resets'].dtype == np.bool_ and obs.dtype == np.float32
+                agent.update(**infos, steps=steps)
+                steps += 48
+                trace.append((actions.copy(), obs.copy(), infos['rewards'].copy(), infos['resets'].copy()))
+            torch.cuda.synchronize()
+            seg = {k: v.clone().cpu() for k, v in agent.replay.buffers.items()}
+            params = torch.cat([n.params for n in agent.model.networks()]).cpu()
+            out.append((trace, seg, params, agent.replay.index))
+            if use_graphs:
+                assert agent._host_sections[('step', 48)][0].graph is not None
+                assert env._host_section.graph is not None
+    finally:
+        config.noise, config.indices, config.graphs = old
+    (t0, s0, p0, i0), (t1, s1, p1, i1) = out
+    assert i0 == i1 == 2
+    for a, b in zip(t0, t1):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    assert sum(int(r[3].sum()) for r in t0) > 0          # resets happened
+    for k in s0:
+        assert torch.equal(s0[k], s1[k]), k
+    assert torch.equal(p0, p1)

@@ -90,8 +90,38 @@ class DeviceVectorEnvironment:
                   ptr(next_observations), ptr(rewards), ptr(resets), ptr(terminations),
                   kernels.stream())
 
+    def _step_host(self, actions):
+        """environment.step(numpy) -> numpy: pinned copy-in, H2D, the step kernel and the five
+        D2H copies as ONE captured graph over fixed staging buffers, one synchronisation."""
+        from .. import graphs
+        if getattr(self, '_bridge', None) is None:
+            self._bridge, self._host_section = kernels.HostBridge(), None
+        b = self._bridge
+        pin_act, dev_act = b.load('actions', actions)
+        outs = [(b.buffers(name, t.shape)[0], t) for name, t in (
+            ('obs', self.observations), ('next_obs', self.next_observations), ('rewards', self.rewards),
+            ('resets', self.resets), ('terminations', self.terminations))]
+        if self._host_section is None:
+            def body():
+                dev_act.copy_(pin_act, non_blocking=True)
+                self.step_into(dev_act, self.observations, self.next_observations, self.rewards,
+                               self.resets, self.terminations)
+                for pinned, dev in outs:
+                    pinned.copy_(dev, non_blocking=True)
+            self._host_section = graphs.CapturedSection(body)
+        self._host_section()
+        torch.cuda.current_stream().synchronize()
+        obs, next_obs, rewards = (b.read(p) for p, _ in outs[:3])
+        resets, terminations = b.read(outs[3][0], np.bool_), b.read(outs[4][0], np.bool_)
+        return obs, dict(observations=next_obs, rewards=rewards, resets=resets, terminations=terminations)
+
     def step(self, actions):
         host = not isinstance(actions, torch.Tensor) or not actions.is_cuda
+        from .. import config
+        if host and config.graphs and config.noise == 'device':
+            actions = np.asarray(actions, np.float32)
+            assert actions.shape == (self.workers, self.spec.action_size), actions.shape
+            return self._step_host(actions)
         actions = kernels.to_device(actions)
         assert actions.shape == (self.workers, self.spec.action_size), actions.shape
         self.step_into(actions, self.observations, self.next_observations, self.rewards,

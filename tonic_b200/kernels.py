@@ -95,6 +95,39 @@ def to_host(*tensors):
     return out[0] if len(out) == 1 else out
 
 
+class HostBridge:
+    """Fixed pinned-host and device staging buffers for ONE call of the reference-facing protocol
+    with numpy arrays (agent.step / environment.step / agent.update): because the addresses never
+    change, the copies and the kernels of the call can be captured into one CUDA graph
+    (tonic_b200/graphs.py) -- one launch and at most one synchronisation per protocol call
+    instead of a dozen small copies and launches."""
+
+    def __init__(self):
+        self.pinned, self.dev = {}, {}
+
+    def buffers(self, name, shape, dtype=F32):
+        key = (name, tuple(shape), dtype)
+        if key not in self.pinned:
+            self.pinned[key] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+            self.dev[key] = torch.empty(tuple(shape), dtype=dtype, device=device())
+        return self.pinned[key], self.dev[key]
+
+    def load(self, name, array, dtype=F32):
+        """numpy -> pinned staging (host copy, converts bool / float64); returns (pinned, device)."""
+        array = np.asarray(array)
+        pinned, dev = self.buffers(name, array.shape, dtype)
+        pinned.numpy()[...] = array
+        transfers['h2d'] += pinned.numel() * pinned.element_size()
+        return pinned, dev
+
+    @staticmethod
+    def read(pinned, dtype=None):
+        """pinned staging -> fresh numpy array owned by the caller (after the synchronisation)."""
+        transfers['d2h'] += pinned.numel() * pinned.element_size()
+        out = pinned.numpy()
+        return out.astype(dtype) if dtype is not None else out.copy()
+
+
 def _count_flops(name, value):
     flops[name] = flops.get(name, 0.0) + value
 

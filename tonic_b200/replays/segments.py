@@ -56,6 +56,43 @@ class Segment:
         """For producers that wrote row `index` of the buffers in place."""
         self.index += 1
 
+    # -- graph-safe store at a DEVICE-resident row index (host-protocol fast path) -----------
+    def prepare_device_store(self):
+        """Outside any captured section: creates / re-synchronises the device row index when the
+        host moved `index` since the last device store (get_full, fused rollouts)."""
+        if getattr(self, '_ring', None) is None:
+            self._ring = torch.zeros(3, dtype=torch.int64, device=kernels.device())
+            self._ring_host = 0
+            self._ring_tables = {}
+        if self._ring_host != self.index % self.max_size:
+            self._ring.copy_(torch.tensor([self.index % self.max_size, self.index, 0]))
+            self._ring_host = self.index % self.max_size
+
+    def store_device(self, **staged):
+        """Segment.store (segments.py:27-36) of rows staged in device tensors with fixed
+        addresses, at row *ring[0], then the device index advances (wraps at T).  CUDA-graph
+        safe; `prepare_device_store` before and `note_device_store` after, both on the host."""
+        import ctypes
+        from .. import _lib
+        keys = tuple(staged)
+        ptrs = [staged[k].data_ptr() for k in keys]
+        table = self._ring_tables.get(keys)
+        if table is None or table[3] != ptrs:
+            n = len(keys)
+            table = self._ring_tables[keys] = (
+                (ctypes.c_void_p * n)(*ptrs),
+                (ctypes.c_void_p * n)(*[self.buffers[k].data_ptr() for k in keys]),
+                (ctypes.c_int64 * n)(*[self.buffers[k][0].numel() for k in keys]), ptrs)
+        _lib.call('tb_ring_store', table[0], table[1], table[2], len(keys), _lib.ptr(self._ring),
+                  kernels.stream())
+        _lib.call('tb_ring_advance', _lib.ptr(self._ring), self.max_size, self.num_workers,
+                  kernels.stream())
+
+    def note_device_store(self):
+        """Host mirror of one `store_device` (called outside the captured section)."""
+        self.index += 1
+        self._ring_host = self.index % self.max_size
+
     # -- returns / advantages -----------------------------------------------------------
     def compute_returns(self, values, next_values):
         shape = self.buffers['rewards'].shape

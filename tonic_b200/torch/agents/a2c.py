@@ -77,8 +77,69 @@ class A2C(agent.Agent):
         if eps is None:     # same streams whatever the number of ranks
             kernels.counter_add(self._noise_counter, workers * world)
 
+    def _host_fast_path(self):
+        """Reference protocol with numpy arrays in the product configuration (device noise):
+        each protocol call is one captured graph over fixed staging buffers (kernels.HostBridge)."""
+        return config.graphs and config.noise == 'device' and distributed.world() == 1
+
+    def _step_host(self, observations):
+        """agent.step(numpy) -> numpy: pinned copy-in, H2D, actor forward, sample, D2H: one graph."""
+        if getattr(self, '_bridge', None) is None:
+            self._bridge, self._host_sections = kernels.HostBridge(), {}
+        N = observations.shape[0]
+        self._buffers(N)
+        pin_obs, dev_obs = self._bridge.load('step_obs', observations)
+        pin_act, _ = self._bridge.buffers('step_actions', (N, self.action_size))
+        key = ('step', N)
+        if key not in self._host_sections:
+            last = self._bridge.buffers('last_obs', observations.shape)[1]
+
+            def body():
+                dev_obs.copy_(pin_obs, non_blocking=True)
+                self._sample(dev_obs, self._actions[:N], self._log_probs[:N])
+                last.copy_(dev_obs)                      # a2c.py:48: the agent keeps a copy
+                pin_act.copy_(self._actions[:N], non_blocking=True)
+            self._host_sections[key] = (graphs.CapturedSection(body), last)
+        section, last = self._host_sections[key]
+        section()
+        torch.cuda.current_stream().synchronize()
+        self.last_observations, self.last_actions, self.last_log_probs = last, self._actions[:N], self._log_probs[:N]
+        return self._bridge.read(pin_act)
+
+    def _update_host(self, observations, rewards, resets, terminations):
+        """agent.update(numpy ...): pinned copy-in, 4 H2D copies, segment store at the device row
+        index, normaliser record: one graph, no synchronisation."""
+        seg, b = self.replay, self._bridge
+        N = rewards.shape[0]
+        if seg.buffers is None:
+            O = observations.shape[1]
+            seg.allocate(observations=(N, O), actions=(N, self.action_size), next_observations=(N, O),
+                         rewards=(N,), resets=(N,), terminations=(N,), log_probs=(N,))
+        seg.prepare_device_store()
+        staged = [b.load('upd_next_obs', observations), b.load('upd_rewards', rewards),
+                  b.load('upd_resets', resets), b.load('upd_terminations', terminations)]
+        key = ('update', N)
+        if key not in self._host_sections:
+            last = self._bridge.buffers('last_obs', observations.shape)[1]
+            normalizer = self.model.observation_normalizer
+
+            def body():
+                for pinned, dev in staged:
+                    dev.copy_(pinned, non_blocking=True)
+                seg.store_device(observations=last, actions=self._actions[:N],
+                                 next_observations=staged[0][1], rewards=staged[1][1],
+                                 resets=staged[2][1], terminations=staged[3][1],
+                                 log_probs=self._log_probs[:N])
+                if normalizer:
+                    normalizer.record(last)
+            self._host_sections[key] = (graphs.CapturedSection(body), None)
+        self._host_sections[key][0]()
+        seg.note_device_store()
+
     def step(self, observations, steps):
         host = not (isinstance(observations, torch.Tensor) and observations.is_cuda)
+        if host and self._host_fast_path():
+            return self._step_host(np.asarray(observations, np.float32))
         observations = kernels.to_device(observations)
         self._buffers(observations.shape[0])
         self._sample(observations, self._actions, self._log_probs)
@@ -186,6 +247,15 @@ class A2C(agent.Agent):
 
     # -- learning ---------------------------------------------------------------
     def update(self, observations, rewards, resets, terminations, steps):
+        if isinstance(observations, np.ndarray) and self._host_fast_path() \
+                and getattr(self, '_bridge', None) is not None \
+                and isinstance(self.last_observations, torch.Tensor) \
+                and ('step', observations.shape[0]) in self._host_sections \
+                and self.last_observations is self._host_sections[('step', observations.shape[0])][1]:
+            self._update_host(observations, np.asarray(rewards), np.asarray(resets), np.asarray(terminations))
+            if self.replay.ready():
+                self._update()
+            return
         self.replay.store(
             observations=self.last_observations, actions=self.last_actions,
             next_observations=observations, rewards=rewards, resets=resets,
