@@ -365,6 +365,11 @@ int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float*
                        const double* d_stats, float kl_threshold, int32_t* d_stop,
                        const int32_t* d_skip, void* stream);
 
+/* Profiling aid for tb_mlp_wgrad_fused: 16 clock64() stamps of CTA (0, 0) (slots: 0 setup done,
+ * 1 MMAs issued, 2 accumulator complete, 3 narrow gradients done, 4 partial slot written,
+ * 5 at the grid barrier, 6 barrier passed, 7 reduction + Adam done).  Not on the product path. */
+int tb_wgrad_timeline(uint64_t* out16);
+
 /* ---- global-norm gradient clipping ---------------------------------------------
  * Reference: torch.nn.utils.clip_grad_norm_(self.variables, self.gradient_clip) between
  * loss.backward() and optimizer.step() (tonic/torch/updaters/actors.py:37-38,96-98,

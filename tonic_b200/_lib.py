@@ -102,6 +102,7 @@ _PROTOTYPES = {
     'tb_mlp_forward_tc': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_vp, c_vp, c_vp,
                                   c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_tc_timeline': (c_int, [c_vp]),
+    'tb_wgrad_timeline': (c_int, [c_vp]),
     'tb_q_target_discounts': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp]),
     'tb_replay_accumulate_n_steps': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                                              c_i32, c_vp]),

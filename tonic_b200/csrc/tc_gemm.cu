@@ -507,6 +507,10 @@ constexpr int tca_smem_bytes() {
            2 * 32 * KIN * 4 + 1024 + 256;
 }
 
+__device__ __forceinline__ void tcw_stamp(unsigned long long* timeline, int slot) {
+    if (timeline && blockIdx.x == 0 && blockIdx.y == 0) timeline[slot] = (unsigned long long)clock64();
+}
+
 struct TcWgradAllParams {
     TcWgradParams w;            // tensor-core part (gpart, n_params, off_w2, off_b2, rows_per_split)
     TbMlpShape sh;
@@ -518,6 +522,7 @@ struct TcWgradAllParams {
     int n_split;
     float* flat;                // [n_params] reduced gradient (sum over rows)
     unsigned long long* sync;   // grid-barrier counter (monotonic)
+    unsigned long long* timeline;   // profiling aid: clock64() stamps of CTA (0, 0), or NULL
     // optional fused optimizer step (single process, no gradient clipping): the reduction phase
     // applies Adam to its slice right away -- same arithmetic and device-side controls as adam_kernel
     int fuse_adam;
@@ -564,7 +569,8 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     uint64_t* empty_bar = bars + Cfg::STAGES;
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    __shared__ float ds[2][TCW_ROWS][TCA_ND];            // dout rows of the chunk (4 KB)
+    __shared__ __align__(16) float ds[2][TCW_ROWS][TCA_ND];      // dout rows of the chunk (3 KB)
+    static_assert(KIN % 4 == 0 && TCA_ND % 4 == 0 && TCA_NO % 4 == 0, "16-byte shared-memory rows");
     // row-group 1 -> row-group 0 exchange of the narrow sums: lives in the epilogue warps'
     // staging block (18 KB), which they only touch after named barrier 2 (see below)
     float (*comb)[KIN] = reinterpret_cast<float (*)[KIN]>(epi);          // [128][KIN] <= 16 KB
@@ -593,6 +599,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) { tcw_stamp(q.timeline, 0); }                 // setup done
 
     if (warp == 0) {
         if (lane == 0) {
@@ -651,6 +658,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
             tcgen05_commit(tmem_full);
+            tcw_stamp(q.timeline, 1);                                 // all MMAs issued
         }
     } else if (warp >= 4 && warp < TCA_NARROW_WARP0) {
         // ---- epilogue: accumulator -> this split's partial slot (dW2 rows, db2) ----------------
@@ -661,6 +669,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             mbar_wait(tmem_full, 0);
             tcgen05_fence_after();
         }
+        if (w == 0 && lane == 0) tcw_stamp(q.timeline, 2);             // accumulator complete
         // the staging block doubles as the narrow warps' exchange buffer: wait until they left it
         asm volatile("bar.sync 2, 384;" ::: "memory");
 #pragma unroll 1
@@ -695,6 +704,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             sum = __uint_as_float(v[0]);
         }
         p.gpart[(size_t)split * p.n_params + p.off_b2 + tile * TC_BM + w * 32 + lane] = sum;
+        if (w == 0 && lane == 0) tcw_stamp(q.timeline, 4);             // partial slot written
     } else if (warp >= TCA_NARROW_WARP0) {
         // ---- narrow gradients on the FFMA pipe: thread (g, c): column n = 128 tile + c, rows of
         // parity g; 16 rows per chunk and thread, the loads of the next chunk are issued before
@@ -720,27 +730,44 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                 dh[u] = ldg_nc_volatile(q.h2 + r * 256 + n);
             }
         };
-        auto stage_rows = [&](int chunk) {
+        // xin / dout rows of a chunk: global -> registers (loads in flight during the FFMA block of
+        // the current chunk) -> shared memory (after it)
+        constexpr int NX = (TCW_ROWS * KIN + 255) / 256, NDS = (TCW_ROWS * TCA_ND + 255) / 256;
+        float sx[NX], sd[NDS];
+        auto stage_load = [&](int chunk) {
             const int64_t base = m_begin + (int64_t)chunk * TCW_ROWS;
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                const int v = t + 256 * k, r = v / KIN, j = v % KIN;
+                sx[k] = (v < TCW_ROWS * KIN && base + r < m_end && j <= d_in)
+                    ? ldg_nc_volatile(q.xin + (base + r) * ldx + j) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < NDS; ++k) {
+                const int v = t + 256 * k, r = v / TCA_ND, o = v % TCA_ND;
+                sd[k] = (v < TCW_ROWS * TCA_ND && base + r < m_end && o < nd)
+                    ? ldg_nc_volatile(q.dout + (base + r) * q.ld_dout + o) : 0.0f;
+            }
+        };
+        auto stage_store = [&](int chunk) {
             float* x = xs + (chunk & 1) * TCW_ROWS * KIN;
-            for (int v = t; v < TCW_ROWS * KIN; v += 256) {
-                const int r = v / KIN, j = v % KIN;
-                x[v] = (base + r < m_end && j <= d_in) ? q.xin[(base + r) * ldx + j] : 0.0f;
-            }
-            for (int v = t; v < TCW_ROWS * TCA_ND; v += 256) {
-                const int r = v / TCA_ND, o = v % TCA_ND;
-                ds[chunk & 1][r][o] = (base + r < m_end && o < nd) ? q.dout[(base + r) * q.ld_dout + o] : 0.0f;
-            }
+            float* d = &ds[chunk & 1][0][0];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) if (t + 256 * k < TCW_ROWS * KIN) x[t + 256 * k] = sx[k];
+#pragma unroll
+            for (int k = 0; k < NDS; ++k) if (t + 256 * k < TCW_ROWS * TCA_ND) d[t + 256 * k] = sd[k];
         };
         if (n_chunks > 0) {
             load_rows(0, a1, hv);
-            stage_rows(0);
+            stage_load(0);
+            stage_store(0);
         }
         for (int ch = 0; ch < n_chunks; ++ch) {
             asm volatile("bar.sync 1, 256;" ::: "memory");      // staging of chunk ch visible; buffer of ch+1 free
-            if (ch + 1 < n_chunks) {
+            const bool more = ch + 1 < n_chunks;
+            if (more) {
                 load_rows(ch + 1, na1, nhv);
-                stage_rows(ch + 1);
+                stage_load(ch + 1);
             }
             const int rows = (int)min((int64_t)TCW_ROWS, m_end - (m_begin + (int64_t)ch * TCW_ROWS));
             const float* x = xs + (ch & 1) * TCW_ROWS * KIN;
@@ -750,15 +777,32 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             for (int u = 0; u < 16; ++u) {
                 const int r = g + 2 * u;
                 if (r < rows) {
+                    // 16-byte shared-memory reads (rows are 16-byte aligned: KIN, TCA_ND multiples of 4)
+                    const float4* x4 = reinterpret_cast<const float4*>(x + r * KIN);
 #pragma unroll
-                    for (int j = 0; j < KIN; ++j) w1[j] = fmaf(a1[u], x[r * KIN + j], w1[j]);
+                    for (int j = 0; j < KIN / 4; ++j) {
+                        const float4 xv = x4[j];
+                        w1[4 * j] = fmaf(a1[u], xv.x, w1[4 * j]);
+                        w1[4 * j + 1] = fmaf(a1[u], xv.y, w1[4 * j + 1]);
+                        w1[4 * j + 2] = fmaf(a1[u], xv.z, w1[4 * j + 2]);
+                        w1[4 * j + 3] = fmaf(a1[u], xv.w, w1[4 * j + 3]);
+                    }
+                    const float4* d4 = reinterpret_cast<const float4*>(&ds[ch & 1][r][0]);
 #pragma unroll
-                    for (int o = 0; o < TCA_NO; ++o) w3[o] = fmaf(ds[ch & 1][r][o], hv[u], w3[o]);
+                    for (int o = 0; o < TCA_NO / 4; ++o) {
+                        const float4 dv = d4[o];
+                        w3[4 * o] = fmaf(dv.x, hv[u], w3[4 * o]);
+                        w3[4 * o + 1] = fmaf(dv.y, hv[u], w3[4 * o + 1]);
+                        w3[4 * o + 2] = fmaf(dv.z, hv[u], w3[4 * o + 2]);
+                        w3[4 * o + 3] = fmaf(dv.w, hv[u], w3[4 * o + 3]);
+                    }
                 }
             }
+            if (more) stage_store(ch + 1);
 #pragma unroll
             for (int u = 0; u < 16; ++u) { a1[u] = na1[u]; hv[u] = nhv[u]; }
         }
+        if (t == 0) tcw_stamp(q.timeline, 3);                     // narrow gradients accumulated
         // combine the two row groups (fixed order: group 0 + group 1) in two rounds through the
         // exchange block, then write this split's partial slot
         if (g == 1) {
@@ -806,41 +850,46 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     }
     // ---- grid-wide barrier, then the fixed-order reduction of this CTA's parameter slice -------
     const unsigned int n_ctas = gridDim.x * gridDim.y;
+    if (threadIdx.x == 0) tcw_stamp(q.timeline, 5);                   // arriving at the grid barrier
     grid_barrier(q.sync, n_ctas);
     const int b = blockIdx.y * gridDim.x + blockIdx.x;
-    const int per = (((p.n_params + (int)n_ctas - 1) / (int)n_ctas) + 127) & ~127;     // multiple of 128
+    const int per = (((p.n_params + (int)n_ctas - 1) / (int)n_ctas) + 31) & ~31;
     const int lo = b * per, hi = min(p.n_params, lo + per);
-    float* red = reinterpret_cast<float*>(smem);          // [3][128] partial sums of lanes 1..3 (stages are idle)
-    const int qd = threadIdx.x >> 7, e = threadIdx.x & 127;       // 4 quarter-sums x 128 parameters per pass
     // fused Adam (updaters/actors.py:22,71: no step when every advantage of the minibatch is zero)
     const bool do_step = q.fuse_adam && !(q.stats && q.stats[TB_STAT_NONZERO_ADV] == 0.0);
     const int t_step = q.fuse_adam ? q.opt.d_step[0] + 1 : 0;
-    float* s_corr = red + 3 * 128;                        // step_size, bc2_sqrt
+    float* s_corr = reinterpret_cast<float*>(smem);       // step_size, bc2_sqrt (the stages are idle)
     if (do_step && threadIdx.x == 0) adam_corrections(q.opt, t_step, &s_corr[0], &s_corr[1]);
-    for (int i0 = lo; i0 < hi; i0 += 128) {
-        const int i = i0 + e;
-        float acc = 0.0f;
-        if (i < hi) {
-            const float* src = p.gpart + i;
-            int s = qd;
-            for (; s + 12 < q.n_split; s += 16) {       // 4 independent loads in flight
-                const float v0 = __ldcg(src + (size_t)s * p.n_params);
-                const float v1 = __ldcg(src + (size_t)(s + 4) * p.n_params);
-                const float v2 = __ldcg(src + (size_t)(s + 8) * p.n_params);
-                const float v3 = __ldcg(src + (size_t)(s + 12) * p.n_params);
-                acc += v0; acc += v1; acc += v2; acc += v3;
-            }
-            for (; s < q.n_split; s += 4) acc += __ldcg(src + (size_t)s * p.n_params);
+    __syncthreads();
+    if (threadIdx.x == 0) tcw_stamp(q.timeline, 6);               // grid barrier passed
+    for (int i = lo + (int)threadIdx.x; i < hi; i += TCA_THREADS) {
+        // same summation order as adam_kernel: g_k = sum over s = k (mod 4) in increasing s, then
+        // (g0 + g1) + (g2 + g3); 16 independent L2 loads in flight (__ldcg: written by other SMs)
+        const float* src = p.gpart + i;
+        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+        int sidx = 0;
+        for (; sidx + 16 <= q.n_split; sidx += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(sidx + u) * p.n_params);
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) { g0 += v[u]; g1 += v[u + 1]; g2 += v[u + 2]; g3 += v[u + 3]; }
         }
-        __syncthreads();
-        if (qd > 0) red[(qd - 1) * 128 + e] = acc;
-        __syncthreads();
-        if (qd == 0 && i < hi) {
-            const float g = (acc + red[e]) + (red[128 + e] + red[256 + e]);
-            q.flat[i] = g;
-            if (do_step) adam_apply(q.opt, q.sh, q.packed, i, g * q.grad_scale, s_corr[0], s_corr[1]);
+        for (; sidx + 4 <= q.n_split; sidx += 4) {
+            g0 += __ldcg(src + (size_t)(sidx + 0) * p.n_params);
+            g1 += __ldcg(src + (size_t)(sidx + 1) * p.n_params);
+            g2 += __ldcg(src + (size_t)(sidx + 2) * p.n_params);
+            g3 += __ldcg(src + (size_t)(sidx + 3) * p.n_params);
         }
+        for (int k = 0; sidx < q.n_split; ++sidx, ++k) {
+            const float v = __ldcg(src + (size_t)sidx * p.n_params);
+            if (k == 0) g0 += v; else if (k == 1) g1 += v; else g2 += v;
+        }
+        const float g = (g0 + g1) + (g2 + g3);
+        q.flat[i] = g;
+        if (do_step) adam_apply(q.opt, q.sh, q.packed, i, g * q.grad_scale, s_corr[0], s_corr[1]);
     }
+    if (threadIdx.x == 0) tcw_stamp(q.timeline, 7);               // reduction (+ Adam) done
     if (q.fuse_adam) {
         // last CTA to finish publishes the new step count and the KL early-stop flag
         // (ppo.py:45-46 with updaters/actors.py:103,112), exactly like adam_kernel
@@ -984,6 +1033,23 @@ extern "C" int tb_tc_wgrad256(const float* d_dz_hi, const float* d_dz_lo, const 
     return check_launch("tb_tc_wgrad256");
 }
 
+namespace tb { static unsigned long long* g_wgrad_timeline = nullptr; }
+
+// Profiling aid for tb_mlp_wgrad_fused (like tb_tc_timeline): first call allocates 16 clock64()
+// slots that CTA (0, 0) of later launches fills; out16 != NULL reads them back (host pointer).
+extern "C" int tb_wgrad_timeline(uint64_t* out16) {
+    using namespace tb;
+    if (!g_wgrad_timeline) {
+        TB_REQUIRE(cudaMalloc(&g_wgrad_timeline, 16 * sizeof(unsigned long long)) == cudaSuccess, TB_ENOTSUP,
+                   "tb_wgrad_timeline: cudaMalloc failed");
+        cudaMemset(g_wgrad_timeline, 0, 16 * sizeof(unsigned long long));
+    }
+    if (out16)
+        TB_REQUIRE(cudaMemcpy(out16, g_wgrad_timeline, 16 * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost) == cudaSuccess, TB_ENOTSUP, "tb_wgrad_timeline: copy failed");
+    return 0;
+}
+
 // All weight gradients of one minibatch in one launch, reduced to the flat gradient
 // (see tc_wgrad_all_kernel).  d_sync: one uint64 (zero-initialised once), the grid-barrier
 // counter of this network.
@@ -1025,6 +1091,7 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     q.sh = *shape; q.xin = d_xin; q.h2 = d_h2; q.dz1 = d_dz1; q.dout = d_dout; q.ld_dout = ld_dout;
     q.n_extra = n_extra; q.off_extra = off_extra; q.n_split = n_split; q.flat = d_flat;
     q.sync = reinterpret_cast<unsigned long long*>(d_sync);
+    q.timeline = g_wgrad_timeline;
     q.fuse_adam = opt != nullptr;
     if (opt) q.opt = *opt; else memset(&q.opt, 0, sizeof(q.opt));
     q.packed = d_packed; q.grad_scale = grad_scale; q.stats = d_stats; q.kl_threshold = kl_threshold;
