@@ -255,11 +255,14 @@ def test_mlp_backward_wgrad_vs_autograd(K, gemm_mode, d_in, hidden, n_out, act, 
     net.backward(dout_d, rows, dx=dx, dx_col0=dx_col0)
     off_extra = net.layout.offsets['extra'][0]
     gpart = net.wgrad(dout_d, rows, n_split, n_extra=n_extra, off_extra=off_extra)
-    grad = gpart[:n_split].sum(0)
-    w2_splits = net.w2_splits(n_split)
-    if w2_splits:      # tensor-core path: the W2 block only has w2_splits partial sums
-        lo, hi = net.w2_range()
-        grad[lo:hi] = gpart[:w2_splits, lo:hi].sum(0)
+    if getattr(net, 'reduced', False):      # fused kernel: already the flat gradient
+        grad = gpart.clone()
+    else:
+        grad = gpart[:n_split].sum(0)
+        w2_splits = net.w2_splits(n_split)
+        if w2_splits:      # tensor-core path: the W2 block only has w2_splits partial sums
+            lo, hi = net.w2_range()
+            grad[lo:hi] = gpart[:w2_splits, lo:hi].sum(0)
     grad = grad.cpu()
 
     p = {k: v.requires_grad_() for k, v in host_params(net).items()}

@@ -23,8 +23,10 @@ def test_train_cli_learns_and_checkpoints(tmp_path, monkeypatch):
         environment="tonic.environments.SynthControl('HalfCheetah', max_episode_steps=100)",
         test_environment=None, before_training=None, after_training=None, parallel=1,
         sequential=256, seed=0, name='ppo-test', environment_name='synth', checkpoint='last')
-    trainer = train.train(trainer='tonic.Trainer(steps=int(4e5), epoch_steps=int(1e5), '
-                                  'save_steps=int(4e5), test_episodes=2, show_progress=False)',
+    # 391 vector steps of 256 workers per epoch (100,096 steps): the 4th epoch ends at 400,384
+    # steps, training stops at the first multiple of 256 >= 410,000 (trainer.py:93-112)
+    trainer = train.train(trainer='tonic.Trainer(steps=int(4.1e5), epoch_steps=int(1e5), '
+                                  'save_steps=int(1e6), test_episodes=2, show_progress=False)',
                           path=None, **common)
     run = os.path.join('synth', 'ppo-test', '0')
     rows = open(os.path.join(run, 'log.csv')).read().strip().splitlines()
@@ -50,11 +52,11 @@ def test_train_cli_learns_and_checkpoints(tmp_path, monkeypatch):
     assert trainer2.steps >= int(1e5)
 
 
-def _reward_curve(seed, fast, iterations=20):
-    """Mean per-step reward of every collected segment of one PPO run (2 x 256 tanh MLPs, 256
-    environments, T = 64, 4 epochs x 8 minibatches of 2048) in parity mode (host torch / numpy
-    RNG streams, eager launches) or in the benchmarked fast mode (device Philox noise, device
-    Feistel permutations, CUDA-graph replay)."""
+def _score_curve(seed, fast, iterations=20):
+    """Mean score of the episodes finished during every collected segment of one PPO run (2 x 256
+    tanh MLPs, 256 environments, 100-step episodes, T = 64, 4 epochs x 8 minibatches of 2048) in
+    parity mode (host torch / numpy RNG streams, eager launches) or in the benchmarked fast mode
+    (device Philox noise, device Feistel permutations, CUDA-graph replay)."""
     import tonic_b200
     import tonic_b200.torch
     from tonic_b200 import config
@@ -76,38 +78,38 @@ def _reward_curve(seed, fast, iterations=20):
     agent.initialize(env.observation_space, env.action_space, seed=seed)
     env.start()
     curve = []
-    inner = agent._update
-
-    def record_then_update():
-        curve.append(float(agent.replay.buffers['rewards'].mean().item()))
-        inner()
-    agent._update = record_then_update
     for _ in range(iterations):
         assert agent.rollout(env, 64) == 64
+        scores, lengths = env.finished_episodes()
+        assert len(scores) > 0
+        curve.append(float(np.mean(scores)))
     return np.array(curve)
 
 
 def test_fast_mode_returns_stay_in_the_parity_mode_band():
     """north_star: "returns matching reference within tolerance" for the BENCHED configuration.
     The parity mode is pinned to the reference step by step (tests/test_gpu_agents.py); here the
-    fast mode's learning curves (5 seeds) must be statistically indistinguishable from the
-    parity mode's: same start, same improvement, final level within the seed-to-seed band."""
+    fast mode's learning curves (episode returns, 5 seeds) must be statistically
+    indistinguishable from the parity mode's: same start, same improvement, final level within
+    the seed-to-seed band."""
     from tonic_b200 import config
     saved = config.noise, config.indices
     try:
-        parity = np.array([_reward_curve(s, fast=False) for s in range(5)])
-        fast = np.array([_reward_curve(s, fast=True) for s in range(5)])
+        parity = np.array([_score_curve(s, fast=False) for s in range(5)])
+        fast = np.array([_score_curve(s, fast=True) for s in range(5)])
     finally:
         config.noise, config.indices = saved
     assert parity.shape == fast.shape == (5, 20)
-    # first segment: same initial policy and environments, only the noise stream differs
-    np.testing.assert_allclose(fast[:, 0].mean(), parity[:, 0].mean(), atol=0.15 * abs(parity[:, 0].mean()) + 0.05)
+    print('parity', np.round(parity.mean(0), 2), 'fast', np.round(fast.mean(0), 2))
+    p_start, f_start = parity[:, :2].mean(), fast[:, :2].mean()
     p_end, f_end = parity[:, -5:].mean(1), fast[:, -5:].mean(1)
-    gain_p, gain_f = p_end.mean() - parity[:, 0].mean(), f_end.mean() - fast[:, 0].mean()
-    assert gain_p > 0 and gain_f > 0, (gain_p, gain_f)            # both learn
-    band = 3.0 * (p_end.std() + f_end.std()) / np.sqrt(5) + 0.1 * abs(gain_p)
+    gain_p, gain_f = p_end.mean() - p_start, f_end.mean() - f_start
+    assert gain_p > 1.0 and gain_f > 1.0, (gain_p, gain_f)          # both learn
+    # same start (same initial policy and environments, only the noise stream differs)
+    assert abs(f_start - p_start) <= 0.25 * gain_p + 0.5, (f_start, p_start)
+    band = 3.0 * (p_end.std() + f_end.std()) / np.sqrt(5) + 0.15 * abs(gain_p)
     assert abs(f_end.mean() - p_end.mean()) <= band, (f_end, p_end, band)
-    # the whole curve of the fast mode lies inside the parity envelope widened by the same band
+    # the mean curve of the fast mode lies inside the parity envelope widened by the same band
     lo, hi = parity.min(0) - band, parity.max(0) + band
     inside = ((fast.mean(0) >= lo) & (fast.mean(0) <= hi)).mean()
     assert inside >= 0.9, (inside, fast.mean(0), lo, hi)
