@@ -480,7 +480,7 @@ def build_offpolicy(name, envs_local, total_envs, batch, seed=0):
     model = wrapper(actor=actor, critic=critic, observation_normalizer=n.MeanStd())
     # the ring is local to the rank: 1M transitions per GPU (BASELINE configs[2])
     replay = tonic_b200.replays.Buffer(size=REPLAY_SIZE, batch_iterations=50, batch_size=batch,
-                                       steps_before_batches=REPLAY_SIZE * (total_envs // envs_local),
+                                       steps_before_batches=1 << 60,      # the bench fills the ring first
                                        steps_between_batches=50)
     if kind == 'SAC':
         exploration = tonic_b200.explorations.NoActionNoise(start_steps=0)
