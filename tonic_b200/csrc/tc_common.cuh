@@ -199,4 +199,21 @@ static inline int make_map(CUtensorMap* map, const float* base, int64_t rows, in
     return 0;
 }
 
+// 2-D row-major float matrix [rows, 256]; box = [box_cols floats, box_rows]; no swizzle (plain
+// row-major tile in shared memory).
+static inline int make_map_plain(CUtensorMap* map, const float* base, int64_t rows, int box_cols,
+                                 int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    TB_REQUIRE(fn, TB_ENOTSUP, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TB_REQUIRE(r == CUDA_SUCCESS, TB_EINVAL, "cuTensorMapEncodeTiled (plain) failed with %d", (int)r);
+    return 0;
+}
+
 }  // namespace tb

@@ -499,12 +499,28 @@ constexpr int TCA_THREADS = 512;
 constexpr int TCA_NARROW_WARP0 = 8;          // warps 8..15
 constexpr int TCA_NO = 8;                    // head outputs with a dW3 row (n_out <= 8)
 constexpr int TCA_ND = 12;                   // dout columns with a column sum (n_out + extras <= 12)
-// dynamic shared memory: operand stages | epilogue staging / exchange block | ones block (4 KB)
-// | xin rows of two chunks | alignment slack + barriers
+constexpr int TCA_ROWS = 16;                 // rows per pipeline chunk (two K = 8 MMA steps)
+constexpr int TCA_STAGES = 3;
+// One pipeline stage: MMA operands of a 16-row chunk in the MN-major 128B / 32B-atom swizzle
+// (boxes of 32 columns x 16 rows = 2 KB) and the narrow warps' dz1 / h2 column halves
+// ([16][128] float32, unswizzled).
+template <int KIN>
+struct TcaLayout {
+    static constexpr int BOX = 32 * TCA_ROWS * 4;                 // 2048
+    static constexpr int A_BYTES = (TC_BM / 32) * BOX;            // 8 KB  dz2 column half
+    static constexpr int B_BYTES = (TC_BN / 32) * BOX;            // 16 KB h1
+    static constexpr int N_BYTES = TCA_ROWS * 128 * 4;            // 8 KB
+    static constexpr int A_HI = 0, A_LO = A_BYTES, B_HI = 2 * A_BYTES, B_LO = 2 * A_BYTES + B_BYTES;
+    static constexpr int N_DZ1 = 2 * (A_BYTES + B_BYTES), N_H2 = N_DZ1 + N_BYTES;
+    static constexpr int STAGE_BYTES = N_H2 + N_BYTES;            // 64 KB
+    static_assert(STAGE_BYTES % 1024 == 0, "stages keep the 1024-byte swizzle alignment");
+};
+// dynamic shared memory: stages | epilogue staging | ones block (4 KB) | xin / dout rows of two
+// chunks | barriers | alignment slack
 template <int PASSES, int KIN>
 constexpr int tca_smem_bytes() {
-    return TcCfg<PASSES>::STAGES * TcCfg<PASSES>::STAGE_BYTES + TcCfg<PASSES>::EPI_BYTES + 4096 +
-           2 * 32 * KIN * 4 + 1024 + 256;
+    return TCA_STAGES * TcaLayout<KIN>::STAGE_BYTES + TcCfg<PASSES>::EPI_BYTES + 4096 +
+           2 * TCA_ROWS * (KIN + TCA_ND) * 4 + 256 + 1024;
 }
 
 __device__ __forceinline__ void tcw_stamp(unsigned long long* timeline, int slot) {
@@ -554,37 +570,37 @@ template <int PASSES, int KIN>
 __global__ void __launch_bounds__(TCA_THREADS, 1)
 tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
                     const __grid_constant__ CUtensorMap map_h_hi, const __grid_constant__ CUtensorMap map_h_lo,
+                    const __grid_constant__ CUtensorMap map_dz1, const __grid_constant__ CUtensorMap map_h2,
                     const TcWgradAllParams q) {
-    using Cfg = TcCfg<PASSES>;
+    using L = TcaLayout<KIN>;
     const TcWgradParams& p = q.w;
     if (skip_requested(p.skip)) return;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-    // [8 x 32] block of ones (B operand of the bias-gradient MMAs), then the narrow warps' xin rows
-    float* ones = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
-    float* xs = ones + 1024;                             // [2][32][KIN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xs + 2 * 32 * KIN);
+    float* epi = reinterpret_cast<float*>(smem + TCA_STAGES * L::STAGE_BYTES);
+    // [8 x 32] block of ones (B operand of the bias-gradient MMAs), then the narrow warps' xin / dout rows
+    float* ones = reinterpret_cast<float*>(smem + TCA_STAGES * L::STAGE_BYTES + TcCfg<PASSES>::EPI_BYTES);
+    float* xs = ones + 1024;                             // [2][16][KIN]
+    float* dsm = xs + 2 * TCA_ROWS * KIN;                // [2][16][TCA_ND]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + 2 * TCA_ROWS * TCA_ND);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + Cfg::STAGES;
-    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;
+    uint64_t* empty_bar = bars + TCA_STAGES;
+    uint64_t* tmem_full = bars + 2 * TCA_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    __shared__ __align__(16) float ds[2][TCW_ROWS][TCA_ND];      // dout rows of the chunk (3 KB)
     static_assert(KIN % 4 == 0 && TCA_ND % 4 == 0 && TCA_NO % 4 == 0, "16-byte shared-memory rows");
-    // row-group 1 -> row-group 0 exchange of the narrow sums: lives in the epilogue warps'
-    // staging block (18 KB), which they only touch after named barrier 2 (see below)
-    float (*comb)[KIN] = reinterpret_cast<float (*)[KIN]>(epi);          // [128][KIN] <= 16 KB
-    static_assert(128 * KIN * 4 <= Cfg::EPI_BYTES && 128 * TCA_NO * 4 <= Cfg::EPI_BYTES, "exchange block too large");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;                                 // 0 / 1: columns 128*tile..
     const int split = blockIdx.y;
     const int64_t m_begin = (int64_t)split * p.rows_per_split;
     const int64_t m_end = min(p.n_rows, m_begin + p.rows_per_split);
-    const int n_chunks = m_end > m_begin ? (int)((m_end - m_begin + TCW_ROWS - 1) / TCW_ROWS) : 0;
+    const int n_chunks = m_end > m_begin ? (int)((m_end - m_begin + TCA_ROWS - 1) / TCA_ROWS) : 0;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TCA_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);          // released by the MMA commit AND by the narrow warps
+        }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -602,28 +618,29 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     if (threadIdx.x == 0) { tcw_stamp(q.timeline, 0); }                 // setup done
 
     if (warp == 0) {
+        // ===== TMA producer: per 16-row chunk the MMA operands (dz2 half, h1, hi / lo) and the
+        // narrow warps' dz1 / h2 column halves, 3 stages deep =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                const int m0 = (int)(m_begin + (int64_t)c * TCW_ROWS);
+                unsigned char* st = smem + stage * L::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * (L::A_BYTES + L::B_BYTES) + 2 * L::N_BYTES);
+                const int m0 = (int)(m_begin + (int64_t)c * TCA_ROWS);
                 for (int b = 0; b < TC_BM / 32; ++b)
-                    tma_load_2d(st + b * 4096, &map_dz_hi, &full_bar[stage], tile * TC_BM + b * 32, m0);
-                unsigned char* bh = st + Cfg::PARTS * TCW_A_BYTES;
+                    tma_load_2d(st + L::A_HI + b * L::BOX, &map_dz_hi, &full_bar[stage], tile * TC_BM + b * 32, m0);
                 for (int b = 0; b < TC_BN / 32; ++b)
-                    tma_load_2d(bh + b * 4096, &map_h_hi, &full_bar[stage], b * 32, m0);
+                    tma_load_2d(st + L::B_HI + b * L::BOX, &map_h_hi, &full_bar[stage], b * 32, m0);
                 if (PASSES == 3) {
                     for (int b = 0; b < TC_BM / 32; ++b)
-                        tma_load_2d(st + TCW_A_BYTES + b * 4096, &map_dz_lo, &full_bar[stage],
-                                    tile * TC_BM + b * 32, m0);
-                    unsigned char* bl = st + 2 * TCW_A_BYTES + TCW_B_BYTES;
+                        tma_load_2d(st + L::A_LO + b * L::BOX, &map_dz_lo, &full_bar[stage], tile * TC_BM + b * 32, m0);
                     for (int b = 0; b < TC_BN / 32; ++b)
-                        tma_load_2d(bl + b * 4096, &map_h_lo, &full_bar[stage], b * 32, m0);
+                        tma_load_2d(st + L::B_LO + b * L::BOX, &map_h_lo, &full_bar[stage], b * 32, m0);
                 }
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                tma_load_2d(st + L::N_DZ1, &map_dz1, &full_bar[stage], tile * TC_BM, m0);
+                tma_load_2d(st + L::N_H2, &map_h2, &full_bar[stage], tile * TC_BM, m0);
+                if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -631,17 +648,18 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t idesc16 = (kIdescTf32MN & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
-            const uint64_t b_ones = umma_desc_mnmajor_sw128(ones);
+            const uint64_t b_ones = umma_desc_mnmajor_sw128(ones, L::BOX);
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&full_bar[stage], phase);
                 tcgen05_fence_after();
-                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                const uint64_t a_hi = umma_desc_mnmajor_sw128(st);
-                const uint64_t a_lo = umma_desc_mnmajor_sw128(st + TCW_A_BYTES);
-                const uint64_t b_hi = umma_desc_mnmajor_sw128(st + Cfg::PARTS * TCW_A_BYTES);
-                const uint64_t b_lo = umma_desc_mnmajor_sw128(st + 2 * TCW_A_BYTES + TCW_B_BYTES);
+                unsigned char* st = smem + stage * L::STAGE_BYTES;
+                // 16-row boxes: 32-column groups are BOX = 2048 bytes apart (LBO)
+                const uint64_t a_hi = umma_desc_mnmajor_sw128(st + L::A_HI, L::BOX);
+                const uint64_t a_lo = umma_desc_mnmajor_sw128(st + L::A_LO, L::BOX);
+                const uint64_t b_hi = umma_desc_mnmajor_sw128(st + L::B_HI, L::BOX);
+                const uint64_t b_lo = umma_desc_mnmajor_sw128(st + L::B_LO, L::BOX);
 #pragma unroll
-                for (int k = 0; k < TCW_ROWS / 8; ++k) {
+                for (int k = 0; k < TCA_ROWS / 8; ++k) {
                     const uint64_t koff = (uint64_t)(k * 1024 >> 4);     // next 8-row group
                     if (PASSES == 3) {
                         tcgen05_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
@@ -655,7 +673,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                     if (PASSES == 3) tcgen05_mma_tf32(tmem_base + TC_BN, a_lo + koff, b_ones, idesc16, 1);
                 }
                 tcgen05_commit(&empty_bar[stage]);
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
             }
             tcgen05_commit(tmem_full);
             tcw_stamp(q.timeline, 1);                                 // all MMAs issued
@@ -670,8 +688,6 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             tcgen05_fence_after();
         }
         if (w == 0 && lane == 0) tcw_stamp(q.timeline, 2);             // accumulator complete
-        // the staging block doubles as the narrow warps' exchange buffer: wait until they left it
-        asm volatile("bar.sync 2, 384;" ::: "memory");
 #pragma unroll 1
         for (int c = 0; c < TC_BN / 32; ++c) {
             if (n_chunks > 0) {
@@ -706,9 +722,10 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         p.gpart[(size_t)split * p.n_params + p.off_b2 + tile * TC_BM + w * 32 + lane] = sum;
         if (w == 0 && lane == 0) tcw_stamp(q.timeline, 4);             // partial slot written
     } else if (warp >= TCA_NARROW_WARP0) {
-        // ---- narrow gradients on the FFMA pipe: thread (g, c): column n = 128 tile + c, rows of
-        // parity g; 16 rows per chunk and thread, the loads of the next chunk are issued before
-        // the current one is consumed -------------------------------------------------------------
+        // ---- narrow gradients on the FFMA pipe.  Thread (g, c): column n = 128 tile + c, rows of
+        // parity g.  dz1 / h2 of the chunk arrive in the stage by TMA (3 chunks ahead of the
+        // consumer: plain loads issued here starved behind the operand stream); the few xin / dout
+        // rows are prefetched one chunk ahead through registers -----------------------------------
         const int t = threadIdx.x - TCA_NARROW_WARP0 * 32;       // 0..255
         const int c = t & 127, g = t >> 7;
         const int n = tile * 128 + c;
@@ -720,91 +737,88 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         for (int j = 0; j < KIN; ++j) w1[j] = 0.0f;
 #pragma unroll
         for (int o = 0; o < TCA_NO; ++o) w3[o] = 0.0f;
-        float a1[16], hv[16], na1[16], nhv[16];
-        auto load_rows = [&](int chunk, float (&da)[16], float (&dh)[16]) {
-            const int64_t base = m_begin + (int64_t)chunk * TCW_ROWS;
-#pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int64_t r = min(base + g + 2 * u, m_end - 1);
-                da[u] = ldg_nc_volatile(q.dz1 + r * 256 + n);
-                dh[u] = ldg_nc_volatile(q.h2 + r * 256 + n);
-            }
-        };
-        // xin / dout rows of a chunk: global -> registers (loads in flight during the FFMA block of
-        // the current chunk) -> shared memory (after it)
-        constexpr int NX = (TCW_ROWS * KIN + 255) / 256, NDS = (TCW_ROWS * TCA_ND + 255) / 256;
+        constexpr int NX = (TCA_ROWS * KIN + 255) / 256, NDS = (TCA_ROWS * TCA_ND + 255) / 256;
         float sx[NX], sd[NDS];
         auto stage_load = [&](int chunk) {
-            const int64_t base = m_begin + (int64_t)chunk * TCW_ROWS;
+            const int64_t base = m_begin + (int64_t)chunk * TCA_ROWS;
 #pragma unroll
             for (int k = 0; k < NX; ++k) {
                 const int v = t + 256 * k, r = v / KIN, j = v % KIN;
-                sx[k] = (v < TCW_ROWS * KIN && base + r < m_end && j <= d_in)
+                sx[k] = (v < TCA_ROWS * KIN && base + r < m_end && j <= d_in)
                     ? ldg_nc_volatile(q.xin + (base + r) * ldx + j) : 0.0f;
             }
 #pragma unroll
             for (int k = 0; k < NDS; ++k) {
                 const int v = t + 256 * k, r = v / TCA_ND, o = v % TCA_ND;
-                sd[k] = (v < TCW_ROWS * TCA_ND && base + r < m_end && o < nd)
+                sd[k] = (v < TCA_ROWS * TCA_ND && base + r < m_end && o < nd)
                     ? ldg_nc_volatile(q.dout + (base + r) * q.ld_dout + o) : 0.0f;
             }
         };
         auto stage_store = [&](int chunk) {
-            float* x = xs + (chunk & 1) * TCW_ROWS * KIN;
-            float* d = &ds[chunk & 1][0][0];
+            float* x = xs + (chunk & 1) * TCA_ROWS * KIN;
+            float* d = dsm + (chunk & 1) * TCA_ROWS * TCA_ND;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) if (t + 256 * k < TCW_ROWS * KIN) x[t + 256 * k] = sx[k];
+            for (int k = 0; k < NX; ++k) if (t + 256 * k < TCA_ROWS * KIN) x[t + 256 * k] = sx[k];
 #pragma unroll
-            for (int k = 0; k < NDS; ++k) if (t + 256 * k < TCW_ROWS * TCA_ND) d[t + 256 * k] = sd[k];
+            for (int k = 0; k < NDS; ++k) if (t + 256 * k < TCA_ROWS * TCA_ND) d[t + 256 * k] = sd[k];
         };
         if (n_chunks > 0) {
-            load_rows(0, a1, hv);
             stage_load(0);
             stage_store(0);
         }
+        int stage = 0;
+        uint32_t phase = 0;
         for (int ch = 0; ch < n_chunks; ++ch) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // staging of chunk ch visible; buffer of ch+1 free
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // xin / dout of chunk ch visible; other buffer free
             const bool more = ch + 1 < n_chunks;
-            if (more) {
-                load_rows(ch + 1, na1, nhv);
-                stage_load(ch + 1);
-            }
-            const int rows = (int)min((int64_t)TCW_ROWS, m_end - (m_begin + (int64_t)ch * TCW_ROWS));
-            const float* x = xs + (ch & 1) * TCW_ROWS * KIN;
+            if (more) stage_load(ch + 1);
+            mbar_wait(&full_bar[stage], phase);                 // dz1 / h2 of this chunk landed
+            const unsigned char* st = smem + stage * L::STAGE_BYTES;
+            const float* s_dz1 = reinterpret_cast<const float*>(st + L::N_DZ1);
+            const float* s_h2 = reinterpret_cast<const float*>(st + L::N_H2);
+            const int rows = (int)min((int64_t)TCA_ROWS, m_end - (m_begin + (int64_t)ch * TCA_ROWS));
+            const float* x = xs + (ch & 1) * TCA_ROWS * KIN;
+            const float* d = dsm + (ch & 1) * TCA_ROWS * TCA_ND;
             if (tile == 0 && t < nd)
-                for (int r = 0; r < rows; ++r) dsum += ds[ch & 1][r][t];
+                for (int r = 0; r < rows; ++r) dsum += d[r * TCA_ND + t];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < TCA_ROWS / 2; ++u) {
                 const int r = g + 2 * u;
                 if (r < rows) {
-                    // 16-byte shared-memory reads (rows are 16-byte aligned: KIN, TCA_ND multiples of 4)
+                    const float a1 = s_dz1[r * 128 + c], hv = s_h2[r * 128 + c];
                     const float4* x4 = reinterpret_cast<const float4*>(x + r * KIN);
 #pragma unroll
                     for (int j = 0; j < KIN / 4; ++j) {
                         const float4 xv = x4[j];
-                        w1[4 * j] = fmaf(a1[u], xv.x, w1[4 * j]);
-                        w1[4 * j + 1] = fmaf(a1[u], xv.y, w1[4 * j + 1]);
-                        w1[4 * j + 2] = fmaf(a1[u], xv.z, w1[4 * j + 2]);
-                        w1[4 * j + 3] = fmaf(a1[u], xv.w, w1[4 * j + 3]);
+                        w1[4 * j] = fmaf(a1, xv.x, w1[4 * j]);
+                        w1[4 * j + 1] = fmaf(a1, xv.y, w1[4 * j + 1]);
+                        w1[4 * j + 2] = fmaf(a1, xv.z, w1[4 * j + 2]);
+                        w1[4 * j + 3] = fmaf(a1, xv.w, w1[4 * j + 3]);
                     }
-                    const float4* d4 = reinterpret_cast<const float4*>(&ds[ch & 1][r][0]);
+                    const float4* d4 = reinterpret_cast<const float4*>(d + r * TCA_ND);
 #pragma unroll
                     for (int o = 0; o < TCA_NO / 4; ++o) {
                         const float4 dv = d4[o];
-                        w3[4 * o] = fmaf(dv.x, hv[u], w3[4 * o]);
-                        w3[4 * o + 1] = fmaf(dv.y, hv[u], w3[4 * o + 1]);
-                        w3[4 * o + 2] = fmaf(dv.z, hv[u], w3[4 * o + 2]);
-                        w3[4 * o + 3] = fmaf(dv.w, hv[u], w3[4 * o + 3]);
+                        w3[4 * o] = fmaf(dv.x, hv, w3[4 * o]);
+                        w3[4 * o + 1] = fmaf(dv.y, hv, w3[4 * o + 1]);
+                        w3[4 * o + 2] = fmaf(dv.z, hv, w3[4 * o + 2]);
+                        w3[4 * o + 3] = fmaf(dv.w, hv, w3[4 * o + 3]);
                     }
                 }
             }
             if (more) stage_store(ch + 1);
-#pragma unroll
-            for (int u = 0; u < 16; ++u) { a1[u] = na1[u]; hv[u] = nhv[u]; }
+            // this group's reads of the stage are done: one arrival per chunk for the whole group
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (t == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
         }
         if (t == 0) tcw_stamp(q.timeline, 3);                     // narrow gradients accumulated
         // combine the two row groups (fixed order: group 0 + group 1) in two rounds through the
-        // exchange block, then write this split's partial slot
+        // dz1 / h2 block of stage 0 (the producer is done and only these warps read that block),
+        // then write this split's partial slot
+        float (*comb)[KIN] = reinterpret_cast<float (*)[KIN]>(smem + L::N_DZ1);       // [128][KIN] <= 16 KB
+        static_assert(128 * KIN * 4 <= 2 * L::N_BYTES, "exchange block too large");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (g == 1) {
 #pragma unroll
             for (int j = 0; j < KIN; ++j) comb[c][j] = w1[j];
@@ -815,7 +829,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             for (int j = 0; j < KIN; ++j) w1[j] += comb[c][j];
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        float (*comb3)[TCA_NO] = reinterpret_cast<float (*)[TCA_NO]>(epi);
+        float (*comb3)[TCA_NO] = reinterpret_cast<float (*)[TCA_NO]>(smem + L::N_DZ1);
         if (g == 1) {
 #pragma unroll
             for (int o = 0; o < TCA_NO; ++o) comb3[c][o] = w3[o];
@@ -824,9 +838,6 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         if (g == 0) {
 #pragma unroll
             for (int o = 0; o < TCA_NO; ++o) w3[o] += comb3[c][o];
-        }
-        asm volatile("bar.arrive 2, 384;" ::: "memory");       // exchange block released to the epilogue warps
-        if (g == 0) {
             float* out = p.gpart + (size_t)split * p.n_params;
 #pragma unroll
             for (int j = 0; j < KIN; ++j) {
@@ -864,22 +875,23 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     if (threadIdx.x == 0) tcw_stamp(q.timeline, 6);               // grid barrier passed
     for (int i = lo + (int)threadIdx.x; i < hi; i += TCA_THREADS) {
         // same summation order as adam_kernel: g_k = sum over s = k (mod 4) in increasing s, then
-        // (g0 + g1) + (g2 + g3); 16 independent L2 loads in flight (__ldcg: written by other SMs)
+        // (g0 + g1) + (g2 + g3); 32 independent L2 loads in flight (__ldcg: written by other SMs)
         const float* src = p.gpart + i;
         float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
         int sidx = 0;
-        for (; sidx + 16 <= q.n_split; sidx += 16) {
-            float v[16];
+        for (; sidx + 32 <= q.n_split; sidx += 32) {
+            float v[32];
 #pragma unroll
-            for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(sidx + u) * p.n_params);
+            for (int u = 0; u < 32; ++u) v[u] = __ldcg(src + (size_t)(sidx + u) * p.n_params);
 #pragma unroll
-            for (int u = 0; u < 16; u += 4) { g0 += v[u]; g1 += v[u + 1]; g2 += v[u + 2]; g3 += v[u + 3]; }
+            for (int u = 0; u < 32; u += 4) { g0 += v[u]; g1 += v[u + 1]; g2 += v[u + 2]; g3 += v[u + 3]; }
         }
         for (; sidx + 4 <= q.n_split; sidx += 4) {
-            g0 += __ldcg(src + (size_t)(sidx + 0) * p.n_params);
-            g1 += __ldcg(src + (size_t)(sidx + 1) * p.n_params);
-            g2 += __ldcg(src + (size_t)(sidx + 2) * p.n_params);
-            g3 += __ldcg(src + (size_t)(sidx + 3) * p.n_params);
+            const float v0 = __ldcg(src + (size_t)(sidx + 0) * p.n_params);
+            const float v1 = __ldcg(src + (size_t)(sidx + 1) * p.n_params);
+            const float v2 = __ldcg(src + (size_t)(sidx + 2) * p.n_params);
+            const float v3 = __ldcg(src + (size_t)(sidx + 3) * p.n_params);
+            g0 += v0; g1 += v1; g2 += v2; g3 += v3;
         }
         for (int k = 0; sidx < q.n_split; ++sidx, ++k) {
             const float v = __ldcg(src + (size_t)sidx * p.n_params);
@@ -1076,15 +1088,17 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_mlp_wgrad_fused: passes must be 1 or 3");
     TB_REQUIRE(shape->off_b2 == shape->off_w2 + 256 * 256, TB_EINVAL,
                "tb_mlp_wgrad_fused: b2 must follow W2 in the flat layout");
-    CUtensorMap maps[4];
+    CUtensorMap maps[6];
     int rc;
-    if ((rc = make_map(&maps[0], d_dz2_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-    if ((rc = make_map(&maps[1], d_dz2_lo, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-    if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-    if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TCW_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[0], d_dz2_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[1], d_dz2_lo, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map_plain(&maps[4], d_dz1, n_rows, 128, TCA_ROWS))) return rc;
+    if ((rc = make_map_plain(&maps[5], d_h2, n_rows, 128, TCA_ROWS))) return rc;
     TcWgradAllParams q;
     q.w.n_rows = n_rows;
-    q.w.rows_per_split = ((n_rows + n_split - 1) / n_split + TCW_ROWS - 1) / TCW_ROWS * TCW_ROWS;
+    q.w.rows_per_split = ((n_rows + n_split - 1) / n_split + TCA_ROWS - 1) / TCA_ROWS * TCA_ROWS;
     q.w.gpart = d_gpart; q.w.n_params = shape->n_params; q.w.off_w2 = shape->off_w2;
     q.w.off_b2 = shape->off_b2; q.w.skip = d_skip;
     q.w.dbg_lbo = q.w.dbg_sbo = q.w.dbg_kstep = q.w.dbg_idesc_xor = 0;
@@ -1109,7 +1123,7 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
             configured = true;                                                                       \
         }                                                                                            \
         tc_wgrad_all_kernel<P_, K_><<<grid, TCA_THREADS, tca_smem_bytes<P_, K_>(), s>>>(             \
-            maps[0], maps[1], maps[2], maps[3], q);                                                  \
+            maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], q);                                \
     }
     if (passes == 3) { if (small_in) TB_WGRAD_ALL(3, 20) else TB_WGRAD_ALL(3, 32) }
     else { if (small_in) TB_WGRAD_ALL(1, 20) else TB_WGRAD_ALL(1, 32) }
