@@ -302,6 +302,17 @@ def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_s
         outs.append(flat.cpu())
     assert torch.equal(outs[0], outs[1])
     assert int(sync.item()) == 2 * 2 * n_split          # two barriers of 2 * n_split CTAs
+    if passes == 3:
+        # plain float32 h1 / dz2 (lo == NULL): the kernel splits the tiles in shared memory into
+        # the same hi / lo operands -> bit-identical gradient
+        d_h1, d_dz2 = h1.cuda(), dz2.cuda()
+        flat = torch.full((layout.n_params,), float('nan'), device='cuda')
+        _lib.call('tb_mlp_wgrad_fused', ctypes.byref(sh), K.ptr(dev[0]), K.ptr(d_h1), None,
+                  K.ptr(dev[1]), K.ptr(dev[2]), K.ptr(d_dz2), None, K.ptr(dev[3]), ld, n_extra,
+                  off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), passes,
+                  None, None, 0.0, None, -1.0, None, None, K.stream())
+        torch.cuda.synchronize()
+        assert torch.equal(flat.cpu(), outs[0])
     got = outs[0].double()
     used = torch.zeros(layout.n_params, dtype=torch.bool)
     for name, (off, size) in o.items():

@@ -1088,9 +1088,12 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
     using namespace tb;
     int rc = check_tc_shape(shape, "tb_mlp_backward_tc");
     if (rc) return rc;
-    TB_REQUIRE(d_params && d_packed && d_dout && d_h1_hi && d_h1_lo && d_h2 && d_dz2_hi && d_dz2_lo &&
+    TB_REQUIRE(d_params && d_packed && d_dout && d_h1_hi && d_h2 && d_dz2_hi &&
                d_dz1 && n_rows > 0 && ld_dout >= shape->n_out, TB_EINVAL,
                "tb_mlp_backward_tc: bad arguments");
+    // d_h1_lo == NULL / d_dz2_lo == NULL: plain float32 activations (fused kernels only)
+    TB_REQUIRE((d_h1_lo && d_dz2_lo) || shape->n_out <= 8, TB_EINVAL,
+               "tb_mlp_backward_tc: the unfused chain needs the tf32 splits (lo arrays)");
     TB_REQUIRE(!d_dx || (dx_cols >= 1 && dx_cols <= 256 && dx_col0 >= 0 &&
                          dx_col0 + dx_cols <= shape->d_in), TB_EINVAL,
                "tb_mlp_backward_tc: dx column range invalid");
@@ -1100,6 +1103,8 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
         const char* v = getenv("TONIC_B200_FUSED_BWD");
         return !(v && v[0] == '0');
     }();
+    TB_REQUIRE((d_h1_lo && d_dz2_lo) || (fused_bwd && shape->n_out <= 8), TB_EINVAL,
+               "tb_mlp_backward_tc: plain activations need the fused backward kernel");
     if (fused_bwd && shape->n_out <= 8) {
         // head gradient + hidden-layer GEMM + activation gradient in one kernel (csrc/tc_mlp.cu)
         rc = tb_tc_mlp_backward(shape, d_params, d_packed, d_dout, ld_dout, d_h1_hi, d_h1_lo, d_h2, n_rows,

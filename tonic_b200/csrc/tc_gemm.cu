@@ -566,7 +566,11 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsign
     __syncthreads();
 }
 
-template <int PASSES, int KIN>
+// PLAIN: dz2 / h1 are single float32 arrays; the TMA lands them in the "hi" operand slots and
+// the FFMA warps split every tile in shared memory (hi = tf32 truncation in place, lo = x - hi
+// in the "lo" slot: bit-identical to the splits the forward / backward kernels used to store)
+// before the MMA thread is released -- half the activation bytes through L2.
+template <int PASSES, int KIN, bool PLAIN>
 __global__ void __launch_bounds__(TCA_THREADS, 1)
 tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
                     const __grid_constant__ CUtensorMap map_h_hi, const __grid_constant__ CUtensorMap map_h_lo,
@@ -586,8 +590,10 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + TCA_STAGES;
     uint64_t* tmem_full = bars + 2 * TCA_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* split_bar = tmem_full + 1;                 // [STAGES] operands split (PLAIN)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(split_bar + TCA_STAGES);
     static_assert(KIN % 4 == 0 && TCA_ND % 4 == 0 && TCA_NO % 4 == 0, "16-byte shared-memory rows");
+    static_assert(!PLAIN || PASSES == 3, "plain activations are split for the 3-pass mode");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x;                                 // 0 / 1: columns 128*tile..
@@ -600,6 +606,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         for (int s = 0; s < TCA_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 2);          // released by the MMA commit AND by the narrow warps
+            mbar_init(&split_bar[s], 1);
         }
         mbar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -626,13 +633,14 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char* st = smem + stage * L::STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * (L::A_BYTES + L::B_BYTES) + 2 * L::N_BYTES);
+                mbar_expect_tx(&full_bar[stage],
+                               ((PASSES == 3 && !PLAIN) ? 2 : 1) * (L::A_BYTES + L::B_BYTES) + 2 * L::N_BYTES);
                 const int m0 = (int)(m_begin + (int64_t)c * TCA_ROWS);
                 for (int b = 0; b < TC_BM / 32; ++b)
                     tma_load_2d(st + L::A_HI + b * L::BOX, &map_dz_hi, &full_bar[stage], tile * TC_BM + b * 32, m0);
                 for (int b = 0; b < TC_BN / 32; ++b)
                     tma_load_2d(st + L::B_HI + b * L::BOX, &map_h_hi, &full_bar[stage], b * 32, m0);
-                if (PASSES == 3) {
+                if (PASSES == 3 && !PLAIN) {
                     for (int b = 0; b < TC_BM / 32; ++b)
                         tma_load_2d(st + L::A_LO + b * L::BOX, &map_dz_lo, &full_bar[stage], tile * TC_BM + b * 32, m0);
                     for (int b = 0; b < TC_BN / 32; ++b)
@@ -650,7 +658,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             const uint32_t idesc16 = (kIdescTf32MN & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
             const uint64_t b_ones = umma_desc_mnmajor_sw128(ones, L::BOX);
             for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(PLAIN ? &split_bar[stage] : &full_bar[stage], phase);
                 tcgen05_fence_after();
                 unsigned char* st = smem + stage * L::STAGE_BYTES;
                 // 16-row boxes: 32-column groups are BOX = 2048 bytes apart (LBO)
@@ -772,8 +780,33 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             asm volatile("bar.sync 1, 256;" ::: "memory");      // xin / dout of chunk ch visible; other buffer free
             const bool more = ch + 1 < n_chunks;
             if (more) stage_load(ch + 1);
-            mbar_wait(&full_bar[stage], phase);                 // dz1 / h2 of this chunk landed
-            const unsigned char* st = smem + stage * L::STAGE_BYTES;
+            mbar_wait(&full_bar[stage], phase);                 // operands and dz1 / h2 of this chunk landed
+            unsigned char* st = smem + stage * L::STAGE_BYTES;
+            if (PLAIN) {
+                // split the dz2 (8 KB) and h1 (16 KB) tiles: 1536 float4 over 256 threads; element
+                // positions are the same in the hi and lo tiles, so the swizzle does not matter
+                float4* a_hi = reinterpret_cast<float4*>(st + L::A_HI);
+                float4* a_lo = reinterpret_cast<float4*>(st + L::A_LO);
+                float4* b_hi = reinterpret_cast<float4*>(st + L::B_HI);
+                float4* b_lo = reinterpret_cast<float4*>(st + L::B_LO);
+                auto split4 = [](float4* hi, float4* lo, int i) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                };
+#pragma unroll
+                for (int k = 0; k < L::A_BYTES / 16 / 256; ++k) split4(a_hi, a_lo, t + 256 * k);
+#pragma unroll
+                for (int k = 0; k < L::B_BYTES / 16 / 256; ++k) split4(b_hi, b_lo, t + 256 * k);
+                fence_proxy_async_smem();                       // generic-proxy writes -> tensor core
+                asm volatile("bar.sync 3, 256;" ::: "memory");
+                if (t == 0) mbar_arrive(&split_bar[stage]);
+            }
             const float* s_dz1 = reinterpret_cast<const float*>(st + L::N_DZ1);
             const float* s_h2 = reinterpret_cast<const float*>(st + L::N_H2);
             const int rows = (int)min((int64_t)TCA_ROWS, m_end - (m_begin + (int64_t)ch * TCA_ROWS));
@@ -1077,8 +1110,10 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     TB_REQUIRE(!opt || (opt->d_params && opt->d_m && opt->d_v && opt->d_step && shape &&
                         opt->n_params == shape->n_params), TB_EINVAL,
                "tb_mlp_wgrad_fused: optimizer / shape mismatch");
-    TB_REQUIRE(shape && d_xin && d_h1_hi && d_h1_lo && d_h2 && d_dz1 && d_dz2_hi && d_dz2_lo && d_dout &&
+    TB_REQUIRE(shape && d_xin && d_h1_hi && d_h2 && d_dz1 && d_dz2_hi && d_dout &&
                d_gpart && d_flat && d_sync && n_rows > 0, TB_EINVAL, "tb_mlp_wgrad_fused: null pointer");
+    TB_REQUIRE((d_h1_lo == nullptr) == (d_dz2_lo == nullptr), TB_EINVAL,
+               "tb_mlp_wgrad_fused: h1 and dz2 must both be tf32 splits or both plain (lo == NULL)");
     TB_REQUIRE(shape->hidden == 256 && shape->off_w2_hi > 0 && shape->d_in + 1 <= 32 &&
                shape->n_out >= 1 && shape->n_out <= TCA_NO && shape->n_out + n_extra <= TCA_ND &&
                ld_dout >= shape->n_out + n_extra, TB_ENOTSUP,
@@ -1091,9 +1126,9 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     CUtensorMap maps[6];
     int rc;
     if ((rc = make_map(&maps[0], d_dz2_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-    if ((rc = make_map(&maps[1], d_dz2_lo, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[1], d_dz2_lo ? d_dz2_lo : d_dz2_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-    if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+    if ((rc = make_map(&maps[3], d_h1_lo ? d_h1_lo : d_h1_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     if ((rc = make_map_plain(&maps[4], d_dz1, n_rows, 128, TCA_ROWS))) return rc;
     if ((rc = make_map_plain(&maps[5], d_h2, n_rows, 128, TCA_ROWS))) return rc;
     TcWgradAllParams q;
@@ -1114,19 +1149,22 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     cudaStream_t s = as_stream(stream);
     ProfScope prof_scope("tb_mlp_wgrad_fused", stream);
     const bool small_in = shape->d_in + 1 <= 20;
-#define TB_WGRAD_ALL(P_, K_)                                                                         \
+    const bool plain = d_h1_lo == nullptr;
+    TB_REQUIRE(!plain || passes == 3, TB_EINVAL, "tb_mlp_wgrad_fused: plain activations need passes == 3");
+#define TB_WGRAD_ALL(P_, K_, PL_)                                                                    \
     {                                                                                                \
         static bool configured = false;                                                              \
         if (!configured) {                                                                           \
-            cudaFuncSetAttribute(tc_wgrad_all_kernel<P_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            cudaFuncSetAttribute(tc_wgrad_all_kernel<P_, K_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  tca_smem_bytes<P_, K_>());                                          \
             configured = true;                                                                       \
         }                                                                                            \
-        tc_wgrad_all_kernel<P_, K_><<<grid, TCA_THREADS, tca_smem_bytes<P_, K_>(), s>>>(             \
+        tc_wgrad_all_kernel<P_, K_, PL_><<<grid, TCA_THREADS, tca_smem_bytes<P_, K_>(), s>>>(        \
             maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], q);                                \
     }
-    if (passes == 3) { if (small_in) TB_WGRAD_ALL(3, 20) else TB_WGRAD_ALL(3, 32) }
-    else { if (small_in) TB_WGRAD_ALL(1, 20) else TB_WGRAD_ALL(1, 32) }
+    if (plain) { if (small_in) TB_WGRAD_ALL(3, 20, true) else TB_WGRAD_ALL(3, 32, true) }
+    else if (passes == 3) { if (small_in) TB_WGRAD_ALL(3, 20, false) else TB_WGRAD_ALL(3, 32, false) }
+    else { if (small_in) TB_WGRAD_ALL(1, 20, false) else TB_WGRAD_ALL(1, 32, false) }
 #undef TB_WGRAD_ALL
     return check_launch("tb_mlp_wgrad_fused");
 }

@@ -348,7 +348,11 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         float* stg = epi + rw * 32 * TCM_STG_STRIDE;
         const int d_in = p.d_in;
         const int ldx = (d_in + 1 + 3) & ~3;
-        const bool save_h1 = p.h1_hi != nullptr, save_h2 = p.h2 != nullptr;
+        // h1 for the backward pass: as the tf32 split (two arrays, TMA stores of the operand tiles)
+        // or, with h1_lo == NULL, as ONE plain float32 array written straight from registers (the
+        // fused weight-gradient kernel splits it on the fly: half the activation traffic)
+        const bool save_h1 = p.h1_hi != nullptr && p.h1_lo != nullptr, save_h2 = p.h2 != nullptr;
+        const bool plain_h1 = p.h1_hi != nullptr && p.h1_lo == nullptr;
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         int it = 0;
         if (stamper) tc_stamp(p.timeline, 31);
@@ -432,6 +436,12 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
                 if (stamper) tc_stamp(p.timeline, 20 + c);    // operand published
+                if (plain_h1 && row < p.n_rows) {             // 128 contiguous bytes of this row
+                    float4* dst = reinterpret_cast<float4*>(p.h1_hi + row * TC_BN + c * 32);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        dst[u] = make_float4(hv[4 * u], hv[4 * u + 1], hv[4 * u + 2], hv[4 * u + 3]);
+                }
                 if (save_h1) {
                     // saved activations for backward: the operand tile IS the tf32 split of h1 in
                     // the layout TMA expects -> one thread stores it asynchronously (the MMA and
@@ -729,6 +739,7 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         const bool issuer = q == 0 && lane == 0;            // this group's TMA-store thread
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         const bool stamper = (rw == 0 || rw == 4) && lane == 0;
+        const bool plain_dz2 = p.dz2_lo == nullptr;
         int it = 0;
         for (int tile = blockIdx.x; (CLUSTER == 2 ? (tile & ~1) : tile) < n_tiles; tile += gridDim.x, ++it) {
             const int64_t row0 = (int64_t)tile * TC_BM + q * 32;
@@ -795,21 +806,34 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                 mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
                 if (stamper) tc_stamp(p.timeline, 12 + c);     // stage free
                 unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
-                group_sync(wg);
+                if (!plain_dz2) {
+                    if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
+                    group_sync(wg);
+                }
                 store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z);
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
                 if (stamper) tc_stamp(p.timeline, 20 + c);     // published
-                // dz2 (tf32 split) for the weight-gradient kernels: the operand tile is already in
-                // the TMA layout -> asynchronous store by one thread
-                group_sync(wg);
-                if (issuer) {
-                    tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
-                    if (PASSES == 3) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
-                    bulk_commit();
+                if (plain_dz2) {
+                    // dz2 as ONE plain float32 array straight from registers (dz2_lo == NULL): the
+                    // fused weight-gradient kernel splits it on the fly
+                    if (live) {
+                        float4* dst = reinterpret_cast<float4*>(p.dz2_hi + row * TC_BN + c * 32);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                            dst[u] = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
+                    }
+                } else {
+                    // dz2 (tf32 split) for the weight-gradient kernels: the operand tile is already in
+                    // the TMA layout -> asynchronous store by one thread
+                    group_sync(wg);
+                    if (issuer) {
+                        tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
+                        if (PASSES == 3) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                        bulk_commit();
+                    }
                 }
             }
             // ---- b) epilogue: dz1 = acc * act'(h1).  h1 (hi + lo) is read with coalesced 64-byte
@@ -824,7 +848,7 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                     const int64_t r = row0 + 2 * i + (lane >> 4);
                     const int64_t e = r * TC_BN + c * 32 + half * 16 + (lane & 15);
                     ua[i] = r < p.n_rows ? __ldg(p.h1_hi + e) : 0.0f;
-                    ub[i] = (PASSES == 3 && r < p.n_rows) ? __ldg(p.h1_lo + e) : 0.0f;
+                    ub[i] = (PASSES == 3 && p.h1_lo && r < p.n_rows) ? __ldg(p.h1_lo + e) : 0.0f;
                 }
             };
             load_h1(wg, 0);
@@ -999,8 +1023,7 @@ static int tc_mlp_forward_impl(const TbMlpShape* shape, const float* d_params, c
     TB_REQUIRE(in->dim1 + (in->d_x2 ? in->dim2 : 0) == shape->d_in, TB_EINVAL,
                "tb_tc_mlp_forward: input widths do not add up to d_in");
     TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_forward: passes must be 1 or 3");
-    TB_REQUIRE((d_h1_hi == nullptr) == (d_h1_lo == nullptr), TB_EINVAL,
-               "tb_tc_mlp_forward: h1 hi / lo must be given together");
+    TB_REQUIRE(d_h1_hi || !d_h1_lo, TB_EINVAL, "tb_tc_mlp_forward: h1 lo without hi");
     // experimental: 2-CTA clusters with multicast of the weight-operand chunks (3-pass mode only;
     // written and compiled in round 1, not yet validated on hardware -> off unless requested)
     static const bool cluster_env = [] {
@@ -1014,7 +1037,7 @@ static int tc_mlp_forward_impl(const TbMlpShape* shape, const float* d_params, c
     if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, b_box_rows))) return rc;
     if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, b_box_rows))) return rc;
     maps[2] = maps[3] = maps[4] = maps[0];       // placeholders when nothing is saved
-    if (d_h1_hi) {
+    if (d_h1_hi && d_h1_lo) {      // tf32 split saved by TMA; d_h1_lo == NULL: plain float32 from registers
         if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TC_BM))) return rc;
         if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TC_BM))) return rc;
     }
@@ -1076,8 +1099,8 @@ extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params
                                   float* d_dz2_hi, float* d_dz2_lo, float* d_dz1, int32_t passes,
                                   const int32_t* d_skip, void* stream) {
     using namespace tb;
-    TB_REQUIRE(shape && d_params && d_packed && d_dout && d_h1_hi && d_h1_lo && d_h2 && d_dz2_hi &&
-               d_dz2_lo && d_dz1 && n_rows > 0, TB_EINVAL, "tb_tc_mlp_backward: null pointer");
+    TB_REQUIRE(shape && d_params && d_packed && d_dout && d_h1_hi && d_h2 && d_dz2_hi &&
+               d_dz1 && n_rows > 0, TB_EINVAL, "tb_tc_mlp_backward: null pointer");
     TB_REQUIRE(shape->hidden == 256 && shape->off_w2t_hi > 0 && shape->n_out >= 1 &&
                shape->n_out <= TC_MAX_HEAD && ld_dout >= shape->n_out, TB_ENOTSUP,
                "tb_tc_mlp_backward: needs hidden == 256 and n_out <= 8 (got %d, %d)", shape->hidden,
@@ -1094,7 +1117,7 @@ extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params
     if ((rc = make_map(&maps[0], d_packed + shape->off_w2t_hi, TC_BN, b_box_rows))) return rc;
     if ((rc = make_map(&maps[1], d_packed + shape->off_w2t_lo, TC_BN, b_box_rows))) return rc;
     if ((rc = make_map(&maps[2], d_dz2_hi, n_rows, TC_BM))) return rc;
-    if ((rc = make_map(&maps[3], d_dz2_lo, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[3], d_dz2_lo ? d_dz2_lo : d_dz2_hi, n_rows, TC_BM))) return rc;
     if ((rc = make_map(&maps[4], d_dz1, n_rows, TC_BM))) return rc;
     TcMlpBwdParams p;
     p.n_rows = n_rows; p.dout = d_dout; p.ld_dout = ld_dout; p.n_head = shape->n_out;

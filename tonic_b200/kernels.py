@@ -159,6 +159,7 @@ class MlpLayout:
             self.offsets[name] = (off, size)
             off = round_up(off + size, 4)
         self.n_params = off
+        self.n_extra = sum(int(sz) for _, sz in extras)
         self.off_w1t = 0
         self.off_w2t = round_up(d_in * H, 4)
         self.n_packed = self.off_w2t + H * H
@@ -203,6 +204,7 @@ _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 _FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
 _FUSED_WGRAD = os.environ.get('TONIC_B200_FUSED_WGRAD', '1') != '0'
 _FUSED_ADAM = os.environ.get('TONIC_B200_FUSED_ADAM', '1') != '0'
+_PLAIN_ACTS = os.environ.get('TONIC_B200_PLAIN_ACTS', '1') != '0'
 
 
 class DeviceMlp:
@@ -262,6 +264,15 @@ class DeviceMlp:
             self._gpart = torch.zeros(n_split, self.layout.n_params, dtype=F32, device=device())
         return self._gpart
 
+    def plain_activations(self):
+        """h1 / dz2 kept as ONE float32 array each (instead of tf32 hi / lo pairs): the fused
+        forward / backward kernels write them straight from registers and the fused
+        weight-gradient kernel splits the tiles in shared memory.  Needs all three fused kernels
+        and the 3-pass mode."""
+        L = self.layout
+        return (_PLAIN_ACTS and self.passes() == 3 and _FUSED_FWD and _FUSED_BWD and L.fused_forward
+                and L.n_out <= 8 and self.fused_wgrad(L.n_extra))
+
     def fused_wgrad(self, n_extra=0):
         """All weight gradients in one launch, reduced in the kernel to ONE flat gradient
         (csrc/tc_gemm.cu::tc_wgrad_all_kernel)."""
@@ -320,7 +331,8 @@ class DeviceMlp:
                 _lib.call('tb_tc_mlp_forward_vloss', ctypes.byref(L.shape), ptr(params), ptr(packed),
                           ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
                           *((None, None, None) if not save
-                            else (ptr(self.h1), ptr(self.h1_lo), ptr(self.h2))),
+                            else (ptr(self.h1), None if self.plain_activations() else ptr(self.h1_lo),
+                                  ptr(self.h2))),
                           passes, ptr(targets), ptr(idx), ptr(dout),
                           dout.shape[-1] if dout.dim() > 1 else 1, ptr(stats), _lib.STAT_VALUE, 1,
                           ptr(skip), stream())
@@ -328,7 +340,8 @@ class DeviceMlp:
             _lib.call('tb_mlp_forward_tc', ctypes.byref(L.shape), ptr(params), ptr(packed),
                       ctypes.byref(inp.struct), rows, ptr(out), ptr(self.xin) if save else None,
                       *((None, None, None) if fused and not save
-                        else (ptr(self.h1), ptr(self.h1_lo), ptr(self.h2))),
+                        else (ptr(self.h1), None if fused and self.plain_activations() else ptr(self.h1_lo),
+                              ptr(self.h2))),
                       passes, ptr(skip), stream())
             return out
         _count_flops('tb_mlp_forward', flops)
@@ -351,8 +364,9 @@ class DeviceMlp:
                 _count_flops('tb_tc_gemm256_bwd', 2.0 * rows * L.hidden * L.hidden)
             _lib.call('tb_mlp_backward_tc', ctypes.byref(L.shape), ptr(params),
                       ptr(self.packed if packed is None else packed), ptr(dout), dout.shape[-1],
-                      ptr(self.h1), ptr(self.h1_lo), ptr(self.h2), rows, ptr(self.dz2),
-                      ptr(self.dz2_lo), ptr(self.dz1), ptr(dx), dx_col0,
+                      ptr(self.h1), None if self.plain_activations() else ptr(self.h1_lo), ptr(self.h2),
+                      rows, ptr(self.dz2), None if self.plain_activations() else ptr(self.dz2_lo),
+                      ptr(self.dz1), ptr(dx), dx_col0,
                       0 if dx is None else dx.shape[-1], passes, ptr(skip), stream())
             return
         _count_flops('tb_mlp_backward', flops)
@@ -381,15 +395,19 @@ class DeviceMlp:
             if fuse is not None:
                 adam, scale, stats, kl, stop = fuse
                 opt, packed = ctypes.byref(adam.struct), self.packed
+            plain = self.plain_activations()
             _lib.call('tb_mlp_wgrad_fused', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
-                      ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
-                      ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
+                      None if plain else ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
+                      None if plain else ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
                       ptr(gpart), n_split, ptr(flat), ptr(self._wgrad_sync), passes, opt,
                       ptr(packed), scale, ptr(stats), kl, ptr(stop), ptr(skip), stream())
             self.reduced = True
             self.applied = fuse is not None
             return flat
         self.reduced = False
+        if self.plain_activations():
+            raise _lib.TonicB200Error('plain activations were saved but the fused weight-gradient '
+                                      f'kernel does not cover n_extra={n_extra}')
         if passes:
             _count_flops('tb_mlp_wgrad_tc', flops)
             _count_flops('tb_tc_wgrad256', 2.0 * rows * L.hidden * L.hidden)
