@@ -199,6 +199,32 @@ static inline int make_map(CUtensorMap* map, const float* base, int64_t rows, in
     return 0;
 }
 
+// The same [rows, 256] matrix seen as (32 columns, rows, 8 column groups): ONE box of
+// (32, box_rows, n_groups) lands in shared memory as n_groups consecutive [box_rows x 128 B]
+// blocks -- the MN-major operand layout (SWIZZLE_128B_ATOM_32B) that otherwise takes one 2-D
+// box per 32-column group (TMA issue, not bandwidth, bounded the weight-gradient mainloop).
+static inline int make_map_groups(CUtensorMap* map, const float* base, int64_t rows, int box_rows,
+                                  int n_groups) {
+    EncodeTiledFn fn = encode_fn();
+    TB_REQUIRE(fn, TB_ENOTSUP, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)(TC_K / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)TC_K * sizeof(float), 32 * sizeof(float)};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)n_groups};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;      // the caller falls back to per-group 2-D boxes
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0),
+        "r"(c1), "r"(c2) : "memory");
+}
+
 // 2-D row-major float matrix [rows, 256]; box = [box_cols floats, box_rows]; no swizzle (plain
 // row-major tile in shared memory).
 static inline int make_map_plain(CUtensorMap* map, const float* base, int64_t rows, int box_cols,

@@ -539,6 +539,7 @@ struct TcWgradAllParams {
     float* flat;                // [n_params] reduced gradient (sum over rows)
     unsigned long long* sync;   // grid-barrier counter (monotonic)
     unsigned long long* timeline;   // profiling aid: clock64() stamps of CTA (0, 0), or NULL
+    int tma3d;                  // operand tiles by one 3-D box each (else one 2-D box per column group)
     // optional fused optimizer step (single process, no gradient clipping): the reduction phase
     // applies Adam to its slice right away -- same arithmetic and device-side controls as adam_kernel
     int fuse_adam;
@@ -575,6 +576,8 @@ __global__ void __launch_bounds__(TCA_THREADS, 1)
 tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_constant__ CUtensorMap map_dz_lo,
                     const __grid_constant__ CUtensorMap map_h_hi, const __grid_constant__ CUtensorMap map_h_lo,
                     const __grid_constant__ CUtensorMap map_dz1, const __grid_constant__ CUtensorMap map_h2,
+                    const __grid_constant__ CUtensorMap map3_dz_hi, const __grid_constant__ CUtensorMap map3_dz_lo,
+                    const __grid_constant__ CUtensorMap map3_h_hi, const __grid_constant__ CUtensorMap map3_h_lo,
                     const TcWgradAllParams q) {
     using L = TcaLayout<KIN>;
     const TcWgradParams& p = q.w;
@@ -636,6 +639,19 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                 mbar_expect_tx(&full_bar[stage],
                                ((PASSES == 3 && !PLAIN) ? 2 : 1) * (L::A_BYTES + L::B_BYTES) + 2 * L::N_BYTES);
                 const int m0 = (int)(m_begin + (int64_t)c * TCA_ROWS);
+                if (q.tma3d) {
+                    // one 3-D box per operand tile (4 / 8 column groups x 16 rows x 128 B)
+                    tma_load_3d(st + L::A_HI, &map3_dz_hi, &full_bar[stage], 0, m0, tile * (TC_BM / 32));
+                    tma_load_3d(st + L::B_HI, &map3_h_hi, &full_bar[stage], 0, m0, 0);
+                    if (PASSES == 3 && !PLAIN) {
+                        tma_load_3d(st + L::A_LO, &map3_dz_lo, &full_bar[stage], 0, m0, tile * (TC_BM / 32));
+                        tma_load_3d(st + L::B_LO, &map3_h_lo, &full_bar[stage], 0, m0, 0);
+                    }
+                    tma_load_2d(st + L::N_DZ1, &map_dz1, &full_bar[stage], tile * TC_BM, m0);
+                    tma_load_2d(st + L::N_H2, &map_h2, &full_bar[stage], tile * TC_BM, m0);
+                    if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
+                    continue;
+                }
                 for (int b = 0; b < TC_BM / 32; ++b)
                     tma_load_2d(st + L::A_HI + b * L::BOX, &map_dz_hi, &full_bar[stage], tile * TC_BM + b * 32, m0);
                 for (int b = 0; b < TC_BN / 32; ++b)
@@ -1131,7 +1147,18 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     if ((rc = make_map(&maps[3], d_h1_lo ? d_h1_lo : d_h1_hi, n_rows, TCA_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
     if ((rc = make_map_plain(&maps[4], d_dz1, n_rows, 128, TCA_ROWS))) return rc;
     if ((rc = make_map_plain(&maps[5], d_h2, n_rows, 128, TCA_ROWS))) return rc;
+    CUtensorMap maps3[4];
+    static const bool want3d = [] { const char* v = getenv("TONIC_B200_WGRAD_TMA3D"); return !(v && v[0] == '0'); }();
+    bool tma3d = want3d;
+    if (tma3d) {
+        tma3d = make_map_groups(&maps3[0], d_dz2_hi, n_rows, TCA_ROWS, TC_BM / 32) == 0 &&
+                make_map_groups(&maps3[1], d_dz2_lo ? d_dz2_lo : d_dz2_hi, n_rows, TCA_ROWS, TC_BM / 32) == 0 &&
+                make_map_groups(&maps3[2], d_h1_hi, n_rows, TCA_ROWS, TC_BN / 32) == 0 &&
+                make_map_groups(&maps3[3], d_h1_lo ? d_h1_lo : d_h1_hi, n_rows, TCA_ROWS, TC_BN / 32) == 0;
+    }
+    if (!tma3d) for (int i = 0; i < 4; ++i) maps3[i] = maps[i];
     TcWgradAllParams q;
+    q.tma3d = tma3d ? 1 : 0;
     q.w.n_rows = n_rows;
     q.w.rows_per_split = ((n_rows + n_split - 1) / n_split + TCA_ROWS - 1) / TCA_ROWS * TCA_ROWS;
     q.w.gpart = d_gpart; q.w.n_params = shape->n_params; q.w.off_w2 = shape->off_w2;
@@ -1160,7 +1187,7 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
             configured = true;                                                                       \
         }                                                                                            \
         tc_wgrad_all_kernel<P_, K_, PL_><<<grid, TCA_THREADS, tca_smem_bytes<P_, K_>(), s>>>(        \
-            maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], q);                                \
+            maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps3[0], maps3[1], maps3[2], maps3[3], q); \
     }
     if (plain) { if (small_in) TB_WGRAD_ALL(3, 20, true) else TB_WGRAD_ALL(3, 32, true) }
     else if (passes == 3) { if (small_in) TB_WGRAD_ALL(3, 20, false) else TB_WGRAD_ALL(3, 32, false) }
