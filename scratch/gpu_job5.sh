@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/r2f; mkdir -p $O
+O=gpurun_out/r2g; mkdir -p $O
 run() { name=$1; shift; ( "$@" ) > $O/$name.log 2>&1; echo "== $name rc=$?" >> $O/summary.log; }
 : > $O/summary.log
 run t_wgrad timeout 120 python -m pytest tests/test_gpu_tc.py -x -q -m gpu -k "wgrad_fused"

@@ -135,11 +135,17 @@ def test_ppo_iteration_at_the_benched_shape_matches_reference(golden):
     ref = by_key(g['info_keys'], g['info_mean'])
     assert set(got) == set(ref) and all(len(got[k]) == len(ref[k]) for k in ref)
     assert len(got['critic/loss']) == 320 and len(got['actor/loss']) == int(got['actor/iterations'][0])
-    # absolute floors: the surrogate loss is a cancelling mean of unit-scale terms; one sample of
-    # the 16384 changing side of the clip boundary moves clip_fraction by 6.1e-5; the KL is a
-    # difference of log-probabilities of size ~1e-3
+    # First epoch: 1e-4 relative, with absolute floors where the statistic is a cancelling mean
+    # (the surrogate loss: unit-scale terms cancelling to ~1e-2), a difference of log-probabilities
+    # (KL ~1e-3) or a count (one of 16384 samples crossing the clip boundary = 6.1e-5).
+    # Whole update: the reference ITSELF is only reproducible to the spread recorded in
+    # tests/golden/ppo_bench_thread_sensitivity.json (same torch code, 1 vs 8 BLAS threads): the
+    # bar is 3x that spread (+ the first-epoch bar).
+    import json
+    import os
+    spread = json.load(open(os.path.join(os.path.dirname(__file__), 'golden',
+                                         'ppo_bench_thread_sensitivity.json')))['whole_update_max_abs']
     floor_first = {'actor/loss': 1e-4, 'actor/kl': 2e-6, 'actor/clip_fraction': 3.1 / 16384}
-    floor_whole = {'actor/loss': 3e-4, 'actor/kl': 1e-4, 'actor/clip_fraction': 0.01}
     worst = {}
     for k in ref:
         a, b = np.array(got[k]), np.array(ref[k])
@@ -149,9 +155,9 @@ def test_ppo_iteration_at_the_benched_shape_matches_reference(golden):
         err = np.abs(a - b)
         worst[k] = (float(err[:32].max()), float((err[:32] / (np.abs(b[:32]) + 1e-12)).max()),
                     float(err.max()), float((err / (np.abs(b) + 1e-12)).max()))
-        ok_first = err[:32] <= 1e-4 * np.abs(b[:32]) + floor_first.get(k, 2e-6)
-        ok_whole = err <= 2e-3 * np.abs(b) + floor_whole.get(k, 2e-5)
-        assert ok_first.all() and ok_whole.all(), (k, worst[k])
+        bar_first = 1e-4 * np.abs(b) + floor_first.get(k, 2e-6)
+        assert (err[:32] <= bar_first[:32]).all(), (k, worst[k])
+        assert (err <= bar_first + 3.0 * spread[k]).all(), (k, worst[k], spread[k])
     print('benched shape (abs, rel) errors first epoch | whole update:', worst)
     # final weights (320 Adam steps per network at B = 16384)
     w = bench_shape.weight_digests(agent.model.state_dict(), 'digest_w/')

@@ -707,6 +707,41 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         const int w = warp - 4;
         float* stg = epi + w * 32 * TC_STAGE_ROWSTRIDE;
         float* out = p.gpart + (size_t)split * p.n_params + p.off_w2 + (size_t)(tile * TC_BM + w * 32) * TC_BN;
+        if (PLAIN) {
+            // during the mainloop these four warps are the SPLITTERS: as soon as a chunk has landed
+            // they rewrite the dz2 (8 KB) and h1 (16 KB) tiles as hi = tf32 truncation (in place)
+            // and lo = x - hi (lo slot) -- element positions are the same in both tiles, so the
+            // swizzle does not matter -- and release the MMA thread; they run up to 3 stages ahead
+            const int ts = threadIdx.x - 128;                       // 0..127
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                mbar_wait(&full_bar[stage], phase);
+                unsigned char* st = smem + stage * L::STAGE_BYTES;
+                float4* a_hi = reinterpret_cast<float4*>(st + L::A_HI);
+                float4* a_lo = reinterpret_cast<float4*>(st + L::A_LO);
+                float4* b_hi = reinterpret_cast<float4*>(st + L::B_HI);
+                float4* b_lo = reinterpret_cast<float4*>(st + L::B_LO);
+                auto split4 = [](float4* hi, float4* lo, int i) {
+                    const float4 v = hi[i];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[i] = h;
+                    lo[i] = l;
+                };
+#pragma unroll
+                for (int k = 0; k < L::A_BYTES / 16 / 128; ++k) split4(a_hi, a_lo, ts + 128 * k);
+#pragma unroll
+                for (int k = 0; k < L::B_BYTES / 16 / 128; ++k) split4(b_hi, b_lo, ts + 128 * k);
+                fence_proxy_async_smem();                       // generic-proxy writes -> tensor core
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (ts == 0) mbar_arrive(&split_bar[stage]);
+                if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
         if (n_chunks > 0) {
             mbar_wait(tmem_full, 0);
             tcgen05_fence_after();
@@ -797,32 +832,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             const bool more = ch + 1 < n_chunks;
             if (more) stage_load(ch + 1);
             mbar_wait(&full_bar[stage], phase);                 // operands and dz1 / h2 of this chunk landed
-            unsigned char* st = smem + stage * L::STAGE_BYTES;
-            if (PLAIN) {
-                // split the dz2 (8 KB) and h1 (16 KB) tiles: 1536 float4 over 256 threads; element
-                // positions are the same in the hi and lo tiles, so the swizzle does not matter
-                float4* a_hi = reinterpret_cast<float4*>(st + L::A_HI);
-                float4* a_lo = reinterpret_cast<float4*>(st + L::A_LO);
-                float4* b_hi = reinterpret_cast<float4*>(st + L::B_HI);
-                float4* b_lo = reinterpret_cast<float4*>(st + L::B_LO);
-                auto split4 = [](float4* hi, float4* lo, int i) {
-                    const float4 v = hi[i];
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                    hi[i] = h;
-                    lo[i] = l;
-                };
-#pragma unroll
-                for (int k = 0; k < L::A_BYTES / 16 / 256; ++k) split4(a_hi, a_lo, t + 256 * k);
-#pragma unroll
-                for (int k = 0; k < L::B_BYTES / 16 / 256; ++k) split4(b_hi, b_lo, t + 256 * k);
-                fence_proxy_async_smem();                       // generic-proxy writes -> tensor core
-                asm volatile("bar.sync 3, 256;" ::: "memory");
-                if (t == 0) mbar_arrive(&split_bar[stage]);
-            }
+            const unsigned char* st = smem + stage * L::STAGE_BYTES;
             const float* s_dz1 = reinterpret_cast<const float*>(st + L::N_DZ1);
             const float* s_h2 = reinterpret_cast<const float*>(st + L::N_H2);
             const int rows = (int)min((int64_t)TCA_ROWS, m_end - (m_begin + (int64_t)ch * TCA_ROWS));
