@@ -269,6 +269,25 @@ int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params, const flo
                        float* d_dz2_lo, float* d_dz1, int32_t passes, const int32_t* d_skip,
                        void* stream);
 
+/* Forward -> loss -> backward of one network-minibatch in ONE launch (tcgen05, one 128-row
+ * tile per CTA): tb_tc_mlp_forward (training mode) + the loss kernel + tb_tc_mlp_backward.
+ *   loss_kind 0: value regression, dout = 2 (v - d_targets[d_idx[row]])    (updaters/critics.py:18-28)
+ *   loss_kind 1: clipped-ratio (ratio_clip > 0) / policy-gradient loss of the detached-scale
+ *                Gaussian head, arithmetic of tb_gauss_policy_loss      (updaters/actors.py:21-50,70-112)
+ * z2 stays in TMEM (h2 is recomputed for the backward pass), the head output and its gradient stay
+ * on the SM.  Written for the weight-gradient kernel: d_xin, h1 (d_h1_hi / d_h1_lo tf32 split, or
+ * plain float32 in d_h1_hi when d_h1_lo == NULL), d_h2, dz2 (same convention), d_dz1, d_dout
+ * [n_rows, ld_dout] (policy: columns [0, A) loc gradients, [A, 2A) log_scale terms).  d_out
+ * (optional): head outputs.  d_stats: TB_STAT_* sums (zeroed by the caller).  Same shape limits
+ * as tb_tc_mlp_forward / tb_tc_mlp_backward.                                                   */
+int tb_tc_mlp_train(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                    const TbMlpInput* in, int64_t n_rows, int32_t loss_kind, const int64_t* d_idx,
+                    const float* d_targets, const float* d_log_scale, const float* d_actions,
+                    const float* d_advantages, const float* d_old_log_probs, float ratio_clip,
+                    float entropy_coeff, double* d_stats, float* d_out, float* d_xin, float* d_h1_hi,
+                    float* d_h1_lo, float* d_h2, float* d_dout, int32_t ld_dout, float* d_dz2_hi,
+                    float* d_dz2_lo, float* d_dz1, int32_t passes, const int32_t* d_skip, void* stream);
+
 /* Profiling aid for the fused forward kernel: the first call allocates a device buffer
  * of 64 clock64() stamps that CTA 0 of every later tb_tc_mlp_forward launch fills
  * (slots documented in csrc/tc_mlp.cu); a non-NULL `out64` reads them back (host

@@ -390,3 +390,68 @@ def test_wgrad_fused_adam_equals_separate_step(K, n_out, n_extra, with_stats):
             assert int(a[5][0]) == (1 if stats_vec is not None else 0)       # kl 0.02 > 0.015 -> stop
         else:
             assert int(a[4][0]) == 0 and torch.equal(a[0], init) and int(a[5][0]) == 0
+
+
+@pytest.mark.parametrize('kind,n_out,act,rows', [
+    ('value', 1, 'tanh', 16384), ('policy', 6, 'tanh', 16384), ('value', 1, 'relu', 1000),
+    ('policy', 3, 'tanh', 77), ('policy', 8, 'relu', 148 * 128 + 9), ('a2c', 6, 'tanh', 333)])
+def test_tc_mlp_train_equals_forward_loss_backward(K, kind, n_out, act, rows):
+    """tb_tc_mlp_train (forward -> loss -> backward in one launch, z2 kept in TMEM) against the
+    three-kernel chain tb_tc_mlp_forward -> tb_gauss_policy_loss / fused MSE -> tb_tc_mlp_backward:
+    same arithmetic -> bit-identical activations and gradients, statistics to double round-off."""
+    from tonic_b200 import _lib
+    d_in = 17
+    policy = kind != 'value'
+    extras = [('log_scale', n_out)] if policy else ()
+    g = torch.Generator().manual_seed(rows + n_out)
+    layout = K.MlpLayout(d_in, 256, n_out, act, extras)
+    init = torch.randn(layout.n_params, generator=g) * 0.12
+    pool = torch.randn(rows + 40, d_in, generator=g).cuda()
+    idx = torch.randperm(rows + 40, generator=g)[:rows].cuda()
+    mean, std = (torch.randn(d_in, generator=g) * 0.1).cuda(), (torch.rand(d_in, generator=g) + 0.5).cuda()
+    targets = torch.randn(rows + 40, generator=g).cuda()
+    actions = torch.randn(rows + 40, n_out, generator=g).cuda()
+    adv = torch.randn(rows + 40, generator=g).cuda()
+    adv[idx[:5]] = 0.0
+    old_lp = (torch.randn(rows + 40, generator=g) * 0.3 - 5.0).cuda()
+    ratio_clip = 0.0 if kind == 'a2c' else 0.2
+    results = []
+    for fused in (False, True):
+        net = K.DeviceMlp(layout)
+        net.params.copy_(init)
+        net.pack()
+        stats = torch.zeros(_lib.STAT_COUNT, dtype=torch.float64, device='cuda')
+        dout = torch.zeros(rows, 2 * n_out if policy else 1, device='cuda')
+        out = torch.zeros(rows, n_out, device='cuda')
+        inp = K.MlpInput(pool, mean, std, idx=idx)
+        if fused:
+            assert net.fused_train()
+            if policy:
+                off, size = layout.offsets['log_scale']
+                net.train_step(inp, rows, dout, stats, idx=idx, out=out,
+                               policy=dict(log_scale=net.params[off:off + size], actions=actions, advantages=adv,
+                                           log_probs=old_lp, ratio_clip=ratio_clip, entropy_coeff=0.01))
+            else:
+                net.train_step(inp, rows, dout, stats, idx=idx, targets=targets, out=out)
+        else:
+            if policy:
+                off, size = layout.offsets['log_scale']
+                net.forward(inp, rows, out, save=True)
+                K.gauss_policy_loss(out, net.params[off:off + size], actions, adv, old_lp, idx, rows, dout,
+                                    stats, ratio_clip, 0.01)
+            else:
+                net.forward(inp, rows, out, save=True, vloss=(targets, idx, dout, stats))
+                assert net.vloss_fused
+            net.backward(dout, rows)
+        torch.cuda.synchronize()
+        acts = [net.xin[:rows], net.h1[:rows], net.h2[:rows], net.dz2[:rows], net.dz1[:rows]]
+        if not net.plain_activations():
+            acts += [net.h1_lo[:rows], net.dz2_lo[:rows]]
+        results.append(([t.clone() for t in acts], dout.clone(), out.clone(), stats.cpu().numpy()))
+    (a0, d0, o0, s0), (a1, d1, o1, s1) = results
+    assert torch.equal(o0, o1) and torch.equal(d0, d1)
+    for x, y in zip(a0, a1):
+        assert torch.equal(x, y)
+    assert float(a0[4].abs().max()) > 0 and torch.isfinite(a0[4]).all()
+    np.testing.assert_allclose(s1, s0, rtol=1e-12, atol=1e-12)
+    assert s0[_lib.STAT_ROWS] == rows

@@ -917,6 +917,583 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
     }
 }
 
+
+// =====================================================================================
+// One kernel per network-minibatch for the activation passes: forward -> loss -> backward.
+//
+//     x -> h1 = act(x W1^T + b1) -> h2 = act(h1 W2^T + b2) -> out = h2 W3^T + b3
+//     loss / dout:  LOSS_VALUE   squared error against targets[idx]   (updaters/critics.py:18-28)
+//                   LOSS_POLICY  clipped-ratio / policy-gradient loss of the detached-scale Gaussian
+//                                head (updaters/actors.py:21-50,70-112, models/actors.py:37-66)
+//     dz2 = (dout W3) * act'(h2) -> dz1 = (dz2 W2) * act'(h1)
+//
+// i.e. tc_mlp_forward_kernel (training mode), the loss kernel and tc_mlp_backward_kernel as ONE
+// launch per 128-row tile: z2 never leaves TMEM (h2 is recomputed from the accumulator for the
+// backward pass instead of being re-read from global memory), the head output and dout stay in
+// registers / shared memory, and one launch + pipeline fill / drain disappears from the chain.
+// Accumulator 0 (TMEM columns 0..255) holds z1, then -- once the mid epilogue has consumed it --
+// the dz1 GEMM; accumulator 1 holds z2.  Per tile the two shared-memory stages are used 17 times:
+// layer 1, 8 K chunks of layer 2 (B = W2), 8 K chunks of the backward GEMM (B = W2^T).
+// What still goes to global memory is what the weight-gradient kernel consumes: xin, h1
+// (tf32 split or plain), h2, dz2 (split or plain), dz1, dout.
+// =====================================================================================
+enum { TC_LOSS_VALUE = 0, TC_LOSS_POLICY = 1 };
+
+struct TcTrainParams {
+    TcMlpParams f;              // forward part (input assembly, W1 image, biases, head, saves)
+    // loss
+    const int64_t* idx;         // minibatch indices of the rows (NULL = identity)
+    const float* targets;       // LOSS_VALUE: returns, indexed by idx[row]
+    const float* log_scale;     // LOSS_POLICY: [A]
+    const float* actions;       // [., A] indexed by idx[row]
+    const float* advantages;    // [.]
+    const float* old_log_probs; // [.]
+    float ratio_clip, entropy_coeff;
+    double* stats;              // TB_STAT_* block (zeroed by the caller)
+    float* dout;                // [n_rows, ld_dout]: head gradient (+ log_scale columns) for the weight gradients
+    int ld_dout;
+    // backward part
+    float* dz2_hi; float* dz2_lo;   // tf32 split, or plain float32 when dz2_lo == NULL
+    float* dz1;
+};
+
+template <int PASSES, int ACT, int LOSS>
+__global__ void __launch_bounds__(TCM_THREADS, 1)
+tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                    const __grid_constant__ CUtensorMap map_w2t_hi, const __grid_constant__ CUtensorMap map_w2t_lo,
+                    const __grid_constant__ CUtensorMap map_h1_hi, const __grid_constant__ CUtensorMap map_h1_lo,
+                    const __grid_constant__ CUtensorMap map_h2, const __grid_constant__ CUtensorMap map_dz2_hi,
+                    const __grid_constant__ CUtensorMap map_dz2_lo, const __grid_constant__ CUtensorMap map_dz1,
+                    const TcTrainParams q) {
+    using Cfg = TcMlpCfg<PASSES>;
+    const TcMlpParams& p = q.f;
+    if (skip_requested(p.skip)) return;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* epi = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    float* s_head_w = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+    float* s_b1 = s_head_w + TC_MAX_HEAD * TC_BN;
+    float* s_b2 = s_b1 + TC_BN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES +
+                                                 Cfg::CONST_BYTES);
+    uint64_t* full_bar = bars;                        // [STAGES] B operand landed
+    uint64_t* a_ready = bars + Cfg::STAGES;           // [STAGES] A operand written by a row-warp group
+    uint64_t* empty_bar = bars + 2 * Cfg::STAGES;     // [STAGES] MMAs reading the stage retired
+    uint64_t* acc_full = bars + 3 * Cfg::STAGES;      // [2] accumulator complete
+    uint64_t* x_ready = acc_full + 2;                 // layer-1 A operand written (all row warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+    __shared__ float s_scale[TC_MAX_HEAD], s_dsc[TC_MAX_HEAD];     // policy head: scale, dscale/dlog_scale
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    constexpr int CH = TC_K / TC_BK;                  // 8 chunks
+    constexpr int USES = 1 + 2 * CH;                  // stage uses per tile: layer 1 + 8 + 8
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&a_ready[s], TCM_ROW_WARPS / 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_init(x_ready, TCM_ROW_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < TC_BN; i += TCM_THREADS) {
+        s_b1[i] = p.b1[i];
+        s_b2[i] = p.b2[i];
+    }
+    for (int i = threadIdx.x; i < TC_MAX_HEAD * TC_BN; i += TCM_THREADS)
+        s_head_w[i] = i < p.n_head * TC_BN ? p.head_w[i] : 0.0f;
+    if (LOSS == TC_LOSS_POLICY && (int)threadIdx.x < p.n_head)
+        s_scale[threadIdx.x] = detached_scale(q.log_scale[threadIdx.x], &s_dsc[threadIdx.x]);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int k_steps1 = (p.d_in + 7) >> 3;           // layer-1 MMAs (K = 8 each) per pass
+
+    if (warp == 0) {
+        // ===================== producer: W1 image, W2 chunks, W2^T chunks =====================
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int u = 0; u < USES; ++u, ++g) {
+                    const int stage = g & 1;
+                    mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
+                    unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], (PASSES == 3 ? 2 : 1) * TC_B_BYTES);
+                    if (u == 0) {
+                        bulk_load(st + Cfg::B_HI, p.w1_img_hi, TC_B_BYTES, &full_bar[stage]);
+                        if (PASSES == 3) bulk_load(st + Cfg::B_LO, p.w1_img_lo, TC_B_BYTES, &full_bar[stage]);
+                    } else if (u <= CH) {
+                        tma_load_2d(st + Cfg::B_HI, &map_w2_hi, &full_bar[stage], (u - 1) * TC_BK, 0);
+                        if (PASSES == 3) tma_load_2d(st + Cfg::B_LO, &map_w2_lo, &full_bar[stage], (u - 1) * TC_BK, 0);
+                    } else {
+                        tma_load_2d(st + Cfg::B_HI, &map_w2t_hi, &full_bar[stage], (u - 1 - CH) * TC_BK, 0);
+                        if (PASSES == 3)
+                            tma_load_2d(st + Cfg::B_LO, &map_w2t_lo, &full_bar[stage], (u - 1 - CH) * TC_BK, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int g = 0, it = 0;
+            uint32_t a_phase = 0;                     // bit s: parity of the next completion of a_ready[s]
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                for (int u = 0; u < USES; ++u, ++g) {
+                    const int stage = g & 1;
+                    const uint32_t parity = (g >> 1) & 1;
+                    mbar_wait(&full_bar[stage], parity);
+                    if (u == 0) mbar_wait(x_ready, it & 1);
+                    else mbar_wait(&a_ready[stage], (a_phase >> stage) & 1u), a_phase ^= 1u << stage;
+                    tcgen05_fence_after();
+                    unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                    const uint64_t a_hi = umma_desc_kmajor_sw128(st);
+                    const uint64_t a_lo = umma_desc_kmajor_sw128(st + Cfg::A_LO);
+                    const uint64_t b_hi = umma_desc_kmajor_sw128(st + Cfg::B_HI);
+                    const uint64_t b_lo = umma_desc_kmajor_sw128(st + Cfg::B_LO);
+                    // accumulator 0: layer 1 (u = 0) and the backward GEMM (u > 8); accumulator 1: layer 2
+                    const uint32_t d_tmem = tmem_base + ((u >= 1 && u <= CH) ? (uint32_t)TC_BN : 0u);
+                    const int ks = u == 0 ? k_steps1 : TC_BK / 8;
+                    const bool fresh = u == 0 || u == 1 || u == CH + 1;
+                    for (int k = 0; k < ks; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 32 >> 4);
+                        const uint32_t accumulate = (fresh && k == 0) ? 0u : 1u;
+                        if (PASSES == 3) {
+                            tcgen05_mma_tf32(d_tmem, a_lo + koff, b_hi + koff, kIdescTf32, accumulate);
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_lo + koff, kIdescTf32, 1);
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, 1);
+                        } else {
+                            tcgen05_mma_tf32(d_tmem, a_hi + koff, b_hi + koff, kIdescTf32, accumulate);
+                        }
+                    }
+                    tcgen05_commit(&empty_bar[stage]);
+                    if (u == 0 || u == USES - 1) tcgen05_commit(&acc_full[0]);
+                    if (u == CH) tcgen05_commit(&acc_full[1]);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== row warps =====================
+        const int rw = warp - 4, qd = rw & 3, wg = rw >> 2;
+        const int trow = qd * 32 + lane;
+        const bool issuer = qd == 0 && lane == 0;            // this group's TMA-store thread
+        float* stg = epi + rw * 32 * TCM_STG_STRIDE;
+        const int d_in = p.d_in;
+        const int ldx = (d_in + 1 + 3) & ~3;
+        const bool split_h1 = p.h1_lo != nullptr, split_dz2 = q.dz2_lo != nullptr;
+        const uint32_t t_lane = (uint32_t)(qd * 32) << 16;
+        const int A = p.n_head;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int64_t row0 = (int64_t)tile * TC_BM + qd * 32;
+            const int64_t row = (int64_t)tile * TC_BM + trow;
+            const bool live = row < p.n_rows;
+            const int g0 = it * USES;                 // stage use index of this tile's layer 1
+            const int64_t src = live ? (q.idx ? q.idx[row] : row) : 0;      // loss inputs of this row
+            // ---- a) layer-1 A operand: this thread's 16 input columns ---------------------------
+            {
+                float xv[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) xv[j] = 0.0f;
+                if (live) {
+                    const int64_t r = p.in.d_idx ? p.in.d_idx[row] : row;
+                    const int64_t r2 = p.in.gather2 ? r : row;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = 16 * wg + j;
+                        if (c < d_in) {
+                            float val;
+                            if (c < p.in.dim1) {
+                                val = p.in.d_x1[r * p.in.dim1 + c];
+                                if (p.in.d_mean)      // mean_stds.py:36  (val - mean) / std
+                                    val = __fdiv_rn(__fsub_rn(val, p.in.d_mean[c]), p.in.d_std[c]);
+                            } else {
+                                val = p.in.d_x2[r2 * p.in.dim2 + (c - p.in.dim1)];
+                            }
+                            xv[j] = val;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = 16 * wg + j;
+                        if (c < ldx) p.xin_save[row * ldx + c] = c < d_in ? xv[j] : (c == d_in ? 1.0f : 0.0f);
+                    }
+                    if (wg == 1)
+                        for (int c = 32; c < ldx; ++c) p.xin_save[row * ldx + c] = c == d_in ? 1.0f : 0.0f;
+                }
+                const int stage = g0 & 1;
+                mbar_wait(&empty_bar[stage], ((g0 >> 1) & 1) ^ 1);
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                store_operand_half<PASSES>(st, st + Cfg::A_LO, trow, wg, xv);
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_ready);
+            }
+            // ---- b) mid epilogue: h1 chunks -> layer-2 A operand (+ saved for the weight gradient) --
+            mbar_wait(&acc_full[0], 0);               // first completion of the tile (two per tile)
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = wg; c < CH; c += 2) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + t_lane + (uint32_t)(c * 32), v);
+                float hv[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_b1 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = b4[j / 4];
+                    hv[j] = tc_act<ACT>(__uint_as_float(v[j]) + b.x);
+                    hv[j + 1] = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+                    hv[j + 2] = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+                    hv[j + 3] = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+                }
+                const int g = g0 + 1 + c, stage = g & 1;
+                mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                if (split_h1) {       // the TMA stores of this group's previous chunk have left the stage
+                    if (issuer) bulk_wait_read<0>();
+                    group_sync(wg);
+                }
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv);
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[stage]);
+                if (split_h1) {
+                    group_sync(wg);
+                    if (issuer) {
+                        tma_store_2d(&map_h1_hi, st, c * TC_BK, tile * TC_BM);
+                        if (PASSES == 3) tma_store_2d(&map_h1_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                        bulk_commit();
+                    }
+                } else if (live) {    // plain float32 h1 straight from registers
+                    float4* dst = reinterpret_cast<float4*>(p.h1_hi + row * TC_BN + c * 32);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        dst[u] = make_float4(hv[4 * u], hv[4 * u + 1], hv[4 * u + 2], hv[4 * u + 3]);
+                }
+            }
+            // ---- c) pass 1 over z2: h2 (saved), head output ------------------------------------
+            mbar_wait(&acc_full[1], it & 1);
+            tcgen05_fence_after();
+            float hacc[TC_MAX_HEAD];
+#pragma unroll
+            for (int o = 0; o < TC_MAX_HEAD; ++o) hacc[o] = 0.0f;
+            // both stages are idle now (all layer-2 MMAs retired): group wg stages h2 in the A
+            // buffers of stage wg; the h1 stores that may still read them must have left
+            unsigned char* own_stage = smem + wg * Cfg::STAGE_BYTES;
+            if (split_h1) {
+                if (issuer) bulk_wait_read<0>();
+                row_warps_sync();                     // (the other group's stores read both stages over time)
+            }
+            int n_staged = 0;
+#pragma unroll 1
+            for (int c = wg; c < CH; c += 2) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + t_lane + (uint32_t)(TC_BN + c * 32), v);
+                float hv[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = b4[j / 4];
+                    hv[j] = tc_act<ACT>(__uint_as_float(v[j]) + b.x);
+                    hv[j + 1] = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+                    hv[j + 2] = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+                    hv[j + 3] = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+                }
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o) {
+                    if (o < A) {
+                        const float4* w4 = reinterpret_cast<const float4*>(s_head_w + o * TC_BN + c * 32);
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 wv = w4[j / 4];
+                            s0 = fmaf(hv[j], wv.x, s0);
+                            s1 = fmaf(hv[j + 1], wv.y, s1);
+                            s2 = fmaf(hv[j + 2], wv.z, s2);
+                            s3 = fmaf(hv[j + 3], wv.w, s3);
+                        }
+                        hacc[o] += (s0 + s1) + (s2 + s3);
+                    }
+                }
+                // h2 for the weight-gradient kernel: staged in the TMA layout, stored asynchronously
+                constexpr int NBUF = PASSES == 3 ? 2 : 1;
+                unsigned char* buf = own_stage + (n_staged % NBUF) * TC_A_BYTES;
+                if (n_staged >= NBUF) {
+                    if (issuer) bulk_wait_read<NBUF - 1>();
+                    group_sync(wg);
+                }
+                store_plain_row(buf, trow, hv);
+                fence_proxy_async_smem();
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_h2, buf, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
+                }
+                ++n_staged;
+            }
+            // ---- head output, loss, dout: group 1 hands its partial sums to group 0, group 0
+            // computes the row's loss terms and hands the head gradient back -----------------------
+            if (wg == 1) {
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o) stg[lane * TCM_STG_STRIDE + o] = hacc[o];
+            }
+            row_warps_sync();
+            float dv[TC_MAX_HEAD];
+#pragma unroll
+            for (int o = 0; o < TC_MAX_HEAD; ++o) dv[o] = 0.0f;
+            double st_a = 0.0, st_b = 0.0, st_c = 0.0, st_d = 0.0, st_rows = 0.0;
+            if (wg == 0) {
+                const float* other = epi + (rw + 4) * 32 * TCM_STG_STRIDE + lane * TCM_STG_STRIDE;
+                float outv[TC_MAX_HEAD];
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o)
+                    outv[o] = o < A ? (hacc[o] + other[o]) + __ldg(p.head_b + o) : 0.0f;
+                if (live) {
+                    if (p.head_out) {
+#pragma unroll
+                        for (int o = 0; o < TC_MAX_HEAD; ++o)
+                            if (o < A) p.head_out[row * A + o] = outv[o];
+                    }
+                    if (LOSS == TC_LOSS_VALUE) {
+                        // same arithmetic as mse_loss_kernel (csrc/heads.cu)
+                        const float d = outv[0] - q.targets[src];
+                        dv[0] = 2.0f * d;
+                        q.dout[row * q.ld_dout] = dv[0];
+                        st_a = (double)d * (double)d;
+                        st_b = outv[0];
+                        st_rows = 1.0;
+                    } else {
+                        // same arithmetic as gauss_policy_loss_kernel (csrc/heads.cu)
+                        const float adv = q.advantages[src], old_lp = q.old_log_probs[src];
+                        float lp = 0.0f, dd[TC_MAX_HEAD], loc[TC_MAX_HEAD];
+#pragma unroll
+                        for (int a = 0; a < TC_MAX_HEAD; ++a) {
+                            if (a < A) {
+                                loc[a] = tanhf(outv[a]);
+                                const float sc = s_scale[a];
+                                dd[a] = q.actions[src * A + a] - loc[a];
+                                lp += -(dd[a] * dd[a]) / (2.0f * (sc * sc)) - logf(sc) - kLogSqrt2Pi;
+                            }
+                        }
+                        float g_lp, loss;
+                        if (q.ratio_clip > 0.0f) {                               // actors.py:84-90
+                            const float ratio = expf(lp - old_lp);
+                            const float lo = 1.0f - q.ratio_clip, hi = 1.0f + q.ratio_clip;
+                            const float clipped = fminf(fmaxf(ratio, lo), hi);
+                            const float s1 = adv * ratio, s2 = adv * clipped;
+                            loss = -fminf(s1, s2);
+                            const float w1 = s1 < s2 ? 1.0f : (s1 == s2 ? 0.5f : 0.0f);
+                            const float w2 = (1.0f - w1) * ((ratio >= lo && ratio <= hi) ? 1.0f : 0.0f);
+                            g_lp = -adv * ratio * (w1 + w2);
+                            st_c = (ratio > hi || ratio < lo) ? 1.0 : 0.0;        // actors.py:105
+                        } else {                                                 // actors.py:34
+                            loss = -adv * lp;
+                            g_lp = -adv;
+                        }
+#pragma unroll
+                        for (int a = 0; a < TC_MAX_HEAD; ++a) {
+                            if (a < A) {
+                                const float sc = s_scale[a];
+                                const float inv_var = 1.0f / (sc * sc);
+                                dv[a] = g_lp * dd[a] * inv_var * (1.0f - loc[a] * loc[a]);
+                                q.dout[row * q.ld_dout + a] = dv[a];
+                                const float dlp_dsc = dd[a] * dd[a] * inv_var / sc - 1.0f / sc;
+                                const float dent_dsc = 1.0f / sc;
+                                q.dout[row * q.ld_dout + A + a] =
+                                    (g_lp * dlp_dsc - (q.entropy_coeff / (float)A) * dent_dsc) * s_dsc[a];
+                            }
+                        }
+                        st_a = loss;
+                        st_b = old_lp - lp;                                       // actors.py:103
+                        st_d = adv != 0.0f ? 1.0 : 0.0;
+                        st_rows = 1.0;
+                    }
+                }
+                // head gradient of this row for the other group
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o) stg[lane * TCM_STG_STRIDE + 8 + o] = dv[o];
+                st_a = warp_sum(st_a); st_b = warp_sum(st_b); st_rows = warp_sum(st_rows);
+                if (LOSS == TC_LOSS_POLICY) { st_c = warp_sum(st_c); st_d = warp_sum(st_d); }
+            }
+            row_warps_sync();
+            if (wg == 1) {
+                const float* other = epi + (rw - 4) * 32 * TCM_STG_STRIDE + lane * TCM_STG_STRIDE + 8;
+#pragma unroll
+                for (int o = 0; o < TC_MAX_HEAD; ++o) dv[o] = other[o];
+            } else if (lane == 0) {
+                // one atomic per warp and statistic (4 warps per tile)
+                if (LOSS == TC_LOSS_VALUE) {
+                    atomicAdd(&q.stats[TB_STAT_LOSS], st_a);
+                    atomicAdd(&q.stats[TB_STAT_VALUE], st_b);
+                    atomicAdd(&q.stats[TB_STAT_ROWS], st_rows);
+                } else {
+                    float ent_row = 0.0f, std_row = 0.0f;
+                    for (int a = 0; a < A; ++a) {
+                        ent_row += kEntropyConst + logf(s_scale[a]);
+                        std_row += s_scale[a];
+                    }
+                    atomicAdd(&q.stats[TB_STAT_LOSS], st_a);
+                    atomicAdd(&q.stats[TB_STAT_KL], st_b);
+                    atomicAdd(&q.stats[TB_STAT_CLIPPED], st_c);
+                    atomicAdd(&q.stats[TB_STAT_NONZERO_ADV], st_d);
+                    atomicAdd(&q.stats[TB_STAT_ROWS], st_rows);
+                    atomicAdd(&q.stats[TB_STAT_ENTROPY], st_rows * (double)ent_row);
+                    atomicAdd(&q.stats[TB_STAT_STD], st_rows * (double)std_row);
+                }
+            }
+            // ---- d) pass 2 over z2: dz2 = (dout W3) * act'(h2) -> A operand of the backward GEMM ----
+            // the h2 stores must have left the A buffers before they are rewritten
+            if (issuer) bulk_wait_read<0>();
+            row_warps_sync();
+#pragma unroll 1
+            for (int c = wg; c < CH; c += 2) {
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + t_lane + (uint32_t)(TC_BN + c * 32), v);
+                float z[32];
+                const float4* b4 = reinterpret_cast<const float4*>(s_b2 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b = b4[j / 4];
+                    z[j] = tc_act<ACT>(__uint_as_float(v[j]) + b.x);
+                    z[j + 1] = tc_act<ACT>(__uint_as_float(v[j + 1]) + b.y);
+                    z[j + 2] = tc_act<ACT>(__uint_as_float(v[j + 2]) + b.z);
+                    z[j + 3] = tc_act<ACT>(__uint_as_float(v[j + 3]) + b.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int o = 0; o < TC_MAX_HEAD; ++o) {
+                        if (o < A) {
+                            const float4 wv = *reinterpret_cast<const float4*>(s_head_w + o * TC_BN + c * 32 + j);
+                            s0 = fmaf(dv[o], wv.x, s0);
+                            s1 = fmaf(dv[o], wv.y, s1);
+                            s2 = fmaf(dv[o], wv.z, s2);
+                            s3 = fmaf(dv[o], wv.w, s3);
+                        }
+                    }
+                    z[j] = s0 * tc_act_grad<ACT>(z[j]);
+                    z[j + 1] = s1 * tc_act_grad<ACT>(z[j + 1]);
+                    z[j + 2] = s2 * tc_act_grad<ACT>(z[j + 2]);
+                    z[j + 3] = s3 * tc_act_grad<ACT>(z[j + 3]);
+                }
+                const int g = g0 + 1 + CH + c, stage = g & 1;
+                mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
+                unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
+                if (split_dz2) {
+                    if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
+                    group_sync(wg);
+                }
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z);
+                fence_proxy_async_smem();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[stage]);
+                if (split_dz2) {
+                    group_sync(wg);
+                    if (issuer) {
+                        tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
+                        if (PASSES == 3) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                        bulk_commit();
+                    }
+                } else if (live) {
+                    float4* dst = reinterpret_cast<float4*>(q.dz2_hi + row * TC_BN + c * 32);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        dst[u] = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
+                }
+            }
+            // ---- e) epilogue of the backward GEMM: dz1 = acc0 * act'(h1) (h1 re-read from global
+            // memory with coalesced 64-byte row segments, as in tc_mlp_backward_kernel) ------------
+            float ua[16], ub[16];
+            auto load_h1 = [&](int c, int half) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int64_t r = row0 + 2 * i + (lane >> 4);
+                    const int64_t e = r * TC_BN + c * 32 + half * 16 + (lane & 15);
+                    // written by this CTA a few microseconds ago: L2 (not the read-only path)
+                    ua[i] = r < p.n_rows ? __ldcg(p.h1_hi + e) : 0.0f;
+                    ub[i] = (PASSES == 3 && split_h1 && r < p.n_rows) ? __ldcg(p.h1_lo + e) : 0.0f;
+                }
+            };
+            if (split_h1) {           // this CTA's h1 TMA stores are complete (not only read) before the re-read
+                if (issuer) bulk_wait_all();
+            }
+            __threadfence_block();
+            row_warps_sync();
+            load_h1(wg, 0);
+            mbar_wait(&acc_full[0], 1);               // second completion of the tile
+            tcgen05_fence_after();
+            if (issuer) bulk_wait_read<0>();          // dz2 stores have left this group's buffers
+            row_warps_sync();
+            own_stage = smem + wg * Cfg::STAGE_BYTES;
+            n_staged = 0;
+#pragma unroll 1
+            for (int c = wg; c < CH; c += 2) {
+                constexpr int NBUF = PASSES == 3 ? 2 : 1;
+                unsigned char* buf = own_stage + (n_staged % NBUF) * TC_A_BYTES;
+                if (n_staged >= NBUF) {
+                    if (issuer) bulk_wait_read<NBUF - 1>();
+                    group_sync(wg);
+                }
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t v[16];
+                    tcgen05_ld_32x16(tmem_base + t_lane + (uint32_t)(c * 32 + half * 16), v);
+                    float* mine = stg + lane * TCM_STG_STRIDE;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4*>(mine + j) = make_float4(
+                            __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+                    __syncwarp();
+                    const int cc = half * 16 + (lane & 15);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = 2 * i + (lane >> 4);
+                        const float gval = tc_act_grad<ACT>(ua[i] + ub[i]) * stg[r * TCM_STG_STRIDE + (lane & 15)];
+                        *reinterpret_cast<float*>(buf + sw128_offset(qd * 32 + r, cc >> 2) + ((cc & 3) << 2)) = gval;
+                    }
+                    __syncwarp();
+                    if (half == 0) load_h1(c, 1);
+                    else if (c + 2 < CH) load_h1(c + 2, 0);
+                }
+                fence_proxy_async_smem();
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_dz1, buf, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
+                }
+                ++n_staged;
+            }
+            // this tile's TMEM reads are complete before the next tile's MMAs are released, and
+            // the stores have left the operand buffers before the next tile rewrites them
+            tcgen05_fence_before();
+            if (issuer) bulk_wait_read<0>();
+            row_warps_sync();
+        }
+        if (issuer) bulk_wait_all();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512)
+                     : "memory");
+    }
+}
+
 template <int PASSES, int ACT, int CLUSTER>
 static int launch_tc_mlp_bwd(const CUtensorMap* maps, const TcMlpBwdParams& p, cudaStream_t s) {
     using Cfg = TcMlpCfg<PASSES>;
@@ -1136,4 +1713,92 @@ extern "C" int tb_tc_mlp_backward(const TbMlpShape* shape, const float* d_params
         else launch_tc_mlp_bwd<1, TB_ACT_RELU, 1>(maps, p, as_stream(stream));
     }
     return check_launch("tb_tc_mlp_backward");
+}
+
+namespace tb {
+
+template <int PASSES, int ACT, int LOSS>
+static int launch_tc_train(const CUtensorMap* maps, const TcTrainParams& q, cudaStream_t s) {
+    using Cfg = TcMlpCfg<PASSES>;
+    auto kernel = tc_mlp_train_kernel<PASSES, ACT, LOSS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        configured = true;
+    }
+    const int n_tiles = (int)((q.f.n_rows + TC_BM - 1) / TC_BM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    kernel<<<grid, TCM_THREADS, Cfg::SMEM_BYTES, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                                    maps[6], maps[7], maps[8], maps[9], q);
+    return 0;
+}
+
+}  // namespace tb
+
+extern "C" int tb_tc_mlp_train(const TbMlpShape* shape, const float* d_params, const float* d_packed,
+                               const TbMlpInput* in, int64_t n_rows, int32_t loss_kind,
+                               const int64_t* d_idx, const float* d_targets, const float* d_log_scale,
+                               const float* d_actions, const float* d_advantages,
+                               const float* d_old_log_probs, float ratio_clip, float entropy_coeff,
+                               double* d_stats, float* d_out, float* d_xin, float* d_h1_hi, float* d_h1_lo,
+                               float* d_h2, float* d_dout, int32_t ld_dout, float* d_dz2_hi,
+                               float* d_dz2_lo, float* d_dz1, int32_t passes, const int32_t* d_skip,
+                               void* stream) {
+    using namespace tb;
+    TB_REQUIRE(shape && d_params && d_packed && in && in->d_x1 && n_rows > 0 && d_stats && d_xin && d_h1_hi &&
+               d_h2 && d_dout && d_dz2_hi && d_dz1, TB_EINVAL, "tb_tc_mlp_train: null pointer");
+    TB_REQUIRE(shape->hidden == 256 && shape->off_w2_hi > 0 && shape->off_w2t_hi > 0 && shape->off_w1_img_hi > 0 &&
+               shape->d_in >= 1 && shape->d_in <= 32 && shape->n_out >= 1 && shape->n_out <= TC_MAX_HEAD,
+               TB_ENOTSUP, "tb_tc_mlp_train: needs hidden == 256, d_in <= 32, n_out <= 8 (got %d, %d, %d)",
+               shape->hidden, shape->d_in, shape->n_out);
+    TB_REQUIRE(in->dim1 + (in->d_x2 ? in->dim2 : 0) == shape->d_in, TB_EINVAL,
+               "tb_tc_mlp_train: input widths do not add up to d_in");
+    TB_REQUIRE(passes == 1 || passes == 3, TB_EINVAL, "tb_tc_mlp_train: passes must be 1 or 3");
+    TB_REQUIRE((d_h1_lo == nullptr) == (d_dz2_lo == nullptr), TB_EINVAL,
+               "tb_tc_mlp_train: h1 and dz2 both as tf32 splits or both plain (lo == NULL)");
+    if (loss_kind == TC_LOSS_VALUE) {
+        TB_REQUIRE(shape->n_out == 1 && d_targets && ld_dout >= 1, TB_EINVAL,
+                   "tb_tc_mlp_train: the value loss needs a single output and targets");
+    } else {
+        TB_REQUIRE(loss_kind == TC_LOSS_POLICY && d_log_scale && d_actions && d_advantages && d_old_log_probs &&
+                   ld_dout >= 2 * shape->n_out, TB_EINVAL,
+                   "tb_tc_mlp_train: the policy loss needs log_scale, actions, advantages, old log-probs "
+                   "and ld_dout >= 2 * act_dim");
+    }
+    CUtensorMap maps[10];
+    int rc;
+    if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[2], d_packed + shape->off_w2t_hi, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[3], d_packed + shape->off_w2t_lo, TC_BN, TC_BN))) return rc;
+    if ((rc = make_map(&maps[4], d_h1_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[5], d_h1_lo ? d_h1_lo : d_h1_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[6], d_h2, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[7], d_dz2_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[8], d_dz2_lo ? d_dz2_lo : d_dz2_hi, n_rows, TC_BM))) return rc;
+    if ((rc = make_map(&maps[9], d_dz1, n_rows, TC_BM))) return rc;
+    TcTrainParams q;
+    TcMlpParams& p = q.f;
+    p.n_rows = n_rows; p.in = *in; p.d_in = shape->d_in; p.act = shape->act;
+    p.w1_img_hi = d_packed + shape->off_w1_img_hi; p.w1_img_lo = d_packed + shape->off_w1_img_lo;
+    p.b1 = d_params + shape->off_b1; p.b2 = d_params + shape->off_b2;
+    p.xin_save = d_xin; p.h1_hi = d_h1_hi; p.h1_lo = d_h1_lo; p.h2 = d_h2;
+    p.head_w = d_params + shape->off_w3; p.head_b = d_params + shape->off_b3; p.head_out = d_out;
+    p.n_head = shape->n_out; p.skip = d_skip; p.timeline = nullptr;
+    p.loss_targets = nullptr; p.loss_idx = nullptr; p.loss_dout = nullptr; p.loss_ld = 1;
+    p.loss_stats = nullptr; p.loss_stat_slot = 0; p.loss_count_rows = 0;
+    q.idx = d_idx; q.targets = d_targets; q.log_scale = d_log_scale; q.actions = d_actions;
+    q.advantages = d_advantages; q.old_log_probs = d_old_log_probs; q.ratio_clip = ratio_clip;
+    q.entropy_coeff = entropy_coeff; q.stats = d_stats; q.dout = d_dout; q.ld_dout = ld_dout;
+    q.dz2_hi = d_dz2_hi; q.dz2_lo = d_dz2_lo; q.dz1 = d_dz1;
+    ProfScope prof_scope("tb_tc_mlp_train", stream);
+    cudaStream_t s = as_stream(stream);
+    const bool tanh_act = shape->act == TB_ACT_TANH;
+#define TB_TRAIN(P_, L_)                                                                \
+    { if (tanh_act) launch_tc_train<P_, TB_ACT_TANH, L_>(maps, q, s);                   \
+      else launch_tc_train<P_, TB_ACT_RELU, L_>(maps, q, s); }
+    if (passes == 3) { if (loss_kind == TC_LOSS_VALUE) TB_TRAIN(3, TC_LOSS_VALUE) else TB_TRAIN(3, TC_LOSS_POLICY) }
+    else { if (loss_kind == TC_LOSS_VALUE) TB_TRAIN(1, TC_LOSS_VALUE) else TB_TRAIN(1, TC_LOSS_POLICY) }
+#undef TB_TRAIN
+    return check_launch("tb_tc_mlp_train");
 }

@@ -204,7 +204,8 @@ _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 _FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
 _FUSED_WGRAD = os.environ.get('TONIC_B200_FUSED_WGRAD', '1') != '0'
 _FUSED_ADAM = os.environ.get('TONIC_B200_FUSED_ADAM', '1') != '0'
-_PLAIN_ACTS = os.environ.get('TONIC_B200_PLAIN_ACTS', '1') != '0'
+_PLAIN_ACTS = os.environ.get('TONIC_B200_PLAIN_ACTS', '0') != '0'     # measured: no gain on B200
+_FUSED_TRAIN = os.environ.get('TONIC_B200_FUSED_TRAIN', '1') != '0'
 
 
 class DeviceMlp:
@@ -350,6 +351,33 @@ class DeviceMlp:
                   ptr(self.xin) if save else None, ptr(self.h1) if save else None,
                   ptr(self.h2) if save else None, ptr(skip), stream())
         return out
+
+    def fused_train(self):
+        """forward -> loss -> backward as ONE launch (csrc/tc_mlp.cu::tc_mlp_train_kernel)."""
+        L = self.layout
+        return (bool(self.passes()) and _FUSED_TRAIN and _FUSED_FWD and _FUSED_BWD and L.fused_forward
+                and L.n_out <= 8)
+
+    def train_step(self, inp, rows, dout, stats, idx=None, targets=None, policy=None, out=None,
+                   skip=None):
+        """Value regression (`targets`) or Gaussian policy loss (`policy` = dict(log_scale, actions,
+        advantages, log_probs, ratio_clip, entropy_coeff)) on the minibatch `inp`: activations for
+        the weight-gradient kernel end up in the workspaces, the head gradient in `dout`."""
+        L = self.layout
+        self.workspace(rows)
+        plain = self.plain_activations()
+        flops = 2.0 * rows * (L.d_in * L.hidden + L.hidden * L.hidden + L.hidden * L.n_out) \
+            + 2.0 * rows * L.hidden * (L.n_out + L.hidden)
+        _count_flops('tb_tc_mlp_train', flops)
+        pol = policy or {}
+        _lib.call('tb_tc_mlp_train', ctypes.byref(L.shape), ptr(self.params), ptr(self.packed),
+                  ctypes.byref(inp.struct), rows, 0 if policy is None else 1, ptr(idx), ptr(targets),
+                  ptr(pol.get('log_scale')), ptr(pol.get('actions')), ptr(pol.get('advantages')),
+                  ptr(pol.get('log_probs')), float(pol.get('ratio_clip', 0.0)),
+                  float(pol.get('entropy_coeff', 0.0)), ptr(stats), ptr(out), ptr(self.xin),
+                  ptr(self.h1), None if plain else ptr(self.h1_lo), ptr(self.h2), ptr(dout),
+                  dout.shape[-1] if dout.dim() > 1 else 1, ptr(self.dz2),
+                  None if plain else ptr(self.dz2_lo), ptr(self.dz1), self.passes(), ptr(skip), stream())
 
     def backward(self, dout, rows, dx=None, dx_col0=0, skip=None, params=None, packed=None):
         L = self.layout

@@ -53,7 +53,15 @@ class _GaussianPolicyUpdater:
         actor, net = self.actor, self.actor.network
         A = actor.action_size
         dout = None
-        if rows > 0:
+        if rows > 0 and net.mlp.fused_train():
+            # forward -> policy loss -> backward in one launch
+            pre, dout = self._scratch(rows)
+            net.mlp.train_step(actor.input(observations, idx), rows, dout, stats, idx=idx,
+                               policy=dict(log_scale=net.extra('log_scale'), actions=actions,
+                                           advantages=advantages, log_probs=log_probs,
+                                           ratio_clip=self.ratio_clip, entropy_coeff=self.entropy_coeff),
+                               out=pre, skip=stop)
+        elif rows > 0:
             pre, dout = self._scratch(rows)
             actor.pre_activations(observations, out=pre, idx=idx, rows=rows, save=True, skip=stop)
             kernels.gauss_policy_loss(pre, net.extra('log_scale'), actions, advantages,

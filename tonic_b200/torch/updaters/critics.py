@@ -36,7 +36,12 @@ class VRegression:
     def launch(self, observations, returns, idx, rows, stats, rows_global=None):
         critic, net = self.critic, self.critic.network
         dout = None
-        if rows > 0:
+        if rows > 0 and net.mlp.fused_train():
+            # forward -> squared-error loss -> backward in one launch
+            values, dout = self._scratch(rows)
+            net.mlp.train_step(critic.input(observations, None, idx), rows, dout, stats, idx=idx,
+                               targets=returns, out=values)
+        elif rows > 0:
             values, dout = self._scratch(rows)
             # the tensor-core forward kernel evaluates the squared-error loss in its epilogue
             critic.values(observations, out=values, idx=idx, rows=rows, save=True,
