@@ -162,9 +162,12 @@ def test_ppo_iteration_at_the_benched_shape_matches_reference(golden):
     # final weights (320 Adam steps per network at B = 16384)
     w = bench_shape.weight_digests(agent.model.state_dict(), 'digest_w/')
     assert set(w) == {k for k in g if k.startswith('digest_w/')}
+    sizes = {'digest_w/' + k: v.numel() for k, v in agent.model.state_dict().items()}
     for k, v in w.items():
         np.testing.assert_allclose(v[2:], g[k][2:], rtol=1e-3, atol=2e-4, err_msg=k)
-        np.testing.assert_allclose(v[1], g[k][1], rtol=1e-3, err_msg=k)
+        # sum of |w|: 1e-3 relative; tiny tensors (log_scale: 6 values near zero) get the per-element
+        # absolute tolerance of the line above
+        np.testing.assert_allclose(v[1], g[k][1], rtol=1e-3, atol=2e-4 * min(sizes[k], 8), err_msg=k)
 
 
 def test_greedy_and_test_time_actions_match_reference_kats():

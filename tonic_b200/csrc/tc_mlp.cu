@@ -986,6 +986,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (int)((p.n_rows + TC_BM - 1) / TC_BM);
+    if (threadIdx.x == 0) tc_stamp(p.timeline, 0);
     constexpr int CH = TC_K / TC_BK;                  // 8 chunks
     constexpr int USES = 1 + 2 * CH;                  // stage uses per tile: layer 1 + 8 + 8
 
@@ -1018,6 +1019,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int k_steps1 = (p.d_in + 7) >> 3;           // layer-1 MMAs (K = 8 each) per pass
+    if (threadIdx.x == 0) tc_stamp(p.timeline, 1);    // setup done
 
     if (warp == 0) {
         // ===================== producer: W1 image, W2 chunks, W2^T chunks =====================
@@ -1093,6 +1095,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
         const bool split_h1 = p.h1_lo != nullptr, split_dz2 = q.dz2_lo != nullptr;
         const uint32_t t_lane = (uint32_t)(qd * 32) << 16;
         const int A = p.n_head;
+        const bool stamper = rw == 0 && lane == 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int64_t row0 = (int64_t)tile * TC_BM + qd * 32;
@@ -1139,10 +1142,12 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(x_ready);
+                if (stamper) tc_stamp(p.timeline, 2);         // layer-1 A operand published
             }
             // ---- b) mid epilogue: h1 chunks -> layer-2 A operand (+ saved for the weight gradient) --
             mbar_wait(&acc_full[0], 0);               // first completion of the tile (two per tile)
             tcgen05_fence_after();
+            if (stamper) tc_stamp(p.timeline, 3);             // z1 complete
 #pragma unroll 1
             for (int c = wg; c < CH; c += 2) {
                 uint32_t v[32];
@@ -1184,8 +1189,10 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                 }
             }
             // ---- c) pass 1 over z2: h2 (saved), head output ------------------------------------
+            if (stamper) tc_stamp(p.timeline, 4);             // mid epilogue done (group 0)
             mbar_wait(&acc_full[1], it & 1);
             tcgen05_fence_after();
+            if (stamper) tc_stamp(p.timeline, 5);             // z2 complete
             float hacc[TC_MAX_HEAD];
 #pragma unroll
             for (int o = 0; o < TC_MAX_HEAD; ++o) hacc[o] = 0.0f;
@@ -1245,6 +1252,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
             }
             // ---- head output, loss, dout: group 1 hands its partial sums to group 0, group 0
             // computes the row's loss terms and hands the head gradient back -----------------------
+            if (stamper) tc_stamp(p.timeline, 6);             // pass 1 (h2, head sums) done
             if (wg == 1) {
 #pragma unroll
                 for (int o = 0; o < TC_MAX_HEAD; ++o) stg[lane * TCM_STG_STRIDE + o] = hacc[o];
@@ -1357,6 +1365,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
             // the h2 stores must have left the A buffers before they are rewritten
             if (issuer) bulk_wait_read<0>();
             row_warps_sync();
+            if (stamper) tc_stamp(p.timeline, 7);             // loss / head gradient exchanged, h2 stores read
 #pragma unroll 1
             for (int c = wg; c < CH; c += 2) {
                 uint32_t v[32];
@@ -1428,6 +1437,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                     ub[i] = (PASSES == 3 && split_h1 && r < p.n_rows) ? __ldcg(p.h1_lo + e) : 0.0f;
                 }
             };
+            if (stamper) tc_stamp(p.timeline, 8);             // pass 2 (dz2 operands) done
             if (split_h1) {           // this CTA's h1 TMA stores are complete (not only read) before the re-read
                 if (issuer) bulk_wait_all();
             }
@@ -1436,6 +1446,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
             load_h1(wg, 0);
             mbar_wait(&acc_full[0], 1);               // second completion of the tile
             tcgen05_fence_after();
+            if (stamper) tc_stamp(p.timeline, 9);             // backward GEMM complete
             if (issuer) bulk_wait_read<0>();          // dz2 stores have left this group's buffers
             row_warps_sync();
             own_stage = smem + wg * Cfg::STAGE_BYTES;
@@ -1483,6 +1494,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
             tcgen05_fence_before();
             if (issuer) bulk_wait_read<0>();
             row_warps_sync();
+            if (stamper) tc_stamp(p.timeline, 10);            // dz1 epilogue done
         }
         if (issuer) bulk_wait_all();
     }
@@ -1784,7 +1796,7 @@ extern "C" int tb_tc_mlp_train(const TbMlpShape* shape, const float* d_params, c
     p.b1 = d_params + shape->off_b1; p.b2 = d_params + shape->off_b2;
     p.xin_save = d_xin; p.h1_hi = d_h1_hi; p.h1_lo = d_h1_lo; p.h2 = d_h2;
     p.head_w = d_params + shape->off_w3; p.head_b = d_params + shape->off_b3; p.head_out = d_out;
-    p.n_head = shape->n_out; p.skip = d_skip; p.timeline = nullptr;
+    p.n_head = shape->n_out; p.skip = d_skip; p.timeline = g_timeline;
     p.loss_targets = nullptr; p.loss_idx = nullptr; p.loss_dout = nullptr; p.loss_ld = 1;
     p.loss_stats = nullptr; p.loss_stat_slot = 0; p.loss_count_rows = 0;
     q.idx = d_idx; q.targets = d_targets; q.log_scale = d_log_scale; q.actions = d_actions;
