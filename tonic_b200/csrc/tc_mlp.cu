@@ -981,7 +981,9 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
     uint64_t* empty_bar = bars + 2 * Cfg::STAGES;     // [STAGES] MMAs reading the stage retired
     uint64_t* acc_full = bars + 3 * Cfg::STAGES;      // [2] accumulator complete
     uint64_t* x_ready = acc_full + 2;                 // layer-1 A operand written (all row warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + 1);
+    uint64_t* h1_full = x_ready + 1;                  // [2 groups][2 slots] h1 tile re-loaded by TMA
+    uint64_t* tile_free = h1_full + 4;                // all row warps are done with the stages (next tile may load)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_free + 1);
     __shared__ float s_scale[TC_MAX_HEAD], s_dsc[TC_MAX_HEAD];     // policy head: scale, dscale/dlog_scale
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -999,6 +1001,8 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
         mbar_init(x_ready, TCM_ROW_WARPS);
+        for (int k = 0; k < 4; ++k) mbar_init(&h1_full[k], 1);
+        mbar_init(tile_free, TCM_ROW_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -1024,8 +1028,10 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
     if (warp == 0) {
         // ===================== producer: W1 image, W2 chunks, W2^T chunks =====================
         if (lane == 0) {
-            int g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int g = 0, itp = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++itp) {
+                // the row warps re-use the B regions of both stages in their last phase (h1 tiles)
+                if (itp > 0) mbar_wait(tile_free, (itp - 1) & 1);
                 for (int u = 0; u < USES; ++u, ++g) {
                     const int stage = g & 1;
                     mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
@@ -1111,19 +1117,21 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                 if (live) {
                     const int64_t r = p.in.d_idx ? p.in.d_idx[row] : row;
                     const int64_t r2 = p.in.gather2 ? r : row;
+                    // all 16 gathered loads in flight before the first use (two dependent DRAM
+                    // round trips -- index, then row -- are this phase's critical path)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = 16 * wg + j;
-                        if (c < d_in) {
-                            float val;
-                            if (c < p.in.dim1) {
-                                val = p.in.d_x1[r * p.in.dim1 + c];
-                                if (p.in.d_mean)      // mean_stds.py:36  (val - mean) / std
-                                    val = __fdiv_rn(__fsub_rn(val, p.in.d_mean[c]), p.in.d_std[c]);
-                            } else {
-                                val = p.in.d_x2[r2 * p.in.dim2 + (c - p.in.dim1)];
-                            }
-                            xv[j] = val;
+                        if (c < d_in)
+                            xv[j] = c < p.in.dim1 ? ldg_nc_volatile(p.in.d_x1 + r * p.in.dim1 + c)
+                                                  : ldg_nc_volatile(p.in.d_x2 + r2 * p.in.dim2 + (c - p.in.dim1));
+                    }
+                    if (p.in.d_mean) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int c = 16 * wg + j;
+                            if (c < p.in.dim1 && c < d_in)      // mean_stds.py:36  (val - mean) / std
+                                xv[j] = __fdiv_rn(__fsub_rn(xv[j], p.in.d_mean[c]), p.in.d_std[c]);
                         }
                     }
 #pragma unroll
@@ -1424,76 +1432,76 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                         dst[u] = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
                 }
             }
-            // ---- e) epilogue of the backward GEMM: dz1 = acc0 * act'(h1) (h1 re-read from global
-            // memory with coalesced 64-byte row segments, as in tc_mlp_backward_kernel) ------------
-            float ua[16], ub[16];
-            auto load_h1 = [&](int c, int half) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int64_t r = row0 + 2 * i + (lane >> 4);
-                    const int64_t e = r * TC_BN + c * 32 + half * 16 + (lane & 15);
-                    // written by this CTA a few microseconds ago: L2 (not the read-only path)
-                    ua[i] = r < p.n_rows ? __ldcg(p.h1_hi + e) : 0.0f;
-                    ub[i] = (PASSES == 3 && split_h1 && r < p.n_rows) ? __ldcg(p.h1_lo + e) : 0.0f;
-                }
-            };
+            // ---- e) epilogue of the backward GEMM: dz1 = acc0 * act'(h1).  h1 comes back from L2 by
+            // TMA into the (now idle) B regions of this group's stage -- the rows this CTA stored a few
+            // microseconds ago, in the operand-tile layout, so every thread reads its own row with
+            // 16-byte shared-memory loads: no global-load latency chain, no transposes ----------------
             if (stamper) tc_stamp(p.timeline, 8);             // pass 2 (dz2 operands) done
-            if (split_h1) {           // this CTA's h1 TMA stores are complete (not only read) before the re-read
-                if (issuer) bulk_wait_all();
+            if (split_h1) {
+                if (issuer) bulk_wait_all();          // this group's h1 TMA stores are complete
+            } else {
+                asm volatile("fence.proxy.async;" ::: "memory");      // plain stores -> visible to the TMA loads
+                __threadfence_block();
             }
-            __threadfence_block();
-            row_warps_sync();
-            load_h1(wg, 0);
-            mbar_wait(&acc_full[0], 1);               // second completion of the tile
+            mbar_wait(&acc_full[0], 1);               // second completion of the tile: all MMAs retired
             tcgen05_fence_after();
             if (stamper) tc_stamp(p.timeline, 9);             // backward GEMM complete
-            if (issuer) bulk_wait_read<0>();          // dz2 stores have left this group's buffers
+            if (issuer) bulk_wait_read<0>();          // dz2 stores have left the A buffers
             row_warps_sync();
             own_stage = smem + wg * Cfg::STAGE_BYTES;
-            n_staged = 0;
+            constexpr int SLOT_BYTES = (PASSES == 3 ? 2 : 1) * TC_A_BYTES;     // hi (+ lo) tile of one chunk
+            unsigned char* slots = own_stage + Cfg::B_HI;
+            auto load_h1_tile = [&](int k) {          // issuer only: chunk wg + 2 k -> slot k & 1
+                const int c = wg + 2 * k, slot = k & 1;
+                uint64_t* bar = &h1_full[wg * 2 + slot];
+                fence_proxy_async_smem();
+                mbar_expect_tx(bar, (PASSES == 3 && split_h1 ? 2 : 1) * TC_A_BYTES);
+                tma_load_2d(slots + slot * SLOT_BYTES, &map_h1_hi, bar, c * TC_BK, tile * TC_BM);
+                if (PASSES == 3 && split_h1)
+                    tma_load_2d(slots + slot * SLOT_BYTES + TC_A_BYTES, &map_h1_lo, bar, c * TC_BK, tile * TC_BM);
+            };
+            if (issuer) { load_h1_tile(0); load_h1_tile(1); }
 #pragma unroll 1
-            for (int c = wg; c < CH; c += 2) {
+            for (int k = 0; k < CH / 2; ++k) {
+                const int c = wg + 2 * k, slot = k & 1;
                 constexpr int NBUF = PASSES == 3 ? 2 : 1;
-                unsigned char* buf = own_stage + (n_staged % NBUF) * TC_A_BYTES;
-                if (n_staged >= NBUF) {
+                unsigned char* buf = own_stage + (k % NBUF) * TC_A_BYTES;
+                mbar_wait(&h1_full[wg * 2 + slot], (uint32_t)((it * (CH / 4) + (k >> 1)) & 1));
+                uint32_t v[32];
+                tcgen05_ld_32x32(tmem_base + t_lane + (uint32_t)(c * 32), v);
+                float gv[32];
+                const unsigned char* hi_tile = slots + slot * SLOT_BYTES;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float4 h = *reinterpret_cast<const float4*>(hi_tile + sw128_offset(trow, u));
+                    if (PASSES == 3 && split_h1) {
+                        const float4 l = *reinterpret_cast<const float4*>(hi_tile + TC_A_BYTES + sw128_offset(trow, u));
+                        h.x += l.x; h.y += l.y; h.z += l.z; h.w += l.w;
+                    }
+                    gv[4 * u] = tc_act_grad<ACT>(h.x) * __uint_as_float(v[4 * u]);
+                    gv[4 * u + 1] = tc_act_grad<ACT>(h.y) * __uint_as_float(v[4 * u + 1]);
+                    gv[4 * u + 2] = tc_act_grad<ACT>(h.z) * __uint_as_float(v[4 * u + 2]);
+                    gv[4 * u + 3] = tc_act_grad<ACT>(h.w) * __uint_as_float(v[4 * u + 3]);
+                }
+                if (k >= NBUF) {                      // the store that read this staging buffer has left it
                     if (issuer) bulk_wait_read<NBUF - 1>();
                     group_sync(wg);
                 }
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t v[16];
-                    tcgen05_ld_32x16(tmem_base + t_lane + (uint32_t)(c * 32 + half * 16), v);
-                    float* mine = stg + lane * TCM_STG_STRIDE;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(mine + j) = make_float4(
-                            __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
-                    __syncwarp();
-                    const int cc = half * 16 + (lane & 15);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int r = 2 * i + (lane >> 4);
-                        const float gval = tc_act_grad<ACT>(ua[i] + ub[i]) * stg[r * TCM_STG_STRIDE + (lane & 15)];
-                        *reinterpret_cast<float*>(buf + sw128_offset(qd * 32 + r, cc >> 2) + ((cc & 3) << 2)) = gval;
-                    }
-                    __syncwarp();
-                    if (half == 0) load_h1(c, 1);
-                    else if (c + 2 < CH) load_h1(c + 2, 0);
-                }
+                store_plain_row(buf, trow, gv);
                 fence_proxy_async_smem();
-                group_sync(wg);
+                group_sync(wg);                       // staging tile complete; slot fully read by the group
                 if (issuer) {
                     tma_store_2d(&map_dz1, buf, c * TC_BK, tile * TC_BM);
                     bulk_commit();
+                    if (k + 2 < CH / 2) load_h1_tile(k + 2);
                 }
-                ++n_staged;
             }
             // this tile's TMEM reads are complete before the next tile's MMAs are released, and
             // the stores have left the operand buffers before the next tile rewrites them
             tcgen05_fence_before();
             if (issuer) bulk_wait_read<0>();
             row_warps_sync();
+            if (lane == 0) mbar_arrive(tile_free);
             if (stamper) tc_stamp(p.timeline, 10);            // dz1 epilogue done
         }
         if (issuer) bulk_wait_all();
