@@ -12,6 +12,7 @@ K.device()
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 n_out, n_extra = (6, 6) if 'actor' in sys.argv else (1, 0)
 PLAIN = 'plain' in sys.argv
+PASSES = 1 if 'p1' in sys.argv else 3
 extras = [('log_scale', n_extra)] if n_extra else ()
 layout = K.MlpLayout(17, 256, n_out, 'tanh', extras)
 net = K.DeviceMlp(layout)
@@ -32,7 +33,7 @@ _lib.call('tb_wgrad_timeline', None)
 def run(fuse):
     _lib.call('tb_mlp_wgrad_fused', ctypes.byref(layout.shape), K.ptr(xin), K.ptr(h1_hi), None if PLAIN else K.ptr(h1_lo),
               K.ptr(h2), K.ptr(dz1), K.ptr(dz2_hi), None if PLAIN else K.ptr(dz2_lo), K.ptr(dout), n_out + n_extra, n_extra,
-              off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), 3,
+              off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), PASSES,
               ctypes.byref(adam.struct) if fuse else None, K.ptr(net.packed) if fuse else None,
               1.0 / rows, None, -1.0, None, None, K.stream())
 
@@ -51,6 +52,6 @@ for fuse in (False, True):
     _lib.call('tb_wgrad_timeline', buf)
     t = np.array(buf[:], dtype=np.float64)
     us = lambda i: (t[i] - t[0]) / 1965.0      # noqa: E731
-    print(f'fuse_adam={fuse} plain={PLAIN} rows={rows} n_out={n_out}: {s.elapsed_time(e) / 50 * 1e3:.1f} us per launch')
+    print(f'passes={PASSES} fuse_adam={fuse} plain={PLAIN} rows={rows} n_out={n_out}: {s.elapsed_time(e) / 50 * 1e3:.1f} us per launch')
     print(f'  (from setup done) MMAs issued {us(1):.2f} | accumulator complete {us(2):.2f} | narrow done {us(3):.2f}'
           f' | partials written {us(4):.2f} | at barrier {us(5):.2f} | barrier passed {us(6):.2f} | reduced {us(7):.2f}')
