@@ -288,6 +288,11 @@ int tb_tc_mlp_train(const TbMlpShape* shape, const float* d_params, const float*
                     float* d_h1_lo, float* d_h2, float* d_dout, int32_t ld_dout, float* d_dz2_hi,
                     float* d_dz2_lo, float* d_dz1, int32_t passes, const int32_t* d_skip, void* stream);
 
+/* Hardware check, not on the product path: on != 0 makes the fused forward / backward / train
+ * kernels store the PLAIN float32 value in the "hi" operand tile (lo stays x - trunc(x)); results
+ * bit-identical to on == 0 show that tcgen05 kind::tf32 ignores the 13 low mantissa bits.      */
+int tb_debug_plain_hi(int32_t on);
+
 /* Profiling aid for the fused forward kernel: the first call allocates a device buffer
  * of 64 clock64() stamps that CTA 0 of every later tb_tc_mlp_forward launch fills
  * (slots documented in csrc/tc_mlp.cu); a non-NULL `out64` reads them back (host

@@ -104,6 +104,7 @@ _PROTOTYPES = {
     'tb_tc_mlp_train': (c_int, [_P(TbMlpShape), c_vp, c_vp, _P(TbMlpInput), c_i64, c_i32, c_vp, c_vp, c_vp,
                                 c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                 c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'tb_debug_plain_hi': (c_int, [c_i32]),
     'tb_tc_timeline': (c_int, [c_vp]),
     'tb_wgrad_timeline': (c_int, [c_vp]),
     'tb_q_target_discounts': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp]),

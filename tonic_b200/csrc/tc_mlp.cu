@@ -89,6 +89,10 @@ struct TcMlpCfg {
 __device__ __forceinline__ float tc_tf32_hi(float x) {
     return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
+// Hardware check (tb_debug_plain_hi): non-zero = the "hi" operand tiles hold the PLAIN float32
+// values (the tensor core ignores the 13 low mantissa bits of a kind::tf32 operand), lo stays
+// x - trunc(x).  Bit-identical results with both settings prove the truncation.
+__device__ int g_plain_hi = 0;
 
 template <int ACT>
 __device__ __forceinline__ float tc_act(float x) {
@@ -159,7 +163,8 @@ __device__ __forceinline__ void store_operand_row(unsigned char* hi_tile, unsign
         float4 h;
         h.x = tc_tf32_hi(v[4 * u]); h.y = tc_tf32_hi(v[4 * u + 1]);
         h.z = tc_tf32_hi(v[4 * u + 2]); h.w = tc_tf32_hi(v[4 * u + 3]);
-        *reinterpret_cast<float4*>(hi_tile + off) = h;
+        *reinterpret_cast<float4*>(hi_tile + off) =
+            g_plain_hi ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : h;
         if (PASSES == 3) {
             float4 l;
             l.x = v[4 * u] - h.x; l.y = v[4 * u + 1] - h.y;
@@ -179,7 +184,8 @@ __device__ __forceinline__ void store_operand_half(unsigned char* hi_tile, unsig
         float4 h;
         h.x = tc_tf32_hi(v[4 * u]); h.y = tc_tf32_hi(v[4 * u + 1]);
         h.z = tc_tf32_hi(v[4 * u + 2]); h.w = tc_tf32_hi(v[4 * u + 3]);
-        *reinterpret_cast<float4*>(hi_tile + off) = h;
+        *reinterpret_cast<float4*>(hi_tile + off) =
+            g_plain_hi ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : h;
         if (PASSES == 3) {
             float4 l;
             l.x = v[4 * u] - h.x; l.y = v[4 * u + 1] - h.y;
@@ -1821,4 +1827,11 @@ extern "C" int tb_tc_mlp_train(const TbMlpShape* shape, const float* d_params, c
     else { if (loss_kind == TC_LOSS_VALUE) TB_TRAIN(1, TC_LOSS_VALUE) else TB_TRAIN(1, TC_LOSS_POLICY) }
 #undef TB_TRAIN
     return check_launch("tb_tc_mlp_train");
+}
+
+extern "C" int tb_debug_plain_hi(int32_t on) {
+    int v = on;
+    TB_REQUIRE(cudaMemcpyToSymbol(tb::g_plain_hi, &v, sizeof(int)) == cudaSuccess, TB_ENOTSUP,
+               "tb_debug_plain_hi: cudaMemcpyToSymbol failed");
+    return 0;
 }
