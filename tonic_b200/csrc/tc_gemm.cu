@@ -709,9 +709,9 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         float* out = p.gpart + (size_t)split * p.n_params + p.off_w2 + (size_t)(tile * TC_BM + w * 32) * TC_BN;
         if (PLAIN) {
             // during the mainloop these four warps are the SPLITTERS: as soon as a chunk has landed
-            // they rewrite the dz2 (8 KB) and h1 (16 KB) tiles as hi = tf32 truncation (in place)
-            // and lo = x - hi (lo slot) -- element positions are the same in both tiles, so the
-            // swizzle does not matter -- and release the MMA thread; they run up to 3 stages ahead
+            // they derive the lo tiles (x - tf32 truncation) of dz2 (8 KB) and h1 (16 KB) -- element
+            // positions are the same in the hi and lo tiles, so the swizzle does not matter -- and
+            // release the MMA thread; they run up to 3 stages ahead
             const int ts = threadIdx.x - 128;                       // 0..127
             int stage = 0;
             uint32_t phase = 0;
@@ -722,14 +722,15 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                 float4* a_lo = reinterpret_cast<float4*>(st + L::A_LO);
                 float4* b_hi = reinterpret_cast<float4*>(st + L::B_HI);
                 float4* b_lo = reinterpret_cast<float4*>(st + L::B_LO);
-                auto split4 = [](float4* hi, float4* lo, int i) {
+                // the hi slot keeps the plain value (the tensor core ignores its 13 low mantissa
+                // bits: scratch/probe_tf32_truncation.py); only lo = x - trunc(x) is written
+                auto split4 = [](const float4* hi, float4* lo, int i) {
                     const float4 v = hi[i];
-                    float4 h, l;
-                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                    hi[i] = h;
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
                     lo[i] = l;
                 };
 #pragma unroll

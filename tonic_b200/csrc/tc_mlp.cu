@@ -89,10 +89,11 @@ struct TcMlpCfg {
 __device__ __forceinline__ float tc_tf32_hi(float x) {
     return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
-// Hardware check (tb_debug_plain_hi): non-zero = the "hi" operand tiles hold the PLAIN float32
-// values (the tensor core ignores the 13 low mantissa bits of a kind::tf32 operand), lo stays
-// x - trunc(x).  Bit-identical results with both settings prove the truncation.
-__device__ int g_plain_hi = 0;
+// tcgen05 kind::tf32 ignores the 13 low mantissa bits of its operands (scratch/
+// probe_tf32_truncation.py: bit-identical results with masked and unmasked "hi" tiles on B200).
+// `plain` = the hi tile keeps the PLAIN float32 value (lo stays x - trunc(x)): the tile is then
+// both the MMA operand and, stored by TMA, the saved activation itself -- no separate lo array.
+__device__ int g_plain_hi = 0;        // tb_debug_plain_hi: force plain hi tiles everywhere (hardware check)
 
 template <int ACT>
 __device__ __forceinline__ float tc_act(float x) {
@@ -156,7 +157,7 @@ __device__ __forceinline__ void row_warps_sync() {
 // write 32 consecutive K values of one operand row (as hi / lo parts) into swizzled tiles
 template <int PASSES>
 __device__ __forceinline__ void store_operand_row(unsigned char* hi_tile, unsigned char* lo_tile, int row,
-                                                  const float (&v)[32]) {
+                                                  const float (&v)[32], bool plain = false) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
         const uint32_t off = sw128_offset(row, u);
@@ -164,7 +165,7 @@ __device__ __forceinline__ void store_operand_row(unsigned char* hi_tile, unsign
         h.x = tc_tf32_hi(v[4 * u]); h.y = tc_tf32_hi(v[4 * u + 1]);
         h.z = tc_tf32_hi(v[4 * u + 2]); h.w = tc_tf32_hi(v[4 * u + 3]);
         *reinterpret_cast<float4*>(hi_tile + off) =
-            g_plain_hi ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : h;
+            (plain || g_plain_hi) ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : h;
         if (PASSES == 3) {
             float4 l;
             l.x = v[4 * u] - h.x; l.y = v[4 * u + 1] - h.y;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void store_operand_row(unsigned char* hi_tile, unsign
 // write 16 consecutive K values (units 4 half .. 4 half + 3) of one operand row
 template <int PASSES>
 __device__ __forceinline__ void store_operand_half(unsigned char* hi_tile, unsigned char* lo_tile, int row,
-                                                   int half, const float (&v)[16]) {
+                                                   int half, const float (&v)[16], bool plain = false) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
         const uint32_t off = sw128_offset(row, 4 * half + u);
@@ -185,7 +186,7 @@ __device__ __forceinline__ void store_operand_half(unsigned char* hi_tile, unsig
         h.x = tc_tf32_hi(v[4 * u]); h.y = tc_tf32_hi(v[4 * u + 1]);
         h.z = tc_tf32_hi(v[4 * u + 2]); h.w = tc_tf32_hi(v[4 * u + 3]);
         *reinterpret_cast<float4*>(hi_tile + off) =
-            g_plain_hi ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : h;
+            (plain || g_plain_hi) ? make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]) : h;
         if (PASSES == 3) {
             float4 l;
             l.x = v[4 * u] - h.x; l.y = v[4 * u + 1] - h.y;
@@ -357,7 +358,7 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
         // h1 for the backward pass: as the tf32 split (two arrays, TMA stores of the operand tiles)
         // or, with h1_lo == NULL, as ONE plain float32 array written straight from registers (the
         // fused weight-gradient kernel splits it on the fly: half the activation traffic)
-        const bool save_h1 = p.h1_hi != nullptr && p.h1_lo != nullptr, save_h2 = p.h2 != nullptr;
+        const bool save_h1 = p.h1_hi != nullptr, save_h2 = p.h2 != nullptr;
         const bool plain_h1 = p.h1_hi != nullptr && p.h1_lo == nullptr;
         const uint32_t t_lane = (uint32_t)(q * 32) << 16;
         int it = 0;
@@ -437,17 +438,11 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                     if (issuer) bulk_wait_read<0>();
                     group_sync(wg);
                 }
-                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv);
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv, plain_h1);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
                 if (stamper) tc_stamp(p.timeline, 20 + c);    // operand published
-                if (plain_h1 && row < p.n_rows) {             // 128 contiguous bytes of this row
-                    float4* dst = reinterpret_cast<float4*>(p.h1_hi + row * TC_BN + c * 32);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        dst[u] = make_float4(hv[4 * u], hv[4 * u + 1], hv[4 * u + 2], hv[4 * u + 3]);
-                }
                 if (save_h1) {
                     // saved activations for backward: the operand tile IS the tf32 split of h1 in
                     // the layout TMA expects -> one thread stores it asynchronously (the MMA and
@@ -455,7 +450,7 @@ tc_mlp_forward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                     group_sync(wg);
                     if (issuer) {
                         tma_store_2d(&map_h1_hi, st, c * TC_BK, tile * TC_BM);
-                        if (PASSES == 3) tma_store_2d(&map_h1_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                        if (PASSES == 3 && !plain_h1) tma_store_2d(&map_h1_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
                         bulk_commit();
                     }
                 }
@@ -812,34 +807,22 @@ tc_mlp_backward_kernel(const __grid_constant__ CUtensorMap map_b_hi,
                 mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
                 if (stamper) tc_stamp(p.timeline, 12 + c);     // stage free
                 unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                if (!plain_dz2) {
-                    if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
-                    group_sync(wg);
-                }
-                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z);
+                if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
+                group_sync(wg);
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z, plain_dz2);
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
                 if (stamper) tc_stamp(p.timeline, 20 + c);     // published
-                if (plain_dz2) {
-                    // dz2 as ONE plain float32 array straight from registers (dz2_lo == NULL): the
-                    // fused weight-gradient kernel splits it on the fly
-                    if (live) {
-                        float4* dst = reinterpret_cast<float4*>(p.dz2_hi + row * TC_BN + c * 32);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            dst[u] = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
-                    }
-                } else {
-                    // dz2 (tf32 split) for the weight-gradient kernels: the operand tile is already in
-                    // the TMA layout -> asynchronous store by one thread
-                    group_sync(wg);
-                    if (issuer) {
-                        tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
-                        if (PASSES == 3) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
-                        bulk_commit();
-                    }
+                // dz2 for the weight-gradient kernels: the operand tile is already in the TMA layout
+                // (tf32 split: hi and lo tiles; plain: the hi tile holds the float32 values) ->
+                // asynchronous store by one thread
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
+                    if (PASSES == 3 && !plain_dz2) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
                 }
             }
             // ---- b) epilogue: dz1 = acc * act'(h1).  h1 (hi + lo) is read with coalesced 64-byte
@@ -1179,27 +1162,21 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                 const int g = g0 + 1 + c, stage = g & 1;
                 mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
                 unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                if (split_h1) {       // the TMA stores of this group's previous chunk have left the stage
-                    if (issuer) bulk_wait_read<0>();
-                    group_sync(wg);
-                }
-                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv);
+                // the TMA stores of this group's previous chunk have left the stage
+                if (issuer) bulk_wait_read<0>();
+                group_sync(wg);
+                // plain mode: the hi tile keeps the float32 value (the tensor core ignores the low
+                // mantissa bits) and IS the saved h1; split mode: tf32-exact hi + lo, both saved
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, hv, !split_h1);
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
-                if (split_h1) {
-                    group_sync(wg);
-                    if (issuer) {
-                        tma_store_2d(&map_h1_hi, st, c * TC_BK, tile * TC_BM);
-                        if (PASSES == 3) tma_store_2d(&map_h1_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
-                        bulk_commit();
-                    }
-                } else if (live) {    // plain float32 h1 straight from registers
-                    float4* dst = reinterpret_cast<float4*>(p.h1_hi + row * TC_BN + c * 32);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        dst[u] = make_float4(hv[4 * u], hv[4 * u + 1], hv[4 * u + 2], hv[4 * u + 3]);
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_h1_hi, st, c * TC_BK, tile * TC_BM);
+                    if (PASSES == 3 && split_h1) tma_store_2d(&map_h1_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
                 }
             }
             // ---- c) pass 1 over z2: h2 (saved), head output ------------------------------------
@@ -1213,10 +1190,8 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
             // both stages are idle now (all layer-2 MMAs retired): group wg stages h2 in the A
             // buffers of stage wg; the h1 stores that may still read them must have left
             unsigned char* own_stage = smem + wg * Cfg::STAGE_BYTES;
-            if (split_h1) {
-                if (issuer) bulk_wait_read<0>();
-                row_warps_sync();                     // (the other group's stores read both stages over time)
-            }
+            if (issuer) bulk_wait_read<0>();
+            row_warps_sync();                         // (the other group's stores read both stages over time)
             int n_staged = 0;
 #pragma unroll 1
             for (int c = wg; c < CH; c += 2) {
@@ -1415,27 +1390,18 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
                 const int g = g0 + 1 + CH + c, stage = g & 1;
                 mbar_wait(&empty_bar[stage], ((g >> 1) & 1) ^ 1);
                 unsigned char* st = smem + stage * Cfg::STAGE_BYTES;
-                if (split_dz2) {
-                    if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
-                    group_sync(wg);
-                }
-                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z);
+                if (issuer) bulk_wait_read<0>();    // stores of the previous chunk have left the stage
+                group_sync(wg);
+                store_operand_row<PASSES>(st, st + Cfg::A_LO, trow, z, !split_dz2);
                 fence_proxy_async_smem();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[stage]);
-                if (split_dz2) {
-                    group_sync(wg);
-                    if (issuer) {
-                        tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
-                        if (PASSES == 3) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
-                        bulk_commit();
-                    }
-                } else if (live) {
-                    float4* dst = reinterpret_cast<float4*>(q.dz2_hi + row * TC_BN + c * 32);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        dst[u] = make_float4(z[4 * u], z[4 * u + 1], z[4 * u + 2], z[4 * u + 3]);
+                group_sync(wg);
+                if (issuer) {
+                    tma_store_2d(&map_dz2_hi, st, c * TC_BK, tile * TC_BM);
+                    if (PASSES == 3 && split_dz2) tma_store_2d(&map_dz2_lo, st + Cfg::A_LO, c * TC_BK, tile * TC_BM);
+                    bulk_commit();
                 }
             }
             // ---- e) epilogue of the backward GEMM: dz1 = acc0 * act'(h1).  h1 comes back from L2 by
@@ -1443,12 +1409,7 @@ tc_mlp_train_kernel(const __grid_constant__ CUtensorMap map_w2_hi, const __grid_
             // microseconds ago, in the operand-tile layout, so every thread reads its own row with
             // 16-byte shared-memory loads: no global-load latency chain, no transposes ----------------
             if (stamper) tc_stamp(p.timeline, 8);             // pass 2 (dz2 operands) done
-            if (split_h1) {
-                if (issuer) bulk_wait_all();          // this group's h1 TMA stores are complete
-            } else {
-                asm volatile("fence.proxy.async;" ::: "memory");      // plain stores -> visible to the TMA loads
-                __threadfence_block();
-            }
+            if (issuer) bulk_wait_all();              // this group's h1 TMA stores are complete
             mbar_wait(&acc_full[0], 1);               // second completion of the tile: all MMAs retired
             tcgen05_fence_after();
             if (stamper) tc_stamp(p.timeline, 9);             // backward GEMM complete
@@ -1640,9 +1601,9 @@ static int tc_mlp_forward_impl(const TbMlpShape* shape, const float* d_params, c
     if ((rc = make_map(&maps[0], d_packed + shape->off_w2_hi, TC_BN, b_box_rows))) return rc;
     if ((rc = make_map(&maps[1], d_packed + shape->off_w2_lo, TC_BN, b_box_rows))) return rc;
     maps[2] = maps[3] = maps[4] = maps[0];       // placeholders when nothing is saved
-    if (d_h1_hi && d_h1_lo) {      // tf32 split saved by TMA; d_h1_lo == NULL: plain float32 from registers
+    if (d_h1_hi) {      // tf32 split (two arrays) or, with d_h1_lo == NULL, ONE plain float32 array
         if ((rc = make_map(&maps[2], d_h1_hi, n_rows, TC_BM))) return rc;
-        if ((rc = make_map(&maps[3], d_h1_lo, n_rows, TC_BM))) return rc;
+        if ((rc = make_map(&maps[3], d_h1_lo ? d_h1_lo : d_h1_hi, n_rows, TC_BM))) return rc;
     }
     if (d_h2 && (rc = make_map(&maps[4], d_h2, n_rows, TC_BM))) return rc;
     TcMlpParams p;

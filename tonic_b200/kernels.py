@@ -204,7 +204,7 @@ _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 _FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
 _FUSED_WGRAD = os.environ.get('TONIC_B200_FUSED_WGRAD', '1') != '0'
 _FUSED_ADAM = os.environ.get('TONIC_B200_FUSED_ADAM', '1') != '0'
-_PLAIN_ACTS = os.environ.get('TONIC_B200_PLAIN_ACTS', '0') != '0'     # measured: no gain on B200
+_PLAIN_ACTS = os.environ.get('TONIC_B200_PLAIN_ACTS', '1') != '0'
 _FUSED_TRAIN = os.environ.get('TONIC_B200_FUSED_TRAIN', '1') != '0'
 
 
