@@ -501,6 +501,13 @@ constexpr int TCA_NO = 8;                    // head outputs with a dW3 row (n_o
 constexpr int TCA_ND = 12;                   // dout columns with a column sum (n_out + extras <= 12)
 constexpr int TCA_ROWS = 16;                 // rows per pipeline chunk (two K = 8 MMA steps)
 constexpr int TCA_STAGES = 3;
+constexpr int TCA_XRING = 4;                 // chunk buffers of the xin / dout rows (cp.async, 3 chunks ahead)
+
+// 4-byte asynchronous copy global -> shared; ok == false writes a zero (src-size 0)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(ok ? 4 : 0) : "memory");
+}
 // One pipeline stage: MMA operands of a 16-row chunk in the MN-major 128B / 32B-atom swizzle
 // (boxes of 32 columns x 16 rows = 2 KB) and the narrow warps' dz1 / h2 column halves
 // ([16][128] float32, unswizzled).
@@ -520,7 +527,7 @@ struct TcaLayout {
 template <int PASSES, int KIN>
 constexpr int tca_smem_bytes() {
     return TCA_STAGES * TcaLayout<KIN>::STAGE_BYTES + TcCfg<PASSES>::EPI_BYTES + 4096 +
-           2 * TCA_ROWS * (KIN + TCA_ND) * 4 + 256 + 1024;
+           TCA_XRING * TCA_ROWS * (KIN + TCA_ND) * 4 + 256 + 1024;
 }
 
 __device__ __forceinline__ void tcw_stamp(unsigned long long* timeline, int slot) {
@@ -587,9 +594,9 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     float* epi = reinterpret_cast<float*>(smem + TCA_STAGES * L::STAGE_BYTES);
     // [8 x 32] block of ones (B operand of the bias-gradient MMAs), then the narrow warps' xin / dout rows
     float* ones = reinterpret_cast<float*>(smem + TCA_STAGES * L::STAGE_BYTES + TcCfg<PASSES>::EPI_BYTES);
-    float* xs = ones + 1024;                             // [2][16][KIN]
-    float* dsm = xs + 2 * TCA_ROWS * KIN;                // [2][16][TCA_ND]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + 2 * TCA_ROWS * TCA_ND);
+    float* xs = ones + 1024;                             // [XRING][16][KIN]
+    float* dsm = xs + TCA_XRING * TCA_ROWS * KIN;        // [XRING][16][TCA_ND]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + TCA_XRING * TCA_ROWS * TCA_ND);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + TCA_STAGES;
     uint64_t* tmem_full = bars + 2 * TCA_STAGES;
@@ -797,48 +804,51 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         for (int j = 0; j < KIN; ++j) w1[j] = 0.0f;
 #pragma unroll
         for (int o = 0; o < TCA_NO; ++o) w3[o] = 0.0f;
+        // xin / dout rows of the chunks: cp.async (4-byte, zero-filled outside the split / the used
+        // columns) into a ring of TCA_XRING chunk buffers, TCA_XRING - 1 chunks ahead -- the global
+        // latency of these small rows paced the whole pipeline when they were staged one chunk ahead
         constexpr int NX = (TCA_ROWS * KIN + 255) / 256, NDS = (TCA_ROWS * TCA_ND + 255) / 256;
-        float sx[NX], sd[NDS];
-        auto stage_load = [&](int chunk) {
-            const int64_t base = m_begin + (int64_t)chunk * TCA_ROWS;
+        auto stage_async = [&](int chunk) {
+            if (chunk < n_chunks) {
+                const int64_t base = m_begin + (int64_t)chunk * TCA_ROWS;
+                float* x = xs + (chunk % TCA_XRING) * TCA_ROWS * KIN;
+                float* d = dsm + (chunk % TCA_XRING) * TCA_ROWS * TCA_ND;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) {
-                const int v = t + 256 * k, r = v / KIN, j = v % KIN;
-                sx[k] = (v < TCA_ROWS * KIN && base + r < m_end && j <= d_in)
-                    ? ldg_nc_volatile(q.xin + (base + r) * ldx + j) : 0.0f;
+                for (int k = 0; k < NX; ++k) {
+                    const int v = t + 256 * k, r = v / KIN, j = v % KIN;
+                    if (v < TCA_ROWS * KIN) {
+                        const bool ok = base + r < m_end && j <= d_in;
+                        cp_async4(x + v, q.xin + (ok ? (base + r) * ldx + j : 0), ok);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NDS; ++k) {
+                    const int v = t + 256 * k, r = v / TCA_ND, o = v % TCA_ND;
+                    if (v < TCA_ROWS * TCA_ND) {
+                        const bool ok = base + r < m_end && o < nd;
+                        cp_async4(d + v, q.dout + (ok ? (base + r) * q.ld_dout + o : 0), ok);
+                    }
+                }
             }
-#pragma unroll
-            for (int k = 0; k < NDS; ++k) {
-                const int v = t + 256 * k, r = v / TCA_ND, o = v % TCA_ND;
-                sd[k] = (v < TCA_ROWS * TCA_ND && base + r < m_end && o < nd)
-                    ? ldg_nc_volatile(q.dout + (base + r) * q.ld_dout + o) : 0.0f;
-            }
+            asm volatile("cp.async.commit_group;" ::: "memory");      // one group per chunk (may be empty)
         };
-        auto stage_store = [&](int chunk) {
-            float* x = xs + (chunk & 1) * TCA_ROWS * KIN;
-            float* d = dsm + (chunk & 1) * TCA_ROWS * TCA_ND;
 #pragma unroll
-            for (int k = 0; k < NX; ++k) if (t + 256 * k < TCA_ROWS * KIN) x[t + 256 * k] = sx[k];
-#pragma unroll
-            for (int k = 0; k < NDS; ++k) if (t + 256 * k < TCA_ROWS * TCA_ND) d[t + 256 * k] = sd[k];
-        };
-        if (n_chunks > 0) {
-            stage_load(0);
-            stage_store(0);
-        }
+        for (int k = 0; k < TCA_XRING - 1; ++k) stage_async(k);
         int stage = 0;
         uint32_t phase = 0;
         for (int ch = 0; ch < n_chunks; ++ch) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // xin / dout of chunk ch visible; other buffer free
-            const bool more = ch + 1 < n_chunks;
-            if (more) stage_load(ch + 1);
+            // this thread's copies of chunk ch have landed (the TCA_XRING - 2 newer groups may be in
+            // flight); the barrier publishes everybody's and frees the buffer chunk ch + XRING - 1 reuses
+            asm volatile("cp.async.wait_group %0;" ::"n"(TCA_XRING - 2) : "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            stage_async(ch + TCA_XRING - 1);
             mbar_wait(&full_bar[stage], phase);                 // operands and dz1 / h2 of this chunk landed
             const unsigned char* st = smem + stage * L::STAGE_BYTES;
             const float* s_dz1 = reinterpret_cast<const float*>(st + L::N_DZ1);
             const float* s_h2 = reinterpret_cast<const float*>(st + L::N_H2);
             const int rows = (int)min((int64_t)TCA_ROWS, m_end - (m_begin + (int64_t)ch * TCA_ROWS));
-            const float* x = xs + (ch & 1) * TCA_ROWS * KIN;
-            const float* d = dsm + (ch & 1) * TCA_ROWS * TCA_ND;
+            const float* x = xs + (ch % TCA_XRING) * TCA_ROWS * KIN;
+            const float* d = dsm + (ch % TCA_XRING) * TCA_ROWS * TCA_ND;
             if (tile == 0 && t < nd)
                 for (int r = 0; r < rows; ++r) dsum += d[r * TCA_ND + t];
 #pragma unroll
@@ -866,12 +876,12 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                     }
                 }
             }
-            if (more) stage_store(ch + 1);
             // this group's reads of the stage are done: one arrival per chunk for the whole group
             asm volatile("bar.sync 3, 256;" ::: "memory");
             if (t == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (t == 0) tcw_stamp(q.timeline, 3);                     // narrow gradients accumulated
         // combine the two row groups (fixed order: group 0 + group 1) in two rounds through the
         // dz1 / h2 block of stage 0 (the producer is done and only these warps read that block),
