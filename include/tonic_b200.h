@@ -389,7 +389,7 @@ int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float*
                        const double* d_stats, float kl_threshold, int32_t* d_stop,
                        const int32_t* d_skip, void* stream);
 
-/* Profiling aid for tb_mlp_wgrad_fused: 16 clock64() stamps of CTA (0, 0) (slots: 0 setup done,
+/* Profiling aid for tb_mlp_wgrad_fused: 64 clock64() stamps of CTA (0, 0) (out16: 64 values; slots: 0 setup done,
  * 1 MMAs issued, 2 accumulator complete, 3 narrow gradients done, 4 partial slot written,
  * 5 at the grid barrier, 6 barrier passed, 7 reduction + Adam done).  Not on the product path. */
 int tb_wgrad_timeline(uint64_t* out16);

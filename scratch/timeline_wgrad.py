@@ -48,10 +48,11 @@ for fuse in (False, True):
         run(fuse)
     e.record()
     torch.cuda.synchronize()
-    buf = (ctypes.c_uint64 * 16)()
+    buf = (ctypes.c_uint64 * 64)()
     _lib.call('tb_wgrad_timeline', buf)
     t = np.array(buf[:], dtype=np.float64)
     us = lambda i: (t[i] - t[0]) / 1965.0      # noqa: E731
     print(f'passes={PASSES} fuse_adam={fuse} plain={PLAIN} rows={rows} n_out={n_out}: {s.elapsed_time(e) / 50 * 1e3:.1f} us per launch')
     print(f'  (from setup done) MMAs issued {us(1):.2f} | accumulator complete {us(2):.2f} | narrow done {us(3):.2f}'
           f' | partials written {us(4):.2f} | at barrier {us(5):.2f} | barrier passed {us(6):.2f} | reduced {us(7):.2f}')
+    print('  chunk: TMA issue / landed / MMA start: ' + '  '.join(f'{c}: {us(16 + c):.2f}/{us(32 + c):.2f}/{us(48 + c):.2f}' for c in range(14)))

@@ -642,6 +642,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             uint32_t phase = 0;
             for (int c = 0; c < n_chunks; ++c) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (c < 14) tcw_stamp(q.timeline, 16 + c);           // stage free -> TMA issue of chunk c
                 unsigned char* st = smem + stage * L::STAGE_BYTES;
                 mbar_expect_tx(&full_bar[stage],
                                ((PASSES == 3 && !PLAIN) ? 2 : 1) * (L::A_BYTES + L::B_BYTES) + 2 * L::N_BYTES);
@@ -681,7 +682,10 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             const uint32_t idesc16 = (kIdescTf32MN & ~(0x3Fu << 17)) | ((16u >> 3) << 17);
             const uint64_t b_ones = umma_desc_mnmajor_sw128(ones, L::BOX);
             for (int c = 0; c < n_chunks; ++c) {
-                mbar_wait(PLAIN ? &split_bar[stage] : &full_bar[stage], phase);
+                mbar_wait(&full_bar[stage], phase);
+                if (c < 14) tcw_stamp(q.timeline, 32 + c);           // chunk c landed
+                if (PLAIN) mbar_wait(&split_bar[stage], phase);
+                if (c < 14) tcw_stamp(q.timeline, 48 + c);           // (split done ->) MMAs of chunk c issued next
                 tcgen05_fence_after();
                 unsigned char* st = smem + stage * L::STAGE_BYTES;
                 // 16-row boxes: 32-column groups are BOX = 2048 bytes apart (LBO)
@@ -1122,12 +1126,12 @@ namespace tb { static unsigned long long* g_wgrad_timeline = nullptr; }
 extern "C" int tb_wgrad_timeline(uint64_t* out16) {
     using namespace tb;
     if (!g_wgrad_timeline) {
-        TB_REQUIRE(cudaMalloc(&g_wgrad_timeline, 16 * sizeof(unsigned long long)) == cudaSuccess, TB_ENOTSUP,
+        TB_REQUIRE(cudaMalloc(&g_wgrad_timeline, 64 * sizeof(unsigned long long)) == cudaSuccess, TB_ENOTSUP,
                    "tb_wgrad_timeline: cudaMalloc failed");
-        cudaMemset(g_wgrad_timeline, 0, 16 * sizeof(unsigned long long));
+        cudaMemset(g_wgrad_timeline, 0, 64 * sizeof(unsigned long long));
     }
     if (out16)
-        TB_REQUIRE(cudaMemcpy(out16, g_wgrad_timeline, 16 * sizeof(unsigned long long),
+        TB_REQUIRE(cudaMemcpy(out16, g_wgrad_timeline, 64 * sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost) == cudaSuccess, TB_ENOTSUP, "tb_wgrad_timeline: copy failed");
     return 0;
 }
