@@ -812,25 +812,40 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         // columns) into a ring of TCA_XRING chunk buffers, TCA_XRING - 1 chunks ahead -- the global
         // latency of these small rows paced the whole pipeline when they were staged one chunk ahead
         constexpr int NX = (TCA_ROWS * KIN + 255) / 256, NDS = (TCA_ROWS * TCA_ND + 255) / 256;
+        // (row, column) of this thread's elements inside a chunk never change: precomputed
+        int x_row[NX], x_off[NX], d_row[NDS], d_off[NDS];
+#pragma unroll
+        for (int k = 0; k < NX; ++k) {
+            const int v = t + 256 * k, r = v / KIN, j = v % KIN;
+            x_row[k] = (v < TCA_ROWS * KIN && j <= d_in) ? r : -1;         // -1: zero fill (padding column)
+            x_off[k] = r * ldx + j;
+        }
+#pragma unroll
+        for (int k = 0; k < NDS; ++k) {
+            const int v = t + 256 * k, r = v / TCA_ND, o = v % TCA_ND;
+            d_row[k] = (v < TCA_ROWS * TCA_ND && o < nd) ? r : -1;
+            d_off[k] = r * q.ld_dout + o;
+        }
         auto stage_async = [&](int chunk) {
             if (chunk < n_chunks) {
                 const int64_t base = m_begin + (int64_t)chunk * TCA_ROWS;
+                const int valid = (int)min((int64_t)TCA_ROWS, m_end - base);
                 float* x = xs + (chunk % TCA_XRING) * TCA_ROWS * KIN;
                 float* d = dsm + (chunk % TCA_XRING) * TCA_ROWS * TCA_ND;
+                const float* gx = q.xin + base * ldx;
+                const float* gd = q.dout + base * q.ld_dout;
 #pragma unroll
                 for (int k = 0; k < NX; ++k) {
-                    const int v = t + 256 * k, r = v / KIN, j = v % KIN;
-                    if (v < TCA_ROWS * KIN) {
-                        const bool ok = base + r < m_end && j <= d_in;
-                        cp_async4(x + v, q.xin + (ok ? (base + r) * ldx + j : 0), ok);
+                    if (t + 256 * k < TCA_ROWS * KIN) {
+                        const bool ok = x_row[k] >= 0 && x_row[k] < valid;
+                        cp_async4(x + t + 256 * k, ok ? gx + x_off[k] : q.xin, ok);
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < NDS; ++k) {
-                    const int v = t + 256 * k, r = v / TCA_ND, o = v % TCA_ND;
-                    if (v < TCA_ROWS * TCA_ND) {
-                        const bool ok = base + r < m_end && o < nd;
-                        cp_async4(d + v, q.dout + (ok ? (base + r) * q.ld_dout + o : 0), ok);
+                    if (t + 256 * k < TCA_ROWS * TCA_ND) {
+                        const bool ok = d_row[k] >= 0 && d_row[k] < valid;
+                        cp_async4(d + t + 256 * k, ok ? gd + d_off[k] : q.dout, ok);
                     }
                 }
             }
@@ -841,10 +856,12 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         int stage = 0;
         uint32_t phase = 0;
         for (int ch = 0; ch < n_chunks; ++ch) {
-            // this thread's copies of chunk ch have landed (the TCA_XRING - 2 newer groups may be in
-            // flight); the barrier publishes everybody's and frees the buffer chunk ch + XRING - 1 reuses
+            // ONE barrier per chunk: (a) every thread's copies of chunk ch have landed (the
+            // TCA_XRING - 2 newer groups may be in flight) and are published, (b) everybody is done
+            // with chunk ch - 1: its stage goes back to the producer and its ring buffer is reused
             asm volatile("cp.async.wait_group %0;" ::"n"(TCA_XRING - 2) : "memory");
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ch > 0 && t == 0) mbar_arrive(&empty_bar[(stage + TCA_STAGES - 1) % TCA_STAGES]);
             stage_async(ch + TCA_XRING - 1);
             mbar_wait(&full_bar[stage], phase);                 // operands and dz1 / h2 of this chunk landed
             const unsigned char* st = smem + stage * L::STAGE_BYTES;
@@ -853,8 +870,18 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             const int rows = (int)min((int64_t)TCA_ROWS, m_end - (m_begin + (int64_t)ch * TCA_ROWS));
             const float* x = xs + (ch % TCA_XRING) * TCA_ROWS * KIN;
             const float* d = dsm + (ch % TCA_XRING) * TCA_ROWS * TCA_ND;
-            if (tile == 0 && t < nd)
-                for (int r = 0; r < rows; ++r) dsum += d[r * TCA_ND + t];
+            if (tile == 0 && t < nd) {
+                // column sum of dout (rows beyond the split are zero-filled): 16 independent loads,
+                // fixed pairwise order
+                float dvv[TCA_ROWS];
+#pragma unroll
+                for (int r = 0; r < TCA_ROWS; ++r) dvv[r] = d[r * TCA_ND + t];
+#pragma unroll
+                for (int w = TCA_ROWS / 2; w > 0; w >>= 1)
+#pragma unroll
+                    for (int r = 0; r < w; ++r) dvv[r] += dvv[r + w];
+                dsum += dvv[0];
+            }
 #pragma unroll
             for (int u = 0; u < TCA_ROWS / 2; ++u) {
                 const int r = g + 2 * u;
@@ -880,11 +907,11 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                     }
                 }
             }
-            // this group's reads of the stage are done: one arrival per chunk for the whole group
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            if (t == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
         }
+        // the last chunk's stage (nobody refills it, but the producer's bookkeeping stays balanced)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (n_chunks > 0 && t == 0) mbar_arrive(&empty_bar[(stage + TCA_STAGES - 1) % TCA_STAGES]);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (t == 0) tcw_stamp(q.timeline, 3);                     // narrow gradients accumulated
         // combine the two row groups (fixed order: group 0 + group 1) in two rounds through the
