@@ -547,6 +547,7 @@ struct TcWgradAllParams {
     unsigned long long* sync;   // grid-barrier counter (monotonic)
     unsigned long long* timeline;   // profiling aid: clock64() stamps of CTA (0, 0), or NULL
     int tma3d;                  // operand tiles by one 3-D box each (else one 2-D box per column group)
+    int dbg;                    // timing experiments only (TB_WGRAD_DBG): 1 = no bias-gradient MMAs, 2 = no FFMA block
     // optional fused optimizer step (single process, no gradient clipping): the reduction phase
     // applies Adam to its slice right away -- same arithmetic and device-side controls as adam_kernel
     int fuse_adam;
@@ -704,8 +705,10 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
                         tcgen05_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, kIdescTf32MN, (c | k) != 0);
                     }
                     // db2[n] = sum_m dz2[m, n]: the A operand against a block of ones (N = 16)
-                    tcgen05_mma_tf32(tmem_base + TC_BN, a_hi + koff, b_ones, idesc16, (c | k) != 0);
-                    if (PASSES == 3) tcgen05_mma_tf32(tmem_base + TC_BN, a_lo + koff, b_ones, idesc16, 1);
+                    if (!(q.dbg & 1)) {
+                        tcgen05_mma_tf32(tmem_base + TC_BN, a_hi + koff, b_ones, idesc16, (c | k) != 0);
+                        if (PASSES == 3) tcgen05_mma_tf32(tmem_base + TC_BN, a_lo + koff, b_ones, idesc16, 1);
+                    }
                 }
                 tcgen05_commit(&empty_bar[stage]);
                 if (++stage == TCA_STAGES) { stage = 0; phase ^= 1; }
@@ -885,7 +888,7 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
 #pragma unroll
             for (int u = 0; u < TCA_ROWS / 2; ++u) {
                 const int r = g + 2 * u;
-                if (r < rows) {
+                if (r < rows && !(q.dbg & 2)) {
                     const float a1 = s_dz1[r * 128 + c], hv = s_h2[r * 128 + c];
                     const float4* x4 = reinterpret_cast<const float4*>(x + r * KIN);
 #pragma unroll
@@ -1211,6 +1214,7 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     if (!tma3d) for (int i = 0; i < 4; ++i) maps3[i] = maps[i];
     TcWgradAllParams q;
     q.tma3d = tma3d ? 1 : 0;
+    { const char* v = getenv("TB_WGRAD_DBG"); q.dbg = v ? atoi(v) : 0; }
     q.w.n_rows = n_rows;
     q.w.rows_per_split = ((n_rows + n_split - 1) / n_split + TCA_ROWS - 1) / TCA_ROWS * TCA_ROWS;
     q.w.gpart = d_gpart; q.w.n_params = shape->n_params; q.w.off_w2 = shape->off_w2;
