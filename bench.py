@@ -304,19 +304,27 @@ def run_ppo(args):
     skipped = profiled_iterations['critic'] - timed_iterations['critic'] - (
         profiled_iterations['actor'] - timed_iterations['actor'])
     rows_local = batch // world
-    gemm_names = ('tb_tc_mlp_forward', 'tb_tc_mlp_backward', 'tb_tc_gemm256_fwd', 'tb_tc_gemm256_bwd',
-                  'tb_tc_wgrad256', 'tb_mlp_wgrad_fused', 'tb_mlp_forward', 'tb_mlp_backward',
-                  'tb_mlp_wgrad')
+    gemm_names = ('tb_tc_mlp_train', 'tb_tc_mlp_forward', 'tb_tc_mlp_backward', 'tb_tc_gemm256_fwd',
+                  'tb_tc_gemm256_bwd', 'tb_tc_wgrad256', 'tb_mlp_wgrad_fused', 'tb_mlp_forward',
+                  'tb_mlp_backward', 'tb_mlp_wgrad')
     # algorithmic FLOPs of ONE skipped launch (they are actor-minibatch launches)
     actor_launch_flops = {
+        'tb_tc_mlp_train': 2.0 * rows_local * (OBS * HIDDEN + HIDDEN * HIDDEN + HIDDEN * ACT)
+        + 2.0 * rows_local * HIDDEN * (ACT + HIDDEN),
         'tb_tc_mlp_forward': 2.0 * rows_local * (OBS * HIDDEN + HIDDEN * HIDDEN + HIDDEN * ACT),
         'tb_tc_mlp_backward': 2.0 * rows_local * HIDDEN * (ACT + HIDDEN),
         'tb_mlp_wgrad_fused': 2.0 * rows_local * (HIDDEN * HIDDEN + HIDDEN * (OBS + 2)
                                                   + 2 * ACT * (HIDDEN + 1))}
     # rollout launches of the forward kernel evaluate 4096 rows, not a minibatch: count separately
+    # entry points the skipped actor minibatches went through (device flag -> no-op launches)
+    if 'tb_tc_mlp_train' in prof:
+        skip_names = ('tb_tc_mlp_train', 'tb_mlp_wgrad_fused')
+    else:
+        skip_names = tuple(n for n in gemm_names if n not in ('tb_tc_mlp_train',))
+
     def executed_flops(name):
         total = kernels.flops.get(name, 0.0)
-        if name in gemm_names:
+        if name in skip_names:
             per_launch = actor_launch_flops.get(name, 2.0 * rows_local * HIDDEN * HIDDEN)
             if name in ('tb_mlp_forward', 'tb_mlp_backward', 'tb_mlp_wgrad'):
                 per_launch = total / max(prof.get(name, (1, 0))[0], 1)
@@ -347,15 +355,15 @@ def run_ppo(args):
         kernel=top, bound='tensor', achieved=round(achieved, 3), peak=pk['tflops'],
         unit='TFLOP/s', frac=round(achieved / pk['tflops'], 5),
         traffic=traffic.get(top), peak_source=pk['source'], launches=top_count,
-        executed_launches=top_count - (skipped if top in gemm_names else 0),
-        avg_launch_us=round(top_ms / max(top_count - skipped, 1) * 1e3, 2),
+        executed_launches=top_count - (skipped if top in skip_names else 0),
+        avg_launch_us=round(top_ms / max(top_count - (skipped if top in skip_names else 0), 1) * 1e3, 2),
         share_of_kernel_time=round(top_ms / total_kernel_ms, 4),
-        flops_per_launch=round(top_flops / max(top_count - skipped, 1), 1),
+        flops_per_launch=round(top_flops / max(top_count - (skipped if top in skip_names else 0), 1), 1),
         tensor_pipe_tflops=round(achieved * max(passes, 1), 3),
         note=('dominant GEMM entry point by CUDA-event time in an eager (graphs off) pass of the '
               'same K steps with the same kernels; achieved = algorithmic fp32-equivalent FLOPs of the '
-              'executed launches (fused forward: 2*rows*(d_in*256 + 256*256 + 256*n_out); fused '
-              'backward: 2*rows*256*(n_out + 256); fused weight gradients: 2*rows*(256*256 + '
+              'executed launches (forward->loss->backward kernel: 2*rows*(d_in*256 + 256*256 + 256*n_out) + '
+              '2*rows*256*(n_out + 256); weight-gradient + Adam kernel: 2*rows*(256*256 + '
               '256*(d_in+2) + (n_out+extras)*257)) / event time; ' +
               ('FP32 FFMA kernels' if passes == 0 else
                f'tcgen05 kind::tf32 with {passes} MMA pass(es) per product, so the tensor pipe '
