@@ -366,6 +366,13 @@ int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2
                        int32_t w2_begin, int32_t w2_end, int32_t n_params, float* d_out,
                        const int32_t* d_skip, void* stream);
 
+/* base[r] = address, in THIS process, of rank r's symmetric region of
+ * tb_peer_region_bytes(n_params) bytes (zero-initialised; obtained from
+ * torch.distributed._symmetric_memory or cudaIpc / fabric handles).            */
+typedef struct {
+    int32_t world, rank;
+    void* base[8];
+} TbPeers;
 /* ALL weight gradients of one network-minibatch in one launch, reduced to the flat gradient
  * (reference: loss.backward() filling .grad of every variable, torch/updaters/actors.py:33,95,
  * critics.py:23,81).  dW2 / db2 run on the tensor cores (tcgen05, 3xTF32), the narrow
@@ -379,7 +386,18 @@ int tb_reduce_partials(const float* d_gpart, int32_t n_split, int32_t n_split_w2
  * opt != NULL (single process, no gradient clipping): the reduction phase also performs the
  * optimizer step of tb_adam_step on its slice -- g = grad_scale * flat[i], Adam, refresh of
  * d_packed, and the same device-side controls (d_stats / kl_threshold / d_stop) -- so the
- * chain forward -> backward -> weight gradients + Adam is three launches.                   */
+ * chain forward -> backward -> weight gradients + Adam is three launches.
+ * peers != NULL with world > 1 (one replica per GPU; needs opt): the gradient
+ * all-reduce runs inside the same launch.  After the grid barrier every thread stores its
+ * reduced element, paired with the epoch tag in one 8-byte word, into its rank's lane of EVERY
+ * rank's symmetric region (tb_peer_region_bytes_fused bytes each, zero-initialised) with NVLink
+ * stores -- no fence, no flag round trip; it then polls the same element in every lane of its
+ * LOCAL region until the tags match, sums the lanes in rank order and applies Adam with
+ * grad_scale = 1 / (global rows).  d_reduce_stats (double[TB_STAT_COUNT] or NULL) is
+ * summed over the ranks in place; the PPO controls (d_stats != NULL) act on that global block.
+ * d_epoch: one zero-initialised uint64 per region, advanced by the launch.  Every rank must
+ * launch the same sequence of exchanges (a rank that never arrives traps the waiting kernels
+ * after 20 s instead of hanging the node).                                                    */
 int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float* d_h1_hi,
                        const float* d_h1_lo, const float* d_h2, const float* d_dz1,
                        const float* d_dz2_hi, const float* d_dz2_lo, const float* d_dout,
@@ -387,11 +405,13 @@ int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, const float*
                        float* d_gpart, int32_t n_split, float* d_flat, uint64_t* d_sync,
                        int32_t passes, const TbAdam* opt, float* d_packed, float grad_scale,
                        const double* d_stats, float kl_threshold, int32_t* d_stop,
-                       const int32_t* d_skip, void* stream);
+                       const int32_t* d_skip, const TbPeers* peers, uint64_t* d_epoch,
+                       double* d_reduce_stats, void* stream);
 
 /* Profiling aid for tb_mlp_wgrad_fused: 64 clock64() stamps of CTA (0, 0) (out16: 64 values; slots: 0 setup done,
  * 1 MMAs issued, 2 accumulator complete, 3 narrow gradients done, 4 partial slot written,
- * 5 at the grid barrier, 6 barrier passed, 7 reduction + Adam done).  Not on the product path. */
+ * 5 at the grid barrier, 6 barrier passed, 7 reduction + Adam done; several ranks: 8 slice pushed,
+ * 9 statistics of every rank seen).  Not on the product path. */
 int tb_wgrad_timeline(uint64_t* out16);
 
 /* ---- global-norm gradient clipping ---------------------------------------------
@@ -409,14 +429,11 @@ int tb_grad_clip(float* d_grad, int32_t n, const double* d_sumsq, float grad_sca
                  float max_norm, const int32_t* d_skip, void* stream);
 
 /* ---- fused gradient all-reduce + Adam over NVLink peer memory (multi-GPU) ---- */
-/* base[r] = address, in THIS process, of rank r's symmetric region of
- * tb_peer_region_bytes(n_params) bytes (zero-initialised; obtained from
- * torch.distributed._symmetric_memory or cudaIpc / fabric handles).            */
-typedef struct {
-    int32_t world, rank;
-    void* base[8];
-} TbPeers;
 int64_t tb_peer_region_bytes(int32_t n_params);
+/* Region size of the exchange that runs inside tb_mlp_wgrad_fused (push model: every rank
+ * stores its reduced parameter slices into its lane of every rank's region; layout in
+ * csrc/peers.cuh).                                                               */
+int64_t tb_peer_region_bytes_fused(int32_t n_params);
 /* This rank's flat gradient (sum of the n_split partial sums; zeros when d_gpart is
  * NULL) and statistics block -> its slot (epoch & 1) of the region, then a
  * system-scope release flag into every peer's region.                          */

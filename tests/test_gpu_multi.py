@@ -17,7 +17,7 @@ def test_two_ranks_reproduce_single_process_reference():
            '--master-addr', '127.0.0.1', '--master-port', '29517',
            os.path.join(ROOT, 'tests', 'multi_rank_scenario.py'),
            'ppo_small', 'ppo_ragged', 'a2c_small', 'td3_small', 'sac_small', 'ddpg_small']
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=540)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'multi_rank_output.log'), 'w') as f:
         f.write(res.stdout + '\n----\n' + res.stderr)

@@ -80,6 +80,7 @@ _PROTOTYPES = {
     'tb_grad_sqnorm': (c_int, [c_vp, c_i32, c_vp, c_vp, c_vp]),
     'tb_grad_clip': (c_int, [c_vp, c_i32, c_vp, c_f, c_f, c_vp, c_vp]),
     'tb_peer_region_bytes': (c_i64, [c_i32]),
+    'tb_peer_region_bytes_fused': (c_i64, [c_i32]),
     'tb_peer_publish': (c_int, [_P(TbPeers), c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp,
                                 c_vp, c_vp]),
     'tb_adam_step_peers': (c_int, [_P(TbAdam), _P(TbMlpShape), c_vp, _P(TbPeers), c_f, c_vp, c_vp, c_vp,
@@ -123,7 +124,7 @@ _PROTOTYPES = {
                                 c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     'tb_mlp_wgrad_fused': (c_int, [_P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                    c_i32, c_i32, c_i64, c_vp, c_i32, c_vp, c_vp, c_i32, _P(TbAdam), c_vp,
-                                   c_f, c_vp, c_f, c_vp, c_vp, c_vp]),
+                                   c_f, c_vp, c_f, c_vp, c_vp, _P(TbPeers), c_vp, c_vp, c_vp]),
     'tb_tc_wgrad256': (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp,
                                c_vp]),
     'tb_permutation': (c_int, [c_u64, c_u64, c_vp, c_i64, c_vp, c_vp]),

@@ -8,6 +8,7 @@
 // eps 1e-8, no weight decay); early stop tonic/torch/agents/ppo.py:45-46 with
 // updaters/actors.py:103,112; soft update models/actor_critics.py:68-72,126-130.
 #include "adam.cuh"
+#include "peers.cuh"
 
 namespace tb {
 
@@ -332,6 +333,10 @@ adam_peers_kernel(TbAdam opt, TbMlpShape sh, float* __restrict__ packed, TbPeers
 
 extern "C" int64_t tb_peer_region_bytes(int32_t n_params) {
     return (int64_t)(tb::kPeerFlagBytes + 2 * tb::peer_slot_bytes(n_params));
+}
+
+extern "C" int64_t tb_peer_region_bytes_fused(int32_t n_params) {
+    return (int64_t)(2 * tb::peer_fused_slot_bytes(n_params));
 }
 
 extern "C" int tb_peer_publish(const TbPeers* peers, const float* d_gpart, int32_t n_split,

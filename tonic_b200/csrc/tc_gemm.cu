@@ -28,6 +28,7 @@
 // PASSES = 1 is plain TF32 (fast mode).
 #include "tc_common.cuh"
 #include "adam.cuh"
+#include "peers.cuh"
 
 namespace tb {
 
@@ -557,6 +558,12 @@ struct TcWgradAllParams {
     const double* stats;        // minibatch statistics (PPO controls) or NULL
     float kl_threshold;
     int32_t* stop;
+    // several ranks (peers.world > 1, needs fuse_adam): the reduction phase exchanges the slices
+    // over NVLink peer memory (peers.cuh) before Adam; reduce_stats = statistics block summed over
+    // the ranks in place (also the PPO controls when `stats` is set)
+    TbPeers peers;
+    unsigned long long* epoch;
+    double* reduce_stats;
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned int n_ctas) {
@@ -970,11 +977,16 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     const int b = blockIdx.y * gridDim.x + blockIdx.x;
     const int per = (((p.n_params + (int)n_ctas - 1) / (int)n_ctas) + 31) & ~31;
     const int lo = b * per, hi = min(p.n_params, lo + per);
+    const bool multi = q.peers.world > 1;
+    const unsigned long long epoch = multi ? *q.epoch : 0ULL;
+    const int slot = (int)(epoch & 1);
+    const unsigned int tag = (unsigned int)(epoch + 1);
+    double* s_stats = reinterpret_cast<double*>(smem + 64);       // global statistics (several ranks)
     // fused Adam (updaters/actors.py:22,71: no step when every advantage of the minibatch is zero)
-    const bool do_step = q.fuse_adam && !(q.stats && q.stats[TB_STAT_NONZERO_ADV] == 0.0);
+    bool do_step = q.fuse_adam && !(q.stats && q.stats[TB_STAT_NONZERO_ADV] == 0.0);
     const int t_step = q.fuse_adam ? q.opt.d_step[0] + 1 : 0;
     float* s_corr = reinterpret_cast<float*>(smem);       // step_size, bc2_sqrt (the stages are idle)
-    if (do_step && threadIdx.x == 0) adam_corrections(q.opt, t_step, &s_corr[0], &s_corr[1]);
+    if (q.fuse_adam && threadIdx.x == 0) adam_corrections(q.opt, t_step, &s_corr[0], &s_corr[1]);
     __syncthreads();
     if (threadIdx.x == 0) tcw_stamp(q.timeline, 6);               // grid barrier passed
     for (int i = lo + (int)threadIdx.x; i < hi; i += TCA_THREADS) {
@@ -1002,8 +1014,49 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
             if (k == 0) g0 += v; else if (k == 1) g1 += v; else g2 += v;
         }
         const float g = (g0 + g1) + (g2 + g3);
+        if (multi) {
+            // this rank's lane of the slot in every rank's region (NVLink stores, value + tag)
+            for (int r = 0; r < q.peers.world; ++r)
+                peer_put(peer_fused_grad(q.peers.base[r], slot, q.peers.rank, p.n_params) + i,
+                         __float_as_uint(g), tag);
+            continue;
+        }
         q.flat[i] = g;
         if (do_step) adam_apply(q.opt, q.sh, q.packed, i, g * q.grad_scale, s_corr[0], s_corr[1]);
+    }
+    if (multi) {
+        void* mine = q.peers.base[q.peers.rank];
+        const bool solo = q.dbg == 4;          // timing experiment: do not wait for the other ranks
+        if (b == 0 && threadIdx.x < TB_STAT_COUNT) {
+            const unsigned long long v = __double_as_longlong(q.reduce_stats ? q.reduce_stats[threadIdx.x] : 0.0);
+            for (int r = 0; r < q.peers.world; ++r) {
+                uint2* dst = peer_fused_stats(q.peers.base[r], slot, q.peers.rank, p.n_params) + 2 * threadIdx.x;
+                peer_put(dst, (unsigned int)v, tag);
+                peer_put(dst + 1, (unsigned int)(v >> 32), tag);
+            }
+        }
+        if (threadIdx.x == 0) tcw_stamp(q.timeline, 8);           // slice pushed
+        // global statistics: CTA 0 of every rank sent its block to THIS rank's region
+        if (threadIdx.x < TB_STAT_COUNT) {
+            double sum = 0.0;
+            for (int r = 0; r < q.peers.world; ++r) {
+                const uint2* src = peer_fused_stats(mine, slot, solo ? q.peers.rank : r, p.n_params) + 2 * threadIdx.x;
+                const unsigned long long lo32 = peer_get(src, tag), hi32 = peer_get(src + 1, tag);
+                sum += __longlong_as_double((long long)(lo32 | (hi32 << 32)));
+            }
+            s_stats[threadIdx.x] = sum;
+            if (b == 0 && q.reduce_stats) q.reduce_stats[threadIdx.x] = sum;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) tcw_stamp(q.timeline, 9);           // statistics of every rank seen
+        do_step = q.fuse_adam && !(q.stats && s_stats[TB_STAT_NONZERO_ADV] == 0.0);
+        for (int i = lo + (int)threadIdx.x; i < hi; i += TCA_THREADS) {
+            float g = 0.0f;
+            for (int r = 0; r < q.peers.world; ++r)
+                g += __uint_as_float(peer_get(peer_fused_grad(mine, slot, solo ? q.peers.rank : r, p.n_params) + i, tag));
+            q.flat[i] = g;
+            if (do_step) adam_apply(q.opt, q.sh, q.packed, i, g * q.grad_scale, s_corr[0], s_corr[1]);
+        }
     }
     if (threadIdx.x == 0) tcw_stamp(q.timeline, 7);               // reduction (+ Adam) done
     if (q.fuse_adam) {
@@ -1016,10 +1069,12 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         __syncthreads();
         if (is_last && threadIdx.x == 0) {
             q.opt.d_step[1] = 0;
+            if (multi) *q.epoch = epoch + 1;
             if (do_step) {
                 q.opt.d_step[0] = t_step;
                 if (q.stop && q.stats && q.kl_threshold >= 0.0f) {
-                    const float kl = (float)(q.stats[TB_STAT_KL] / q.stats[TB_STAT_ROWS]);
+                    const float kl = multi ? (float)(s_stats[TB_STAT_KL] / s_stats[TB_STAT_ROWS])
+                                           : (float)(q.stats[TB_STAT_KL] / q.stats[TB_STAT_ROWS]);
                     if (kl > q.kl_threshold) *q.stop = 1;
                 }
             }
@@ -1176,8 +1231,13 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
                                   float* d_gpart, int32_t n_split, float* d_flat, uint64_t* d_sync,
                                   int32_t passes, const TbAdam* opt, float* d_packed, float grad_scale,
                                   const double* d_stats, float kl_threshold, int32_t* d_stop,
-                                  const int32_t* d_skip, void* stream) {
+                                  const int32_t* d_skip, const TbPeers* peers, uint64_t* d_epoch,
+                                  double* d_reduce_stats, void* stream) {
     using namespace tb;
+    TB_REQUIRE(!peers || peers->world <= 1 || (opt && d_epoch && peers->world <= kPeerLanes &&
+                                               peers->rank >= 0 && peers->rank < peers->world), TB_EINVAL,
+               "tb_mlp_wgrad_fused: the peer exchange needs the fused optimizer step, an epoch counter "
+               "and at most %d ranks", kPeerLanes);
     TB_REQUIRE(!opt || (opt->d_params && opt->d_m && opt->d_v && opt->d_step && shape &&
                         opt->n_params == shape->n_params), TB_EINVAL,
                "tb_mlp_wgrad_fused: optimizer / shape mismatch");
@@ -1228,6 +1288,9 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     if (opt) q.opt = *opt; else memset(&q.opt, 0, sizeof(q.opt));
     q.packed = d_packed; q.grad_scale = grad_scale; q.stats = d_stats; q.kl_threshold = kl_threshold;
     q.stop = d_stop;
+    if (peers && peers->world > 1) q.peers = *peers; else memset(&q.peers, 0, sizeof(q.peers));
+    q.epoch = reinterpret_cast<unsigned long long*>(d_epoch);
+    q.reduce_stats = d_reduce_stats;
     dim3 grid(TC_BN / TC_BM, n_split);
     cudaStream_t s = as_stream(stream);
     ProfScope prof_scope("tb_mlp_wgrad_fused", stream);

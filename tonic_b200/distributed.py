@@ -51,12 +51,16 @@ class PeerRegion:
     Creating it is a collective: every rank must construct its regions in the same
     order (they are created on the first update of each network)."""
 
-    def __init__(self, n_params):
+    def __init__(self, n_params, fused=False):
+        """fused: the push-model layout the fused weight-gradient kernel exchanges through
+        (csrc/peers.cuh) instead of the publish / pull pair's."""
         import ctypes
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib, kernels
         dev = kernels.device()
-        nbytes = int(_lib.load().tb_peer_region_bytes(n_params))
+        lib = _lib.load()
+        nbytes = int(lib.tb_peer_region_bytes_fused(n_params) if fused
+                     else lib.tb_peer_region_bytes(n_params))
         self.buffer = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=dev)
         self.buffer.zero_()
         if hasattr(symm_mem, 'enable_symm_mem_for_group'):

@@ -203,6 +203,7 @@ class MlpInput:
 _FUSED_FWD = os.environ.get('TONIC_B200_FUSED_FWD', '1') != '0'
 _FUSED_BWD = os.environ.get('TONIC_B200_FUSED_BWD', '1') != '0'
 _FUSED_WGRAD = os.environ.get('TONIC_B200_FUSED_WGRAD', '1') != '0'
+_PEER_FUSED = os.environ.get('TONIC_B200_PEER_FUSED', '1') != '0'
 _FUSED_ADAM = os.environ.get('TONIC_B200_FUSED_ADAM', '1') != '0'
 _PLAIN_ACTS = os.environ.get('TONIC_B200_PLAIN_ACTS', '1') != '0'
 _FUSED_TRAIN = os.environ.get('TONIC_B200_FUSED_TRAIN', '1') != '0'
@@ -254,6 +255,14 @@ class DeviceMlp:
             from . import distributed
             self._peer_region = distributed.PeerRegion(self.layout.n_params)
         return self._peer_region
+
+    def peer_region_fused(self):
+        """Symmetric region of the exchange inside the fused weight-gradient kernel (collective on
+        first use, like `peer_region`)."""
+        if getattr(self, '_peer_region_fused', None) is None:
+            from . import distributed
+            self._peer_region_fused = distributed.PeerRegion(self.layout.n_params, fused=True)
+        return self._peer_region_fused
 
     def flat_grad(self):
         if getattr(self, '_flat_grad', None) is None:
@@ -403,8 +412,9 @@ class DeviceMlp:
                   dx_col0, 0 if dx is None else dx.shape[-1], ptr(skip), stream())
 
     def wgrad(self, dout, rows, n_split, n_extra=0, off_extra=0, skip=None, fuse=None):
-        """`fuse` = (adam, grad_scale, stats, kl_threshold, stop): the fused kernel also runs the
-        optimizer step (single process, no clipping); `self.applied` tells the caller."""
+        """`fuse` = (adam, grad_scale, stats, kl_threshold, stop, reduce_stats): the fused kernel also
+        runs the optimizer step (no clipping) and, with several ranks, the gradient exchange over
+        NVLink peer memory before it; `self.applied` tells the caller."""
         self.applied = False
         gpart = self.gpart(n_split)
         L = self.layout
@@ -418,17 +428,23 @@ class DeviceMlp:
             if getattr(self, '_wgrad_sync', None) is None:
                 self._wgrad_sync = torch.zeros(1, dtype=torch.int64, device=device())
             flat = self.flat_grad()
-            opt = packed = stats = stop = None
+            opt = packed = stats = stop = peers = epoch = reduce_stats = None
             scale, kl = 0.0, -1.0
             if fuse is not None:
-                adam, scale, stats, kl, stop = fuse
+                adam, scale, stats, kl, stop, reduce_stats = fuse
                 opt, packed = ctypes.byref(adam.struct), self.packed
+                from . import distributed
+                if distributed.world() > 1:      # gradient exchange inside the same launch
+                    region = self.peer_region_fused()
+                    peers, epoch = ctypes.byref(region.struct), region.epoch
+                    reduce_stats = stats if reduce_stats is None else reduce_stats
             plain = self.plain_activations()
             _lib.call('tb_mlp_wgrad_fused', ctypes.byref(L.shape), ptr(self.xin), ptr(self.h1),
                       None if plain else ptr(self.h1_lo), ptr(self.h2), ptr(self.dz1), ptr(self.dz2),
                       None if plain else ptr(self.dz2_lo), ptr(dout), dout.shape[-1], n_extra, off_extra, rows,
                       ptr(gpart), n_split, ptr(flat), ptr(self._wgrad_sync), passes, opt,
-                      ptr(packed), scale, ptr(stats), kl, ptr(stop), ptr(skip), stream())
+                      ptr(packed), scale, ptr(stats), kl, ptr(stop), ptr(skip), peers, ptr(epoch),
+                      ptr(reduce_stats), stream())
             self.reduced = True
             self.applied = fuse is not None
             return flat
@@ -525,16 +541,17 @@ def make_clipper(gradient_clip):
 def wgrad_and_apply(adam, mlp, dout, rows, rows_global, n_extra=0, off_extra=0, skip=None,
                     stats=None, kl_threshold=-1.0, stop=None, reduce_stats=None, clip=None):
     """Weight gradients of the minibatch whose activations `mlp` holds, then the optimizer step
-    (loss.backward() ... optimizer.step(), e.g. updaters/critics.py:23-26).  Single process without
-    gradient clipping on the tensor-core path: ONE launch (weight gradients, in-kernel reduction
-    and Adam).  Otherwise weight gradients -> [clip] -> [exchange] -> Adam (`apply_gradients`)."""
+    (loss.backward() ... optimizer.step(), e.g. updaters/critics.py:23-26).  Without gradient
+    clipping on the tensor-core path: ONE launch (weight gradients, in-kernel reduction, the
+    exchange between ranks when every rank owns rows of every minibatch, and Adam).  Otherwise weight gradients -> [clip] -> [exchange] -> Adam (`apply_gradients`)."""
     from . import distributed
     n_split = mlp.splits_for(rows, n_extra)
     gpart = None
     if rows > 0:
         fuse = None
-        if (_FUSED_ADAM and clip is None and distributed.world() == 1 and mlp.fused_wgrad(n_extra)):
-            fuse = (adam, 1.0 / rows_global, stats, kl_threshold, stop)
+        if (_FUSED_ADAM and clip is None and mlp.fused_wgrad(n_extra) and
+                (distributed.world() == 1 or balanced_exchange())):
+            fuse = (adam, 1.0 / rows_global, stats, kl_threshold, stop, reduce_stats)
         gpart = mlp.wgrad(dout, rows, n_split, n_extra=n_extra, off_extra=off_extra, skip=skip,
                           fuse=fuse)
         if mlp.applied:
@@ -593,6 +610,16 @@ def apply_gradients(adam, mlp, gpart, n_split, rows_local, rows_global, skip=Non
         distributed.all_reduce(reduce_stats)
     adam.step(mlp, flat, 1, 1.0 / rows_global, skip=skip, stats=stats,
               kl_threshold=kl_threshold, stop=stop)
+
+
+def balanced_exchange():
+    """Several ranks: may the gradient exchange run inside the fused weight-gradient kernel?  Every
+    rank must then launch that kernel for every minibatch, i.e. own rows of every minibatch: true
+    for the device permutations (each rank contributes batch_size / world rows), not for the
+    reference-exact global permutation of the parity mode, where a rank's share of a minibatch can
+    be empty -- that mode keeps the publish / pull kernels."""
+    from . import config
+    return config.peer_reduce and config.indices == 'device' and _PEER_FUSED
 
 
 def config_peer_reduce():
