@@ -78,6 +78,12 @@ def check_fused_exchange(verbose=True):
     try:
         fused = _fast_mode_weights(True)
         pulled = _fast_mode_weights(False)
+        # the reduce-scatter + all-gather form ranks > 2 use (read per launch from the environment)
+        os.environ['TONIC_B200_PEER_TWO_PHASE'] = '1'
+        try:
+            two_phase = _fast_mode_weights(True)
+        finally:
+            del os.environ['TONIC_B200_PEER_TWO_PHASE']
     finally:
         for k, v in saved.items():
             setattr(logger, k, v)
@@ -87,6 +93,7 @@ def check_fused_exchange(verbose=True):
     assert torch.equal(fused, ref), 'replica weights diverged (fused exchange)'
     diff = (fused - pulled).abs().max().item()
     assert torch.equal(fused, pulled), f'fused exchange differs from the publish / pull kernels: {diff}'
+    assert torch.equal(two_phase, pulled), 'two-phase exchange differs from the publish / pull kernels'
     if dist.get_rank() == 0 and verbose:
         print(f'fused exchange: {dist.get_world_size()} ranks, bit-identical to the publish / pull '
               'kernels, replicas in lock-step', flush=True)

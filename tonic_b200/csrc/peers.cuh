@@ -8,8 +8,13 @@
 // lanes 0..world-1 until the tag matches and sums them in rank order -- every rank computes the
 // same bits, replicas stay identical.
 //
-//     slot s (= epoch & 1): {float bits, tag} grad[8 lanes][n_pad] |
+//     slot s (= epoch & 1): {float bits, tag} grad[8 lanes][n_pad] | {float bits, tag} sum[n_pad] |
 //                           {half of a double, tag} stats[8 lanes][2 * TB_STAT_COUNT]
+//
+// More than two ranks: two hops instead of the all-to-all.  Element i goes only to its OWNER
+// (groups of 32 elements, round robin over the ranks); the owner sums the lanes in rank order and
+// stores the result into sum[i] of every rank -- 2 / world of the bytes, still a fixed order,
+// still one value for all replicas.
 //     tag = low 32 bits of epoch + 1 (the region starts zeroed; a tag recurs after 2^32 epochs
 //     of the same slot parity, far beyond any run)
 //
@@ -25,15 +30,21 @@ constexpr int kPeerLanes = 8;
 
 __host__ __device__ inline int peer_pad(int n_params) { return (n_params + 31) & ~31; }
 __host__ __device__ inline size_t peer_fused_slot_bytes(int n_params) {
-    return ((size_t)kPeerLanes * peer_pad(n_params) * 8 + (size_t)kPeerLanes * 2 * TB_STAT_COUNT * 8 + 255) / 256 * 256;
+    return ((size_t)(kPeerLanes + 1) * peer_pad(n_params) * 8 + (size_t)kPeerLanes * 2 * TB_STAT_COUNT * 8 + 255) / 256 * 256;
 }
+// owner of element i in the two-phase exchange: warp-sized groups of 32 elements, round robin
+__host__ __device__ inline int peer_owner(int i, int world) { return (i >> 5) % world; }
 __device__ __forceinline__ uint2* peer_fused_grad(void* base, int slot, int lane, int n_params) {
     return reinterpret_cast<uint2*>(reinterpret_cast<char*>(base) + slot * peer_fused_slot_bytes(n_params)) +
            (size_t)lane * peer_pad(n_params);
 }
+// the reduced gradient the owners broadcast (two-phase exchange)
+__device__ __forceinline__ uint2* peer_fused_sum(void* base, int slot, int n_params) {
+    return peer_fused_grad(base, slot, kPeerLanes, n_params);
+}
 __device__ __forceinline__ uint2* peer_fused_stats(void* base, int slot, int lane, int n_params) {
     return reinterpret_cast<uint2*>(reinterpret_cast<char*>(base) + slot * peer_fused_slot_bytes(n_params) +
-                                    (size_t)kPeerLanes * peer_pad(n_params) * 8) + (size_t)lane * 2 * TB_STAT_COUNT;
+                                    (size_t)(kPeerLanes + 1) * peer_pad(n_params) * 8) + (size_t)lane * 2 * TB_STAT_COUNT;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;

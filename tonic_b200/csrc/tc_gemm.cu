@@ -564,6 +564,7 @@ struct TcWgradAllParams {
     TbPeers peers;
     unsigned long long* epoch;
     double* reduce_stats;
+    int two_phase;              // force the reduce-scatter + all-gather exchange (TONIC_B200_PEER_TWO_PHASE=1)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned int n_ctas) {
@@ -981,6 +982,9 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
     const unsigned long long epoch = multi ? *q.epoch : 0ULL;
     const int slot = (int)(epoch & 1);
     const unsigned int tag = (unsigned int)(epoch + 1);
+    // more than two ranks: reduce-scatter + all-gather of flagged words (2 hops, 2 / world of the
+    // all-to-all bytes); two ranks: the direct exchange (1 hop)
+    const bool two_phase = multi && (q.peers.world > 2 || q.two_phase);
     double* s_stats = reinterpret_cast<double*>(smem + 64);       // global statistics (several ranks)
     // fused Adam (updaters/actors.py:22,71: no step when every advantage of the minibatch is zero)
     bool do_step = q.fuse_adam && !(q.stats && q.stats[TB_STAT_NONZERO_ADV] == 0.0);
@@ -1015,10 +1019,16 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         }
         const float g = (g0 + g1) + (g2 + g3);
         if (multi) {
-            // this rank's lane of the slot in every rank's region (NVLink stores, value + tag)
-            for (int r = 0; r < q.peers.world; ++r)
-                peer_put(peer_fused_grad(q.peers.base[r], slot, q.peers.rank, p.n_params) + i,
+            if (two_phase) {
+                // reduce-scatter leg: only to the rank that owns this warp-sized group of elements
+                peer_put(peer_fused_grad(q.peers.base[peer_owner(i, q.peers.world)], slot, q.peers.rank, p.n_params) + i,
                          __float_as_uint(g), tag);
+            } else {
+                // this rank's lane of the slot in every rank's region (NVLink stores, value + tag)
+                for (int r = 0; r < q.peers.world; ++r)
+                    peer_put(peer_fused_grad(q.peers.base[r], slot, q.peers.rank, p.n_params) + i,
+                             __float_as_uint(g), tag);
+            }
             continue;
         }
         q.flat[i] = g;
@@ -1050,10 +1060,25 @@ tc_wgrad_all_kernel(const __grid_constant__ CUtensorMap map_dz_hi, const __grid_
         __syncthreads();
         if (threadIdx.x == 0) tcw_stamp(q.timeline, 9);           // statistics of every rank seen
         do_step = q.fuse_adam && !(q.stats && s_stats[TB_STAT_NONZERO_ADV] == 0.0);
+        if (two_phase) {
+            // owners: sum the lanes in rank order, all-gather leg of the sum to every rank
+            for (int i = lo + (int)threadIdx.x; i < hi; i += TCA_THREADS) {
+                if (peer_owner(i, q.peers.world) != q.peers.rank) continue;
+                float g = 0.0f;
+                for (int r = 0; r < q.peers.world; ++r)
+                    g += __uint_as_float(peer_get(peer_fused_grad(mine, slot, r, p.n_params) + i, tag));
+                for (int r = 0; r < q.peers.world; ++r)
+                    peer_put(peer_fused_sum(q.peers.base[r], slot, p.n_params) + i, __float_as_uint(g), tag);
+            }
+        }
         for (int i = lo + (int)threadIdx.x; i < hi; i += TCA_THREADS) {
             float g = 0.0f;
-            for (int r = 0; r < q.peers.world; ++r)
-                g += __uint_as_float(peer_get(peer_fused_grad(mine, slot, solo ? q.peers.rank : r, p.n_params) + i, tag));
+            if (two_phase) {
+                g = __uint_as_float(peer_get(peer_fused_sum(mine, slot, p.n_params) + i, tag));
+            } else {
+                for (int r = 0; r < q.peers.world; ++r)
+                    g += __uint_as_float(peer_get(peer_fused_grad(mine, slot, solo ? q.peers.rank : r, p.n_params) + i, tag));
+            }
             q.flat[i] = g;
             if (do_step) adam_apply(q.opt, q.sh, q.packed, i, g * q.grad_scale, s_corr[0], s_corr[1]);
         }
@@ -1291,6 +1316,7 @@ extern "C" int tb_mlp_wgrad_fused(const TbMlpShape* shape, const float* d_xin, c
     if (peers && peers->world > 1) q.peers = *peers; else memset(&q.peers, 0, sizeof(q.peers));
     q.epoch = reinterpret_cast<unsigned long long*>(d_epoch);
     q.reduce_stats = d_reduce_stats;
+    { const char* v = getenv("TONIC_B200_PEER_TWO_PHASE"); q.two_phase = (v && v[0] == '1') ? 1 : 0; }
     dim3 grid(TC_BN / TC_BM, n_split);
     cudaStream_t s = as_stream(stream);
     ProfScope prof_scope("tb_mlp_wgrad_fused", stream);
