@@ -293,6 +293,14 @@ int tb_tc_mlp_train(const TbMlpShape* shape, const float* d_params, const float*
  * bit-identical to on == 0 show that tcgen05 kind::tf32 ignores the 13 low mantissa bits.      */
 int tb_debug_plain_hi(int32_t on);
 
+/* Test aid, not on the product path: batches of at most 4096 rows run the first layer of wide
+ * inputs (d_in > 32), the input gradient dx and wide heads (n_out > 8) of the unfused tensor-core
+ * chain on small-CTA kernels (16 rows x 32 columns per CTA instead of 64 x 256: a 100-row
+ * off-policy minibatch covers 56 SMs instead of 2).  Every output is the same sequential fmaf
+ * chain, so on == 0 (the 64-row tile kernels only) must give bit-identical results.
+ * TONIC_B200_SKINNY=0 has the same effect from the environment.                              */
+int tb_debug_skinny(int32_t on);
+
 /* Profiling aid for the fused forward kernel: the first call allocates a device buffer
  * of 64 clock64() stamps that CTA 0 of every later tb_tc_mlp_forward launch fills
  * (slots documented in csrc/tc_mlp.cu); a non-NULL `out64` reads them back (host

@@ -196,7 +196,8 @@ def torch_forward(p, x, act):
 
 @pytest.mark.parametrize('d_in,hidden,n_out,act,rows', [
     (17, 64, 6, 'tanh', 1), (17, 256, 6, 'tanh', 200), (17, 256, 1, 'tanh', 64),
-    (5, 128, 2, 'relu', 63), (393, 256, 1, 'relu', 130), (28, 64, 34, 'relu', 65)])
+    (5, 128, 2, 'relu', 63), (393, 256, 1, 'relu', 130), (28, 64, 34, 'relu', 65),
+    (393, 256, 1, 'relu', 4200), (40, 256, 34, 'tanh', 90), (40, 256, 34, 'relu', 4200)])
 def test_mlp_forward(K, gemm_mode, d_in, hidden, n_out, act, rows):
     net = make_mlp(K, d_in, hidden, n_out, act)
     x = torch.randn(rows, d_in)
@@ -214,6 +215,39 @@ def test_mlp_forward(K, gemm_mode, d_in, hidden, n_out, act, rows):
                                atol=2e-5 * max(1.0, float(h2.abs().max())))
     np.testing.assert_array_equal(net.xin[:rows, :d_in].cpu(), x)
     np.testing.assert_array_equal(net.xin[:rows, d_in].cpu(), torch.ones(rows))
+
+
+@pytest.mark.parametrize('d_in,n_out,act,rows', [(393, 1, 'relu', 100), (376, 34, 'relu', 100),
+                                                  (111, 8, 'tanh', 257), (40, 34, 'tanh', 3)])
+def test_small_batch_kernels_equal_the_tile_kernels(K, d_in, n_out, act, rows):
+    """Off-policy minibatches (100 rows, replays/buffers.py:8-12) run the wide first layer, the
+    input gradient and wide heads on small-CTA kernels; they must reproduce the 64-row tile kernels
+    bit for bit (same fmaf chain per output), so that results do not depend on the batch size."""
+    from tonic_b200 import _lib, config
+    if config.gemm == 'ffma':
+        pytest.skip('tensor-core chain only')
+    got = {}
+    g = torch.Generator().manual_seed(d_in + rows)
+    x = torch.randn(rows + 20, d_in - 5, generator=g).cuda()
+    x2 = torch.randn(rows, 5, generator=g).cuda()
+    idx = torch.randperm(rows + 20, generator=g)[:rows].cuda()
+    mean, std = torch.randn(d_in - 5, generator=g).cuda(), (torch.rand(d_in - 5, generator=g) + 0.5).cuda()
+    dout = torch.randn(rows, K.round_up(n_out, 4), generator=g).cuda()
+    try:
+        for on in (1, 0):
+            _lib.call('tb_debug_skinny', on)
+            net = make_mlp(K, d_in, 256, n_out, act)
+            out = torch.empty(rows, n_out, device='cuda')
+            net.forward(K.MlpInput(x, mean, std, x2=x2, gather2=False, idx=idx), rows, out, save=True)
+            dx = torch.empty(rows, 5, device='cuda')
+            net.backward(dout, rows, dx=dx, dx_col0=d_in - 5)
+            torch.cuda.synchronize()
+            got[on] = [t[:rows].clone() for t in (out, net.h1, net.h1_lo, net.h2, net.xin, dx)]
+    finally:
+        _lib.call('tb_debug_skinny', 1)
+    for a, b, name in zip(got[1], got[0], ('out', 'h1_hi', 'h1_lo', 'h2', 'xin', 'dx')):
+        assert torch.isfinite(a).all(), name
+        assert torch.equal(a, b), name
 
 
 def test_mlp_forward_gather_normalise_concat(K, gemm_mode):
@@ -241,7 +275,8 @@ def test_mlp_forward_gather_normalise_concat(K, gemm_mode):
 
 @pytest.mark.parametrize('d_in,hidden,n_out,act,rows,n_split', [
     (17, 64, 6, 'tanh', 100, 3), (17, 256, 6, 'tanh', 1000, 7), (17, 256, 1, 'tanh', 64, 1),
-    (14, 256, 1, 'relu', 257, 4), (393, 256, 1, 'relu', 130, 2), (40, 128, 34, 'relu', 90, 5)])
+    (14, 256, 1, 'relu', 257, 4), (393, 256, 1, 'relu', 130, 2), (40, 128, 34, 'relu', 90, 5),
+    (393, 256, 1, 'tanh', 4200, 3)])     # (tanh: no ReLU kinks to flip between fp32 evaluations)
 def test_mlp_backward_wgrad_vs_autograd(K, gemm_mode, d_in, hidden, n_out, act, rows, n_split):
     n_extra = 3
     net = make_mlp(K, d_in, hidden, n_out, act, extras=[('extra', n_extra)])

@@ -106,6 +106,7 @@ _PROTOTYPES = {
                                 c_vp, c_vp, c_vp, c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32,
                                 c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'tb_debug_plain_hi': (c_int, [c_i32]),
+    'tb_debug_skinny': (c_int, [c_i32]),
     'tb_tc_timeline': (c_int, [c_vp]),
     'tb_wgrad_timeline': (c_int, [c_vp]),
     'tb_q_target_discounts': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_d, c_i64, c_vp, c_vp]),

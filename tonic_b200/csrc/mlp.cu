@@ -783,12 +783,140 @@ mlp_layer1_kernel(TbMlpShape sh, const float* __restrict__ params, const float* 
     store_tile<H>(acc, h1_lo + m0 * H, H, valid, [](float a, int, int) { return a - tf32_hi(a); });
 }
 
-// out[m][o] = b3[o] + h2[m, :] . W3[o, :]
-template <int H>
+// ---- small batches (off-policy updates: 100 rows; SURVEY.md 8, replays/buffers.py:8-12) --------
+// The 64-row tile kernels above put a 100-row minibatch on 2 of the 148 SMs.  These variants cut
+// the same work into many small CTAs (16 rows x 32 output columns) with the weights of the column
+// block staged once in shared memory.  Every output is still one sequential fmaf chain over k in
+// increasing order, i.e. bit-identical to the tile kernels: results do not depend on which variant
+// a batch size selects.
+constexpr int SK_ROWS = 16;          // rows per CTA (two per thread)
+constexpr int SK_COLS = 32;          // output columns per CTA (one per lane)
+constexpr int SK_MAX_ROWS = 4096;    // above this the tile kernels stream fewer weight bytes through L2
+
+__host__ __device__ inline size_t skinny_layer1_smem(int d_in) {
+    return (size_t)(SK_ROWS * ((d_in + 3) & ~3) + d_in * SK_COLS) * sizeof(float) + SK_ROWS * sizeof(int64_t);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(NTHREADS)
+mlp_layer1_skinny_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ packed,
+                         TbMlpInput in, int64_t n_rows, float* __restrict__ xin_save,
+                         float* __restrict__ h1_hi, float* __restrict__ h1_lo, const int32_t* d_skip) {
+    constexpr int H = 256;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d_in = sh.d_in, kp = (d_in + 3) & ~3, ldx = (d_in + 1 + 3) & ~3;
+    float* xs = reinterpret_cast<float*>(smem_raw);            // [SK_ROWS][kp]
+    float* ws = xs + SK_ROWS * kp;                             // [d_in][SK_COLS]
+    int64_t* srow = reinterpret_cast<int64_t*>(ws + d_in * SK_COLS);
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * SK_ROWS;
+    const int c0 = blockIdx.y * SK_COLS;
+    const int valid = (int)min((int64_t)SK_ROWS, n_rows - m0);
+    if (tid < SK_ROWS) srow[tid] = tid < valid ? (in.d_idx ? in.d_idx[m0 + tid] : m0 + tid) : -1;
+    const float* W1T = packed + sh.off_w1t;                    // [d_in][H]
+    for (int v = tid; v < d_in * (SK_COLS / 4); v += NTHREADS) {
+        const int k = v / (SK_COLS / 4), q = v % (SK_COLS / 4);
+        *reinterpret_cast<float4*>(ws + k * SK_COLS + q * 4) =
+            __ldg(reinterpret_cast<const float4*>(W1T + (size_t)k * H + c0) + q);
+    }
+    __syncthreads();
+    const bool save = xin_save && blockIdx.y == 0;
+    for (int v = tid; v < SK_ROWS * kp; v += NTHREADS) {
+        const int m = v / kp, c = v % kp;
+        float val = 0.0f;
+        const int64_t r = srow[m];
+        if (r >= 0 && c < d_in) {
+            if (c < in.dim1) {
+                val = in.d_x1[r * in.dim1 + c];
+                if (in.d_mean) val = __fdiv_rn(__fsub_rn(val, in.d_mean[c]), in.d_std[c]);
+            } else {
+                const int64_t r2 = in.gather2 ? r : (m0 + m);
+                val = in.d_x2[r2 * in.dim2 + (c - in.dim1)];
+            }
+            if (save) xin_save[(m0 + m) * ldx + c] = val;
+        }
+        xs[m * kp + c] = val;
+    }
+    if (save) {
+        for (int v = tid; v < valid * (ldx - d_in); v += NTHREADS) {
+            const int m = v / (ldx - d_in), c = d_in + v % (ldx - d_in);
+            xin_save[(m0 + m) * ldx + c] = (c == d_in) ? 1.0f : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int n = tid & 31, m = tid >> 5;                      // rows m and m + 8
+    const float* x0 = xs + m * kp;
+    const float* x1 = xs + (m + 8) * kp;
+    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 4
+    for (int k = 0; k < d_in; ++k) {
+        const float w = ws[k * SK_COLS + n];
+        acc0 = fmaf(x0[k], w, acc0);
+        acc1 = fmaf(x1[k], w, acc1);
+    }
+    const float bias = __ldg(params + sh.off_b1 + c0 + n);
+    acc0 = ACT == TB_ACT_TANH ? tanh_fast(acc0 + bias) : activate<ACT>(acc0 + bias);
+    acc1 = ACT == TB_ACT_TANH ? tanh_fast(acc1 + bias) : activate<ACT>(acc1 + bias);
+    if (m < valid) {
+        const size_t e = (size_t)(m0 + m) * H + c0 + n;
+        h1_hi[e] = tf32_hi(acc0);
+        h1_lo[e] = acc0 - tf32_hi(acc0);
+    }
+    if (m + 8 < valid) {
+        const size_t e = (size_t)(m0 + m + 8) * H + c0 + n;
+        h1_hi[e] = tf32_hi(acc1);
+        h1_lo[e] = acc1 - tf32_hi(acc1);
+    }
+}
+
+// dx[:, j] = sum_n dz1[:, n] W1[n, col0 + j] for a few columns (the action block of a Q network)
+// and a small batch: 16 rows per CTA, thread (row, column lane), W1 slice staged in shared memory.
+constexpr int SKD_MAX_COLS = 64;
+__host__ __device__ inline size_t skinny_dx_smem(int dx_cols) {
+    return (size_t)(SK_ROWS * (256 + 4) + 256 * dx_cols) * sizeof(float);
+}
+__global__ void __launch_bounds__(NTHREADS)
+mlp_dx_skinny_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ dz1,
+                     int64_t n_rows, float* __restrict__ dx, int dx_col0, int dx_cols, const int32_t* d_skip) {
+    constexpr int H = 256, LD = H + 4;
+    if (skip_requested(d_skip)) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* as = reinterpret_cast<float*>(smem_raw);            // [SK_ROWS][LD]
+    float* ws = as + SK_ROWS * LD;                             // [H][dx_cols]
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * SK_ROWS;
+    const int valid = (int)min((int64_t)SK_ROWS, n_rows - m0);
+    for (int v = tid; v < SK_ROWS * (H / 4); v += NTHREADS) {
+        const int m = v / (H / 4), c4 = v % (H / 4);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < valid) x = __ldg(reinterpret_cast<const float4*>(dz1 + (m0 + m) * H) + c4);
+        *reinterpret_cast<float4*>(as + m * LD + c4 * 4) = x;
+    }
+    const float* W1 = params + sh.off_w1 + dx_col0;            // [H][d_in], columns col0..
+    for (int v = tid; v < H * dx_cols; v += NTHREADS) {
+        const int nn = v / dx_cols, j = v % dx_cols;
+        ws[v] = __ldg(W1 + (size_t)nn * sh.d_in + j);
+    }
+    __syncthreads();
+    const int m = tid >> 4, jl = tid & 15;
+    if (m >= valid) return;
+    const float* arow = as + m * LD;
+    for (int j = jl; j < dx_cols; j += 16) {
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int nn = 0; nn < H; ++nn) acc = fmaf(arow[nn], ws[nn * dx_cols + j], acc);
+        dx[(m0 + m) * dx_cols + j] = acc;
+    }
+}
+
+// out[m][o] = b3[o] + h2[m, :] . W3[o, :]   (ROWS rows per CTA: 64, or 8 for small batches)
+template <int H, int ROWS = TM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_head_kernel(TbMlpShape sh, const float* __restrict__ params, const float* __restrict__ h2,
                 int64_t n_rows, float* __restrict__ out, const int32_t* d_skip) {
     using C = Cfg<H>;
+    constexpr int TM = ROWS;
     if (skip_requested(d_skip)) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* bufB = reinterpret_cast<float*>(smem_raw);          // [TM][LDH]
@@ -1012,6 +1140,13 @@ constexpr size_t head_backward_smem_bytes() { return (size_t)(2 * KC * H + TM * 
 template <int H>
 constexpr size_t dx_smem_bytes() { return (size_t)(TM * Cfg<H>::LDH + 2 * KC * H) * sizeof(float); }
 
+// small-batch variants on / off (TONIC_B200_SKINNY=0, or tb_debug_skinny for the equality tests)
+static int g_skinny = -1;
+static bool skinny_enabled() {
+    if (g_skinny < 0) { const char* v = getenv("TONIC_B200_SKINNY"); g_skinny = (v && v[0] == '0') ? 0 : 1; }
+    return g_skinny != 0;
+}
+
 static int check_tc_shape(const TbMlpShape* sh, const char* who) {
     int rc = check_shape(sh, who);
     if (rc) return rc;
@@ -1021,6 +1156,11 @@ static int check_tc_shape(const TbMlpShape* sh, const char* who) {
 }
 
 }  // namespace tb
+
+extern "C" int tb_debug_skinny(int32_t on) {
+    tb::g_skinny = on ? 1 : 0;
+    return 0;
+}
 
 extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
                                  const float* d_packed, const TbMlpInput* in, int64_t n_rows,
@@ -1048,7 +1188,22 @@ extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
                "tb_mlp_forward_tc: the unfused chain needs the h1 / h2 workspaces");
     const int blocks = (int)((n_rows + TM - 1) / TM);
     cudaStream_t s = as_stream(stream);
-    {
+    const bool small_batch = skinny_enabled() && n_rows <= SK_MAX_ROWS;
+    if (small_batch && skinny_layer1_smem(shape->d_in) <= 200 * 1024) {
+        const size_t smem = skinny_layer1_smem(shape->d_in);
+        const dim3 grid((unsigned)((n_rows + SK_ROWS - 1) / SK_ROWS), 256 / SK_COLS);
+        ProfScope prof_scope("tb_mlp_layer1", stream);
+        if (shape->act == TB_ACT_TANH) {
+            set_smem(mlp_layer1_skinny_kernel<TB_ACT_TANH>, 200 * 1024);
+            mlp_layer1_skinny_kernel<TB_ACT_TANH><<<grid, NTHREADS, smem, s>>>(
+                *shape, d_params, d_packed, *in, n_rows, d_xin, d_h1_hi, d_h1_lo, d_skip);
+        } else {
+            set_smem(mlp_layer1_skinny_kernel<TB_ACT_RELU>, 200 * 1024);
+            mlp_layer1_skinny_kernel<TB_ACT_RELU><<<grid, NTHREADS, smem, s>>>(
+                *shape, d_params, d_packed, *in, n_rows, d_xin, d_h1_hi, d_h1_lo, d_skip);
+        }
+        if ((rc = check_launch("tb_mlp_forward_tc/layer1"))) return rc;
+    } else {
         const size_t smem = layer1_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_layer1", stream);
         if (shape->act == TB_ACT_TANH) {
@@ -1072,8 +1227,14 @@ extern "C" int tb_mlp_forward_tc(const TbMlpShape* shape, const float* d_params,
     {
         const size_t smem = head_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_head", stream);
-        set_smem(mlp_head_kernel<256>, smem);
-        mlp_head_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_h2, n_rows, d_out, d_skip);
+        if (small_batch) {       // 8-row tiles: same arithmetic per output, 8x the CTAs
+            set_smem(mlp_head_kernel<256, 8>, smem);
+            mlp_head_kernel<256, 8><<<(unsigned)((n_rows + 7) / 8), NTHREADS, smem, s>>>(
+                *shape, d_params, d_h2, n_rows, d_out, d_skip);
+        } else {
+            set_smem(mlp_head_kernel<256>, smem);
+            mlp_head_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_h2, n_rows, d_out, d_skip);
+        }
         rc = check_launch("tb_mlp_forward_tc/head");
     }
     return rc;
@@ -1130,11 +1291,18 @@ extern "C" int tb_mlp_backward_tc(const TbMlpShape* shape, const float* d_params
     }
     if (rc || !d_dx) return rc;
     {
-        const size_t smem = dx_smem_bytes<256>();
         ProfScope prof_scope("tb_mlp_dx", stream);
-        set_smem(mlp_dx_kernel<256>, smem);
-        mlp_dx_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_dz1, n_rows, d_dx, dx_col0,
-                                                       dx_cols, d_skip);
+        if (skinny_enabled() && n_rows <= SK_MAX_ROWS && dx_cols <= SKD_MAX_COLS) {
+            const size_t smem = skinny_dx_smem(dx_cols);
+            set_smem(mlp_dx_skinny_kernel, skinny_dx_smem(SKD_MAX_COLS));
+            mlp_dx_skinny_kernel<<<(unsigned)((n_rows + SK_ROWS - 1) / SK_ROWS), NTHREADS, smem, s>>>(
+                *shape, d_params, d_dz1, n_rows, d_dx, dx_col0, dx_cols, d_skip);
+        } else {
+            const size_t smem = dx_smem_bytes<256>();
+            set_smem(mlp_dx_kernel<256>, smem);
+            mlp_dx_kernel<256><<<blocks, NTHREADS, smem, s>>>(*shape, d_params, d_dz1, n_rows, d_dx, dx_col0,
+                                                           dx_cols, d_skip);
+        }
         rc = check_launch("tb_mlp_backward_tc/dx");
     }
     return rc;
