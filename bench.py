@@ -344,6 +344,9 @@ def run_ppo(args):
         'tb_env_step': (8 * OBS + 4 * (2 * OBS + ACT + 4)) * ENVS_PER_GPU,
         'tb_gauss_sample': 4 * (2 * ACT + 2 * ACT + 1) * ENVS_PER_GPU,      # minibatch launches differ: mixed
         'tb_moments_record': 4 * OBS * ENVS_PER_GPU,
+        # sample + record + step in one launch: state read once, loc read, actions / log-probs /
+        # obs / next_obs / flags written (the separate kernels' bytes minus the re-read rows)
+        'tb_act_env_step': (4 * OBS + 4 * ACT + 4 * (2 * OBS + OBS + ACT + 1 + 3) + 12) * ENVS_PER_GPU,
         'tb_lambda_returns': 4 * 6 * TN,
         'tb_advantages': 4 * 3 * TN,               # per phase: read returns / values or advantages, write
         'tb_permutation': 8 * TN,

@@ -98,6 +98,19 @@ int tb_env_step(const TbEnv* env, const float* d_actions, float* d_obs,
                 float* d_next_obs, float* d_rewards, float* d_resets,
                 float* d_terminations, void* stream);
 
+/* One vector step of the on-policy collector after the actor forward pass in ONE launch
+ * (tonic/utils/trainer.py:44-50): tb_gauss_sample (a2c.py:75-85; d_eps == NULL: Philox stream at
+ * counter + *d_counter + env index) -> d_actions [N,A] (unclipped, what the replay stores) and
+ * d_log_probs [N]; tb_moments_record of the acting observations (the environment state rows;
+ * d_moment_sums NULL = no normaliser); tb_env_step with the clipped actions.  SynthControl
+ * without the time feature only.  The caller advances the stream position (tb_counter_add)
+ * once per rollout, not per step.                                                        */
+int tb_act_env_step(const TbEnv* env, const float* d_loc_pre, const float* d_log_scale,
+                    uint64_t seed, uint64_t counter, const uint64_t* d_counter,
+                    float* d_actions, float* d_log_probs, double* d_moment_sums,
+                    float* d_obs, float* d_next_obs, float* d_rewards, float* d_resets,
+                    float* d_terminations, void* stream);
+
 /* Fused rollout of a whole on-policy segment (T vector steps) in ONE launch: per step
  * the actor forward + Normal sample + log-prob (torch/agents/a2c.py:41-52,75-85), the
  * environment transition with auto-reset (environments/distributed.py:28-58), the segment

@@ -245,6 +245,54 @@ def test_cuda_graph_sections_match_eager():
 
 
 @pytest.mark.parametrize('kind', ['PPO', 'A2C'])
+def test_fused_step_kernel_matches_separate_kernels(kind):
+    """One vector step as actor forward + act_env_step_kernel (sample, log-prob, normaliser record,
+    environment step in one launch) against the chain gauss_sample -> counter_add ->
+    moments_record -> env_step: same Philox positions and arithmetic -> bit-identical segments,
+    environment state and episode log; normaliser sums to double round-off."""
+    import torch
+    from tonic_b200 import config
+    base = scenarios.SCENARIOS['ppo_wide' if kind == 'PPO' else 'a2c_small']
+    seg = dict(base['segment'], size=24)
+    cfg = dict(base, workers=100, max_episode_steps=9, segment=seg)     # ragged tile + many resets
+    old = config.noise, config.indices, config.graphs, config.fused_rollout, config.fused_step
+    out = []
+    try:
+        for fused in (False, True):
+            config.noise, config.indices, config.graphs = 'device', 'device', False
+            config.fused_rollout, config.fused_step = False, fused
+            agent, env = product.build(cfg)
+            env.start()
+            norm = agent.model.observation_normalizer
+            sums = []
+            record = norm.update
+            norm.update = lambda: (sums.append(norm.sums.clone()), record())[1]
+            # 10 single steps through the stepwise entry, then the rest of the segment
+            assert agent.rollout(env, 10) == 10
+            assert agent.rollout(env, seg['size']) == seg['size'] - 10
+            torch.cuda.synchronize()
+            n_ep = int(env.episode_count.item())
+            out.append(dict(
+                seg={k: v.clone() for k, v in agent.replay.buffers.items()
+                     if k in ('observations', 'actions', 'next_observations', 'rewards', 'resets',
+                              'terminations', 'log_probs')},
+                sums=sums[0], state=env.state.clone(), obs=env.observations.clone(), episodes=n_ep,
+                scores=torch.sort(env.episode_scores[:n_ep])[0].clone(),
+                counter=int(agent._noise_counter.item())))
+    finally:
+        config.noise, config.indices, config.graphs, config.fused_rollout, config.fused_step = old
+    a, b = out
+    for k in a['seg']:
+        assert torch.equal(a['seg'][k], b['seg'][k]), k
+    assert float(a['seg']['resets'].sum()) > 100       # the reset branch was exercised
+    assert torch.allclose(a['sums'], b['sums'], rtol=1e-12, atol=1e-9)
+    assert a['sums'][-1].item() == b['sums'][-1].item() == 24 * 100
+    assert torch.equal(a['state'], b['state']) and torch.equal(a['obs'], b['obs'])
+    assert a['episodes'] == b['episodes'] > 0 and torch.equal(a['scores'], b['scores'])
+    assert a['counter'] == b['counter'] == 24 * 100
+
+
+@pytest.mark.parametrize('kind', ['PPO', 'A2C'])
 def test_fused_rollout_matches_per_step_launches(kind):
     """The persistent rollout kernel (one launch per segment) against the per-step chain
     actor forward -> gauss_sample -> env_step -> moments_record on the FFMA path: same

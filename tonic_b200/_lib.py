@@ -62,6 +62,8 @@ _PROTOTYPES = {
     'tb_launch_count': (c_i64, []),
     'tb_env_start': (c_int, [_P(TbEnv), c_vp, c_vp]),
     'tb_env_step': (c_int, [_P(TbEnv), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tb_act_env_step': (c_int, [_P(TbEnv), c_vp, c_vp, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                c_vp, c_vp, c_vp]),
     'tb_rollout_fused': (c_int, [_P(TbEnv), _P(TbMlpShape), c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u64, c_u64, c_u64, c_vp, c_vp]),
     'tb_moments_record': (c_int, [c_vp, c_i64, c_i32, c_vp, c_vp]),

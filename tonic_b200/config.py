@@ -33,6 +33,9 @@ fused_rollout 'auto' : with device noise the whole on-policy segment (T vector s
                    uses it unless the per-step chain can be replayed as a CUDA graph on the
                    tensor-core path (then the chain is faster: measured 4.9 vs 6.5 ms per
                    128-step segment of 4096 envs on B200); True = always, False = never.
+fused_step True  : with device noise on the synthetic task one vector step of the on-policy
+                   rollout chain is actor forward + ONE kernel (sample, log-prob, normaliser record,
+                   environment step: csrc/env_step.cu act_env_step_kernel) instead of five launches.
 wgrad_splits     : number of row splits of the weight-gradient kernel.
 """
 
@@ -45,5 +48,6 @@ graphs = os.environ.get('TONIC_B200_GRAPHS', '1') != '0'
 peer_reduce = os.environ.get('TONIC_B200_PEER_REDUCE', '1') != '0'   # fused NVLink reduce + Adam
 graphs_multi_gpu = os.environ.get('TONIC_B200_GRAPHS_MULTI', '1') != '0'   # capture NCCL too
 fused_rollout = {'0': False, '1': True}.get(os.environ.get('TONIC_B200_FUSED_ROLLOUT', 'auto'), 'auto')
+fused_step = os.environ.get('TONIC_B200_FUSED_STEP', '1') != '0'
 wgrad_splits = 37      # FFMA: 4 heavy tiles x 37 splits = 148 CTAs = one per B200 SM
 wgrad_splits_tc = 74   # tensor cores: 2 row tiles x 74 splits = 148 CTAs

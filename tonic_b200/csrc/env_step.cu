@@ -119,6 +119,126 @@ env_step_kernel(TbEnv env, const float* __restrict__ actions, float* __restrict_
     }
 }
 
+// One vector step of the on-policy collector after the actor forward pass, in ONE launch
+// (trainer.py:44-50): Normal(loc, scale).sample() + summed log-prob (a2c.py:75-85; the Philox
+// stream and arithmetic of gauss_sample_kernel, csrc/heads.cu), MeanStd.record of the acting
+// observations (mean_stds.py:36-37: the environment state IS the acting observation row), and
+// Sequential.step (env_step_kernel above).  Replaces gauss_sample + counter_add + moments_record
+// + env_step of the per-step chain: 5 launches per vector step -> 2.
+__global__ void __launch_bounds__(256)
+act_env_step_kernel(TbEnv env, const float* __restrict__ loc_pre, const float* __restrict__ log_scale,
+                    uint64_t seed, uint64_t counter, const uint64_t* __restrict__ d_counter,
+                    float* __restrict__ actions, float* __restrict__ log_probs, double* moment_sums,
+                    float* __restrict__ obs, float* __restrict__ next_obs, float* __restrict__ rewards,
+                    float* __restrict__ resets, float* __restrict__ terminations, int tile_envs) {
+    extern __shared__ float smem[];
+    const int O = env.obs_dim, A = env.act_dim;
+    float* sx = smem;                          // [tile, O] state (= acting obs) -> transition obs
+    float* so = sx + (size_t)tile_envs * O;    // [tile, O] acting obs of the next step (post reset)
+    float* sa = so + (size_t)tile_envs * O;    // [tile, A] clipped actions
+    __shared__ float s_scale[kMaxAct];
+    if (d_counter) counter += *d_counter;      // device-resident stream position (CUDA graphs)
+
+    const int e0 = blockIdx.x * tile_envs;
+    const int count = min(tile_envs, env.n_envs - e0);
+    const int tid = threadIdx.x;
+    const float* gx = env.d_state + (size_t)e0 * O;
+    for (int i = tid; i < count * O; i += blockDim.x) sx[i] = gx[i];
+    if (tid < A) s_scale[tid] = detached_scale(log_scale[tid], nullptr);
+    __syncthreads();
+
+    // ---- MeanStd.record(acting observations): float64 column sums of this tile ------------
+    if (moment_sums) {
+        if (tid < O) {
+            double s = 0.0, q = 0.0;
+            for (int e = 0; e < count; ++e) {
+                const double v = (double)sx[e * O + tid];
+                s += v;
+                q += v * v;
+            }
+            atomicAdd(&moment_sums[tid], s);
+            atomicAdd(&moment_sums[O + tid], q);
+        } else if (tid == 64) {
+            atomicAdd(&moment_sums[2 * O], (double)count);
+        }
+    }
+    // ---- sample (thread per environment; identical to gauss_sample_kernel) -------------------
+    if (tid < count) {
+        const int64_t n = e0 + tid;
+        Philox rng(seed);
+        float lp = 0.0f;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int a = 0; a < A; ++a) {
+            if ((a & 3) == 0) {
+                const uint4 r = rng(counter + (uint64_t)n, (uint64_t)(a >> 2));
+                const float2 p = box_muller(r.x, r.y), q = box_muller(r.z, r.w);
+                z = make_float4(p.x, p.y, q.x, q.y);
+            }
+            const float e = (a & 3) == 0 ? z.x : (a & 3) == 1 ? z.y : (a & 3) == 2 ? z.z : z.w;
+            const float loc = tanhf(loc_pre[n * A + a]);
+            const float sc = s_scale[a];
+            const float act = __fadd_rn(__fmul_rn(e, sc), loc);       // Normal.sample
+            actions[n * A + a] = act;
+            sa[tid * A + a] = fminf(fmaxf(act, -1.0f), 1.0f);         // wrappers.py:22 np.clip
+            const float d = act - loc;
+            lp += -(d * d) / (2.0f * (sc * sc)) - logf(sc) - kLogSqrt2Pi;
+        }
+        log_probs[n] = lp;
+    }
+    __syncthreads();
+
+    // ---- Sequential.step (same as env_step_kernel, no time feature) ---------------------------
+    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int e = warp; e < count; e += nwarps) {
+        const int n = e0 + e;
+        float* x = sx + (size_t)e * O;
+        float reward;
+        int term;
+        env_transition_warp(x, sa + (size_t)e * A, O, A, lane, &reward, &term);
+        int reset = 0;
+        uint32_t episode = 0;
+        if (lane == 0) {
+            int length = env.d_length[n] + 1;
+            reset = term || (length == env.max_episode_steps);      // distributed.py:40
+            double score = env.d_score[n] + (double)reward;         // trainer.py:52
+            episode = env.d_episode[n];
+            if (reset) {                                            // trainer.py:64-71
+                const unsigned long long slot = atomicAdd(env.d_ep_count, 1ull);
+                if (env.log_cap > 0) {
+                    env.d_ep_scores[slot % env.log_cap] = score;
+                    env.d_ep_lengths[slot % env.log_cap] = length;
+                }
+                env.d_episode[n] = episode + 1u;
+                length = 0;
+                score = 0.0;
+            }
+            env.d_length[n] = length;
+            env.d_score[n] = score;
+            rewards[n] = reward;
+            resets[n] = reset ? 1.0f : 0.0f;
+            terminations[n] = term ? 1.0f : 0.0f;
+        }
+        reset = __shfl_sync(0xffffffffu, reset, 0);
+        episode = __shfl_sync(0xffffffffu, episode, 0);
+        float* o = so + (size_t)e * O;
+        if (reset) {                                                // distributed.py:46-48
+            const uint32_t key = reset_key((uint32_t)(env.seed + env.first_worker + n), episode);
+            for (int j = lane; j < O; j += 32) o[j] = reset_coordinate(key, j);
+        } else {
+            for (int j = lane; j < O; j += 32) o[j] = x[j];
+        }
+    }
+    __syncthreads();
+    float* gs = env.d_state + (size_t)e0 * O;
+    float* go = obs + (size_t)e0 * O;
+    float* gn = next_obs + (size_t)e0 * O;
+    for (int i = tid; i < count * O; i += blockDim.x) {
+        gs[i] = so[i];
+        go[i] = so[i];
+        gn[i] = sx[i];
+    }
+}
+
 static int pick_tile(const TbEnv* env, size_t* smem_bytes) {
     const size_t per_env = (size_t)(2 * env->obs_dim + env->act_dim + 2) * sizeof(float);
     int tile = 256;
@@ -157,6 +277,30 @@ extern "C" int tb_env_start(const TbEnv* env, float* d_obs, void* stream) {
     cudaMemsetAsync(env->d_ep_count, 0, sizeof(unsigned long long), tb::as_stream(stream));
     tb::env_start_kernel<<<blocks, 256, 0, tb::as_stream(stream)>>>(*env, d_obs);
     return tb::check_launch("tb_env_start");
+}
+
+extern "C" int tb_act_env_step(const TbEnv* env, const float* d_loc_pre, const float* d_log_scale,
+                               uint64_t seed, uint64_t counter, const uint64_t* d_counter,
+                               float* d_actions, float* d_log_probs, double* d_moment_sums,
+                               float* d_obs, float* d_next_obs, float* d_rewards, float* d_resets,
+                               float* d_terminations, void* stream) {
+    tb::ProfScope prof_scope("tb_act_env_step", stream);
+    TB_REQUIRE(env && d_loc_pre && d_log_scale && d_actions && d_log_probs && d_obs && d_next_obs &&
+               d_rewards && d_resets && d_terminations, TB_EINVAL, "tb_act_env_step: null pointer");
+    TB_REQUIRE(env->task == TB_TASK_SYNTH && !env->time_feature, TB_ENOTSUP,
+               "tb_act_env_step: SynthControl without the time feature only (use tb_gauss_sample + tb_env_step)");
+    TB_REQUIRE(env->act_dim >= 1 && env->act_dim <= tb::kMaxAct && env->obs_dim <= 64, TB_ENOTSUP,
+               "tb_act_env_step: needs act_dim <= %d and obs_dim <= 64", tb::kMaxAct);
+    size_t smem = 0;
+    const int tile = tb::pick_tile(env, &smem);
+    TB_REQUIRE(smem <= 200 * 1024, TB_ENOTSUP, "tb_act_env_step: obs_dim %d too large", env->obs_dim);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(tb::act_env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int blocks = (env->n_envs + tile - 1) / tile;
+    tb::act_env_step_kernel<<<blocks, 256, smem, tb::as_stream(stream)>>>(
+        *env, d_loc_pre, d_log_scale, seed, counter, d_counter, d_actions, d_log_probs, d_moment_sums,
+        d_obs, d_next_obs, d_rewards, d_resets, d_terminations, tile);
+    return tb::check_launch("tb_act_env_step");
 }
 
 extern "C" int tb_env_step(const TbEnv* env, const float* d_actions, float* d_obs,

@@ -655,6 +655,16 @@ def rollout_fused(env_struct, mlp, log_scale, norm_mean, norm_std, T, buffers, e
               ptr(device_counter), stream())
 
 
+def act_env_step(env_struct, loc_pre, log_scale, seed, counter, device_counter, actions, log_probs,
+                 moment_sums, observations, next_observations, rewards, resets, terminations):
+    """Sample + log-prob + normaliser record + environment step of one vector step in one launch
+    (csrc/env_step.cu::act_env_step_kernel; trainer.py:44-50 after the actor forward)."""
+    _lib.call('tb_act_env_step', ctypes.byref(env_struct), ptr(loc_pre), ptr(log_scale), int(seed),
+              int(counter), ptr(device_counter), ptr(actions), ptr(log_probs), ptr(moment_sums),
+              ptr(observations), ptr(next_observations), ptr(rewards), ptr(resets), ptr(terminations),
+              stream())
+
+
 def counter_add(counter, delta):
     _lib.call('tb_counter_add', ptr(counter), int(delta), stream())
 

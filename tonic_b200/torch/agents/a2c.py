@@ -178,16 +178,39 @@ class A2C(agent.Agent):
         b, T = seg.buffers, seg.max_size
         normalizer = self.model.observation_normalizer
 
-        def one_step(t):
+        world, rank = distributed.world(), distributed.rank()
+        fused_step = self._fused_step(env)
+
+        def one_step(t, offset=0):
+            """`offset`: vector steps since the last advance of the device noise counter (a whole
+            captured segment advances it once, at the end)."""
             if t == 0:       # first acting observations come from the environment
                 b['observations'][0].copy_(env.observations)
             obs = b['observations'][t]
+            target = b['observations'][t + 1] if t + 1 < T else env.observations
+            if fused_step:
+                # actor forward, then ONE kernel: sample + log-prob, normaliser record, env step
+                self.model.actor.pre_activations(obs, out=self._pre[:N])
+                if self._noise_counter is None:
+                    self._noise_counter = kernels.new_counter()
+                kernels.act_env_step(
+                    env.struct, self._pre[:N], self.model.actor.network.extra('log_scale'),
+                    self.seed or 0, rank * N + offset * N * world, self._noise_counter,
+                    b['actions'][t], b['log_probs'][t], normalizer.sums if normalizer else None,
+                    target, b['next_observations'][t], b['rewards'][t], b['resets'][t],
+                    b['terminations'][t])
+                return
             self._sample(obs, b['actions'][t], b['log_probs'][t])
             if normalizer:
                 normalizer.record(obs)
-            target = b['observations'][t + 1] if t + 1 < T else env.observations
             env.step_into(b['actions'][t], target, b['next_observations'][t], b['rewards'][t],
                           b['resets'][t], b['terminations'][t])
+
+        def whole_segment():
+            for t in range(T):
+                one_step(t, offset=t)
+            if fused_step:
+                kernels.counter_add(self._noise_counter, T * N * world)
 
         done = 0
         if self._fusable(env) and seg.index == 0 and vector_steps >= T:
@@ -209,13 +232,14 @@ class A2C(agent.Agent):
         elif self._graphable() and seg.index == 0 and vector_steps >= T:
             # whole segment in one CUDA graph (tonic_b200/graphs.py)
             if self._rollout_graph is None:
-                self._rollout_graph = graphs.CapturedSection(
-                    lambda: [one_step(t) for t in range(T)])
+                self._rollout_graph = graphs.CapturedSection(whole_segment)
             self._rollout_graph()
             seg.index = T
             done = T
         while done < vector_steps and seg.index < T:
             one_step(seg.index)
+            if fused_step:
+                kernels.counter_add(self._noise_counter, N * world)
             seg.advance()
             done += 1
         if action_stats is not None and done:
@@ -223,6 +247,15 @@ class A2C(agent.Agent):
         if seg.ready():
             self._update()
         return done
+
+    def _fused_step(self, env):
+        """Device noise on the synthetic task: sampling, the normaliser record and the environment
+        step of one vector step run as one kernel (csrc/env_step.cu::act_env_step_kernel)."""
+        return (config.noise == 'device' and config.fused_step and hasattr(env, 'struct')
+                and not getattr(env, 'time_feature', False)
+                and not getattr(env.spec, 'task_id', 0)
+                and env.struct.obs_dim <= 64 and self.action_size <= 64
+                and hasattr(self.model.actor, 'pre_activations'))
 
     def _fusable(self, env):
         """The fused rollout kernel covers the detached-scale Gaussian actor on
