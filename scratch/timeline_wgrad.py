@@ -35,7 +35,7 @@ def run(fuse):
               K.ptr(h2), K.ptr(dz1), K.ptr(dz2_hi), None if PLAIN else K.ptr(dz2_lo), K.ptr(dout), n_out + n_extra, n_extra,
               off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), PASSES,
               ctypes.byref(adam.struct) if fuse else None, K.ptr(net.packed) if fuse else None,
-              1.0 / rows, None, -1.0, None, None, K.stream())
+              1.0 / rows, None, -1.0, None, None, None, None, None, K.stream())
 
 
 for fuse in (False, True):

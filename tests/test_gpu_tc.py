@@ -297,11 +297,11 @@ def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_s
         _lib.call('tb_mlp_wgrad_fused', ctypes.byref(sh), K.ptr(dev[0]), K.ptr(h1_hi), K.ptr(h1_lo),
                   K.ptr(dev[1]), K.ptr(dev[2]), K.ptr(dz2_hi), K.ptr(dz2_lo), K.ptr(dev[3]), ld, n_extra,
                   off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), passes,
-                  None, None, 0.0, None, -1.0, None, None, K.stream())
+                  None, None, 0.0, None, -1.0, None, None, None, None, None, K.stream())
         torch.cuda.synchronize()
         outs.append(flat.cpu())
     assert torch.equal(outs[0], outs[1])
-    assert int(sync.item()) == 2 * 2 * n_split          # two barriers of 2 * n_split CTAs
+    assert int(sync.item()) == 2 << 32                  # generation 2, no arrivals pending
     if passes == 3:
         # plain float32 h1 / dz2 (lo == NULL): the kernel splits the tiles in shared memory into
         # the same hi / lo operands -> bit-identical gradient
@@ -310,7 +310,7 @@ def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_s
         _lib.call('tb_mlp_wgrad_fused', ctypes.byref(sh), K.ptr(dev[0]), K.ptr(d_h1), None,
                   K.ptr(dev[1]), K.ptr(dev[2]), K.ptr(d_dz2), None, K.ptr(dev[3]), ld, n_extra,
                   off_extra, rows, K.ptr(gpart), n_split, K.ptr(flat), K.ptr(sync), passes,
-                  None, None, 0.0, None, -1.0, None, None, K.stream())
+                  None, None, 0.0, None, -1.0, None, None, None, None, None, K.stream())
         torch.cuda.synchronize()
         assert torch.equal(flat.cpu(), outs[0])
     got = outs[0].double()
@@ -325,6 +325,44 @@ def test_wgrad_fused_all_gradients_one_launch(K, d_in, n_out, n_extra, rows, n_s
     err_w = (got - ref)[used & ~narrow].abs().max().item()
     assert err_n <= 2e-6 * scale * (rows ** 0.5) + 1e-5, (err_n, scale)       # FFMA part: fp32 in any mode
     assert err_w <= tol + 1e-5, (err_w, scale)
+
+
+@pytest.mark.timeout(240, method='thread')
+def test_wgrad_fused_grid_barrier_survives_changing_grid_sizes(K):
+    """Consecutive launches on ONE barrier word with different numbers of CTAs (a ragged last
+    minibatch changes the split count from launch to launch): every launch must complete and give
+    the gradient of its own rows.  (A counter that only grows deadlocks here: the arrival count is
+    not a multiple of the new grid size.)"""
+    import ctypes
+    from tonic_b200 import _lib
+    layout = K.MlpLayout(17, 256, 1, 'tanh')
+    g = torch.Generator().manual_seed(11)
+    big = 2048
+    xin = torch.zeros(big, layout.ldx)
+    xin[:, :17] = torch.randn(big, 17, generator=g)
+    xin[:, 17] = 1.0
+    h1, h2 = torch.tanh(torch.randn(big, 256, generator=g)).cuda(), torch.tanh(torch.randn(big, 256, generator=g)).cuda()
+    dz1, dz2 = (torch.randn(big, 256, generator=g) * 0.1).cuda(), (torch.randn(big, 256, generator=g) * 0.1).cuda()
+    dout = torch.randn(big, 2, generator=g).cuda()
+    xin = xin.cuda()
+    sync = torch.zeros(1, dtype=torch.int64, device='cuda')
+    gpart = torch.zeros(74, layout.n_params, device='cuda')
+    o = layout.offsets
+    launches = [(64, 2), (32, 1), (64, 2), (2048, 64), (33, 1), (1000, 31), (64, 2), (2048, 74), (48, 1)]
+    for k, (rows, n_split) in enumerate(launches):
+        flat = torch.full((layout.n_params,), float('nan'), device='cuda')
+        _lib.call('tb_mlp_wgrad_fused', ctypes.byref(layout.shape), K.ptr(xin), K.ptr(h1), None,
+                  K.ptr(h2), K.ptr(dz1), K.ptr(dz2), None, K.ptr(dout), 2, 0, 0, rows, K.ptr(gpart), n_split,
+                  K.ptr(flat), K.ptr(sync), 3, None, None, 0.0, None, -1.0, None, None, None, None, None,
+                  K.stream())
+        torch.cuda.synchronize()
+        assert int(sync.item()) == (k + 1) << 32
+        want = (dz2[:rows].double().T @ h1[:rows].double()).reshape(-1)
+        got = flat[o['w2'][0]:o['w2'][0] + 65536].double()
+        assert (got - want).abs().max().item() <= 2e-6 * want.abs().max().item() * rows ** 0.5 + 1e-5, (rows, n_split)
+        want_b1 = dz1[:rows].double().sum(0)
+        got_b1 = flat[o['b1'][0]:o['b1'][0] + 256].double()
+        assert (got_b1 - want_b1).abs().max().item() <= 1e-4, (rows, n_split)
 
 
 @pytest.mark.parametrize('n_out,n_extra,with_stats', [(1, 0, False), (6, 6, True)])
@@ -367,7 +405,7 @@ def test_wgrad_fused_adam_equals_separate_step(K, n_out, n_extra, with_stats):
                       K.ptr(flat), K.ptr(sync), 3, opt, K.ptr(net.packed) if fused else None,
                       1.0 / rows if fused else 0.0, K.ptr(stats) if fused else None,
                       0.015 if fused and stats is not None else -1.0, K.ptr(stop) if fused else None,
-                      None, K.stream())
+                      None, None, None, None, K.stream())
             if not fused:
                 adam.step(net, flat, 1, 1.0 / rows, stats=stats, kl_threshold=0.015 if stats is not None else -1.0,
                           stop=stop)

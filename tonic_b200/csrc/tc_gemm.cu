@@ -545,7 +545,7 @@ struct TcWgradAllParams {
     int ld_dout, n_extra, off_extra;
     int n_split;
     float* flat;                // [n_params] reduced gradient (sum over rows)
-    unsigned long long* sync;   // grid-barrier counter (monotonic)
+    unsigned long long* sync;   // grid-barrier word: generation << 32 | arrivals
     unsigned long long* timeline;   // profiling aid: clock64() stamps of CTA (0, 0), or NULL
     int tma3d;                  // operand tiles by one 3-D box each (else one 2-D box per column group)
     int dbg;                    // timing experiments only (TB_WGRAD_DBG): 1 = no bias-gradient MMAs, 2 = no FFMA block
@@ -567,17 +567,26 @@ struct TcWgradAllParams {
     int two_phase;              // force the reduce-scatter + all-gather exchange (TONIC_B200_PEER_TWO_PHASE=1)
 };
 
+// Grid-wide barrier of a launch whose CTAs are all resident.  *counter = generation << 32 |
+// arrivals: the last arrival resets the arrivals and bumps the generation in ONE atomic add, the
+// others spin until the generation moves.  The word is back to "0 arrivals" after every launch, so
+// consecutive launches on the same counter may use different grid sizes (ragged last minibatch).
 __device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned int n_ctas) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned long long old = atomicAdd(counter, 1ULL);
-        const unsigned long long target = (old / n_ctas + 1ULL) * n_ctas;
-        unsigned long long seen;
-        do {
-            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
-            if (seen < target) __nanosleep(40);
-        } while (seen < target);
+        const unsigned int generation = (unsigned int)(old >> 32);
+        if ((unsigned int)old == n_ctas - 1u) {
+            atomicAdd(counter, (1ULL << 32) - (unsigned long long)n_ctas);
+        } else {
+            unsigned long long seen;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(counter) : "memory");
+                if ((unsigned int)(seen >> 32) != generation) break;
+                __nanosleep(40);
+            }
+        }
         __threadfence();
     }
     __syncthreads();
