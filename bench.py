@@ -142,11 +142,18 @@ class Run:
         torch = self.torch
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
+        # `ncu --profile-from-start off` captures exactly the timed region (launch list of the SAME
+        # command under profiles/; a number printed by such a run is never a bench value)
+        profiled = os.environ.get('TB_BENCH_CUDA_PROFILER') == '1'
+        if profiled:
+            torch.cuda.profiler.start()
         start.record()
         for _ in range(steps):
             fn()
         end.record()
         self.barrier()
+        if profiled:
+            torch.cuda.profiler.stop()
         return self.max_over_ranks(start.elapsed_time(end))
 
 
