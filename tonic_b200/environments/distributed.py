@@ -60,11 +60,17 @@ class DeviceVectorEnvironment:
         self.time_feature = tf
         task = int(getattr(self.spec, 'task_id', 0))
         self.state64 = torch.zeros(N, 2, dtype=torch.float64, device=dev) if task else None
-        self.observations = torch.zeros(N, O + tf, dtype=torch.float32, device=dev)
-        self.next_observations = torch.zeros(N, O + tf, dtype=torch.float32, device=dev)
-        self.rewards = torch.zeros(N, dtype=torch.float32, device=dev)
-        self.resets = torch.zeros(N, dtype=torch.float32, device=dev)
-        self.terminations = torch.zeros(N, dtype=torch.float32, device=dev)
+        # one packed block (regions 256-byte aligned): the host protocol fetches all five results
+        # with a single device->host copy
+        sizes = [N * (O + tf), N * (O + tf), N, N, N]
+        offsets, total = [], 0
+        for size in sizes:
+            offsets.append(total)
+            total = (total + size + 63) // 64 * 64
+        self._out_block = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._out_regions = list(zip(offsets, sizes, [(N, O + tf), (N, O + tf), (N,), (N,), (N,)]))
+        (self.observations, self.next_observations, self.rewards, self.resets,
+         self.terminations) = (self._out_block[o:o + n].view(shape) for o, n, shape in self._out_regions)
         self.struct = _lib.TbEnv(
             n_envs=N, obs_dim=O, act_dim=self.spec.action_size,
             max_episode_steps=self.max_episode_steps, seed=self.seed,
@@ -90,30 +96,39 @@ class DeviceVectorEnvironment:
                   ptr(next_observations), ptr(rewards), ptr(resets), ptr(terminations),
                   kernels.stream())
 
+    HOST_SLOTS = 3      # arrays returned by step() stay valid for this many further calls
+
     def _step_host(self, actions):
-        """environment.step(numpy) -> numpy: pinned copy-in, H2D, the step kernel and the five
-        D2H copies as ONE captured graph over fixed staging buffers, one synchronisation."""
+        """environment.step(numpy) -> numpy: pinned copy-in, then H2D + the step kernel as ONE
+        captured graph, ONE device->host copy of the packed result block into a rotating pinned
+        slot, one synchronisation.  The returned arrays are views of that slot (no host copy): they
+        are overwritten HOST_SLOTS calls later -- the reference's agents copy what they keep
+        (torch/agents/a2c.py:48), and so does everything in this package."""
         from .. import graphs
         if getattr(self, '_bridge', None) is None:
             self._bridge, self._host_section = kernels.HostBridge(), None
         b = self._bridge
         pin_act, dev_act = b.load('actions', actions)
-        outs = [(b.buffers(name, t.shape)[0], t) for name, t in (
-            ('obs', self.observations), ('next_obs', self.next_observations), ('rewards', self.rewards),
-            ('resets', self.resets), ('terminations', self.terminations))]
         if self._host_section is None:
             def body():
                 dev_act.copy_(pin_act, non_blocking=True)
                 self.step_into(dev_act, self.observations, self.next_observations, self.rewards,
                                self.resets, self.terminations)
-                for pinned, dev in outs:
-                    pinned.copy_(dev, non_blocking=True)
             self._host_section = graphs.CapturedSection(body)
+            self._host_slots = [torch.empty(self._out_block.numel(), dtype=torch.float32).pin_memory()
+                                for _ in range(self.HOST_SLOTS)]
+            self._host_views = [[slot.numpy()[o:o + n].reshape(shape) for o, n, shape in self._out_regions]
+                                for slot in self._host_slots]
+            self._host_slot = 0
+            self._host_bytes = 4 * sum(n for _, n, _ in self._out_regions)
         self._host_section()
+        self._host_slot = (self._host_slot + 1) % self.HOST_SLOTS
+        self._host_slots[self._host_slot].copy_(self._out_block, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        obs, next_obs, rewards = (b.read(p) for p, _ in outs[:3])
-        resets, terminations = b.read(outs[3][0], np.bool_), b.read(outs[4][0], np.bool_)
-        return obs, dict(observations=next_obs, rewards=rewards, resets=resets, terminations=terminations)
+        kernels.transfers['d2h'] += self._host_bytes
+        obs, next_obs, rewards, resets, terminations = self._host_views[self._host_slot]
+        return obs, dict(observations=next_obs, rewards=rewards, resets=resets.astype(np.bool_),
+                         terminations=terminations.astype(np.bool_))
 
     def step(self, actions):
         host = not isinstance(actions, torch.Tensor) or not actions.is_cuda

@@ -89,7 +89,6 @@ class A2C(agent.Agent):
         N = observations.shape[0]
         self._buffers(N)
         pin_obs, dev_obs = self._bridge.load('step_obs', observations)
-        pin_act, _ = self._bridge.buffers('step_actions', (N, self.action_size))
         key = ('step', N)
         if key not in self._host_sections:
             last = self._bridge.buffers('last_obs', observations.shape)[1]
@@ -98,13 +97,19 @@ class A2C(agent.Agent):
                 dev_obs.copy_(pin_obs, non_blocking=True)
                 self._sample(dev_obs, self._actions[:N], self._log_probs[:N])
                 last.copy_(dev_obs)                      # a2c.py:48: the agent keeps a copy
-                pin_act.copy_(self._actions[:N], non_blocking=True)
-            self._host_sections[key] = (graphs.CapturedSection(body), last)
-        section, last = self._host_sections[key]
+            # the actions come back through rotating pinned slots and are returned as views (no
+            # host copy): valid until the third next call, like the environment's results
+            slots = [torch.empty(N, self.action_size, dtype=torch.float32).pin_memory() for _ in range(3)]
+            self._host_sections[key] = (graphs.CapturedSection(body), last, slots,
+                                        [slot.numpy() for slot in slots], [0])
+        section, last, slots, views, cursor = self._host_sections[key]
         section()
+        cursor[0] = (cursor[0] + 1) % len(slots)
+        slots[cursor[0]].copy_(self._actions[:N], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        kernels.transfers['d2h'] += slots[0].numel() * 4
         self.last_observations, self.last_actions, self.last_log_probs = last, self._actions[:N], self._log_probs[:N]
-        return self._bridge.read(pin_act)
+        return views[cursor[0]]
 
     def _update_host(self, observations, rewards, resets, terminations):
         """agent.update(numpy ...): pinned copy-in, 4 H2D copies, segment store at the device row
