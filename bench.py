@@ -287,6 +287,60 @@ def run_ppo(args):
                                   minibatch_updates=timed_iterations, multi_rank_parity=parity,
                                   quick=True)))
         return
+    # ---- e2e: the reference-facing protocol with HOST arrays ------------------------
+    def host_iteration(observations, steps_count):
+        for _ in range(SEGMENT):
+            actions = agent.step(observations, steps_count)
+            observations, infos = env.step(actions)
+            agent.update(**infos, steps=steps_count)
+            steps_count += ENVS_PER_GPU
+        return observations, steps_count
+
+    def measure(iters, warm):
+        """The reference's protocol with numpy arrays crossing the boundary every vector step."""
+        agent.replay.index = 0
+        observations = env.start(host=True)
+        steps_count = 0
+        for _ in range(warm):
+            observations, steps_count = host_iteration(observations, steps_count)
+        torch.cuda.synchronize()
+        run.barrier()
+        kernels.transfers['h2d'] = kernels.transfers['d2h'] = 0
+        iterations.update(actor=0, critic=0)
+        update_timer.reset()
+        t0 = time.time()
+        for _ in range(iters):
+            observations, steps_count = host_iteration(observations, steps_count)
+        torch.cuda.synchronize()
+        dt = run.max_over_ranks(time.time() - t0)      # slowest rank
+        detail = dict(update_ms=round(run.max_over_ranks(update_timer.mean_ms() or 0.0), 3),
+                      minibatch_updates_per_iteration={k: v // iters for k, v in iterations.items()})
+        detail['protocol_us_per_vector_step'] = round(
+            (dt / iters * 1e3 - detail['update_ms']) / SEGMENT * 1e3, 1)
+        return (iters * SEGMENT * total_envs / dt, kernels.transfers['h2d'] // iters,
+                kernels.transfers['d2h'] // iters, detail)
+    # product configuration: device Philox noise + device permutations, update replayed as a
+    # CUDA graph (3 warm iterations: 2 eager executions size the workspaces, 1 captures)
+    e2e_iters = max(1, min(args.steps, 3))
+    fast, h2d, d2h, e2e_detail = measure(e2e_iters, 3)
+    # parity configuration: host torch RNG noise + numpy-compatible MT19937 permutations
+    parity_value = None
+    if world == 1:
+        config.noise = config.indices = 'host'
+        parity_value, _, _, _ = measure(1, 1)
+        config.noise, config.indices = 'device', args.indices
+        parity_value = round(parity_value, 1)
+    e2e = dict(value=round(fast, 1), unit='env-steps/s', h2d_bytes_per_step=h2d,
+               d2h_bytes_per_step=d2h, steps=e2e_iters, parity_mode_value=parity_value, **e2e_detail,
+               note='agent.step / environment.step / agent.update called with numpy arrays '
+                    'every vector step (pinned staging, copies inside the timed region; bytes '
+                    'are per rank and per PPO iteration of 128 vector steps); value = product configuration '
+                    '(device noise and permutations, graph-replayed update), parity_mode_value '
+                    '= host torch RNG noise + host MT19937 permutations (bit-compatible streams); measured '
+                    'right after the device-resident timed pass (same training phase: the number of actor '
+                    'minibatches before the KL early stop grows with training and is reported beside '
+                    'update_ms); protocol_us_per_vector_step = (iteration - update) / 128')
+
     # ---- instrumented pass: CUDA events around every launch (same workload, same kernels:
     # graphs off so that the C entry points record per-launch events, and the per-step rollout
     # chain the graph replays -- not the FFMA persistent-rollout kernel) ----------------------
@@ -295,6 +349,7 @@ def run_ppo(args):
     if saved_rollout == 'auto':
         config.fused_rollout = False
     kernels.flops.clear()
+    iterations.update(actor=0, critic=0)
     kernels.profile_begin()
     t0 = time.time()
     for _ in range(args.steps):
@@ -308,8 +363,7 @@ def run_ppo(args):
     pk = peaks()
     # FLOPs of launches that the device-side KL flag turned into no-ops are not counted:
     # the skipped actor minibatches are known from the logged iteration counters
-    skipped = profiled_iterations['critic'] - timed_iterations['critic'] - (
-        profiled_iterations['actor'] - timed_iterations['actor'])
+    skipped = profiled_iterations['critic'] - profiled_iterations['actor']
     rows_local = batch // world
     gemm_names = ('tb_tc_mlp_train', 'tb_tc_mlp_forward', 'tb_tc_mlp_backward', 'tb_tc_gemm256_fwd',
                   'tb_tc_gemm256_bwd', 'tb_tc_wgrad256', 'tb_mlp_wgrad_fused', 'tb_mlp_forward',
@@ -386,51 +440,6 @@ def run_ppo(args):
         hbm_kernels=hbm, hbm_peak_gbs=pk['hbm'],
         hbm_note='memory-bound kernels: algorithmic bytes per launch (SURVEY 8d) / CUDA-event time per '
                  'launch; at these sizes (<= 12 MB per launch) they are launch-latency bound, not HBM bound')
-
-    # ---- e2e: the reference-facing protocol with HOST arrays ------------------------
-    def host_iteration(observations, steps_count):
-        for _ in range(SEGMENT):
-            actions = agent.step(observations, steps_count)
-            observations, infos = env.step(actions)
-            agent.update(**infos, steps=steps_count)
-            steps_count += ENVS_PER_GPU
-        return observations, steps_count
-
-    def measure(iters, warm):
-        """The reference's protocol with numpy arrays crossing the boundary every vector step."""
-        agent.replay.index = 0
-        observations = env.start(host=True)
-        steps_count = 0
-        for _ in range(warm):
-            observations, steps_count = host_iteration(observations, steps_count)
-        torch.cuda.synchronize()
-        run.barrier()
-        kernels.transfers['h2d'] = kernels.transfers['d2h'] = 0
-        t0 = time.time()
-        for _ in range(iters):
-            observations, steps_count = host_iteration(observations, steps_count)
-        torch.cuda.synchronize()
-        dt = run.max_over_ranks(time.time() - t0)      # slowest rank
-        return (iters * SEGMENT * total_envs / dt, kernels.transfers['h2d'] // iters,
-                kernels.transfers['d2h'] // iters)
-    # product configuration: device Philox noise + device permutations, update replayed as a
-    # CUDA graph (3 warm iterations: 2 eager executions size the workspaces, 1 captures)
-    e2e_iters = max(1, min(args.steps, 3))
-    fast, h2d, d2h = measure(e2e_iters, 3)
-    # parity configuration: host torch RNG noise + numpy-compatible MT19937 permutations
-    parity_value = None
-    if world == 1:
-        config.noise = config.indices = 'host'
-        parity_value, _, _ = measure(1, 1)
-        config.noise, config.indices = 'device', args.indices
-        parity_value = round(parity_value, 1)
-    e2e = dict(value=round(fast, 1), unit='env-steps/s', h2d_bytes_per_step=h2d,
-               d2h_bytes_per_step=d2h, steps=e2e_iters, parity_mode_value=parity_value,
-               note='agent.step / environment.step / agent.update called with numpy arrays '
-                    'every vector step (pinned staging, copies inside the timed region; bytes '
-                    'are per rank and per PPO iteration of 128 vector steps); value = product configuration '
-                    '(device noise and permutations, graph-replayed update), parity_mode_value '
-                    '= host torch RNG noise + host MT19937 permutations (bit-compatible streams)')
 
     # ---- off-policy configurations (BASELINE configs[2] / [3]) measured in the same run ------
     offpolicy = None
